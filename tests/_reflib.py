@@ -1,0 +1,272 @@
+"""ctypes readers for the CHECKER libraries (test infrastructure only).
+
+* ``oracle/_ref/libabpoa_ref.so``  -- the unmodified reference abPOA + oracle/ref_harness.c
+* ``oracle/_ref/libbar_ref.so``    -- the reference bar/impl/poaBarAligner.c + oracle/bar_ref_harness.c
+* ``oracle/_build/libpoa_oracle.so`` -- the plain-C restatement (oracle/poa_oracle.c, bar_oracle.c)
+
+Nothing in ``cactus_b200`` may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libabpoa_ref.so")
+BAR_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbar_ref.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libpoa_oracle.so")
+
+# Cactus defaults, src/cactus/cactus_progressive_config.xml:307-325
+CACTUS_MAT = [91, -114, -61, -123, -100,
+              -114, 100, -125, -61, -100,
+              -61, -125, 100, -114, -100,
+              -123, -61, -114, 91, -100,
+              -100, -100, -100, -100, 100]
+
+
+class RefParams(C.Structure):
+    _fields_ = [("wb", C.c_int), ("wf", C.c_float),
+                ("gap_open1", C.c_int), ("gap_ext1", C.c_int), ("gap_open2", C.c_int), ("gap_ext2", C.c_int),
+                ("mat", C.c_int * 25),
+                ("k", C.c_int), ("w", C.c_int), ("min_w", C.c_int),
+                ("progressive_poa", C.c_int), ("disable_seeding", C.c_int)]
+
+
+def cactus_params(wb=1000, wf=0.1, o1=400, e1=30, o2=1200, e2=1, mat=None, k=15, w=5, min_w=500,
+                  progressive=1, disable_seeding=1):
+    p = RefParams()
+    p.wb, p.wf = wb, wf
+    p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2 = o1, e1, o2, e2
+    for i, v in enumerate(mat or CACTUS_MAT):
+        p.mat[i] = v
+    p.k, p.w, p.min_w = k, w, min_w
+    p.progressive_poa, p.disable_seeding = progressive, disable_seeding
+    return p
+
+
+def params_dict(p):
+    return dict(wb=p.wb, wf=float(p.wf), o1=p.gap_open1, e1=p.gap_ext1, o2=p.gap_open2, e2=p.gap_ext2,
+                mat=list(p.mat), k=p.k, w=p.w, min_w=p.min_w, progressive=p.progressive_poa,
+                disable_seeding=p.disable_seeding)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def have_bar_ref():
+    return os.path.exists(BAR_REF_SO)
+
+
+def build_oracle():
+    """(Re)build the plain-C oracle; cheap, and keeps tests independent of build() ordering."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return ORACLE_SO
+
+
+_libs = {}
+
+
+def _load(path):
+    if path not in _libs:
+        _libs[path] = C.CDLL(path)
+    return _libs[path]
+
+
+def _flat(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    flat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    return lens, np.ascontiguousarray(flat)
+
+
+def _parse_trace(words, n_seq):
+    w = words
+    assert w[0] == n_seq
+    msa_len, total_cells = int(w[1]), int(w[2])
+    pos = 3
+    read_id_map = [int(x) for x in w[pos:pos + n_seq]]
+    pos += n_seq
+    alns = []
+    for _ in range(n_seq):
+        read_id, qlen, node_n, n_cigar, best, n_rows = (int(x) for x in w[pos:pos + 6])
+        pos += 6
+        cigar = w[pos:pos + n_cigar].astype(np.uint64, copy=True) if n_cigar else np.zeros(0, np.uint64)
+        pos += n_cigar
+        dp_beg = w[pos:pos + n_rows].astype(np.int32)
+        pos += n_rows
+        dp_end = w[pos:pos + n_rows].astype(np.int32)
+        pos += n_rows
+        alns.append(dict(read_id=read_id, qlen=qlen, node_n=node_n, best_score=best,
+                         cigar=cigar.view(np.uint64), dp_beg=dp_beg, dp_end=dp_end))
+    msa = w[pos:].view(np.uint8)[: n_seq * msa_len].reshape(n_seq, msa_len).copy()
+    return dict(msa=msa, msa_len=msa_len, cells=total_cells, read_id_map=read_id_map, alns=alns)
+
+
+def _msa_fn(lib, name):
+    f = getattr(lib, name)
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(RefParams), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    return f
+
+
+def _trace_fn(lib, name):
+    f = getattr(lib, name)
+    f.restype = C.c_void_p
+    f.argtypes = [C.POINTER(RefParams), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    return f
+
+
+def _call_msa(lib, fname, freename, seqs, p):
+    lens, flat = _flat(seqs)
+    out = C.c_void_p()
+    n = _msa_fn(lib, fname)(C.byref(p), len(seqs), lens.ctypes.data, flat.ctypes.data, C.byref(out))
+    msa = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(len(seqs) * max(n, 1),))[: len(seqs) * n]
+    msa = msa.reshape(len(seqs), n).copy()
+    free = getattr(lib, freename)
+    free.argtypes = [C.c_void_p]
+    free(out)
+    return msa
+
+
+def _call_trace(lib, fname, freename, seqs, p):
+    lens, flat = _flat(seqs)
+    nw = C.c_int64()
+    ptr = _trace_fn(lib, fname)(C.byref(p), len(seqs), lens.ctypes.data, flat.ctypes.data, C.byref(nw))
+    words = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(nw.value,)).copy()
+    free = getattr(lib, freename)
+    free.argtypes = [C.c_void_p]
+    free(ptr)
+    return _parse_trace(words, len(seqs))
+
+
+def ref_poa_msa(seqs, p=None):
+    """abpoa_msa of the UNMODIFIED reference. seqs: list of uint8 arrays (0..4). -> uint8 [n_seq, msa_len]."""
+    return _call_msa(_load(REF_SO), "ref_poa_msa", "ref_free", seqs, p or cactus_params())
+
+
+def ref_poa_msa_trace(seqs, p=None):
+    return _call_trace(_load(REF_SO), "ref_poa_msa_trace", "ref_free", seqs, p or cactus_params())
+
+
+def oracle_poa_msa(seqs, p=None):
+    return _call_msa(_load(build_oracle()), "oracle_poa_msa", "oracle_free", seqs, p or cactus_params())
+
+
+def oracle_poa_msa_trace(seqs, p=None):
+    return _call_trace(_load(build_oracle()), "oracle_poa_msa_trace", "oracle_free", seqs, p or cactus_params())
+
+
+# ---------------------------------------------------------------------------------------------------
+# BAR level: msa_make_partial_order_alignment / make_consistent_partial_order_alignments
+# ---------------------------------------------------------------------------------------------------
+class OracleMsa(C.Structure):
+    _fields_ = [("seq_no", C.c_int64), ("column_no", C.c_int64), ("seq_lens", C.POINTER(C.c_int)),
+                ("msa", C.POINTER(C.c_uint8))]
+
+
+def _cstrings(strs):
+    arr = (C.c_char_p * len(strs))(*[s if isinstance(s, bytes) else s.encode() for s in strs])
+    lens = (C.c_int * len(strs))(*[len(s) for s in strs])
+    return arr, lens
+
+
+def _msa_make(libname, strs, window_size, max_prog_rows, max_prog_length_diff, p):
+    p = p or cactus_params()
+    arr, lens = _cstrings(strs)
+    n = len(strs)
+    if libname == "ref":
+        lib = _load(BAR_REF_SO)
+        f = lib.bar_ref_msa_make_partial_order_alignment
+        f.restype = C.c_int64
+        f.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                      C.POINTER(C.c_void_p)]
+        out = C.c_void_p()
+        cols = f(C.byref(p), arr, lens, n, window_size, max_prog_rows, max_prog_length_diff, C.byref(out))
+        msa = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n * max(cols, 1),))[: n * cols]
+        msa = msa.reshape(n, cols).copy()
+        lib.bar_ref_free.argtypes = [C.c_void_p]
+        lib.bar_ref_free(out)
+        return msa
+    lib = _load(build_oracle())
+    f = lib.oracle_msa_make_partial_order_alignment
+    f.restype = C.POINTER(OracleMsa)
+    f.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double]
+    m = f(C.byref(p), arr, lens, n, window_size, max_prog_rows, max_prog_length_diff)
+    cols = m.contents.column_no
+    msa = np.ctypeslib.as_array(m.contents.msa, shape=(n * max(cols, 1),))[: n * cols].reshape(n, cols).copy()
+    lib.oracle_msa_destruct.argtypes = [C.c_void_p]
+    lib.oracle_msa_destruct(m)
+    return msa
+
+
+def ref_msa_make_partial_order_alignment(strs, window_size=10000, max_prog_rows=5000, max_prog_length_diff=1.0, p=None):
+    return _msa_make("ref", strs, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
+def oracle_msa_make_partial_order_alignment(strs, window_size=10000, max_prog_rows=5000, max_prog_length_diff=1.0, p=None):
+    return _msa_make("oracle", strs, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
+def _consistent(libname, ends, right_end_indexes, right_end_row_indexes, overlaps, window_size, max_prog_rows,
+                max_prog_length_diff, p):
+    """ends: list (per end) of list of ASCII strings. right_*/overlaps: list of int lists, same shape."""
+    p = p or cactus_params()
+    end_no = len(ends)
+    keep = []
+    end_lengths = (C.c_int64 * end_no)(*[len(e) for e in ends])
+    es = (C.c_void_p * end_no)()
+    el = (C.c_void_p * end_no)()
+    ri = (C.c_void_p * end_no)()
+    rr = (C.c_void_p * end_no)()
+    ov = (C.c_void_p * end_no)()
+    for i, e in enumerate(ends):
+        arr, lens = _cstrings(e)
+        a = (C.c_int64 * len(e))(*right_end_indexes[i])
+        b = (C.c_int64 * len(e))(*right_end_row_indexes[i])
+        c = (C.c_int64 * len(e))(*overlaps[i])
+        keep += [arr, lens, a, b, c]
+        es[i], el[i] = C.cast(arr, C.c_void_p), C.cast(lens, C.c_void_p)
+        ri[i], rr[i], ov[i] = C.cast(a, C.c_void_p), C.cast(b, C.c_void_p), C.cast(c, C.c_void_p)
+    out = []
+    if libname == "ref":
+        lib = _load(BAR_REF_SO)
+        f = lib.bar_ref_make_consistent_partial_order_alignments
+        f.restype = None
+        f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+        cols = (C.c_int64 * end_no)()
+        outs = (C.c_void_p * end_no)()
+        f(C.byref(p), end_no, end_lengths, es, el, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, cols, outs)
+        lib.bar_ref_free.argtypes = [C.c_void_p]
+        for i in range(end_no):
+            n, c = len(ends[i]), cols[i]
+            m = np.ctypeslib.as_array(C.cast(outs[i], C.POINTER(C.c_uint8)), shape=(n * max(c, 1),))[: n * c]
+            out.append(m.reshape(n, c).copy())
+            lib.bar_ref_free(outs[i])
+        return out
+    lib = _load(build_oracle())
+    f = lib.oracle_make_consistent_partial_order_alignments
+    f.restype = C.POINTER(C.POINTER(OracleMsa))
+    f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int64, C.c_int64, C.c_double]
+    ms = f(C.byref(p), end_no, end_lengths, es, el, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff)
+    lib.oracle_msa_destruct.argtypes = [C.c_void_p]
+    for i in range(end_no):
+        n, c = len(ends[i]), ms[i].contents.column_no
+        m = np.ctypeslib.as_array(ms[i].contents.msa, shape=(n * max(c, 1),))[: n * c]
+        out.append(m.reshape(n, c).copy())
+        lib.oracle_msa_destruct(ms[i])
+    lib.oracle_free.argtypes = [C.c_void_p]
+    lib.oracle_free(ms)
+    return out
+
+
+def ref_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,
+                                                 max_prog_length_diff=1.0, p=None):
+    return _consistent("ref", ends, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
+def oracle_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,
+                                                    max_prog_length_diff=1.0, p=None):
+    return _consistent("oracle", ends, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, p)

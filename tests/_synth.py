@@ -1,0 +1,62 @@
+"""Seeded synthetic end generators for the tests (numpy; small sizes). Test infrastructure."""
+import numpy as np
+
+ASCII = np.frombuffer(b"ACGTN", dtype=np.uint8)
+COMP = {ord("A"): "T", ord("C"): "G", ord("G"): "C", ord("T"): "A", ord("N"): "N"}
+
+
+def evolve(parent, rng, sub=0.02, ins=0.005, dele=0.005, nfrac=0.0):
+    """per-base substitution / insertion / deletion events, like evolveSequence in
+    submodules/cPecan/impl/randomSequences.c (used by bar/tests/poaBarTest.c:36-88)"""
+    out = []
+    for b in parent:
+        r = rng.random()
+        if r < dele:
+            continue
+        if r < dele + sub:
+            out.append((int(b) + int(rng.integers(1, 4))) % 4 if b < 4 else int(rng.integers(0, 4)))
+        else:
+            out.append(int(b))
+        if rng.random() < ins:
+            out.append(int(rng.integers(0, 4)))
+    out = np.array(out, dtype=np.uint8)
+    if nfrac > 0 and len(out):
+        out[rng.random(len(out)) < nfrac] = 4
+    if len(out) == 0:
+        out = np.array([0], dtype=np.uint8)
+    return out
+
+
+def family(rng, K, L, sort=True, **kw):
+    parent = rng.integers(0, 4, L).astype(np.uint8)
+    seqs = [evolve(parent, rng, **kw) for _ in range(K)]
+    if sort:
+        seqs.sort(key=lambda s: -len(s))
+    return seqs
+
+
+def to_ascii(codes):
+    return ASCII[np.asarray(codes, dtype=np.uint8)].tobytes()
+
+
+def revcomp(s):
+    return "".join(COMP[c] for c in reversed(s)).encode()
+
+
+def two_end_problem(rng, K, L, **kw):
+    """Two ends whose strings are reverse complements of each other with full-length overlap, as in
+    bar/tests/poaBarTest.c:93-179 (test_make_consistent_partial_order_alignments_two_ends)."""
+    seqs = family(rng, K, L, sort=False, **kw)
+    s1 = [to_ascii(s) for s in seqs]
+    perm = [int(x) for x in rng.permutation(K)]
+    s2 = [None] * K
+    for i, pi in enumerate(perm):
+        s2[pi] = revcomp(s1[i])
+    ends = [s1, s2]
+    right_end = [[1] * K, [0] * K]
+    inv = [0] * K
+    for i, pi in enumerate(perm):
+        inv[pi] = i
+    right_row = [perm, inv]
+    overlaps = [[len(s) for s in s1], [len(s) for s in s2]]
+    return ends, right_end, right_row, overlaps
