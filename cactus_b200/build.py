@@ -1,0 +1,52 @@
+"""Build libbarb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m cactus_b200.build
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbarb200.so")
+SOURCES = ["poa_kernel.cu", "barb200.cu", "guide_tree.cpp", "host_bar.cpp", "synth.cpp"]
+HEADERS = ["poa_types.h", "poa_graph.cuh", "poa_kernel.cuh", "host_api.h", os.path.join("..", "..", "include", "barb200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+         "-Xcompiler", "-fPIC,-fopenmp,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    bdir = os.path.join(HERE, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(bdir, os.path.splitext(s)[0] + ".o")
+        cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed on %s" % s)
+        if verbose:
+            sys.stderr.write(out)
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,506 @@
+// barb200.cu -- host orchestration + C ABI of libbarb200.so (see include/barb200.h).
+//
+// A *stage* packs a set of POA jobs (one job = one abpoa_msa call of the reference), computes their guide-tree
+// orders on host threads, sizes the per-CTA device slots for the set, uploads everything once and then launches the
+// persistent fused kernel (poa_kernel.cu) with one CTA per slot; CTAs pull jobs from a device-side counter.
+// Jobs that outgrow the optimistic slot sizing (DP planes / MSA columns) come back flagged and are re-run in a
+// second, worst-case-sized launch. No CPU fallback exists: if CUDA is unavailable, creation fails.
+#include <cuda_runtime.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "host_api.h"
+#include "poa_kernel.cuh"
+
+namespace barb200 {
+extern "C" __global__ void poa_msa_kernel(const BatchArgs A);
+}
+using namespace barb200;
+
+struct barb200_ctx {
+    barb200_params p;
+    PoaParams P;
+    HostParams hp;
+    int device = 0, sm_count = 0;
+    size_t smem_optin = 0;
+    std::mutex mu;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_slots = nullptr; size_t slots_bytes = 0;
+    int *d_planes = nullptr; size_t planes_bytes = 0;
+    unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
+};
+
+namespace barb200 {
+void set_error(barb200_ctx *ctx, const std::string &msg) { if (ctx) ctx->err = msg; }
+int host_threads(barb200_ctx *ctx) { return ctx->p.host_threads > 0 ? ctx->p.host_threads : omp_get_max_threads(); }
+int default_progressive(barb200_ctx *ctx) { return ctx->p.progressive_poa; }
+}
+
+#define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
+    set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(_e)); return BARB200_ECUDA; } } while (0)
+
+extern "C" void barb200_params_default(barb200_params *p) {
+    static const int mat[25] = {91, -114, -61, -123, -100, -114, 100, -125, -61, -100, -61, -125, 100, -114, -100,
+                                -123, -61, -114, 91, -100, -100, -100, -100, -100, 100};
+    memset(p, 0, sizeof(*p));
+    memcpy(p->mat, mat, sizeof(mat));
+    p->gap_open1 = 400; p->gap_ext1 = 30; p->gap_open2 = 1200; p->gap_ext2 = 1;
+    p->wb = 1000; p->wf = 0.1f;
+    p->k = 15; p->w = 5; p->min_w = 500;
+    p->progressive_poa = 1; p->disable_seeding = 1;
+    p->device = 0; p->threads_per_block = 0; p->ctas_per_sm = 0; p->mem_fraction = 0.0; p->host_threads = 0;
+    p->collect_phase_clocks = 0;
+}
+
+static void fail(char *errbuf, int n, const std::string &m) { if (errbuf && n > 0) { snprintf(errbuf, n, "%s", m.c_str()); } }
+
+extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, int errbuf_len) {
+    if (!p) { fail(errbuf, errbuf_len, "null params"); return nullptr; }
+    if (p->gap_open1 <= 0 || p->gap_open2 <= 0 || p->gap_ext1 < 0 || p->gap_ext2 < 0 || (p->gap_ext1 == 0 && p->gap_ext2 == 0)) {
+        fail(errbuf, errbuf_len, "only the convex gap model (both gap opens > 0) is supported; that is what Cactus configures"); return nullptr; }
+    if (p->wb < 0) { fail(errbuf, errbuf_len, "partialOrderAlignmentBandConstant must be >= 0 (adaptive band)"); return nullptr; }
+    if (!p->disable_seeding) { fail(errbuf, errbuf_len, "minimizer seeding (partialOrderAlignmentDisableSeeding=0) is not supported"); return nullptr; }
+    if (p->k <= 0 || p->k > 28 || p->w <= 0 || p->w >= 256) { fail(errbuf, errbuf_len, "minimizer k must be in 1..28 and w in 1..255"); return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { fail(errbuf, errbuf_len, std::string("no CUDA device: ") + cudaGetErrorString(e)); return nullptr; }
+    if (p->device < 0 || p->device >= ndev) { fail(errbuf, errbuf_len, "device ordinal out of range"); return nullptr; }
+    barb200_ctx *ctx = new barb200_ctx();
+    ctx->p = *p; ctx->device = p->device;
+    if (cudaSetDevice(p->device) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaSetDevice failed"); delete ctx; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaGetDeviceProperties failed"); delete ctx; return nullptr; }
+    ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    PoaParams &P = ctx->P;
+    memcpy(P.mat, p->mat, sizeof(P.mat));
+    P.o1 = p->gap_open1; P.e1 = p->gap_ext1; P.o2 = p->gap_open2; P.e2 = p->gap_ext2; P.wb = p->wb; P.wf = p->wf;
+    P.max_mat = 0; P.min_mis = 0;
+    for (int i = 0; i < 25; ++i) { P.max_mat = std::max(P.max_mat, P.mat[i]); P.min_mis = std::max(P.min_mis, -P.mat[i]); }
+    // the reference's int32 minus infinity, abpoa_align_simd.c:1299
+    const int oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    P.inf_min = std::max(std::max(INT32_MIN + P.min_mis, INT32_MIN + oe1), INT32_MIN + oe2) + 512 * std::max(P.e1, P.e2);
+    ctx->hp = HostParams{p->k, p->w, p->min_w, p->progressive_poa};
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
+    cudaFuncSetAttribute(poa_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
+    return ctx;
+}
+
+extern "C" void barb200_destroy(barb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->d_planes) cudaFree(ctx->d_planes);
+    if (ctx->d_clk) cudaFree(ctx->d_clk);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *barb200_last_error(barb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void barb200_free(void *p) { free(p); }
+
+extern "C" int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len) {
+    if (!ctx) return BARB200_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaDeviceProp prop; CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    size_t f = 0, t = 0; CUDA_TRY(ctx, cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (mem_total) *mem_total = (int64_t)t;
+    if (mem_free) *mem_free = (int64_t)f;
+    if (name && name_len > 0) snprintf(name, name_len, "%s", prop.name);
+    return BARB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage
+// ---------------------------------------------------------------------------------------------------------
+struct barb200_stage {
+    barb200_ctx *ctx = nullptr;
+    int64_t n_jobs = 0, n_seqs = 0, n_bases = 0;
+    std::vector<int> n_seq, lens, order, progressive;
+    std::vector<int64_t> soff, job_len_off, job_seq_off, job_sum_len;
+    std::vector<int> job_max_len;
+    std::vector<JobDesc> desc;
+    int64_t msa_bytes = 0;
+    bool worst_case = false;
+    // device
+    uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr, *d_order = nullptr; int64_t *d_soff = nullptr;
+    JobDesc *d_desc = nullptr; int *d_msa_len = nullptr, *d_status = nullptr, *d_next = nullptr; long long *d_cells = nullptr;
+    // sizing
+    SlotLayout lay; int T = 0, slots = 0, q_cols = 0, smem_cols = 0; size_t dyn_smem = 0;
+    // results of the last run
+    std::vector<int> status, msa_len; std::vector<long long> cells;
+    std::vector<uint8_t> h_msa;
+    barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;
+    int64_t launches = 0; bool ran = false;
+    uint64_t clk[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static void stage_free_device(barb200_stage *st) {
+    cudaFree(st->d_seqs); cudaFree(st->d_msa); cudaFree(st->d_lens); cudaFree(st->d_order); cudaFree(st->d_soff);
+    cudaFree(st->d_desc); cudaFree(st->d_msa_len); cudaFree(st->d_status); cudaFree(st->d_next); cudaFree(st->d_cells);
+    st->d_seqs = st->d_msa = nullptr; st->d_lens = st->d_order = nullptr; st->d_soff = nullptr; st->d_desc = nullptr;
+    st->d_msa_len = st->d_status = st->d_next = nullptr; st->d_cells = nullptr;
+}
+
+extern "C" void barb200_stage_destroy(barb200_stage *st) {
+    if (!st) return;
+    cudaSetDevice(st->ctx->device);
+    if (st->retry) barb200_stage_destroy(st->retry);
+    stage_free_device(st);
+    delete st;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Decide slot sizes, threads per block, shared memory and the number of resident CTAs for this set of jobs.
+static int plan_stage(barb200_stage *st) {
+    barb200_ctx *ctx = st->ctx;
+    int64_t max_nodes = 4, max_edges = 4, max_len = 1, max_k = 1;
+    int64_t plane_need = 0;
+    for (int64_t j = 0; j < st->n_jobs; ++j) {
+        const int64_t sum = st->job_sum_len[j], ml = st->job_max_len[j], K = st->n_seq[j];
+        max_nodes = std::max(max_nodes, sum + 2); max_edges = std::max(max_edges, sum + K); max_len = std::max(max_len, ml);
+        max_k = std::max(max_k, K);
+        // rows the graph can reach: worst case every base a new node; optimistic: the longest read plus a share of the rest
+        int64_t rows = st->worst_case ? sum + 2 : std::min<int64_t>(sum + 2, ml + (sum - ml) / 8 + 256);
+        plane_need = std::max(plane_need, rows * 5 * (align_up(ml + 1, 4) + 4));
+    }
+    SlotLayout &Y = st->lay;
+    memset(&Y, 0, sizeof(Y));
+    Y.node_cap = (int)max_nodes; Y.in_pool = (int)(4 * max_edges + 64); Y.out_pool = Y.in_pool;
+    Y.W = (int)(1 + ((max_k - 1) >> 6)); Y.cigar_cap = (int)(max_len + max_nodes + 16);
+    Y.plane_cap = align_up(plane_need, 4);
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 16); return r; };
+    const int64_t N = Y.node_cap;
+    Y.o_base = take(N); Y.o_aln_n = take(N); Y.o_aln_id = take(N * 16);
+    Y.o_in_off = take(N * 4); Y.o_in_n = take(N * 4); Y.o_in_cap = take(N * 4);
+    Y.o_out_off = take(N * 4); Y.o_out_n = take(N * 4); Y.o_out_cap = take(N * 4);
+    Y.o_in_id = take((int64_t)Y.in_pool * 4); Y.o_in_w = take((int64_t)Y.in_pool * 4);
+    Y.o_out_id = take((int64_t)Y.out_pool * 4); Y.o_out_w = take((int64_t)Y.out_pool * 4);
+    Y.o_out_rid = take((int64_t)Y.out_pool * 8 * Y.W);
+    Y.o_index_to_node = take(N * 4); Y.o_node_to_index = take(N * 4); Y.o_remain = take(N * 4); Y.o_msa_rank = take(N * 4);
+    Y.o_tmp0 = take(N * 4); Y.o_tmp1 = take(N * 4);
+    Y.o_row_base = take(N); Y.o_row_rd = take(N * 4); Y.o_pre_off = take((N + 1) * 4); Y.o_pre_row = take((int64_t)Y.in_pool * 4);
+    Y.o_row_off = take(N * 8); Y.o_dp_beg = take(N * 4); Y.o_dp_end = take(N * 4); Y.o_row_left = take(N * 4); Y.o_row_right = take(N * 4);
+    Y.o_cigar = take((int64_t)Y.cigar_cap * 8);
+    Y.slot_bytes = align_up(o, 256);
+
+    int T = ctx->p.threads_per_block;
+    if (T <= 0) { T = (int)align_up((max_len + 1 + 3) / 4, 32); T = std::max(64, std::min(512, T)); }
+    T = (int)align_up(std::max(32, std::min(512, T)), 32);
+    st->T = T;
+    st->q_cols = (int)(max_len + 1);
+    const size_t qbytes = (size_t)((st->q_cols + 8 + 15) & ~15);
+    const size_t smem_limit = ctx->smem_optin - 2048 - 2048;     // static shared memory of the kernel + margin
+    size_t rowbuf = (size_t)6 * (st->q_cols + 8) * 4;
+    if (qbytes + rowbuf <= smem_limit) { st->smem_cols = st->q_cols; st->dyn_smem = qbytes + rowbuf; }
+    else { st->smem_cols = 0; st->dyn_smem = qbytes; }
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, poa_msa_kernel, T, st->dyn_smem));
+    if (per_sm < 1) { set_error(ctx, "kernel does not fit on an SM with the requested configuration"); return BARB200_EINVAL; }
+    if (ctx->p.ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->p.ctas_per_sm);
+    int64_t slots = std::min<int64_t>(st->n_jobs, (int64_t)per_sm * ctx->sm_count);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const double frac = ctx->p.mem_fraction > 0 ? ctx->p.mem_fraction : 0.85;
+    const double budget = (double)(free_b + ctx->slots_bytes + ctx->planes_bytes) * frac;
+    const double per_slot = (double)Y.slot_bytes + (double)Y.plane_cap * 4.0;
+    if (per_slot > budget) { set_error(ctx, "a single job needs more device memory than is available"); return BARB200_ENOMEM; }
+    slots = std::max<int64_t>(1, std::min<int64_t>(slots, (int64_t)(budget / per_slot)));
+    st->slots = (int)slots;
+    return BARB200_OK;
+}
+
+static int ensure_arena(barb200_ctx *ctx, size_t slots_bytes, size_t planes_bytes, size_t clk_entries) {
+    if (slots_bytes > ctx->slots_bytes) {
+        if (ctx->d_slots) cudaFree(ctx->d_slots);
+        ctx->d_slots = nullptr; ctx->slots_bytes = 0;
+        if (cudaMalloc(&ctx->d_slots, slots_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(slots) failed"); return BARB200_ENOMEM; }
+        ctx->slots_bytes = slots_bytes;
+    }
+    if (planes_bytes > ctx->planes_bytes) {
+        if (ctx->d_planes) cudaFree(ctx->d_planes);
+        ctx->d_planes = nullptr; ctx->planes_bytes = 0;
+        if (cudaMalloc(&ctx->d_planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(planes) failed"); return BARB200_ENOMEM; }
+        ctx->planes_bytes = planes_bytes;
+    }
+    if (clk_entries > ctx->clk_entries) {
+        if (ctx->d_clk) cudaFree(ctx->d_clk);
+        ctx->d_clk = nullptr; ctx->clk_entries = 0;
+        if (cudaMalloc(&ctx->d_clk, clk_entries * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(clk) failed"); return BARB200_ENOMEM; }
+        ctx->clk_entries = clk_entries;
+    }
+    return BARB200_OK;
+}
+
+static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
+                       const int *progressive, bool worst_case, barb200_stage **out) {
+    if (!ctx || n_jobs < 0 || (n_jobs > 0 && (!n_seq || !seq_lens || !seqs))) { set_error(ctx, "bad arguments"); return BARB200_EINVAL; }
+    cudaSetDevice(ctx->device);
+    barb200_stage *st = new barb200_stage();
+    st->ctx = ctx; st->n_jobs = n_jobs; st->worst_case = worst_case;
+    st->n_seq.assign(n_seq, n_seq + n_jobs);
+    st->job_len_off.resize(n_jobs + 1); st->job_seq_off.resize(n_jobs + 1);
+    st->job_sum_len.resize(n_jobs); st->job_max_len.resize(n_jobs);
+    int64_t ns = 0, nb = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        if (n_seq[j] <= 0) { set_error(ctx, "job without sequences"); delete st; return BARB200_EINVAL; }
+        st->job_len_off[j] = ns; st->job_seq_off[j] = nb;
+        int64_t sum = 0; int ml = 0;
+        for (int i = 0; i < n_seq[j]; ++i) {
+            const int l = seq_lens[ns + i];
+            if (l <= 0) { set_error(ctx, "empty sequence in a POA job (the shim substitutes 'N', poaBarAligner.c:551-562)"); delete st; return BARB200_EINVAL; }
+            sum += l; ml = std::max(ml, l);
+        }
+        st->job_sum_len[j] = sum; st->job_max_len[j] = ml;
+        ns += n_seq[j]; nb += sum;
+    }
+    st->job_len_off[n_jobs] = ns; st->job_seq_off[n_jobs] = nb;
+    st->n_seqs = ns; st->n_bases = nb;
+    st->lens.assign(seq_lens, seq_lens + ns);
+    st->soff.resize(ns); st->order.resize(ns); st->progressive.resize(n_jobs);
+    st->desc.resize(n_jobs);
+    int64_t msa_off = 0; int bad = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        int64_t o = 0;
+        for (int i = 0; i < n_seq[j]; ++i) { st->soff[st->job_len_off[j] + i] = o; o += seq_lens[st->job_len_off[j] + i]; }
+        st->progressive[j] = progressive ? progressive[j] : ctx->hp.progressive_poa;
+        const int64_t sum = st->job_sum_len[j], ml = st->job_max_len[j];
+        int64_t stride = worst_case ? sum : std::min<int64_t>(sum, ml + ml / 2 + 64);
+        stride = align_up(stride, 16);
+        JobDesc &d = st->desc[j];
+        d.n_seq = n_seq[j]; d.seq_off = st->job_seq_off[j]; d.len_off = st->job_len_off[j]; d.msa_off = msa_off; d.msa_stride = (int)stride;
+        msa_off += stride * n_seq[j];
+    }
+    st->msa_bytes = msa_off;
+    // guide-tree orders on host threads
+    const int nthreads = host_threads(ctx);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(| : bad)
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        const int K = n_seq[j];
+        std::vector<const uint8_t *> ptr(K);
+        const uint8_t *base = seqs + st->job_seq_off[j];
+        for (int i = 0; i < K; ++i) {
+            ptr[i] = base + st->soff[st->job_len_off[j] + i];
+            for (int t = 0; t < seq_lens[st->job_len_off[j] + i]; ++t) if (ptr[i][t] > 4) bad = 1;
+        }
+        guide_tree_order(ctx->hp, st->progressive[j], K, ptr.data(), seq_lens + st->job_len_off[j], st->order.data() + st->job_len_off[j]);
+    }
+    if (bad) { set_error(ctx, "sequence code > 4"); delete st; return BARB200_EINVAL; }
+    if (n_jobs == 0) { *out = st; return BARB200_OK; }
+    int rc = plan_stage(st);
+    if (rc) { delete st; return rc; }
+    // device buffers + upload
+    auto dalloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16); };
+    cudaError_t e = cudaSuccess;
+    if ((e = dalloc((void **)&st->d_seqs, nb)) != cudaSuccess || (e = dalloc((void **)&st->d_lens, ns * 4)) != cudaSuccess ||
+        (e = dalloc((void **)&st->d_order, ns * 4)) != cudaSuccess || (e = dalloc((void **)&st->d_soff, ns * 8)) != cudaSuccess ||
+        (e = dalloc((void **)&st->d_desc, n_jobs * sizeof(JobDesc))) != cudaSuccess || (e = dalloc((void **)&st->d_msa, st->msa_bytes)) != cudaSuccess ||
+        (e = dalloc((void **)&st->d_msa_len, n_jobs * 4)) != cudaSuccess || (e = dalloc((void **)&st->d_status, n_jobs * 4)) != cudaSuccess ||
+        (e = dalloc((void **)&st->d_cells, n_jobs * 8)) != cudaSuccess || (e = dalloc((void **)&st->d_next, 4)) != cudaSuccess) {
+        cudaGetLastError(); set_error(ctx, std::string("cudaMalloc(stage) failed: ") + cudaGetErrorString(e));
+        stage_free_device(st); delete st; return BARB200_ENOMEM;
+    }
+    cudaStream_t s = ctx->stream;
+    if ((e = cudaMemcpyAsync(st->d_seqs, seqs, nb, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(st->d_order, st->order.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(st->d_soff, st->soff.data(), ns * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(st->d_desc, st->desc.data(), n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+        set_error(ctx, std::string("H2D failed: ") + cudaGetErrorString(e)); stage_free_device(st); delete st; return BARB200_ECUDA;
+    }
+    *out = st;
+    return BARB200_OK;
+}
+
+extern "C" int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
+                                    const uint8_t *seqs, const int *progressive, barb200_stage **out) {
+    if (!ctx || !out) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, out);
+}
+
+static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
+    barb200_ctx *ctx = st->ctx;
+    cudaSetDevice(ctx->device);
+    st->launches = 0; st->ran = false;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (st->n_jobs == 0) { st->ran = true; return BARB200_OK; }
+    if (st->retry) { barb200_stage_destroy(st->retry); st->retry = nullptr; st->retry_jobs.clear(); }
+    const size_t clk_n = ctx->p.collect_phase_clocks ? (size_t)st->slots * PH_N : 0;
+    int rc = ensure_arena(ctx, (size_t)st->lay.slot_bytes * st->slots, (size_t)st->lay.plane_cap * 4 * st->slots, clk_n);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4, s));
+    if (clk_n) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_clk, 0, clk_n * sizeof(unsigned long long), s));
+    BatchArgs A;
+    A.jobs = st->d_desc; A.n_jobs = (int)st->n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff; A.order = st->d_order;
+    A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
+    A.slots = ctx->d_slots; A.planes = ctx->d_planes; A.next_job = st->d_next;
+    A.phase_clk = clk_n ? ctx->d_clk : nullptr;
+    A.q_cols = st->q_cols; A.smem_cols = st->smem_cols; A.lay = st->lay; A.P = ctx->P;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+    CUDA_TRY(ctx, cudaEventRecord(e0, s));
+    poa_msa_kernel<<<st->slots, st->T, st->dyn_smem, s>>>(A);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { set_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; }
+    CUDA_TRY(ctx, cudaEventRecord(e1, s));
+    st->status.resize(st->n_jobs);
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (se != cudaSuccess) { set_error(ctx, std::string("kernel execution: ") + cudaGetErrorString(se)); return BARB200_ECUDA; }
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    st->launches = 1;
+    if (clk_n) {
+        std::vector<unsigned long long> h(clk_n);
+        CUDA_TRY(ctx, cudaMemcpy(h.data(), ctx->d_clk, clk_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 6; ++k) st->clk[k] = 0;
+        for (int b = 0; b < st->slots; ++b) for (int k = 0; k < 6; ++k) st->clk[k] += h[(size_t)b * PH_N + k];
+    }
+    // capacity misses -> one worst-case-sized retry launch for just those jobs
+    std::vector<int64_t> redo;
+    for (int64_t j = 0; j < st->n_jobs; ++j) {
+        const int sc = st->status[j];
+        if (sc == JOB_OK) continue;
+        if (!st->worst_case && (sc == JOB_ERR_PLANE_CAP || sc == JOB_ERR_MSA_CAP)) redo.push_back(j);
+        else {
+            char buf[160]; snprintf(buf, sizeof(buf), "job %lld failed on the device with status %d", (long long)j, sc);
+            set_error(ctx, buf); return BARB200_EJOB;
+        }
+    }
+    if (!redo.empty()) {
+        std::vector<int> r_nseq, r_lens, r_prog; std::vector<uint8_t> r_seqs;
+        // the retry stage needs host copies of the inputs: fetch them back from the device buffers we own
+        std::vector<uint8_t> h_seqs(st->n_bases);
+        CUDA_TRY(ctx, cudaMemcpy(h_seqs.data(), st->d_seqs, st->n_bases, cudaMemcpyDeviceToHost));
+        for (int64_t j : redo) {
+            r_nseq.push_back(st->n_seq[j]); r_prog.push_back(st->progressive[j]);
+            for (int i = 0; i < st->n_seq[j]; ++i) r_lens.push_back(st->lens[st->job_len_off[j] + i]);
+            r_seqs.insert(r_seqs.end(), h_seqs.begin() + st->job_seq_off[j], h_seqs.begin() + st->job_seq_off[j + 1]);
+        }
+        barb200_stage *rs = nullptr;
+        rc = stage_build(ctx, (int64_t)redo.size(), r_nseq.data(), r_lens.data(), r_seqs.data(), r_prog.data(), true, &rs);
+        if (rc) return rc;
+        float rms = 0.f;
+        rc = stage_run_locked(rs, &rms);
+        if (rc) { barb200_stage_destroy(rs); return rc; }
+        st->retry = rs; st->retry_jobs = redo; st->launches += rs->launches; ms += rms;
+        for (int k = 0; k < 6; ++k) st->clk[k] += rs->clk[k];
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    st->ran = true;
+    return BARB200_OK;
+}
+
+extern "C" int barb200_stage_run(barb200_stage *st, float *kernel_ms) {
+    if (!st) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(st->ctx->mu);
+    return stage_run_locked(st, kernel_ms);
+}
+
+extern "C" int64_t barb200_stage_launches(barb200_stage *st) { return st ? st->launches : 0; }
+
+extern "C" int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[6]) {
+    if (!st || !out) return BARB200_EINVAL;
+    for (int k = 0; k < 6; ++k) out[k] = st->clk[k];
+    return BARB200_OK;
+}
+
+static int stage_fetch_locked(barb200_stage *st, uint8_t **msa_out, int *msa_len, int64_t *cells) {
+    barb200_ctx *ctx = st->ctx;
+    if (!st->ran) { set_error(ctx, "stage_fetch before stage_run"); return BARB200_EINVAL; }
+    if (st->n_jobs == 0) return BARB200_OK;
+    cudaSetDevice(ctx->device);
+    st->msa_len.resize(st->n_jobs); st->cells.resize(st->n_jobs); st->h_msa.resize(st->msa_bytes);
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->msa_len.data(), st->d_msa_len, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->cells.data(), st->d_cells, st->n_jobs * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->h_msa.data(), st->d_msa, st->msa_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    std::vector<uint8_t *> r_out; std::vector<int> r_len; std::vector<int64_t> r_cells;
+    if (st->retry) {
+        const size_t n = st->retry_jobs.size();
+        r_out.assign(n, nullptr); r_len.assign(n, 0); r_cells.assign(n, 0);
+        int rc = stage_fetch_locked(st->retry, r_out.data(), r_len.data(), r_cells.data());
+        if (rc) return rc;
+    }
+    std::vector<int64_t> redo_pos(st->n_jobs, -1);
+    for (size_t i = 0; i < st->retry_jobs.size(); ++i) redo_pos[st->retry_jobs[i]] = (int64_t)i;
+    int oom = 0;
+    const int nthreads = host_threads(ctx);
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : oom)
+    for (int64_t j = 0; j < st->n_jobs; ++j) {
+        if (redo_pos[j] >= 0) {
+            const int64_t i = redo_pos[j];
+            if (msa_out) msa_out[j] = r_out[i]; else free(r_out[i]);
+            if (msa_len) msa_len[j] = r_len[i];
+            if (cells) cells[j] = r_cells[i];
+            continue;
+        }
+        const int K = st->n_seq[j], ml = st->msa_len[j];
+        if (msa_len) msa_len[j] = ml;
+        if (cells) cells[j] = st->cells[j];
+        if (msa_out) {
+            uint8_t *o = (uint8_t *)malloc((size_t)K * (ml > 0 ? ml : 1));
+            if (!o) { oom = 1; msa_out[j] = nullptr; continue; }
+            const uint8_t *src = st->h_msa.data() + st->desc[j].msa_off;
+            for (int i = 0; i < K; ++i) memcpy(o + (size_t)i * ml, src + (size_t)i * st->desc[j].msa_stride, ml);
+            msa_out[j] = o;
+        }
+    }
+    if (oom) { set_error(ctx, "host allocation failed"); return BARB200_ENOMEM; }
+    return BARB200_OK;
+}
+
+extern "C" int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *msa_len, int64_t *cells) {
+    if (!st) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(st->ctx->mu);
+    return stage_fetch_locked(st, msa_out, msa_len, cells);
+}
+
+extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
+                                     const uint8_t *seqs, const int *progressive, uint8_t **msa_out, int *msa_len,
+                                     int64_t *cells) {
+    if (!ctx) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    barb200_stage *st = nullptr;
+    int rc = stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, &st);
+    if (rc) return rc;
+    rc = stage_run_locked(st, nullptr);
+    if (!rc) rc = stage_fetch_locked(st, msa_out, msa_len, cells);
+    barb200_stage_destroy(st);
+    return rc;
+}
+
+namespace barb200 {
+int run_jobs(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results) {
+    const int64_t n = (int64_t)jobs.size();
+    results.assign(n, JobResult());
+    if (n == 0) return BARB200_OK;
+    std::vector<int> n_seq(n), prog(n), lens; std::vector<uint8_t> seqs;
+    for (int64_t j = 0; j < n; ++j) {
+        n_seq[j] = jobs[j].n_seq; prog[j] = jobs[j].progressive;
+        int64_t sum = 0;
+        for (int i = 0; i < jobs[j].n_seq; ++i) { lens.push_back(jobs[j].lens[i]); sum += jobs[j].lens[i]; }
+        seqs.insert(seqs.end(), jobs[j].seqs, jobs[j].seqs + sum);
+    }
+    std::vector<uint8_t *> out(n, nullptr); std::vector<int> ml(n, 0); std::vector<int64_t> cells(n, 0);
+    int rc = barb200_poa_msa_batch(ctx, n, n_seq.data(), lens.data(), seqs.data(), prog.data(), out.data(), ml.data(), cells.data());
+    if (rc) { for (auto p : out) free(p); return rc; }
+    for (int64_t j = 0; j < n; ++j) {
+        results[j].msa_len = ml[j]; results[j].cells = cells[j];
+        results[j].msa.assign(out[j], out[j] + (size_t)jobs[j].n_seq * ml[j]);
+        free(out[j]);
+    }
+    return BARB200_OK;
+}
+}  // namespace barb200

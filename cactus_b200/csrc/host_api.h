@@ -1,0 +1,37 @@
+// host_api.h -- internal C++ interfaces between the host-side translation units of libbarb200.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/barb200.h"
+
+namespace barb200 {
+
+struct HostParams {
+    int k, w, min_w, progressive_poa;
+};
+
+// guide_tree.cpp
+void guide_tree_order(const HostParams &hp, int progressive, int n, const uint8_t *const *seqs, const int *lens, int *order);
+
+// One POA job on the host side: views into caller memory (codes 0..4).
+struct HostJob {
+    int n_seq;
+    const int *lens;          // [n_seq]
+    const uint8_t *seqs;      // concatenated
+    int progressive;
+};
+
+struct JobResult {
+    std::vector<uint8_t> msa; // n_seq * msa_len
+    int msa_len = 0;
+    int64_t cells = 0;
+};
+
+// barb200.cu: run a set of jobs on the device (chunked, retried on capacity misses). Returns BARB200_* code.
+int run_jobs(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results);
+void set_error(barb200_ctx *ctx, const std::string &msg);
+int host_threads(barb200_ctx *ctx);
+int default_progressive(barb200_ctx *ctx);
+
+}  // namespace barb200

@@ -1,0 +1,413 @@
+// poa_graph.cuh -- the partial-order graph: fuse an alignment, topological (BFS) order, edge sort, max_remain,
+// row tables for the DP, MSA rank and row-column fill, and the DP traceback.
+//
+// These are the strictly sequential parts of abPOA's per-sequence loop; on the device they run on one thread
+// of the CTA that owns the job (the column-parallel DP sweep lives in poa_kernel.cu). Written as
+// __host__ __device__ so tests/hosttest can exercise the very same code on the CPU of a GPU-less builder;
+// the product only ever calls them from the kernel.
+//
+// Behaviour (not code) follows the reference abPOA v1.5.6 as Cactus drives it; file:line citations are
+// relative to /root/reference/submodules/abPOA/src/.
+#pragma once
+#include "poa_types.h"
+
+namespace barb200 {
+
+// ---- edge lists ---------------------------------------------------------------------------------------
+HD void graph_reset(Graph &g, int n_seq) {
+    // abpoa_reset + abpoa_init_graph: just SRC and SINK (abpoa_graph.c:103-113, 783-795)
+    g.node_n = 2; g.W = 1 + ((n_seq - 1) >> 6);
+    g.in_used = 0; g.out_used = 0; g.err = JOB_OK;
+    for (int i = 0; i < 2; ++i) {
+        g.base[i] = 0; g.aln_n[i] = 0;
+        g.in_off[i] = 0; g.in_n[i] = 0; g.in_cap[i] = 0;
+        g.out_off[i] = 0; g.out_n[i] = 0; g.out_cap[i] = 0;
+    }
+}
+
+HD int graph_add_node(Graph &g, uint8_t b) {          // abpoa_add_graph_node, abpoa_graph.c:471-478
+    if (g.node_n >= g.node_cap) { g.err = JOB_ERR_NODE_CAP; return g.node_cap - 1; }
+    int id = g.node_n++;
+    g.base[id] = b; g.aln_n[id] = 0;
+    g.in_off[id] = 0; g.in_n[id] = 0; g.in_cap[id] = 0;
+    g.out_off[id] = 0; g.out_n[id] = 0; g.out_cap[id] = 0;
+    return id;
+}
+
+// make room for one more in edge of node t; returns false on pool exhaustion
+HD bool grow_in(Graph &g, int t) {
+    if (g.in_n[t] < g.in_cap[t]) return true;
+    int ncap = g.in_cap[t] ? g.in_cap[t] * 2 : 2;
+    if (g.in_used + ncap > g.in_pool) { g.err = JOB_ERR_EDGE_CAP; return false; }
+    int noff = g.in_used; g.in_used += ncap;
+    for (int i = 0; i < g.in_n[t]; ++i) { g.in_id[noff + i] = g.in_id[g.in_off[t] + i]; g.in_w[noff + i] = g.in_w[g.in_off[t] + i]; }
+    g.in_off[t] = noff; g.in_cap[t] = ncap;
+    return true;
+}
+
+HD bool grow_out(Graph &g, int f) {
+    if (g.out_n[f] < g.out_cap[f]) return true;
+    int ncap = g.out_cap[f] ? g.out_cap[f] * 2 : 2;
+    if (g.out_used + ncap > g.out_pool) { g.err = JOB_ERR_EDGE_CAP; return false; }
+    int noff = g.out_used; g.out_used += ncap;
+    const int W = g.W;
+    for (int i = 0; i < g.out_n[f]; ++i) {
+        g.out_id[noff + i] = g.out_id[g.out_off[f] + i]; g.out_w[noff + i] = g.out_w[g.out_off[f] + i];
+        for (int w = 0; w < W; ++w) g.out_rid[(int64_t)(noff + i) * W + w] = g.out_rid[(int64_t)(g.out_off[f] + i) * W + w];
+    }
+    for (int i = g.out_n[f]; i < ncap; ++i) for (int w = 0; w < W; ++w) g.out_rid[(int64_t)(noff + i) * W + w] = 0;
+    g.out_off[f] = noff; g.out_cap[f] = ncap;
+    return true;
+}
+
+// abpoa_add_graph_edge with w = 1, add_read_id = 1 (abpoa_graph.c:480-556)
+HD void graph_add_edge(Graph &g, int from, int to, int check_edge, int read_id) {
+    int out_i = -1;
+    if (check_edge) {
+        const int io = g.in_off[to], in = g.in_n[to];
+        for (int i = 0; i < in; ++i) if (g.in_id[io + i] == from) { g.in_w[io + i] += 1; break; }
+        const int oo = g.out_off[from], on = g.out_n[from];
+        for (int i = 0; i < on; ++i) if (g.out_id[oo + i] == to) { g.out_w[oo + i] += 1; out_i = i; break; }
+    }
+    if (out_i < 0) {
+        if (!grow_in(g, to) || !grow_out(g, from)) return;
+        int ip = g.in_off[to] + g.in_n[to]; g.in_id[ip] = from; g.in_w[ip] = 1; g.in_n[to]++;
+        out_i = g.out_n[from];
+        int op = g.out_off[from] + out_i; g.out_id[op] = to; g.out_w[op] = 1; g.out_n[from]++;
+    }
+    g.out_rid[(int64_t)(g.out_off[from] + out_i) * g.W + (read_id >> 6)] |= 1ULL << (read_id & 63);
+}
+
+HD void aln_push(Graph &g, int node, int id) {
+    if (g.aln_n[node] >= 4) { g.err = JOB_ERR_ALIGNED_CAP; return; }
+    g.aln_id[node * 4 + g.aln_n[node]] = id; g.aln_n[node]++;
+}
+
+// abpoa_add_graph_aligned_node, abpoa_graph.c:455-463
+HD void graph_add_aligned(Graph &g, int node_id, int new_id) {
+    const int n = g.aln_n[node_id];
+    for (int i = 0; i < n; ++i) { int a = g.aln_id[node_id * 4 + i]; aln_push(g, a, new_id); aln_push(g, new_id, a); }
+    aln_push(g, node_id, new_id); aln_push(g, new_id, node_id);
+}
+
+// abpoa_get_aligned_id, abpoa_graph.c:439-448
+HD int graph_aligned_with_base(const Graph &g, int node_id, uint8_t b) {
+    for (int i = 0; i < g.aln_n[node_id]; ++i) { int a = g.aln_id[node_id * 4 + i]; if (g.base[a] == b) return a; }
+    return -1;
+}
+
+// ---- topological sort ---------------------------------------------------------------------------------
+// abpoa_BFS_set_node_index, abpoa_graph.c:221-266. FIFO over nodes whose in-degree reached zero; a node is
+// only released together with all nodes aligned to it (same MSA column), which follow it in the queue.
+HD void graph_bfs_index(Graph &g) {
+    const int n = g.node_n;
+    int *indeg = g.tmp0, *q = g.tmp1;
+    for (int i = 0; i < n; ++i) indeg[i] = g.in_n[i];
+    int head = 0, tail = 0, index = 0;
+    q[tail++] = SRC_ID;
+    while (head < tail) {
+        const int cur = q[head++];
+        g.index_to_node[index] = cur; g.node_to_index[cur] = index++;
+        if (cur == SINK_ID) return;
+        const int oo = g.out_off[cur], on = g.out_n[cur];
+        for (int i = 0; i < on; ++i) {
+            const int o = g.out_id[oo + i];
+            if (--indeg[o] == 0) {
+                bool ok = true;
+                const int an = g.aln_n[o];
+                for (int j = 0; j < an; ++j) if (indeg[g.aln_id[o * 4 + j]] != 0) { ok = false; break; }
+                if (!ok) continue;
+                q[tail++] = o;
+                for (int j = 0; j < an; ++j) q[tail++] = g.aln_id[o * 4 + j];
+            }
+        }
+    }
+    g.err = JOB_ERR_TOPO;
+}
+
+// abpoa_sort_in_out_ids for ONE node (abpoa_graph.c:192-219): the reference's exchange sort, weight
+// descending, not stable -- the resulting order breaks ties in the DP traceback, so it is reproduced verbatim.
+HD void graph_sort_node_edges(Graph &g, int v) {
+    {
+        const int o = g.in_off[v], n = g.in_n[v];
+        for (int j = 0; j < n - 1; ++j) for (int k = j + 1; k < n; ++k)
+            if (g.in_w[o + j] < g.in_w[o + k]) {
+                int t = g.in_id[o + j]; g.in_id[o + j] = g.in_id[o + k]; g.in_id[o + k] = t;
+                t = g.in_w[o + j]; g.in_w[o + j] = g.in_w[o + k]; g.in_w[o + k] = t;
+            }
+    }
+    {
+        const int o = g.out_off[v], n = g.out_n[v], W = g.W;
+        for (int j = 0; j < n - 1; ++j) for (int k = j + 1; k < n; ++k)
+            if (g.out_w[o + j] < g.out_w[o + k]) {
+                int t = g.out_id[o + j]; g.out_id[o + j] = g.out_id[o + k]; g.out_id[o + k] = t;
+                t = g.out_w[o + j]; g.out_w[o + j] = g.out_w[o + k]; g.out_w[o + k] = t;
+                for (int w = 0; w < W; ++w) {
+                    uint64_t r = g.out_rid[(int64_t)(o + j) * W + w];
+                    g.out_rid[(int64_t)(o + j) * W + w] = g.out_rid[(int64_t)(o + k) * W + w];
+                    g.out_rid[(int64_t)(o + k) * W + w] = r;
+                }
+            }
+    }
+}
+
+// abpoa_BFS_set_node_remain, abpoa_graph.c:268-309: reverse BFS from SINK (-1);
+// remain[v] = remain[first heaviest out neighbour] + 1
+HD void graph_bfs_remain(Graph &g) {
+    const int n = g.node_n;
+    int *outdeg = g.tmp0, *q = g.tmp1;
+    for (int i = 0; i < n; ++i) { outdeg[i] = g.out_n[i]; g.remain[i] = 0; }
+    int head = 0, tail = 0;
+    q[tail++] = SINK_ID; g.remain[SINK_ID] = -1;
+    while (head < tail) {
+        const int cur = q[head++];
+        if (cur != SINK_ID) {
+            int max_w = -1, max_id = -1;
+            const int oo = g.out_off[cur], on = g.out_n[cur];
+            for (int i = 0; i < on; ++i) if (g.out_w[oo + i] > max_w) { max_w = g.out_w[oo + i]; max_id = g.out_id[oo + i]; }
+            g.remain[cur] = g.remain[max_id] + 1;
+        }
+        if (cur == SRC_ID) return;
+        const int io = g.in_off[cur], in = g.in_n[cur];
+        for (int i = 0; i < in; ++i) if (--outdeg[g.in_id[io + i]] == 0) q[tail++] = g.in_id[io + i];
+    }
+    g.err = JOB_ERR_TOPO;
+}
+
+// Row-major tables the DP sweeps: for topological index r the node's base, its remain term and its
+// predecessor ROWS in stored in_id order (what simd_abpoa_init_var collects, abpoa_align_simd.c:550-558).
+HD void graph_build_rows(const Graph &g, RowTables &rt) {
+    const int n = g.node_n, rem_sink = g.remain[SINK_ID];
+    int off = 0;
+    for (int r = 0; r < n; ++r) {
+        const int v = g.index_to_node[r];
+        rt.row_base[r] = g.base[v];
+        rt.row_rd[r] = g.remain[v] - rem_sink - 1;
+        rt.pre_off[r] = off;
+        const int io = g.in_off[v], in = g.in_n[v];
+        for (int k = 0; k < in; ++k) rt.pre_row[off++] = g.node_to_index[g.in_id[io + k]];
+    }
+    rt.pre_off[n] = off;
+}
+
+// abpoa_topological_sort (abpoa_graph.c:322-357), serial form
+HD void graph_topo_sort_serial(Graph &g, RowTables &rt) {
+    graph_bfs_index(g);
+    if (g.err) return;
+    for (int v = 0; v < g.node_n; ++v) graph_sort_node_edges(g, v);
+    graph_bfs_remain(g);
+    if (g.err) return;
+    graph_build_rows(g, rt);
+}
+
+// ---- fusing an alignment into the graph ------------------------------------------------------------------
+// abpoa_add_graph_sequence (abpoa_graph.c:573-593): first sequence becomes a chain SRC -> b0 -> ... -> SINK
+HD void graph_add_first_sequence(Graph &g, const uint8_t *seq, int len, int read_id) {
+    int last = SRC_ID;
+    for (int i = 0; i < len; ++i) { int cur = graph_add_node(g, seq[i]); graph_add_edge(g, last, cur, 0, read_id); last = cur; if (g.err) return; }
+    graph_add_edge(g, last, SINK_ID, 0, read_id);
+}
+
+// abpoa_add_subgraph_alignment(SRC, SINK, inc_both_ends = 1), abpoa_graph.c:689-774
+HD void graph_fuse_alignment(Graph &g, const uint8_t *seq, const uint64_t *cigar, int n_cigar, int read_id) {
+    if (n_cigar == 0) return;
+    int query_id = -1, last_new = 0, last_id = SRC_ID;
+    for (int i = 0; i < n_cigar && !g.err; ++i) {
+        const int op = (int)(cigar[i] & 0xf);
+        if (op == CMATCH) {
+            const int node_id = (int)((cigar[i] >> 34) & 0x3fffffff);
+            ++query_id;
+            const uint8_t b = seq[query_id];
+            if (g.base[node_id] != b) {
+                int a = graph_aligned_with_base(g, node_id, b);
+                if (a != -1) { graph_add_edge(g, last_id, a, 1 - last_new, read_id); last_id = a; last_new = 0; }
+                else {
+                    int nid = graph_add_node(g, b);
+                    graph_add_edge(g, last_id, nid, 0, read_id);
+                    last_id = nid; last_new = 1;
+                    graph_add_aligned(g, node_id, nid);
+                }
+            } else { graph_add_edge(g, last_id, node_id, 1 - last_new, read_id); last_id = node_id; last_new = 0; }
+        } else if (op == CINS) {
+            const int len = (int)((cigar[i] >> 4) & 0x3fffffff);
+            query_id += len;
+            for (int j = len - 1; j >= 0 && !g.err; --j) {
+                int nid = graph_add_node(g, seq[query_id - j]);
+                graph_add_edge(g, last_id, nid, 0, read_id);
+                last_id = nid; last_new = 1;
+            }
+        }   // CDEL: nothing (abpoa_graph.c:759-762)
+    }
+    if (!g.err) graph_add_edge(g, last_id, SINK_ID, 1 - last_new, read_id);
+}
+
+// ---- MSA ----------------------------------------------------------------------------------------------------
+// abpoa_DFS_set_msa_rank (abpoa_graph.c:359-410): LIFO version of the walk above; aligned nodes share a rank.
+// Returns msa_len = rank(SINK) - 1 (abpoa_output.c:157).
+HD int graph_msa_rank(Graph &g) {
+    const int n = g.node_n;
+    int *indeg = g.tmp0, *st = g.tmp1;
+    for (int i = 0; i < n; ++i) indeg[i] = g.in_n[i];
+    int sp = 0, rank = 0;
+    st[sp++] = SRC_ID; g.msa_rank[SRC_ID] = -1;
+    while (sp > 0) {
+        const int cur = st[--sp];
+        if (g.msa_rank[cur] < 0) {
+            g.msa_rank[cur] = rank;
+            for (int i = 0; i < g.aln_n[cur]; ++i) g.msa_rank[g.aln_id[cur * 4 + i]] = rank;
+            ++rank;
+        }
+        if (cur == SINK_ID) return g.msa_rank[SINK_ID] - 1;
+        const int oo = g.out_off[cur], on = g.out_n[cur];
+        for (int i = 0; i < on; ++i) {
+            const int o = g.out_id[oo + i];
+            if (--indeg[o] == 0) {
+                bool ok = true;
+                const int an = g.aln_n[o];
+                for (int j = 0; j < an; ++j) if (indeg[g.aln_id[o * 4 + j]] != 0) { ok = false; break; }
+                if (!ok) continue;
+                st[sp++] = o; g.msa_rank[o] = -1;
+                for (int j = 0; j < an; ++j) { int a = g.aln_id[o * 4 + j]; st[sp++] = a; g.msa_rank[a] = -1; }
+            }
+        }
+    }
+    g.err = JOB_ERR_TOPO;
+    return 0;
+}
+
+// abpoa_generate_rc_msa / abpoa_set_msa_seq for ONE node (abpoa_output.c:105-122, 167-176):
+// every read whose bit is set on one of the node's out edges gets the node's base in column rank-1.
+HD void graph_msa_fill_node(const Graph &g, int v, uint8_t *msa, int64_t stride) {
+    int rank = g.msa_rank[v];
+    for (int j = 0; j < g.aln_n[v]; ++j) rank = imax(rank, g.msa_rank[g.aln_id[v * 4 + j]]);
+    const int oo = g.out_off[v], on = g.out_n[v], W = g.W;
+    const uint8_t b = g.base[v];
+    for (int e = 0; e < on; ++e) for (int w = 0; w < W; ++w) {
+        uint64_t bits = g.out_rid[(int64_t)(oo + e) * W + w];
+        while (bits) {
+#if defined(__CUDA_ARCH__)
+            const int bit = __ffsll((long long)bits) - 1;
+#else
+            const int bit = __builtin_ctzll(bits);
+#endif
+            msa[(int64_t)(w * 64 + bit) * stride + (rank - 1)] = b;
+            bits &= bits - 1;
+        }
+    }
+}
+
+// ---- traceback ------------------------------------------------------------------------------------------------
+HD int plane_cell(const DpState &d, int inf_min, int row, int plane, int j) {
+    const int beg = d.dp_beg[row], end = d.dp_end[row];
+    if (j < beg || j > end) return inf_min;                 // out-of-band lanes hold inf_min (abpoa_align_simd.c:1035-1036)
+    const int beg4 = beg & ~3, wr4 = (end | 3) - beg4 + 1;
+    return d.planes[d.row_off[row] + (int64_t)plane * wr4 + (j - beg4)];
+}
+
+HD void push_cigar(DpState &d, Graph &g, int op, int len, int node_id, int query_id) {   // abpoa_push_cigar, abpoa_align.h:58-78
+    const uint64_t l = (uint64_t)len;
+    if (d.n_cigar == 0 || op != CINS || op != (int)(d.cigar[d.n_cigar - 1] & 0xf)) {
+        if (d.n_cigar >= d.cigar_cap) { g.err = JOB_ERR_CIGAR_CAP; return; }
+        const uint64_t n_id = (uint64_t)(int64_t)node_id, q_id = (uint64_t)(int64_t)query_id;
+        if (op == CMATCH) d.cigar[d.n_cigar++] = n_id << 34 | q_id << 4 | (uint64_t)op;
+        else if (op == CINS) d.cigar[d.n_cigar++] = q_id << 34 | l << 4 | (uint64_t)op;
+        else d.cigar[d.n_cigar++] = n_id << 34 | l << 4 | (uint64_t)op;
+    } else d.cigar[d.n_cigar - 1] += l << 4;
+}
+
+// simd_abpoa_global_get_max (abpoa_align_simd.c:1092-1105): best cell over SINK's predecessors in stored
+// order, column min(L, dp_end), strictly greater wins.
+HD void dp_best_cell(const Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, int L) {
+    const int sink_row = g.node_n - 1;
+    int best = P.inf_min, bi = 0, bj = 0;
+    for (int k = rt.pre_off[sink_row]; k < rt.pre_off[sink_row + 1]; ++k) {
+        const int row = rt.pre_row[k];
+        const int col = L > d.dp_end[row] ? d.dp_end[row] : L;
+        const int sc = plane_cell(d, P.inf_min, row, 0, col);
+        if (sc > best) { best = sc; bi = row; bj = col; }
+    }
+    d.best_score = best; d.best_i = bi; d.best_j = bj;
+}
+
+// simd_abpoa_cg_backtrack (abpoa_align_simd.c:309-458) with put_gap_on_right = put_gap_at_end = 0:
+// op priority M over predecessors in stored order, then E1/E2 per predecessor, then F1, F2, then M again;
+// cur_op carries which gap state the walk is in. Emits the graph cigar in forward order.
+HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
+    const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    d.n_cigar = 0;
+    int i = d.best_i, j = d.best_j, cur_op = OP_ALL;
+    if (j < L) push_cigar(d, g, CINS, L - j, -1, L - 1);
+    while (i > 0 && j > 0 && !g.err) {
+        const int id = g.index_to_node[i];
+        const int s = P.mat[5 * rt.row_base[i] + q[j - 1]];
+        const int p0 = rt.pre_off[i], p1 = rt.pre_off[i + 1];
+        const int hij = plane_cell(d, inf, i, 0, j);
+        bool hit = false;
+        if (cur_op & OP_M) {
+            for (int k = p0; k < p1; ++k) {
+                const int pi = rt.pre_row[k];
+                if (j - 1 < d.dp_beg[pi] || j - 1 > d.dp_end[pi]) continue;
+                if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) {
+                    push_cigar(d, g, CMATCH, 1, id, j - 1); i = pi; --j; hit = true; cur_op = OP_ALL; break;
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_E)) {
+            for (int k = p0; k < p1; ++k) {
+                const int pi = rt.pre_row[k];
+                if (j < d.dp_beg[pi] || j > d.dp_end[pi]) continue;
+                const int ph = plane_cell(d, inf, pi, 0, j);
+                if (cur_op & OP_E1) {
+                    const int pe1 = plane_cell(d, inf, pi, 1, j);
+                    const bool ok = (cur_op & OP_M) ? (hij == pe1) : (plane_cell(d, inf, i, 1, j) == pe1 - e1);
+                    if (ok) { cur_op = (ph - oe1 == pe1) ? (OP_M | OP_F) : OP_E1; push_cigar(d, g, CDEL, 1, id, j - 1); i = pi; hit = true; break; }
+                }
+                if (cur_op & OP_E2) {
+                    const int pe2 = plane_cell(d, inf, pi, 2, j);
+                    const bool ok = (cur_op & OP_M) ? (hij == pe2) : (plane_cell(d, inf, i, 2, j) == pe2 - e2);
+                    if (ok) { cur_op = (ph - oe2 == pe2) ? (OP_M | OP_F) : OP_E2; push_cigar(d, g, CDEL, 1, id, j - 1); i = pi; hit = true; break; }
+                }
+            }
+        }
+        if (!hit && (cur_op & OP_F)) {
+            if (cur_op & OP_F1) {
+                const int f = plane_cell(d, inf, i, 3, j);
+                if (!(cur_op & OP_M) || hij == f) {
+                    if (plane_cell(d, inf, i, 0, j - 1) - oe1 == f) { cur_op = OP_M | OP_E; hit = true; }
+                    else if (plane_cell(d, inf, i, 3, j - 1) - e1 == f) { cur_op = OP_F1; hit = true; }
+                }
+            }
+            if (!hit && (cur_op & OP_F2)) {
+                const int f = plane_cell(d, inf, i, 4, j);
+                if (!(cur_op & OP_M) || hij == f) {
+                    if (plane_cell(d, inf, i, 0, j - 1) - oe2 == f) { cur_op = OP_M | OP_E; hit = true; }
+                    else if (plane_cell(d, inf, i, 4, j - 1) - e2 == f) { cur_op = OP_F2; hit = true; }
+                }
+            }
+            if (hit) { push_cigar(d, g, CINS, 1, id, j - 1); --j; }
+        }
+        if (!hit && (cur_op & OP_M)) {
+            for (int k = p0; k < p1; ++k) {
+                const int pi = rt.pre_row[k];
+                if (j - 1 < d.dp_beg[pi] || j - 1 > d.dp_end[pi]) continue;
+                if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) {
+                    push_cigar(d, g, CMATCH, 1, id, j - 1); i = pi; --j; hit = true; cur_op = OP_ALL; break;
+                }
+            }
+        }
+        if (!hit) { g.err = JOB_ERR_BACKTRACK; return; }
+    }
+    if (g.err) return;
+    if (j > 0) push_cigar(d, g, CINS, j, -1, j - 1);
+    for (int a = 0; a < d.n_cigar >> 1; ++a) { uint64_t t = d.cigar[a]; d.cigar[a] = d.cigar[d.n_cigar - 1 - a]; d.cigar[d.n_cigar - 1 - a] = t; }
+}
+
+// lane count the reference's SIMD path would pick for this alignment (16 = int16 lanes at AVX2, 8 = int32);
+// it leaks into dp_beg through the lane-group snap (abpoa_align_simd.c:957-959, 1293-1302)
+HD int reference_lane_count(const PoaParams &P, int L, int node_n) {
+    const int len = L > node_n ? L : node_n;
+    const int max_score = imax(L * P.max_mat, len * P.e1 + P.o1);
+    return (max_score <= 32767 - P.min_mis - (P.o1 + P.e1) - (P.o2 + P.e2)) ? 16 : 8;
+}
+
+}  // namespace barb200

@@ -1,0 +1,101 @@
+// poa_types.h -- plain-old-data shared by the CUDA kernels and the host orchestration of libbarb200.
+//
+// One *job* is one abpoa_msa() call of the reference (one sliding window of one end,
+// bar/impl/poaBarAligner.c:609): K sequences in, a K x msa_len byte matrix out.
+// One *slot* is the device workspace a resident CTA uses while it works through a job:
+// the partial-order graph, the banded DP planes of the current alignment, the cigar.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+#endif
+
+namespace barb200 {
+
+constexpr int SRC_ID = 0;    // ABPOA_SRC_NODE_ID  (abPOA include/abpoa.h:27)
+constexpr int SINK_ID = 1;   // ABPOA_SINK_NODE_ID (abPOA include/abpoa.h:28)
+constexpr int GAP_CODE = 5;  // abpt->m, the gap byte of msa_base (abpoa_output.c:160-163)
+
+constexpr int OP_M = 0x1, OP_E1 = 0x2, OP_E2 = 0x4, OP_E = 0x6, OP_F1 = 0x8, OP_F2 = 0x10, OP_F = 0x18, OP_ALL = 0x1f;
+constexpr int CMATCH = 0, CINS = 1, CDEL = 2;
+
+enum JobStatus : int {
+    JOB_OK = 0,
+    JOB_ERR_NODE_CAP = 1,    // graph outgrew the slot's node arrays
+    JOB_ERR_EDGE_CAP = 2,    // edge pools exhausted
+    JOB_ERR_PLANE_CAP = 3,   // DP planes outgrew the slot (host retries with a larger slot)
+    JOB_ERR_CIGAR_CAP = 4,
+    JOB_ERR_MSA_CAP = 5,     // msa_len larger than the job's output stride (host retries)
+    JOB_ERR_TOPO = 6,        // "Failed to set node index" in the reference (abpoa_graph.c:265)
+    JOB_ERR_BACKTRACK = 7,   // "Error in cg_backtrack" in the reference (abpoa_align_simd.c:448)
+    JOB_ERR_ALIGNED_CAP = 8
+};
+
+// Scoring / banding parameters: what abpoaParamaters_constructFromCactusParams builds
+// (bar/impl/poaBarAligner.c:24-81) reduced to what the DP reads.
+struct PoaParams {
+    int mat[25];          // 5x5 substitution matrix, row = graph base, col = query base
+    int o1, e1, o2, e2;   // convex gap: min(o1 + k*e1, o2 + k*e2)
+    int wb; float wf;     // adaptive band: w = wb + (int)(wf * qlen)  (abpoa_align_simd.c:474)
+    int max_mat, min_mis; // derived, used for the int16/int32 lane-count rule (abpoa_align_simd.c:1293-1302)
+    int inf_min;          // the reference's int32 "minus infinity" (abpoa_align_simd.c:1299)
+};
+
+// Per-job descriptor (device resident, written by the host before launch).
+struct JobDesc {
+    int n_seq;            // K
+    int64_t seq_off;      // offset of the job's first base in the packed sequence buffer
+    int64_t len_off;      // offset into the lens / order arrays
+    int64_t msa_off;      // offset of the job's output block in the msa buffer
+    int msa_stride;       // column capacity of the output block (rows are msa_stride apart)
+};
+
+// The partial-order graph of one job (abPOA include/abpoa.h:96-116), SoA in the slot workspace.
+// Edge lists are small arrays carved from bump-allocated pools; growing one copies it to a fresh chunk of
+// twice the size (same observable behaviour as the reference's realloc, abpoa_graph.c:49-85).
+struct Graph {
+    int node_n, node_cap;
+    int W;                              // 64-bit words per read-id set = 1 + ((K-1) >> 6)  (abpoa_graph.c:692)
+    int in_used, in_pool, out_used, out_pool;
+    int err;
+    uint8_t *base;                      // [node_cap]
+    uint8_t *aln_n;                     // [node_cap]   number of aligned nodes (<= 4: one per other base)
+    int *aln_id;                        // [node_cap*4]
+    int *in_off, *in_n, *in_cap;        // [node_cap]
+    int *out_off, *out_n, *out_cap;     // [node_cap]
+    int *in_id, *in_w;                  // [in_pool]
+    int *out_id, *out_w;                // [out_pool]
+    uint64_t *out_rid;                  // [out_pool * W] read ids per out edge (abpoa_graph.c:525-544)
+    int *index_to_node, *node_to_index; // [node_cap] topological (BFS) order
+    int *remain;                        // [node_cap] max_remain (abpoa_graph.c:268-309)
+    int *msa_rank;                      // [node_cap]
+    int *tmp0, *tmp1;                   // [node_cap] scratch: degree counters, queues
+};
+
+// Row-major view of the sorted graph that the DP sweeps (built after every topological sort).
+struct RowTables {
+    uint8_t *row_base;   // [node_cap]  base of the node at topological index r
+    int *row_rd;         // [node_cap]  remain[v] - remain[SINK] - 1  (GET_AD_DP_BEGIN/END, abpoa_align.h:34-35)
+    int *pre_off;        // [node_cap+1] CSR into pre_row
+    int *pre_row;        // [in_pool]   predecessor rows in in_id order (abpoa_align_simd.c:550-558)
+};
+
+// Banded DP planes of the current alignment + per-row band bookkeeping.
+// Row r occupies 5 consecutive planes (H, E1, E2, F1, F2) of wr4 ints each at planes + row_off[r],
+// wr4 = (dp_end|3) - (dp_beg&~3) + 1; column j of a plane is at [j - (dp_beg&~3)].
+struct DpState {
+    int *planes; int64_t plane_cap;     // ints
+    int64_t *row_off;                   // [node_cap]
+    int *dp_beg, *dp_end;               // [node_cap]
+    int *row_left, *row_right;          // [node_cap] left/right-most argmax of H in the row (abpoa_align_simd.c:1107-1119)
+    uint64_t *cigar; int n_cigar, cigar_cap;
+    int best_i, best_j, best_score;
+};
+
+HD int imax(int a, int b) { return a > b ? a : b; }
+HD int imin(int a, int b) { return a < b ? a : b; }
+
+}  // namespace barb200

@@ -1,0 +1,58 @@
+// synth.cpp -- seeded synthetic BAR ends of BASELINE.json's "N ends x K seqs x L bp" shape.
+// For end e: xoshiro256** seeded (through splitmix64) with seed + e; parent = L uniform ACGT; K descendants, each base
+// deleted with probability `del`, substituted by a uniformly chosen different base with probability `sub`, and followed by
+// a uniformly random inserted base with probability `ins`; rows sorted by length, longest first (stable), which is the
+// order get_end_sequences hands them to the aligner (bar/impl/poaBarAligner.c:1073-1081).
+#include <stdint.h>
+#include <algorithm>
+#include <numeric>
+#include <vector>
+#include "../../include/barb200.h"
+
+namespace {
+struct Xoshiro {
+    uint64_t s[4];
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    explicit Xoshiro(uint64_t seed) {
+        for (int i = 0; i < 4; ++i) {   // splitmix64
+            uint64_t z = (seed += 0x9e3779b97f4a7c15ULL);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; s[i] = z ^ (z >> 31);
+        }
+    }
+    uint64_t next() {
+        const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+}  // namespace
+
+extern "C" int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
+                                     uint8_t *codes_out, int *lens_out) {
+    if (K <= 0 || L <= 0 || !codes_out || !lens_out) return -1;
+    Xoshiro rng(seed + end_index);
+    std::vector<uint8_t> parent((size_t)L);
+    for (int i = 0; i < L; ++i) parent[i] = (uint8_t)(rng.next() >> 62);
+    std::vector<std::vector<uint8_t>> rows((size_t)K);
+    for (int k = 0; k < K; ++k) {
+        std::vector<uint8_t> &r = rows[k];
+        r.reserve((size_t)L + 16);
+        for (int i = 0; i < L && (int)r.size() < 2 * L + 8; ++i) {
+            const double u = rng.uniform();
+            if (u >= del) r.push_back(u < del + sub ? (uint8_t)((parent[i] + 1 + rng.next() % 3) & 3) : parent[i]);
+            if (rng.uniform() < ins) r.push_back((uint8_t)(rng.next() >> 62));
+        }
+        if (r.empty()) r.push_back(parent[0]);
+    }
+    std::vector<int> idx((size_t)K);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    int64_t o = 0;
+    for (int k = 0; k < K; ++k) {
+        const std::vector<uint8_t> &r = rows[idx[k]];
+        std::copy(r.begin(), r.end(), codes_out + o);
+        lens_out[k] = (int)r.size(); o += (int64_t)r.size();
+    }
+    return o;
+}

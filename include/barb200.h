@@ -1,0 +1,135 @@
+/*
+ * barb200.h -- C ABI of libbarb200.so, the B200-native engine behind Cactus' base-alignment-refinement (BAR)
+ * phase in POA mode. Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
+ *
+ * Drop-in boundary (paths relative to the Cactus source tree, commit 2a4a172f):
+ *   - barb200_poa_msa_batch ........ replaces the abpoa_init / abpoa_msa / abpoa_free triple the shim issues once per
+ *                                    sliding window of every end (bar/impl/poaBarAligner.c:565-628;
+ *                                    submodules/abPOA/include/abpoa.h:150-160), for MANY windows at once.
+ *   - barb200_msa_make_partial_order_alignment[_batch]
+ *                                    replaces msa_make_partial_order_alignment (bar/inc/poaBarAligner.h:76,
+ *                                    bar/impl/poaBarAligner.c:463-749): windows, overlap trimming, stitching.
+ *   - barb200_make_consistent_partial_order_alignments
+ *                                    replaces make_consistent_partial_order_alignments (bar/inc/poaBarAligner.h:108,
+ *                                    bar/impl/poaBarAligner.c:751-801): all ends of a flower in one batched launch,
+ *                                    then the serial cross-end trimming.
+ *   - barb200_params ............... the fields abpoaParamaters_constructFromCactusParams reads from the <bar><poa>
+ *                                    XML element (bar/impl/poaBarAligner.c:24-81; keys listed in
+ *                                    src/cactus/cactus_progressive_config.xml:307-325).
+ * INTEGRATION.md shows the ~40-line C shim that re-exports the reference symbols on top of these.
+ *
+ * Error convention: functions return 0 on success and a negative BARB200_E* code on failure;
+ * barb200_last_error() gives the message. (The reference aborts the process instead, st_errAbort /
+ * err_fatal; the shim in INTEGRATION.md converts a non-zero return into st_errAbort to keep that behaviour.)
+ * There is NO CPU fallback: without a CUDA device barb200_create fails.
+ *
+ * Thread safety: a context may be shared by threads; batch calls on one context are serialised internally
+ * (the reference calls msa_make_partial_order_alignment concurrently from OpenMP teams, bar/impl/bar.c:90-94).
+ */
+#ifndef BARB200_H
+#define BARB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BARB200_OK 0
+#define BARB200_ENODEV (-1)     /* no usable CUDA device / driver */
+#define BARB200_ENOMEM (-2)     /* device or host allocation failed */
+#define BARB200_EINVAL (-3)     /* bad argument (empty sequence, code > 4, gap model other than convex, ...) */
+#define BARB200_ECUDA (-4)      /* a CUDA call or the kernel failed */
+#define BARB200_EJOB (-5)       /* a job failed on the device (graph error the reference would abort on) */
+
+typedef struct barb200_ctx barb200_ctx;
+
+typedef struct {
+    /* scoring and banding -- bar/impl/poaBarAligner.c:36-77 */
+    int mat[25];                 /* partialOrderAlignmentSubMatrix, 5x5 ACGTN */
+    int gap_open1, gap_ext1;     /* partialOrderAlignmentGapOpenPenalty1 / GapExtensionPenalty1 */
+    int gap_open2, gap_ext2;     /* partialOrderAlignmentGapOpenPenalty2 / GapExtensionPenalty2 (convex: both opens > 0) */
+    int wb; float wf;            /* partialOrderAlignmentBandConstant / BandFraction; band = wb + wf*len */
+    /* guide tree -- bar/impl/poaBarAligner.c:46-53 */
+    int k, w, min_w;             /* partialOrderAlignmentMinimizerK / W / MinW */
+    int progressive_poa;         /* partialOrderAlignmentProgressiveMode */
+    int disable_seeding;         /* partialOrderAlignmentDisableSeeding; must be 1 (Cactus' default) */
+    /* engine */
+    int device;                  /* CUDA device ordinal */
+    int threads_per_block;       /* 0 = auto (128..512 by longest query) */
+    int ctas_per_sm;             /* 0 = auto (occupancy / memory limited) */
+    double mem_fraction;         /* fraction of free device memory the slots may take; 0 = 0.85 */
+    int host_threads;            /* threads for host-side packing / guide trees; 0 = all */
+    int collect_phase_clocks;    /* 1: accumulate per-phase SM clock counters (profiling aid) */
+} barb200_params;
+
+/* Cactus' defaults (src/cactus/cactus_progressive_config.xml:307-325) */
+void barb200_params_default(barb200_params *p);
+
+barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, int errbuf_len);
+void barb200_destroy(barb200_ctx *ctx);
+const char *barb200_last_error(barb200_ctx *ctx);
+
+/* One job = one abpoa_msa call: n_seq[i] sequences of codes 0..4 (A,C,G,T,N), concatenated over all jobs in
+ * `seqs` with lengths in `seq_lens` (sum of n_seq entries). progressive[i] (may be NULL = use params) is the
+ * per-job abpt->progressive_poa the shim decides at poaBarAligner.c:567-571.
+ * Outputs: msa_out[i] = malloc'd n_seq[i] x msa_len[i] row-major bytes (0-3 ACGT, 4 N, 5 gap), to be released
+ * with barb200_free; cells[i] (may be NULL) = banded DP cells of the job (sum of dp_end-dp_beg+1). */
+int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
+                          const uint8_t *seqs, const int *progressive, uint8_t **msa_out, int *msa_len,
+                          int64_t *cells);
+
+/* Staged form of the same call for callers (and bench.py) that keep inputs resident in HBM:
+ * stage = host packing + guide trees + H2D once; run = kernel(s) only, may be repeated; fetch = D2H + unpack. */
+typedef struct barb200_stage barb200_stage;
+int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
+                         const uint8_t *seqs, const int *progressive, barb200_stage **out);
+int barb200_stage_run(barb200_stage *st, float *kernel_ms /* may be NULL: device time of the launch(es) */);
+int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *msa_len, int64_t *cells);
+int64_t barb200_stage_launches(barb200_stage *st);   /* kernels launched by the last barb200_stage_run */
+/* per-phase SM clock totals of the last run (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total */
+int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[6]);
+void barb200_stage_destroy(barb200_stage *st);
+
+/* The reference's Msa (bar/inc/poaBarAligner.h:37-43) with one flat matrix instead of row pointers. */
+typedef struct {
+    int64_t seq_no;
+    int64_t column_no;
+    int *seq_lens;       /* [seq_no] input lengths (as the reference's Msa.seq_lens after stitching) */
+    uint8_t *msa;        /* [seq_no * column_no] 0-3 ACGT, 4 N, 5 gap */
+} barb200_msa;
+void barb200_msa_destruct(barb200_msa *m);
+
+/* msa_make_partial_order_alignment for n_ends independent ends at once. seqs[e][i] is the i-th ASCII string of end e
+ * (not necessarily NUL terminated), seq_lens[e][i] its length, seq_no[e] the number of strings.
+ * out[e] receives a new barb200_msa. Inputs are not retained. */
+int barb200_msa_make_partial_order_alignment_batch(barb200_ctx *ctx, int64_t n_ends, const int64_t *seq_no,
+        char ***seqs, int **seq_lens, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff,
+        barb200_msa **out);
+
+/* Single-end convenience with the reference's argument order (bar/inc/poaBarAligner.h:76). */
+barb200_msa *barb200_msa_make_partial_order_alignment(barb200_ctx *ctx, char **seqs, int *seq_lens, int64_t seq_no,
+        int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff);
+
+/* make_consistent_partial_order_alignments (bar/inc/poaBarAligner.h:108): same arguments, abpoa_para_t replaced by
+ * the context. Returns a malloc'd array of end_no barb200_msa* (release each with barb200_msa_destruct and the array
+ * with barb200_free), or NULL on error. */
+barb200_msa **barb200_make_consistent_partial_order_alignments(barb200_ctx *ctx, int64_t end_no, int64_t *end_lengths,
+        char ***end_strings, int **end_string_lengths, int64_t **right_end_indexes, int64_t **right_end_row_indexes,
+        int64_t **overlaps, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff);
+
+/* Seeded synthetic ends of BASELINE.json's "N ends x K seqs x L bp" shape: per end a uniform random
+ * ACGT parent of length L and K descendants with per-base substitution / insertion / deletion events, rows sorted by
+ * length descending. codes_out: caller buffer of at least K*(2*L+16) bytes; lens_out[K]. Returns total bases written.
+ * Host only; deterministic in (seed, end_index). */
+int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
+                          uint8_t *codes_out, int *lens_out);
+
+/* Device facts for reports. */
+int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);
+
+void barb200_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

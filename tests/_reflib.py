@@ -270,3 +270,31 @@ def ref_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=1
 def oracle_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,
                                                     max_prog_length_diff=1.0, p=None):
     return _consistent("oracle", ends, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host build of the product's __host__ __device__ graph code (tests/hosttest), CPU only
+# ---------------------------------------------------------------------------------------------------
+HOSTTEST_SO = os.path.join(ROOT, "tests", "hosttest", "_build", "libhosttest.so")
+
+
+def build_hosttest():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hosttest")])
+    return HOSTTEST_SO
+
+
+def hosttest_poa_msa_trace(seqs, p=None):
+    p = p or cactus_params()
+    lib = _load(build_hosttest())
+    lens, flat = _flat(seqs)
+    nw = C.c_int64()
+    status = C.c_int()
+    f = lib.hosttest_poa_msa_trace
+    f.restype = C.c_void_p
+    f.argtypes = [C.POINTER(RefParams), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    ptr = f(C.byref(p), len(seqs), lens.ctypes.data, flat.ctypes.data, C.byref(nw), C.byref(status))
+    words = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(nw.value,)).copy()
+    lib.hosttest_free.argtypes = [C.c_void_p]
+    lib.hosttest_free(ptr)
+    assert status.value == 0, "hosttest job status %d" % status.value
+    return _parse_trace(words, len(seqs))

@@ -1,0 +1,143 @@
+// hosttest.cpp -- TEST-ONLY build (never shipped, never loaded by cactus_b200): compiles the product's
+// __host__ __device__ graph / traceback code (cactus_b200/csrc/poa_graph.cuh) and its host guide tree
+// (guide_tree.cpp) with g++ so that the CPU suite can check them against the oracle in a container without a GPU.
+// The DP sweep itself is CUDA-only; here it is stood in for by a scalar emulation of the kernel's per-row
+// formulation (gathered band, prefix-maximum form of F) writing the same plane layout, which also pins that
+// formulation's arithmetic. The real kernel is checked on the GPU by tests/test_gpu_*.py.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../../cactus_b200/csrc/poa_graph.cuh"
+#include "../../cactus_b200/csrc/host_api.h"
+
+using namespace barb200;
+
+struct HtParams { int wb; float wf; int o1, e1, o2, e2; int mat[25]; int k, w, min_w; int progressive, disable_seeding; };
+
+static long long emulate_sweep(const Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
+    const int node_n = g.node_n, R = node_n - 1, NEG = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int w = P.wb + (int)(P.wf * L), pn = reference_lane_count(P, L, node_n);
+    long long cur_off = 0, cells = 0;
+    {
+        const int end = std::min(L, std::max(0, L - rt.row_rd[0]) + w), wr4 = (end | 3) + 1;
+        if (5LL * wr4 > d.plane_cap) return -1;
+        int *row = d.planes;
+        for (int j = 0; j < wr4; ++j) {
+            int h, x1, x2, f1, f2;
+            if (j == 0) { h = 0; x1 = -oe1; x2 = -oe2; f1 = f2 = NEG; }
+            else if (j <= end) { f1 = -P.o1 - e1 * j; f2 = -P.o2 - e2 * j; h = std::max(f1, f2); x1 = x2 = NEG; }
+            else h = x1 = x2 = f1 = f2 = NEG;
+            row[j] = h; row[wr4 + j] = x1; row[2 * wr4 + j] = x2; row[3 * wr4 + j] = f1; row[4 * wr4 + j] = f2;
+        }
+        d.dp_beg[0] = 0; d.dp_end[0] = end; d.row_off[0] = 0; d.row_left[0] = 0; d.row_right[0] = 0;
+        cur_off = 5LL * wr4; cells = end + 1;
+    }
+    for (int r = 1; r < R; ++r) {
+        const int b = rt.row_base[r], p0 = rt.pre_off[r], p1 = rt.pre_off[r + 1], dd = L - rt.row_rd[r];
+        int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
+        for (int k = p0; k < p1; ++k) { const int p = rt.pre_row[k]; maxL = std::min(maxL, d.row_left[p] + 1); maxR = std::max(maxR, d.row_right[p] + 1); min_pre_beg = std::min(min_pre_beg, d.dp_beg[p]); }
+        int beg = std::max(0, std::min(maxL, dd) - w); const int end = std::min(L, std::max(maxR, dd) + w);
+        if (beg / pn < min_pre_beg / pn) beg = min_pre_beg;
+        const int beg4 = beg & ~3, wr4 = (end | 3) - beg4 + 1;
+        if (cur_off + 5LL * wr4 > d.plane_cap) return -1;
+        int *rowp = d.planes + cur_off - beg4;
+        int P1 = NEG + beg * e1, P2 = NEG + beg * e2, tmax = NEG - 1000, tl = 0, tr = -1;
+        d.dp_beg[r] = beg; d.dp_end[r] = end; d.row_off[r] = cur_off;
+        for (int j = beg4; j <= (end | 3); ++j) {
+            int m = NEG, x1 = NEG, x2 = NEG;
+            for (int k = p0; k < p1; ++k) {
+                const int p = rt.pre_row[k];
+                m = std::max(m, plane_cell(d, NEG, p, 0, j - 1)); x1 = std::max(x1, plane_cell(d, NEG, p, 1, j)); x2 = std::max(x2, plane_cell(d, NEG, p, 2, j));
+            }
+            const int s = j == 0 ? 0 : (j <= L ? P.mat[5 * b + q[j - 1]] : 0);
+            int hme;
+            if (j < beg || j > end) { hme = NEG; x1 = NEG; x2 = NEG; } else hme = std::max(std::max(m + s, x1), x2);
+            const int A1 = hme - oe1 + (j + 1) * e1, A2 = hme - oe2 + (j + 1) * e2;
+            int f1 = P1 - j * e1, f2 = P2 - j * e2, h;
+            P1 = std::max(P1, A1); P2 = std::max(P2, A2);
+            if (j < beg || j > end) { h = NEG; f1 = NEG; f2 = NEG; }
+            else {
+                h = std::max(std::max(hme, f1), f2);
+                x1 = std::max(x1 - e1, h - oe1); x2 = std::max(x2 - e2, h - oe2);
+                if (h > tmax) { tmax = h; tl = tr = j; } else if (h == tmax) tr = j;
+            }
+            rowp[j] = h; rowp[wr4 + j] = x1; rowp[2 * wr4 + j] = x2; rowp[3 * wr4 + j] = f1; rowp[4 * wr4 + j] = f2;
+        }
+        d.row_left[r] = tl; d.row_right[r] = tr;
+        cur_off += 5LL * wr4; cells += end - beg + 1;
+    }
+    return cells;
+}
+
+// same word layout as oracle/ref_harness.c:ref_poa_msa_trace; returns malloc'd words
+extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const int *lens, const uint8_t *flat, int64_t *n_words, int *status) {
+    PoaParams P; memcpy(P.mat, hp->mat, sizeof(P.mat));
+    P.o1 = hp->o1; P.e1 = hp->e1; P.o2 = hp->o2; P.e2 = hp->e2; P.wb = hp->wb; P.wf = hp->wf; P.max_mat = 0; P.min_mis = 0;
+    for (int i = 0; i < 25; ++i) { P.max_mat = std::max(P.max_mat, P.mat[i]); P.min_mis = std::max(P.min_mis, -P.mat[i]); }
+    P.inf_min = std::max(std::max(INT32_MIN + P.min_mis, INT32_MIN + P.o1 + P.e1), INT32_MIN + P.o2 + P.e2) + 512 * std::max(P.e1, P.e2);
+    std::vector<const uint8_t *> seqs(n_seq); int64_t sum = 0; int maxl = 0;
+    for (int i = 0; i < n_seq; ++i) { seqs[i] = flat + sum; sum += lens[i]; maxl = std::max(maxl, lens[i]); }
+    std::vector<int> order(n_seq);
+    HostParams hpp{hp->k, hp->w, hp->min_w, hp->progressive};
+    guide_tree_order(hpp, hp->progressive, n_seq, seqs.data(), lens, order.data());
+    const int N = (int)sum + 2, EP = (int)(4 * (sum + n_seq) + 64), W = 1 + ((n_seq - 1) >> 6);
+    Graph g; RowTables rt; DpState d;
+    std::vector<uint8_t> base(N), aln_n(N), row_base(N);
+    std::vector<int> aln_id(4 * N), in_off(N), in_n(N), in_cap(N), out_off(N), out_n(N), out_cap(N), in_id(EP), in_w(EP), out_id(EP), out_w(EP),
+        i2n(N), n2i(N), remain(N), rank(N), t0(N), t1(N), row_rd(N), pre_off(N + 1), pre_row(EP), dp_beg(N), dp_end(N), rl(N), rr(N);
+    std::vector<uint64_t> rid((size_t)EP * W), cigar(maxl + N + 16);
+    std::vector<int64_t> row_off(N);
+    const int64_t plane_cap = (int64_t)N * 5 * (maxl + 8);
+    std::vector<int> planes((size_t)std::min<int64_t>(plane_cap, (int64_t)1 << 31));
+    g.node_cap = N; g.in_pool = EP; g.out_pool = EP;
+    g.base = base.data(); g.aln_n = aln_n.data(); g.aln_id = aln_id.data(); g.in_off = in_off.data(); g.in_n = in_n.data(); g.in_cap = in_cap.data();
+    g.out_off = out_off.data(); g.out_n = out_n.data(); g.out_cap = out_cap.data(); g.in_id = in_id.data(); g.in_w = in_w.data();
+    g.out_id = out_id.data(); g.out_w = out_w.data(); g.out_rid = rid.data(); g.index_to_node = i2n.data(); g.node_to_index = n2i.data();
+    g.remain = remain.data(); g.msa_rank = rank.data(); g.tmp0 = t0.data(); g.tmp1 = t1.data();
+    rt.row_base = row_base.data(); rt.row_rd = row_rd.data(); rt.pre_off = pre_off.data(); rt.pre_row = pre_row.data();
+    d.planes = planes.data(); d.plane_cap = (int64_t)planes.size(); d.row_off = row_off.data(); d.dp_beg = dp_beg.data(); d.dp_end = dp_end.data();
+    d.row_left = rl.data(); d.row_right = rr.data(); d.cigar = cigar.data(); d.cigar_cap = (int)cigar.size(); d.n_cigar = 0;
+    graph_reset(g, n_seq);
+    std::vector<int64_t> w;
+    w.push_back(n_seq); w.push_back(0); w.push_back(0);
+    for (int i = 0; i < n_seq; ++i) w.push_back(order[i]);
+    long long cells = 0;
+    for (int a = 0; a < n_seq && !g.err; ++a) {
+        const int read = order[a], L = lens[read]; const uint8_t *q = seqs[read];
+        const int node_n = g.node_n; int n_rows = 0; d.n_cigar = 0; d.best_score = 0;
+        if (a == 0) graph_add_first_sequence(g, q, L, read);
+        else {
+            long long c = emulate_sweep(g, rt, d, P, q, L);
+            if (c < 0) { g.err = JOB_ERR_PLANE_CAP; break; }
+            cells += c; n_rows = node_n - 1;
+            dp_best_cell(g, rt, d, P, L); dp_backtrack(g, rt, d, P, q, L);
+        }
+        w.push_back(read); w.push_back(L); w.push_back(node_n); w.push_back(d.n_cigar); w.push_back(a == 0 ? 0 : d.best_score); w.push_back(n_rows);
+        for (int c = 0; c < d.n_cigar; ++c) w.push_back((int64_t)d.cigar[c]);
+        for (int r = 0; r < n_rows; ++r) w.push_back(d.dp_beg[r]);
+        for (int r = 0; r < n_rows; ++r) w.push_back(d.dp_end[r]);
+        if (g.err) break;
+        if (a > 0) graph_fuse_alignment(g, q, d.cigar, d.n_cigar, read);
+        if (g.err) break;
+        graph_topo_sort_serial(g, rt);
+    }
+    *status = g.err;
+    int msa_len = 0; std::vector<uint8_t> msa;
+    if (!g.err) {
+        msa_len = graph_msa_rank(g);
+        msa.assign((size_t)n_seq * msa_len, GAP_CODE);
+        for (int v = 2; v < g.node_n; ++v) graph_msa_fill_node(g, v, msa.data(), msa_len);
+    }
+    w[1] = msa_len; w[2] = cells;
+    const size_t nb = msa.size(), nw = (nb + 7) / 8, base_w = w.size();
+    w.resize(base_w + nw, 0);
+    if (nb) memcpy(w.data() + base_w, msa.data(), nb);
+    int64_t *out = (int64_t *)malloc(sizeof(int64_t) * w.size());
+    memcpy(out, w.data(), sizeof(int64_t) * w.size());
+    *n_words = (int64_t)w.size();
+    return out;
+}
+
+extern "C" void hosttest_free(void *p) { free(p); }

@@ -1,0 +1,181 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the committed golden vectors of the
+unmodified reference, against the plain-C oracle on seeded inputs, and -- at benchmark scale -- through
+size-independent properties. Bit-exact: these are integer/byte results."""
+import numpy as np
+import pytest
+
+import _golden as G
+import _reflib as R
+from _synth import family, to_ascii, two_end_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import cactus_b200 as cb
+    e = cb.Engine()
+    yield e
+    e.close()
+
+
+def engine_for(params):
+    import cactus_b200 as cb
+    return cb.Engine(cb.PoaParams(
+        partialOrderAlignmentBandConstant=params["wb"], partialOrderAlignmentBandFraction=params["wf"],
+        partialOrderAlignmentGapOpenPenalty1=params["o1"], partialOrderAlignmentGapExtensionPenalty1=params["e1"],
+        partialOrderAlignmentGapOpenPenalty2=params["o2"], partialOrderAlignmentGapExtensionPenalty2=params["e2"],
+        partialOrderAlignmentMinimizerK=params["k"], partialOrderAlignmentMinimizerW=params["w"],
+        partialOrderAlignmentMinimizerMinW=params["min_w"], partialOrderAlignmentProgressiveMode=params["progressive"]))
+
+
+def test_golden_poa(engine):
+    """every golden abpoa_msa case: MSA bytes and banded cell count equal to the reference's"""
+    default = R.params_dict(R.cactus_params())
+    for c in G.poa_cases():
+        same = all(abs(c["params"][k] - default[k]) < 1e-9 for k in c["params"])
+        e = engine if same else engine_for(c["params"])
+        msas, cells = e.poa_msa_batch([c["seqs"]], return_cells=True)
+        assert msas[0].shape == c["msa"].shape and np.array_equal(msas[0], c["msa"]), c["id"]
+        assert int(cells[0]) == c["cells"], c["id"]
+        if not same:
+            e.close()
+
+
+def test_golden_poa_one_batch(engine):
+    """all default-parameter golden cases in ONE launch (mixed K and L in a batch)"""
+    default = R.params_dict(R.cactus_params())
+    cases = [c for c in G.poa_cases() if all(abs(c["params"][k] - default[k]) < 1e-9 for k in c["params"])]
+    msas = engine.poa_msa_batch([c["seqs"] for c in cases])
+    for m, c in zip(msas, cases):
+        assert m.shape == c["msa"].shape and np.array_equal(m, c["msa"]), c["id"]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_vs_oracle(engine, oracle_built, seed):
+    rng = np.random.default_rng(500 + seed)
+    jobs = []
+    for it in range(48):
+        K = int(rng.integers(2, 14))
+        L = int(rng.choice([1, 5, 20, 60, 150, 300, 400, 800, 1500]))
+        kw = dict(sub=float(rng.choice([0.0, 0.02, 0.08, 0.2])), ins=float(rng.choice([0, 0.005, 0.03])),
+                  dele=float(rng.choice([0, 0.005, 0.03])), nfrac=float(rng.choice([0, 0, 0.01])))
+        jobs.append(family(rng, K, L, sort=bool(rng.random() < 0.7), **kw))
+    msas, cells = engine.poa_msa_batch(jobs, return_cells=True)
+    for j, (m, job) in enumerate(zip(msas, jobs)):
+        tr = R.oracle_poa_msa_trace(job)
+        assert m.shape == tr["msa"].shape and np.array_equal(m, tr["msa"]), (seed, j)
+        assert int(cells[j]) == tr["cells"], (seed, j)
+
+
+def test_unrelated_ragged_and_wide(engine, oracle_built):
+    """ragged unrelated rows, N-rich, K > 64 (two read-id words), the int16/int32 lane switch"""
+    rng = np.random.default_rng(42)
+    jobs = []
+    for it in range(24):
+        K = int(rng.integers(2, 90))
+        jobs.append([rng.integers(0, 5 if rng.random() < 0.2 else 4, int(rng.integers(1, 400))).astype(np.uint8) for _ in range(K)])
+    msas = engine.poa_msa_batch(jobs)
+    for j, (m, job) in enumerate(zip(msas, jobs)):
+        o = R.oracle_poa_msa(job)
+        assert m.shape == o.shape and np.array_equal(m, o), j
+
+
+def test_narrow_band_params(oracle_built):
+    """non-default bands force the adaptive band edges into play"""
+    rng = np.random.default_rng(43)
+    for wb, wf, prog in [(10, 0.01, 1), (0, 0.0, 0), (30, 0.02, 1), (5, 0.1, 0)]:
+        p = R.cactus_params(wb=wb, wf=wf, progressive=prog)
+        e = engine_for(R.params_dict(p))
+        jobs = [family(rng, int(rng.integers(2, 10)), int(rng.choice([50, 300, 900])), sub=0.08, ins=0.03, dele=0.03) for _ in range(12)]
+        msas = e.poa_msa_batch(jobs)
+        for j, (m, job) in enumerate(zip(msas, jobs)):
+            o = R.oracle_poa_msa(job, p)
+            assert m.shape == o.shape and np.array_equal(m, o), (wb, wf, j)
+        e.close()
+
+
+def test_long_window_10k(engine, oracle_built):
+    """a full 10 kbp window: rows wider than the shared-memory row cache use the global-memory predecessor path"""
+    rng = np.random.default_rng(44)
+    job = [s[:10000] for s in family(rng, 4, 10000, sub=0.03, ins=0.01, dele=0.01)]
+    m = engine.poa_msa_batch([job])[0]
+    o = R.oracle_poa_msa(job)
+    assert m.shape == o.shape and np.array_equal(m, o)
+
+
+def test_bench_shape_properties(engine, oracle_built):
+    """BASELINE.json's synthetic shape (8 x 2 kbp, Cactus defaults) in bulk: every row spells its input
+    (bar/tests/poaBarTest.c:19-31 validate_msa), no all-gap column, results independent of batch composition,
+    and the first ends equal to the oracle bit for bit."""
+    import cactus_b200 as cb
+    n = 600
+    n_seq, lens, flat = cb.synth_ends(0, n, 8, 2000)
+    st = engine.stage(packed=(n_seq, lens, flat))
+    st.run()
+    msas, cells = st.fetch()
+    st.close()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    for e in range(n):
+        m = msas[e]
+        for i in range(8):
+            s = flat[offs[e * 8 + i]:offs[e * 8 + i + 1]]
+            assert np.array_equal(m[i][m[i] != 5], s), (e, i)
+        assert not np.any(np.all(m == 5, axis=0)), e
+    for e in range(4):
+        job = [flat[offs[e * 8 + i]:offs[e * 8 + i + 1]] for i in range(8)]
+        tr = R.oracle_poa_msa_trace(job)
+        assert np.array_equal(msas[e], tr["msa"]) and int(cells[e]) == tr["cells"], e
+    # same ends, different batch (reversed order, different slot assignment): identical output
+    jobs_rev = [[flat[offs[e * 8 + i]:offs[e * 8 + i + 1]] for i in range(8)] for e in reversed(range(40))]
+    again = engine.poa_msa_batch(jobs_rev)
+    for k, e in enumerate(reversed(range(40))):
+        assert np.array_equal(again[k], msas[e]), e
+
+
+def test_golden_windows_and_two_ends(engine):
+    """poaBarAligner.h level through the C ABI: sliding windows + trimming, and two-end consistency"""
+    for c in G.window_cases():
+        m = engine.msa_make_partial_order_alignment(c["strs"], window_size=c["win"])
+        assert m.msa_seq.shape == c["msa"].shape and np.array_equal(m.msa_seq, c["msa"]), c["id"]
+    for c in G.two_end_cases():
+        ms = engine.make_consistent_partial_order_alignments(c["ends"], c["ri"], c["rr"], c["ov"], window_size=c["win"])
+        for a, b in zip(ms, c["msas"]):
+            assert a.msa_seq.shape == b.shape and np.array_equal(a.msa_seq, b), c["id"]
+
+
+def test_windows_vs_oracle_and_invariant(engine, oracle_built):
+    rng = np.random.default_rng(45)
+    ends, wins = [], []
+    for it in range(16):
+        K = int(rng.integers(1, 8))
+        L = int(rng.choice([10, 50, 200, 700]))
+        strs = [to_ascii(s) for s in family(rng, K, L, sub=0.05, ins=0.02, dele=0.02, nfrac=0.01)]
+        if rng.random() < 0.2 and K > 1:
+            strs[-1] = b""
+        ends.append(strs)
+    for win in (20, 110, 10000):
+        ms = engine.msa_make_partial_order_alignment_batch(ends, window_size=win)
+        for e, m in zip(ends, ms):
+            o = R.oracle_msa_make_partial_order_alignment(e, window_size=win)
+            assert m.msa_seq.shape == o.shape and np.array_equal(m.msa_seq, o), win
+    # the reference's two-end invariant (poaBarTest.c:160-176)
+    for it in range(6):
+        K = int(rng.integers(1, 10))
+        ends2, ri, rr, ov = two_end_problem(rng, K, int(rng.choice([10, 60, 150])), sub=0.05, ins=0.02, dele=0.02)
+        ms = engine.make_consistent_partial_order_alignments(ends2, ri, rr, ov)
+        o = R.oracle_make_consistent_partial_order_alignments(ends2, ri, rr, ov)
+        for a, b in zip(ms, o):
+            assert np.array_equal(a.msa_seq, b)
+        for i in range(K):
+            assert int((ms[0].msa_seq[i] != 5).sum()) + int((ms[1].msa_seq[rr[0][i]] != 5).sum()) == len(ends2[0][i])
+
+
+def test_errors_are_loud(engine):
+    import cactus_b200 as cb
+    with pytest.raises(cb.BarB200Error):
+        engine.poa_msa_batch([[np.array([0, 1, 7], np.uint8), np.array([0, 1], np.uint8)]])
+    with pytest.raises(cb.BarB200Error):
+        engine.poa_msa_batch([[np.array([], np.uint8), np.array([0, 1], np.uint8)]])
+    with pytest.raises(cb.BarB200Error):
+        cb.Engine(cb.PoaParams(partialOrderAlignmentGapOpenPenalty2=0))

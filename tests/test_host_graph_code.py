@@ -1,0 +1,44 @@
+"""CPU check of the product's __host__ __device__ code (cactus_b200/csrc/poa_graph.cuh: graph fusion, topological
+sort, edge sort, max_remain, row tables, MSA rank/fill, traceback) and of its host guide tree (guide_tree.cpp), compiled
+by tests/hosttest for the host and compared with the oracle on seeded inputs and with the golden vectors. The CUDA DP
+sweep is stood in for by a scalar emulation of the kernel's row formulation; the real kernel is tested under -m gpu."""
+import numpy as np
+
+import _golden as G
+import _reflib as R
+from _synth import family
+from test_oracle_vs_ref import assert_same_trace
+
+
+def test_hosttest_golden():
+    for c in G.poa_cases():
+        p = R.cactus_params(**c["params"])
+        tr = R.hosttest_poa_msa_trace(c["seqs"], p)
+        assert np.array_equal(tr["msa"], c["msa"]), c["id"]
+        assert tr["read_id_map"] == c["order"], c["id"]
+        assert tr["cells"] == c["cells"], c["id"]
+        assert np.array_equal(np.concatenate([a["cigar"] for a in tr["alns"]]), c["cigar"]), c["id"]
+        assert np.array_equal(np.concatenate([a["dp_beg"] for a in tr["alns"]]), c["beg"]), c["id"]
+        assert np.array_equal(np.concatenate([a["dp_end"] for a in tr["alns"]]), c["end"]), c["id"]
+
+
+def test_hosttest_random_vs_oracle(oracle_built):
+    rng = np.random.default_rng(77)
+    for it in range(60):
+        K = int(rng.integers(2, 14))
+        L = int(rng.choice([5, 20, 60, 150, 300, 400, 800]))
+        kw = dict(sub=float(rng.choice([0.0, 0.02, 0.08, 0.2])), ins=float(rng.choice([0, 0.005, 0.03])),
+                  dele=float(rng.choice([0, 0.005, 0.03])), nfrac=float(rng.choice([0, 0, 0.01])))
+        seqs = family(rng, K, L, sort=bool(rng.random() < 0.7), **kw)
+        p = R.cactus_params() if rng.random() < 0.5 else R.cactus_params(
+            wb=int(rng.choice([0, 5, 10, 30, 100])), wf=float(rng.choice([0.0, 0.01, 0.02, 0.1])), progressive=int(rng.integers(0, 2)))
+        assert_same_trace(R.oracle_poa_msa_trace(seqs, p), R.hosttest_poa_msa_trace(seqs, p), (it, K, L, kw))
+
+
+def test_hosttest_unrelated_ragged(oracle_built):
+    rng = np.random.default_rng(78)
+    for it in range(40):
+        K = int(rng.integers(2, 70))
+        seqs = [rng.integers(0, 5 if rng.random() < 0.2 else 4, int(rng.integers(1, 300))).astype(np.uint8) for _ in range(K)]
+        p = R.cactus_params(wb=int(rng.choice([0, 1, 5, 10, 1000])), wf=float(rng.choice([0.0, 0.01, 0.1])), progressive=int(rng.integers(0, 2)))
+        assert_same_trace(R.oracle_poa_msa_trace(seqs, p), R.hosttest_poa_msa_trace(seqs, p), (it, K))
