@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- BAR POA DP throughput (Gcell/s, ends/s) of the B200 engine vs the reference CPU BAR path.
+
+Contract (see the round brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+A *step* is one pass of the hot path (batched POA: all abpoa_msa jobs of a batch of ends) over one batch of synthetic
+ends of BASELINE.json's shape: E ends x 8 sequences x 2 kbp per GPU (weak scaling; BASELINE.json configs[2] scaled to
+what one step should take -- configs[1], evolverMammals, needs data that is not available offline).
+
+  value   whole-job Gcell/s, inputs already resident in HBM (stage created before the timed region), device time of
+          the kernel launches (CUDA events on the launching stream), max over ranks.
+  e2e     the same metric through the C-ABI call a caller makes (barb200_poa_msa_batch) with HOST buffers: host
+          packing + guide trees + H2D + kernel + D2H + unpack all inside the timed region.
+  cells   the banded-cell definition of SURVEY.md 8d (sum of dp_end-dp_beg+1), counted by the kernel itself and
+          pinned to the reference's count by the parity tests.
+
+`--impl reference` times the reference's own CPU implementation (unmodified abPOA built from /root/reference into
+oracle/_ref, AVX2, OpenMP over ends with all host threads; the plain-C oracle port if that library is absent) on a
+bounded sample of the same workload and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K_SEQS, L_BP = 8, 2000
+METRIC = "BAR POA DP Gcells/sec and ends/sec at 1/2/4/8 B200 vs reference CPU BAR"
+ALGO_BYTES_PER_CELL = 32.0     # 20 B written + 12 B read per cell (int32 planes)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(n_seq, lens, flat, cells, budget_s=20.0):
+    """reference CPU path on the host cores, bounded sample (about budget_s seconds of wall time)"""
+    import _reflib as R
+    threads = os.cpu_count() or 1
+    K = K_SEQS
+    # calibrate on a few ends, then size the sample
+    n0 = min(len(n_seq), max(2, threads))
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    secs0, kind, _ = R.cpu_poa_msa_many(n_seq[:n0], lens[:n0 * K], flat[:offs[n0 * K]], threads=threads)
+    per_end = secs0 / n0
+    n = int(min(len(n_seq), max(n0, budget_s / max(per_end, 1e-6))))
+    secs, kind, _ = R.cpu_poa_msa_many(n_seq[:n], lens[:n * K], flat[:offs[n * K]], threads=threads)
+    c = float(np.sum(cells[:n]))
+    return {"value": c / secs / 1e9, "unit": "Gcell/s", "ends_per_s": n / secs, "cores": threads, "kind": kind,
+            "sample": "first %d of the step's ends (8 x 2 kbp each), %.1f s wall, OpenMP schedule(dynamic,1) over ends" % (n, secs)}, n, secs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ends-per-step", type=int, default=int(os.environ.get("BARB200_ENDS_PER_STEP", "2368")),
+                    help="ends per GPU per step (default 16 x 148 SMs)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    E = args.ends_per_step
+    config = {"workload": "synthetic %d ends x %d seqs x %d bp per GPU per step, Cactus default POA parameters "
+                          "(convex gap 400/30/1200/1, band 1000+0.1L, progressive order), 2%% sub / 0.5%% ins / 0.5%% del" % (E, K_SEQS, L_BP),
+              "ends_per_gpu_per_step": E, "seqs_per_end": K_SEQS, "bp": L_BP, "parallelism": "ends sharded over %d GPU(s)" % world,
+              "l2": "working set (DP planes, ~100 MB per resident CTA) is far larger than the 126 MB L2"}
+
+    import cactus_b200 as cb
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path; rank 0 only
+        if rank != 0:
+            return 0
+        import _reflib as R
+        n_seq, lens, flat = cb.synth_ends(0, E, K_SEQS, L_BP)
+        threads = os.cpu_count() or 1
+        # cells of the sample from the oracle/reference itself (bounded): per-end count through the trace is slow, so
+        # use the port's cell counter on the sample actually timed
+        K = K_SEQS
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        n0 = min(E, max(2, threads))
+        secs0, kind, _ = R.cpu_poa_msa_many(n_seq[:n0], lens[:n0 * K], flat[:offs[n0 * K]], threads=threads)
+        n = int(min(E, max(n0, args.cpu_budget / max(secs0 / n0, 1e-6) / max(1, args.steps + args.warmup))))
+        lib = R._load(R.build_oracle())
+        import ctypes as C
+        lib.oracle_poa_cells.restype = C.c_int64
+        lib.oracle_poa_cells.argtypes = [C.POINTER(R.RefParams), C.c_int, C.c_void_p, C.c_void_p]
+        p = R.cactus_params()
+        # one representative end's cell count x n would be an estimate; count a few ends exactly and scale
+        ncount = min(n, 4)
+        csum = 0
+        for e in range(ncount):
+            l = np.ascontiguousarray(lens[e * K:(e + 1) * K])
+            f = np.ascontiguousarray(flat[offs[e * K]:offs[(e + 1) * K]])
+            csum += lib.oracle_poa_cells(C.byref(p), K, l.ctypes.data, f.ctypes.data)
+        cells_per_end = csum / ncount
+        for _ in range(args.warmup):
+            R.cpu_poa_msa_many(n_seq[:n], lens[:n * K], flat[:offs[n * K]], threads=threads)
+        t = 0.0
+        for _ in range(args.steps):
+            s, kind, _ = R.cpu_poa_msa_many(n_seq[:n], lens[:n * K], flat[:offs[n * K]], threads=threads)
+            t += s
+        value = cells_per_end * n * args.steps / t / 1e9
+        line = {"metric": METRIC, "value": value, "unit": "Gcell/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "ends_per_s": n * args.steps / t,
+                "cpu_baseline": {"value": value, "unit": "Gcell/s", "cores": threads, "kind": kind,
+                                 "sample": "%d ends (8 x 2 kbp) per step, cells/end from an exact count of %d ends" % (n, ncount)},
+                "e2e": {"value": value, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # rank 0 deals the end list out (scatter) -- the only exchange the path needs before the compute
+    from cactus_b200 import dist as D
+    ranges = D.deal_end_ranges(E * world, world) if rank == 0 else None
+    first_end, n_ends = D.scatter_end_ranges(ranges, dev) if world > 1 else (0, E)
+
+    eng = cb.Engine(cb.PoaParams(device=local_rank))
+    n_seq, lens, flat = cb.synth_ends(first_end, n_ends, K_SEQS, L_BP)
+    stage = eng.stage(packed=(n_seq, lens, flat))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        stage.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.time()
+    dev_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        dev_ms += stage.run()          # CUDA-event time of the launch(es) on the launching stream
+        launches += stage.launches()
+    barrier()
+    wall_ms = (time.time() - t0) * 1e3
+    msas, cells = stage.fetch()
+    my_cells = float(cells.sum())
+
+    # ---- e2e through the host-buffer C-ABI call ----
+    jobs_packed = (n_seq, lens, flat)
+    import ctypes as C
+    def e2e_once():
+        outs = (C.c_void_p * n_ends)()
+        ml = np.zeros(n_ends, np.int32)
+        cc = np.zeros(n_ends, np.int64)
+        eng._check(eng.lib.barb200_poa_msa_batch(eng.ctx, n_ends, n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, None,
+                                                 outs, ml.ctypes.data, cc.ctypes.data))
+        d2h = int((ml.astype(np.int64) * K_SEQS).sum())
+        for i in range(n_ends):
+            eng.lib.barb200_free(outs[i])
+        return d2h
+    e2e_once()
+    barrier()
+    t1 = time.time()
+    e2e_steps = max(1, min(args.steps, 3))
+    d2h = 0
+    for _ in range(e2e_steps):
+        d2h = e2e_once()
+    barrier()
+    e2e_ms = (time.time() - t1) * 1e3 / e2e_steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- reduce over ranks: max time, sum cells; gather alignment checksums on rank 0 ----
+    mx, sm = D.reduce_stats([dev_ms, wall_ms, e2e_ms, my_cells, float(n_ends), float(launches)], dev)
+    checksums = D.gather_checksums(float(sum(int(m.sum()) for m in msas[:64])), dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    dev_ms_max, wall_ms_max, e2e_ms_max = float(mx[0]), float(mx[1]), float(mx[2])
+    tot_cells, tot_ends, tot_launches = float(sm[3]), float(sm[4]), int(sm[5])
+    value = tot_cells * args.steps / dev_ms_max / 1e6          # Gcell/s
+    peak, peak_src = measured_peak()
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch / average launch duration, rank 0's launches
+    launch_ms = dev_ms / max(1, launches)
+    achieved = my_cells * (args.steps / max(1, launches)) * ALGO_BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            bpc = json.load(open(prof))["dram_bytes_per_cell"]
+            traffic = bpc * my_cells * (args.steps / max(1, launches))
+        except Exception:  # noqa: BLE001
+            traffic = None
+    h2d = int(flat.nbytes + lens.nbytes * 2 + lens.size * 8 + n_seq.size * 40)
+    line = {"metric": METRIC, "value": value, "unit": "Gcell/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": config,
+            "ends_per_s": tot_ends * args.steps / dev_ms_max * 1e3,
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "e2e": {"value": tot_cells / e2e_ms_max / 1e6, "unit": "Gcell/s", "ends_per_s": tot_ends / e2e_ms_max * 1e3,
+                    "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + n_ends * 16,
+                    "api": "barb200_poa_msa_batch (host buffers: pack + guide trees + H2D + kernel + D2H + unpack)"},
+            "gpu_launches": tot_launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "poa_msa_kernel",
+                         "bytes_per_cell_algorithmic": ALGO_BYTES_PER_CELL},
+            "clocks": sampler.summary(), "rank_checksums": checksums}
+    if not args.no_cpu_baseline:
+        try:
+            cpu, n_cpu, secs = cpu_baseline(n_seq, lens, flat, cells, args.cpu_budget)
+            line["cpu_baseline"] = cpu
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

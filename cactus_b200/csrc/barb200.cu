@@ -196,7 +196,7 @@ static int plan_stage(barb200_stage *st) {
     if (T <= 0) { T = (int)align_up((max_len + 1 + 3) / 4, 32); T = std::max(64, std::min(512, T)); }
     T = (int)align_up(std::max(32, std::min(512, T)), 32);
     st->T = T;
-    st->q_cols = (int)(max_len + 1);
+    st->q_cols = (int)align_up(max_len + 1, 4);   // multiple of 4: keeps the shared row buffers 16 B aligned
     const size_t qbytes = (size_t)((st->q_cols + 8 + 15) & ~15);
     const size_t smem_limit = ctx->smem_optin - 2048 - 2048;     // static shared memory of the kernel + margin
     size_t rowbuf = (size_t)6 * (st->q_cols + 8) * 4;

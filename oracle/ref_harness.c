@@ -151,3 +151,32 @@ int64_t *ref_poa_msa_trace(const ref_params_t *p, int n_seq, const int *lens, co
 }
 
 void ref_free(void *p) { free(p); }
+
+/* CPU baseline driver: n_jobs independent abpoa_msa calls, OpenMP over jobs with schedule(dynamic,1) -- the
+ * reference's own unit of parallelism (bar/impl/bar.c:90-94, poaBarAligner.c:772). Each job does what one sliding
+ * window costs in the shim: abpoa_init + copy of the parameters + abpoa_msa + abpoa_free (poaBarAligner.c:565-628).
+ * Returns the wall time in seconds; msa_lens[n_jobs] (may be NULL) receives msa_len, checksum (may be NULL) a sum of
+ * all MSA bytes so the work cannot be optimised away. */
+#include <omp.h>
+double ref_poa_msa_many(const ref_params_t *p, int64_t n_jobs, const int *n_seq, const int *lens, const uint8_t *flat,
+                        int threads, int *msa_lens, uint64_t *checksum) {
+    int64_t *len_off = (int64_t *)malloc(sizeof(int64_t) * (n_jobs + 1)), *seq_off = (int64_t *)malloc(sizeof(int64_t) * (n_jobs + 1));
+    int64_t lo = 0, so = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) { len_off[j] = lo; seq_off[j] = so; for (int i = 0; i < n_seq[j]; ++i) so += lens[lo + i]; lo += n_seq[j]; }
+    if (threads <= 0) threads = omp_get_max_threads();
+    { abpoa_para_t *warm = make_para(p); abpoa_free_para(warm); }   /* global tables are initialised once, up front */
+    uint64_t sum = 0;
+    double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : sum)
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        uint8_t *msa = NULL;
+        int ml = ref_poa_msa(p, n_seq[j], lens + len_off[j], flat + seq_off[j], &msa);
+        if (msa_lens) msa_lens[j] = ml;
+        for (int64_t k = 0; k < (int64_t)n_seq[j] * ml; ++k) sum += msa[k];
+        free(msa);
+    }
+    double t1 = omp_get_wtime();
+    if (checksum) *checksum = sum;
+    free(len_off); free(seq_off);
+    return t1 - t0;
+}

@@ -298,3 +298,21 @@ def hosttest_poa_msa_trace(seqs, p=None):
     lib.hosttest_free(ptr)
     assert status.value == 0, "hosttest job status %d" % status.value
     return _parse_trace(words, len(seqs))
+
+
+def cpu_poa_msa_many(n_seq, lens, flat, threads=0, p=None, prefer_ref=True):
+    """Time n independent abpoa_msa calls on the host cores (OpenMP over jobs). Returns (seconds, kind, checksum)."""
+    p = p or cactus_params()
+    n_seq = np.ascontiguousarray(n_seq, np.int32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    flat = np.ascontiguousarray(flat, np.uint8)
+    if prefer_ref and have_ref():
+        lib, name, kind = _load(REF_SO), "ref_poa_msa_many", "reference"
+    else:
+        lib, name, kind = _load(build_oracle()), "oracle_poa_msa_many", "port"
+    f = getattr(lib, name)
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    ck = C.c_uint64()
+    secs = f(C.byref(p), len(n_seq), n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, threads, None, C.byref(ck))
+    return secs, kind, ck.value
