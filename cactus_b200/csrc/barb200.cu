@@ -18,8 +18,20 @@
 #include "poa_kernel.cuh"
 
 namespace barb200 {
-extern "C" __global__ void poa_msa_kernel(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t32(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t64(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t128(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t256(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t640(const BatchArgs A);
+extern "C" __global__ void poa_msa_kernel_t1024(const BatchArgs A);
 }
+typedef void (*poa_kernel_fn)(const barb200::BatchArgs);
+// CTA-size classes: a CTA of T threads sweeps rows of up to 16*T columns (query length + 1)
+// scratch = dynamic shared memory per CTA for the topological sort, sized so that the class's CTAs per SM still fit
+static const struct { int T; poa_kernel_fn fn; int scratch; } kKernels[] = {
+    {32, barb200::poa_msa_kernel_t32, 10 * 1024}, {64, barb200::poa_msa_kernel_t64, 24 * 1024}, {128, barb200::poa_msa_kernel_t128, 48 * 1024},
+    {256, barb200::poa_msa_kernel_t256, 96 * 1024}, {640, barb200::poa_msa_kernel_t640, 200 * 1024}, {1024, barb200::poa_msa_kernel_t1024, 200 * 1024}};
+static const int kNumKernels = 6;
 using namespace barb200;
 
 struct barb200_ctx {
@@ -86,8 +98,8 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     const int oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     P.inf_min = std::max(std::max(INT32_MIN + P.min_mis, INT32_MIN + oe1), INT32_MIN + oe2) + 512 * std::max(P.e1, P.e2);
     ctx->hp = HostParams{p->k, p->w, p->min_w, p->progressive_poa};
+    for (int i = 0; i < kNumKernels; ++i) cudaFuncSetAttribute(kKernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kKernels[i].scratch);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
-    cudaFuncSetAttribute(poa_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
     return ctx;
 }
 
@@ -132,7 +144,7 @@ struct barb200_stage {
     uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr, *d_order = nullptr; int64_t *d_soff = nullptr;
     JobDesc *d_desc = nullptr; int *d_msa_len = nullptr, *d_status = nullptr, *d_next = nullptr; long long *d_cells = nullptr;
     // sizing
-    SlotLayout lay; int T = 0, slots = 0, q_cols = 0, smem_cols = 0; size_t dyn_smem = 0;
+    SlotLayout lay; int T = 0, slots = 0, kernel_class = 0; size_t dyn_smem = 0;
     // results of the last run
     std::vector<int> status, msa_len; std::vector<long long> cells;
     std::vector<uint8_t> h_msa;
@@ -169,7 +181,7 @@ static int plan_stage(barb200_stage *st) {
         max_k = std::max(max_k, K);
         // rows the graph can reach: worst case every base a new node; optimistic: the longest read plus a share of the rest
         int64_t rows = st->worst_case ? sum + 2 : std::min<int64_t>(sum + 2, ml + (sum - ml) / 8 + 256);
-        plane_need = std::max(plane_need, rows * 5 * (align_up(ml + 1, 4) + 4));
+        plane_need = std::max(plane_need, rows * 5 * (align_up(ml + 1, CPT) + CPT));
     }
     SlotLayout &Y = st->lay;
     memset(&Y, 0, sizeof(Y));
@@ -187,23 +199,18 @@ static int plan_stage(barb200_stage *st) {
     Y.o_out_rid = take((int64_t)Y.out_pool * 8 * Y.W);
     Y.o_index_to_node = take(N * 4); Y.o_node_to_index = take(N * 4); Y.o_remain = take(N * 4); Y.o_msa_rank = take(N * 4);
     Y.o_tmp0 = take(N * 4); Y.o_tmp1 = take(N * 4);
-    Y.o_row_base = take(N); Y.o_row_rd = take(N * 4); Y.o_pre_off = take((N + 1) * 4); Y.o_pre_row = take((int64_t)Y.in_pool * 4);
-    Y.o_row_off = take(N * 8); Y.o_dp_beg = take(N * 4); Y.o_dp_end = take(N * 4); Y.o_row_left = take(N * 4); Y.o_row_right = take(N * 4);
+    Y.o_row_rec = take(N * 16); Y.o_pre_row = take((int64_t)Y.in_pool * 4);
+    Y.o_row_off = take(N * 8); Y.o_row_info = take(N * 16);
     Y.o_cigar = take((int64_t)Y.cigar_cap * 8);
     Y.slot_bytes = align_up(o, 256);
 
-    int T = ctx->p.threads_per_block;
-    if (T <= 0) { T = (int)align_up((max_len + 1 + 3) / 4, 32); T = std::max(64, std::min(512, T)); }
-    T = (int)align_up(std::max(32, std::min(512, T)), 32);
-    st->T = T;
-    st->q_cols = (int)align_up(max_len + 1, 4);   // multiple of 4: keeps the shared row buffers 16 B aligned
-    const size_t qbytes = (size_t)((st->q_cols + 8 + 15) & ~15);
-    const size_t smem_limit = ctx->smem_optin - 2048 - 2048;     // static shared memory of the kernel + margin
-    size_t rowbuf = (size_t)6 * (st->q_cols + 8) * 4;
-    if (qbytes + rowbuf <= smem_limit) { st->smem_cols = st->q_cols; st->dyn_smem = qbytes + rowbuf; }
-    else { st->smem_cols = 0; st->dyn_smem = qbytes; }
+    // smallest CTA-size class whose 16 columns per thread cover the longest query (+ column 0)
+    int cls = -1;
+    for (int i = 0; i < kNumKernels; ++i) if ((int64_t)kKernels[i].T * CPT >= max_len + 1 && kKernels[i].T >= ctx->p.threads_per_block) { cls = i; break; }
+    if (cls < 0) { set_error(ctx, "a sequence is longer than the device engine's row limit (16383 bases per window)"); return BARB200_EINVAL; }
+    st->T = kKernels[cls].T; st->kernel_class = cls; st->dyn_smem = kKernels[cls].scratch;
     int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, poa_msa_kernel, T, st->dyn_smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kKernels[cls].fn, st->T, st->dyn_smem));
     if (per_sm < 1) { set_error(ctx, "kernel does not fit on an SM with the requested configuration"); return BARB200_EINVAL; }
     if (ctx->p.ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->p.ctas_per_sm);
     int64_t slots = std::min<int64_t>(st->n_jobs, (int64_t)per_sm * ctx->sm_count);
@@ -346,11 +353,12 @@ static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
     A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
     A.slots = ctx->d_slots; A.planes = ctx->d_planes; A.next_job = st->d_next;
     A.phase_clk = clk_n ? ctx->d_clk : nullptr;
-    A.q_cols = st->q_cols; A.smem_cols = st->smem_cols; A.lay = st->lay; A.P = ctx->P;
+    A.serial_phases = getenv("BARB200_DEBUG_SERIAL") ? 1 : 0;
+    A.scratch_bytes = (int)st->dyn_smem; A.lay = st->lay; A.P = ctx->P;
     cudaEvent_t e0, e1;
     CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
     CUDA_TRY(ctx, cudaEventRecord(e0, s));
-    poa_msa_kernel<<<st->slots, st->T, st->dyn_smem, s>>>(A);
+    kKernels[st->kernel_class].fn<<<st->slots, st->T, st->dyn_smem, s>>>(A);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { set_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; }
     CUDA_TRY(ctx, cudaEventRecord(e1, s));

@@ -1,0 +1,340 @@
+// poa_cta.cuh -- CTA-cooperative forms of the graph phases between two DP sweeps (device only).
+//
+// The reference performs these steps serially per added sequence (abPOA src/abpoa_graph.c). On the device a
+// single thread walking global memory costs ~1 us per dependent step, which would dwarf the DP sweep, so each
+// step is restated in the form that exposes its parallelism while producing the SAME graph:
+//   * first sequence / fusing an alignment (abpoa_graph.c:573-593, 689-774): a path visits every node at most
+//     once and never two nodes of one aligned group, so the per-base updates of one fusion touch disjoint edge lists
+//     and aligned groups; only the ids of new nodes are order dependent (query order) -> one prefix sum;
+//   * topological order (abpoa_graph.c:221-266): inherently one dependent step per node; run by one thread on a
+//     compact copy of the out-edge lists in SHARED memory (~10x lower latency per step) while the other warps
+//     sort the edge lists in global memory (abpoa_graph.c:192-219);
+//   * max_remain (abpoa_graph.c:268-309): remain[v] = remain[heaviest out neighbour] + 1 is a list ranking
+//     -> pointer jumping, log2(n) parallel rounds;
+//   * row tables: prefix sum over in-degrees, then one row per thread.
+#pragma once
+#include <cuda_runtime.h>
+#include "poa_graph.cuh"
+
+namespace barb200 {
+
+// exclusive prefix sum of a[0..n) in place (global or shared memory); returns the total. All threads of the CTA.
+// ws: >= 32 ints of shared memory.
+__device__ int cta_excl_scan(int *a, int n, int *ws) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    const int chunk = (n + T - 1) / T, b = min(n, tid * chunk), e = min(n, b + chunk);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += a[i];
+    int inc = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
+    __syncthreads();                       // ws may still be read by a previous call
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int k = 0; k < nw; ++k) { const int v = ws[k]; if (k < warp) woff += v; total += v; }
+    int run = woff + inc - s;
+    for (int i = b; i < e; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+// ---- edge lists with atomic pool allocation (same lists as graph_add_edge; chunk placement in the pool differs) ----
+__device__ __forceinline__ bool grow_in_par(Graph &g, int t) {
+    if (g.in_n[t] < g.in_cap[t]) return true;
+    const int ncap = g.in_cap[t] ? g.in_cap[t] * 2 : 2;
+    const int noff = atomicAdd(&g.in_used, ncap);
+    if (noff + ncap > g.in_pool) { g.err = JOB_ERR_EDGE_CAP; return false; }
+    for (int i = 0; i < g.in_n[t]; ++i) { g.in_id[noff + i] = g.in_id[g.in_off[t] + i]; g.in_w[noff + i] = g.in_w[g.in_off[t] + i]; }
+    g.in_off[t] = noff; g.in_cap[t] = ncap;
+    return true;
+}
+__device__ __forceinline__ bool grow_out_par(Graph &g, int f) {
+    if (g.out_n[f] < g.out_cap[f]) return true;
+    const int ncap = g.out_cap[f] ? g.out_cap[f] * 2 : 2;
+    const int noff = atomicAdd(&g.out_used, ncap);
+    if (noff + ncap > g.out_pool) { g.err = JOB_ERR_EDGE_CAP; return false; }
+    const int W = g.W;
+    for (int i = 0; i < g.out_n[f]; ++i) {
+        g.out_id[noff + i] = g.out_id[g.out_off[f] + i]; g.out_w[noff + i] = g.out_w[g.out_off[f] + i];
+        for (int w = 0; w < W; ++w) g.out_rid[(int64_t)(noff + i) * W + w] = g.out_rid[(int64_t)(g.out_off[f] + i) * W + w];
+    }
+    for (int i = g.out_n[f]; i < ncap; ++i) for (int w = 0; w < W; ++w) g.out_rid[(int64_t)(noff + i) * W + w] = 0;
+    g.out_off[f] = noff; g.out_cap[f] = ncap;
+    return true;
+}
+// abpoa_add_graph_edge (abpoa_graph.c:480-556) for concurrent callers that own `from`'s out list and `to`'s in list
+__device__ __forceinline__ void graph_add_edge_par(Graph &g, int from, int to, int check_edge, int read_id) {
+    int out_i = -1;
+    if (check_edge) {
+        const int io = g.in_off[to], in = g.in_n[to];
+        for (int i = 0; i < in; ++i) if (g.in_id[io + i] == from) { g.in_w[io + i] += 1; break; }
+        const int oo = g.out_off[from], on = g.out_n[from];
+        for (int i = 0; i < on; ++i) if (g.out_id[oo + i] == to) { g.out_w[oo + i] += 1; out_i = i; break; }
+    }
+    if (out_i < 0) {
+        if (!grow_in_par(g, to) || !grow_out_par(g, from)) return;
+        const int ip = g.in_off[to] + g.in_n[to]; g.in_id[ip] = from; g.in_w[ip] = 1; g.in_n[to]++;
+        out_i = g.out_n[from];
+        const int op = g.out_off[from] + out_i; g.out_id[op] = to; g.out_w[op] = 1; g.out_n[from]++;
+    }
+    g.out_rid[(int64_t)(g.out_off[from] + out_i) * g.W + (read_id >> 6)] |= 1ULL << (read_id & 63);
+}
+
+// abpoa_add_graph_sequence (abpoa_graph.c:573-593) on an empty graph: SRC -> b0 -> ... -> SINK. All threads.
+__device__ void cta_add_first_sequence(Graph &g, const uint8_t *seq, int len, int read_id) {
+    const int tid = threadIdx.x, T = blockDim.x, W = g.W;
+    if (len + 2 > g.node_cap) { if (tid == 0) g.err = JOB_ERR_NODE_CAP; __syncthreads(); return; }
+    if (2 * (len + 1) > g.in_pool || 2 * (len + 1) > g.out_pool) { if (tid == 0) g.err = JOB_ERR_EDGE_CAP; __syncthreads(); return; }
+    const int rw = read_id >> 6; const uint64_t rb = 1ULL << (read_id & 63);
+    // in list of node 2+i: chunk [2i, 2i+2); out list of node 2+i: chunk [2(i+1), 2(i+1)+2); SRC out: [0,2); SINK in: [2len, 2len+2)
+    for (int i = tid; i <= len; i += T) {
+        const int to = i < len ? 2 + i : SINK_ID, from = i == 0 ? SRC_ID : 1 + i;
+        g.in_off[to] = 2 * i; g.in_n[to] = 1; g.in_cap[to] = 2; g.in_id[2 * i] = from; g.in_w[2 * i] = 1;
+        g.out_off[from] = 2 * i; g.out_n[from] = 1; g.out_cap[from] = 2; g.out_id[2 * i] = to; g.out_w[2 * i] = 1;
+        for (int w = 0; w < W; ++w) { g.out_rid[(int64_t)(2 * i) * W + w] = w == rw ? rb : 0; g.out_rid[(int64_t)(2 * i + 1) * W + w] = 0; }
+        if (i < len) { g.base[to] = seq[i]; g.aln_n[to] = 0; }
+    }
+    if (tid == 0) { g.node_n = len + 2; g.in_used = 2 * (len + 1); g.out_used = 2 * (len + 1); }
+    __syncthreads();
+}
+
+// abpoa_add_subgraph_alignment(SRC, SINK, inc_both_ends = 1), abpoa_graph.c:689-774. All threads.
+// Scratch: g.tmp0[q] = node that query base q ends up on, g.tmp1[q] = 1 if that node is new. ws: >= 32 ints shared.
+__device__ void cta_fuse_alignment(Graph &g, const uint8_t *seq, int L, const uint64_t *cigar, int n_cigar, int read_id, int *ws) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (n_cigar == 0) return;
+    int *node_of = g.tmp0, *is_new = g.tmp1;
+    // (1) classify every cigar entry; entries know their query positions (abpoa_align.h:58-78)
+    for (int c = tid; c < n_cigar; c += T) {
+        const uint64_t cg = cigar[c];
+        const int op = (int)(cg & 0xf);
+        if (op == CMATCH) {
+            const int node_id = (int)((cg >> 34) & 0x3fffffff), q = (int)((cg >> 4) & 0x3fffffff);
+            const uint8_t b = seq[q];
+            if (g.base[node_id] == b) { node_of[q] = node_id; is_new[q] = 0; }
+            else {
+                const int a = graph_aligned_with_base(g, node_id, b);
+                if (a != -1) { node_of[q] = a; is_new[q] = 0; } else { node_of[q] = -1 - node_id; is_new[q] = 1; }   // new node aligned to node_id
+            }
+        } else if (op == CINS) {
+            const int qe = (int)((cg >> 34) & 0x3fffffff), len = (int)((cg >> 4) & 0x3fffffff);
+            for (int q = qe - len + 1; q <= qe; ++q) { node_of[q] = INT32_MIN; is_new[q] = 1; }                          // plain new node
+        }
+    }
+    __syncthreads();
+    // (2) ids of the new nodes in query order. is_new becomes the exclusive prefix count; keep the flag in node_of's sign
+    const int n_new = cta_excl_scan(is_new, L, ws);
+    const int first_new = g.node_n;
+    if (first_new + n_new > g.node_cap) { if (tid == 0) g.err = JOB_ERR_NODE_CAP; __syncthreads(); return; }
+    // (3) create the new nodes (+ aligned-group links for mismatch columns)
+    for (int q = tid; q < L; q += T) {
+        const int m = node_of[q];
+        if (m >= 0) { is_new[q] = 0; continue; }
+        const int nid = first_new + is_new[q];
+        g.base[nid] = seq[q]; g.aln_n[nid] = 0;
+        g.in_off[nid] = 0; g.in_n[nid] = 0; g.in_cap[nid] = 0; g.out_off[nid] = 0; g.out_n[nid] = 0; g.out_cap[nid] = 0;
+        if (m != INT32_MIN) graph_add_aligned(g, -1 - m, nid);
+        node_of[q] = nid; is_new[q] = 1;
+    }
+    if (tid == 0) g.node_n = first_new + n_new;
+    __syncthreads();
+    if (g.err) return;
+    // (4) the L+1 edges of the path; check_edge = neither end is new (abpoa_graph.c:731-766)
+    for (int q = tid; q <= L; q += T) {
+        const int from = q == 0 ? SRC_ID : node_of[q - 1], to = q == L ? SINK_ID : node_of[q];
+        const int fresh = (q > 0 && is_new[q - 1]) || (q < L && is_new[q]);
+        graph_add_edge_par(g, from, to, fresh ? 0 : 1, read_id);
+    }
+    __syncthreads();
+}
+
+
+// ---- traceback (simd_abpoa_cg_backtrack, abpoa_align_simd.c:309-458) by ONE WARP -------------------------------
+// The walk is a chain of dependent lookups in planes that live in HBM (~1 us per step for a single thread). Most of
+// it is runs of MATCH ops along first predecessors, and in the ALL state the M test has priority over everything else
+// (:319-336), so a run can be verified for 31 cells at once: lane k takes the cell (c_k, j-k) on the first-predecessor
+// chain c_0 = i, c_{k+1} = first pred of c_k, all lanes load their H in parallel, lane k tests
+// H[c_{k+1}][j-k-1] + s == H[c_k][j-k], and the leading run of hits is emitted as MATCH ops in one go. Wherever the run
+// stops (gap, mismatching first predecessor, band edge) one step of the general serial rule (backtrack_step) is
+// taken by all lanes uniformly. The result is the serial walk's cigar, entry for entry.
+__device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const int *smat8, const uint8_t *q, int L) {
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31, inf = P.inf_min;
+    if (lane == 0) dp_best_cell(g, rt, d, P, L);
+    __syncwarp();
+    int i = d.best_i, j = d.best_j, cur_op = OP_ALL, nc = 0, last_op = -1;
+    uint64_t *cg = d.cigar; const int cap = d.cigar_cap;
+    int fail = 0;
+    auto push = [&](int op, int len, int node_id, int query_id) {               // abpoa_push_cigar, abpoa_align.h:58-78
+        if (nc == 0 || op != CINS || last_op != CINS) {
+            if (nc >= cap) { fail = JOB_ERR_CIGAR_CAP; return; }
+            if (lane == 0) {
+                const uint64_t n_id = (uint64_t)(int64_t)node_id, q_id = (uint64_t)(int64_t)query_id, l = (uint64_t)len;
+                cg[nc] = op == CMATCH ? (n_id << 34 | q_id << 4 | (uint64_t)op) : op == CINS ? (q_id << 34 | l << 4 | (uint64_t)op) : (n_id << 34 | l << 4 | (uint64_t)op);
+            }
+            ++nc;
+        } else if (lane == 0) cg[nc - 1] += (uint64_t)len << 4;
+        last_op = op;
+    };
+    if (j < L) push(CINS, L - j, -1, L - 1);
+    while (i > 0 && j > 0 && !fail) {
+        int run = 0;
+        if (cur_op == OP_ALL) {
+            // rows of the first-predecessor chain: start from the linear guess i-k and re-base after each jump
+            int c = i - lane, pre = -1, base = 0, n_ok = 0;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                pre = -1;
+                if (c > 0) { const RowRec rc = rt.rec[c]; base = rc.base_npre & 0xff; pre = (rc.base_npre >> 8) ? rc.pre0 : -1; }
+                const int nxt = __shfl_down_sync(FULLM, c, 1);
+                const bool ok = lane < 31 && pre >= 0 && pre == nxt;
+                n_ok = __ffs(~__ballot_sync(FULLM, ok)) - 1;               // lanes 0..n_ok hold true chain rows
+                if (n_ok >= 31 || it == 3) break;
+                const int pre_b = __shfl_sync(FULLM, pre, n_ok);
+                if (pre_b < 0) break;                                        // the chain ends at lane n_ok
+                if (lane > n_ok) c = pre_b - (lane - n_ok - 1);
+            }
+            const int jj = j - lane;
+            int hv = inf, inb = 0;
+            if (lane <= n_ok && c >= 0 && jj >= 0) {
+                const RowInfo ri = d.info[c];
+                inb = jj >= ri.beg && jj <= ri.end;
+                if (inb) hv = __ldcg(d.planes + d.row_off[c] + plane_index(ri.beg, ri.end, 0, jj));
+            }
+            const int h_next = __shfl_down_sync(FULLM, hv, 1), inb_next = __shfl_down_sync(FULLM, inb, 1);
+            bool hit = false;
+            if (lane < n_ok && c > 0 && jj >= 1 && inb_next) hit = h_next + smat8[8 * base + q[jj - 1]] == hv;
+            run = __ffs(~__ballot_sync(FULLM, hit)) - 1;
+            if (run > 0) {
+                if (nc + run > cap) fail = JOB_ERR_CIGAR_CAP;
+                else {
+                    if (lane < run) cg[nc + lane] = (uint64_t)g.index_to_node[c] << 34 | (uint64_t)(jj - 1) << 4 | (uint64_t)CMATCH;
+                    nc += run; last_op = CMATCH;
+                    i = __shfl_sync(FULLM, c, run); j -= run;               // cur_op stays ALL
+                }
+            }
+        }
+        if (run == 0 && !fail) {
+            const int id = g.index_to_node[i], jq = j - 1;
+            const int op = backtrack_step(g, rt, d, P, q, i, j, cur_op);
+            if (op < 0) fail = JOB_ERR_BACKTRACK; else push(op, 1, id, jq);
+        }
+    }
+    if (!fail && j > 0) push(CINS, j, -1, j - 1);
+    if (fail) { if (lane == 0) g.err = fail; return; }
+    if (lane == 0) d.n_cigar = nc;
+    __syncwarp();
+    for (int a = lane; a < nc >> 1; a += 32) { const uint64_t t = cg[a]; cg[a] = cg[nc - 1 - a]; cg[nc - 1 - a] = t; }
+    __syncwarp();
+}
+
+// ---- topological sort (abpoa_topological_sort, abpoa_graph.c:322-357) --------------------------------------
+// Shared-memory copy of what abpoa_BFS_set_node_index walks: CSR of out edges (pre-sort order), in-degrees, sizes of
+// the aligned groups, the FIFO (= index_to_node).
+struct BfsScratch { uint32_t *optr; uint16_t *odst, *queue, *indeg; uint8_t *alnn; };
+
+__device__ __forceinline__ size_t bfs_scratch_bytes(int n, int E) { return (size_t)4 * (n + 1) + (size_t)2 * E + 4 * (size_t)n + n + 16; }
+
+__device__ void bfs_index_smem(Graph &g, const BfsScratch &B) {      // one thread
+    const int n = g.node_n;
+    int head = 0, tail = 0;
+    B.queue[tail++] = SRC_ID;
+    while (head < tail) {
+        const int cur = B.queue[head++];
+        if (cur == SINK_ID) {
+            if (head != n) g.err = JOB_ERR_TOPO;       // every node must have been numbered before SINK
+            return;
+        }
+        const uint32_t o0 = B.optr[cur], o1 = B.optr[cur + 1];
+        for (uint32_t i = o0; i < o1; ++i) {
+            const int o = B.odst[i];
+            const int left = (int)B.indeg[o] - 1; B.indeg[o] = (uint16_t)left;
+            if (left == 0) {
+                const int an = B.alnn[o];
+                bool ok = true;
+                for (int j = 0; j < an; ++j) if (B.indeg[g.aln_id[o * 4 + j]] != 0) { ok = false; break; }
+                if (!ok) continue;
+                B.queue[tail++] = (uint16_t)o;
+                for (int j = 0; j < an; ++j) B.queue[tail++] = (uint16_t)g.aln_id[o * 4 + j];
+            }
+        }
+    }
+    g.err = JOB_ERR_TOPO;
+}
+
+// All threads. scr/scr_bytes: dynamic shared memory scratch; ws: >= 32 ints shared.
+__device__ void cta_topo_sort(Graph &g, RowTables &rt, unsigned char *scr, int scr_bytes, int *ws) {
+    const int tid = threadIdx.x, T = blockDim.x, n = g.node_n;
+    // ---- (1) BFS index + edge sort ----
+    for (int v = tid; v < n; v += T) g.tmp0[v] = g.out_n[v];
+    __syncthreads();
+    const int E = cta_excl_scan(g.tmp0, n, ws);
+    if (n < 65536 && bfs_scratch_bytes(n, E) <= (size_t)scr_bytes) {
+        BfsScratch B;
+        B.optr = reinterpret_cast<uint32_t *>(scr);
+        B.odst = reinterpret_cast<uint16_t *>(B.optr + n + 1);
+        B.queue = B.odst + E; B.indeg = B.queue + n;
+        B.alnn = reinterpret_cast<uint8_t *>(B.indeg + n);
+        for (int v = tid; v < n; v += T) {
+            const uint32_t o = (uint32_t)g.tmp0[v];
+            B.optr[v] = o;
+            const int oo = g.out_off[v], on = g.out_n[v];
+            for (int i = 0; i < on; ++i) B.odst[o + i] = (uint16_t)g.out_id[oo + i];
+            B.indeg[v] = (uint16_t)g.in_n[v]; B.alnn[v] = g.aln_n[v];
+        }
+        if (tid == 0) B.optr[n] = (uint32_t)E;
+        __syncthreads();
+        // one thread numbers the nodes from the shared-memory copy; everybody else sorts edge lists meanwhile
+        if (T > 32) {
+            if (tid == 0) bfs_index_smem(g, B);
+            else if (tid >= 32) for (int v = tid - 32; v < n; v += T - 32) graph_sort_node_edges(g, v);
+        } else {
+            if (tid == 0) bfs_index_smem(g, B);
+            __syncwarp();
+            for (int v = tid; v < n; v += T) graph_sort_node_edges(g, v);
+        }
+        __syncthreads();
+        if (g.err) return;
+        for (int k = tid; k < n; k += T) { const int v = B.queue[k]; g.index_to_node[k] = v; g.node_to_index[v] = k; }
+    } else {
+        if (tid == 0) graph_bfs_index(g);
+        __syncthreads();
+        if (g.err) return;
+        for (int v = tid; v < n; v += T) graph_sort_node_edges(g, v);
+    }
+    __syncthreads();
+    // ---- (2) max_remain by pointer jumping: d[v] = #steps to SINK along the first heaviest out edge ----
+    int *nx[2] = {g.tmp0, g.tmp1}, *dd[2] = {g.remain, g.msa_rank};
+    for (int v = tid; v < n; v += T) {
+        int nxt = SINK_ID, dist = 0;
+        if (v != SINK_ID) {
+            int max_w = -1;
+            const int oo = g.out_off[v], on = g.out_n[v];
+            for (int i = 0; i < on; ++i) if (g.out_w[oo + i] > max_w) { max_w = g.out_w[oo + i]; nxt = g.out_id[oo + i]; }
+            dist = 1;
+        }
+        nx[0][v] = nxt; dd[0][v] = dist;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int span = 1; span < n; span <<= 1, cur ^= 1) {
+        for (int v = tid; v < n; v += T) {
+            const int nv = nx[cur][v];
+            dd[cur ^ 1][v] = dd[cur][v] + dd[cur][nv];
+            nx[cur ^ 1][v] = nx[cur][nv];
+        }
+        __syncthreads();
+    }
+    if (cur == 0) { for (int v = tid; v < n; v += T) g.remain[v] -= 1; }
+    else { for (int v = tid; v < n; v += T) g.remain[v] = g.msa_rank[v] - 1; }
+    __syncthreads();
+    // ---- (3) row tables: CSR offsets of the predecessor lists by topological index, then one row per thread ----
+    for (int r = tid; r < n; r += T) g.tmp0[r] = g.in_n[g.index_to_node[r]];
+    __syncthreads();
+    cta_excl_scan(g.tmp0, n, ws);
+    for (int r = tid; r < n; r += T) graph_build_row(g, rt, r, g.tmp0[r]);
+    __syncthreads();
+}
+
+}  // namespace barb200

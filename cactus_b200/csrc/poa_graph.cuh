@@ -9,6 +9,7 @@
 // Behaviour (not code) follows the reference abPOA v1.5.6 as Cactus drives it; file:line citations are
 // relative to /root/reference/submodules/abPOA/src/.
 #pragma once
+#include <stdio.h>
 #include "poa_types.h"
 
 namespace barb200 {
@@ -176,19 +177,23 @@ HD void graph_bfs_remain(Graph &g) {
 
 // Row-major tables the DP sweeps: for topological index r the node's base, its remain term and its
 // predecessor ROWS in stored in_id order (what simd_abpoa_init_var collects, abpoa_align_simd.c:550-558).
-HD void graph_build_rows(const Graph &g, RowTables &rt) {
-    const int n = g.node_n, rem_sink = g.remain[SINK_ID];
-    int off = 0;
-    for (int r = 0; r < n; ++r) {
-        const int v = g.index_to_node[r];
-        rt.row_base[r] = g.base[v];
-        rt.row_rd[r] = g.remain[v] - rem_sink - 1;
-        rt.pre_off[r] = off;
-        const int io = g.in_off[v], in = g.in_n[v];
-        for (int k = 0; k < in; ++k) rt.pre_row[off++] = g.node_to_index[g.in_id[io + k]];
-    }
-    rt.pre_off[n] = off;
+HD void graph_build_row(const Graph &g, RowTables &rt, int r, int off) {
+    const int v = g.index_to_node[r];
+    const int io = g.in_off[v], in = g.in_n[v];
+    for (int k = 0; k < in; ++k) rt.pre_row[off + k] = g.node_to_index[g.in_id[io + k]];
+    RowRec rec;
+    rec.base_npre = g.base[v] | (in << 8);
+    rec.rd = g.remain[v] - g.remain[SINK_ID] - 1;
+    rec.pre_off = off;
+    rec.pre0 = in ? g.node_to_index[g.in_id[io]] : -1;
+    rt.rec[r] = rec;
 }
+HD void graph_build_rows(const Graph &g, RowTables &rt) {
+    int off = 0;
+    for (int r = 0; r < g.node_n; ++r) { graph_build_row(g, rt, r, off); off += g.in_n[g.index_to_node[r]]; }
+}
+HD int row_npre(const RowTables &rt, int r) { return rt.rec[r].base_npre >> 8; }
+HD int row_base(const RowTables &rt, int r) { return rt.rec[r].base_npre & 0xff; }
 
 // abpoa_topological_sort (abpoa_graph.c:322-357), serial form
 HD void graph_topo_sort_serial(Graph &g, RowTables &rt) {
@@ -298,10 +303,9 @@ HD void graph_msa_fill_node(const Graph &g, int v, uint8_t *msa, int64_t stride)
 
 // ---- traceback ------------------------------------------------------------------------------------------------
 HD int plane_cell(const DpState &d, int inf_min, int row, int plane, int j) {
-    const int beg = d.dp_beg[row], end = d.dp_end[row];
+    const int beg = d.info[row].beg, end = d.info[row].end;
     if (j < beg || j > end) return inf_min;                 // out-of-band lanes hold inf_min (abpoa_align_simd.c:1035-1036)
-    const int beg4 = beg & ~3, wr4 = (end | 3) - beg4 + 1;
-    return d.planes[d.row_off[row] + (int64_t)plane * wr4 + (j - beg4)];
+    return d.planes[d.row_off[row] + plane_index(beg, end, plane, j)];
 }
 
 HD void push_cigar(DpState &d, Graph &g, int op, int len, int node_id, int query_id) {   // abpoa_push_cigar, abpoa_align.h:58-78
@@ -320,82 +324,88 @@ HD void push_cigar(DpState &d, Graph &g, int op, int len, int node_id, int query
 HD void dp_best_cell(const Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, int L) {
     const int sink_row = g.node_n - 1;
     int best = P.inf_min, bi = 0, bj = 0;
-    for (int k = rt.pre_off[sink_row]; k < rt.pre_off[sink_row + 1]; ++k) {
+    const int sp0 = rt.rec[sink_row].pre_off, sp1 = sp0 + row_npre(rt, sink_row);
+    for (int k = sp0; k < sp1; ++k) {
         const int row = rt.pre_row[k];
-        const int col = L > d.dp_end[row] ? d.dp_end[row] : L;
+        const int col = L > d.info[row].end ? d.info[row].end : L;
         const int sc = plane_cell(d, P.inf_min, row, 0, col);
         if (sc > best) { best = sc; bi = row; bj = col; }
     }
     d.best_score = best; d.best_i = bi; d.best_j = bj;
 }
 
-// simd_abpoa_cg_backtrack (abpoa_align_simd.c:309-458) with put_gap_on_right = put_gap_at_end = 0:
-// op priority M over predecessors in stored order, then E1/E2 per predecessor, then F1, F2, then M again;
-// cur_op carries which gap state the walk is in. Emits the graph cigar in forward order.
-HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
+// One iteration of simd_abpoa_cg_backtrack's loop (abpoa_align_simd.c:319-450) with put_gap_on_right =
+// put_gap_at_end = 0: op priority M over predecessors in stored order, then E1/E2 per predecessor, then F1, F2,
+// then M again; cur_op carries which gap state the walk is in. Moves (i, j), returns the cigar op (node `id`,
+// query index j_before - 1) or -1 when no op explains the cell (the reference aborts, :448).
+HD int backtrack_step(const Graph &g, const RowTables &rt, const DpState &d, const PoaParams &P, const uint8_t *q,
+                      int &i, int &j, int &cur_op) {
     const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int s = P.mat[5 * row_base(rt, i) + q[j - 1]];
+    const int p0 = rt.rec[i].pre_off, p1 = p0 + row_npre(rt, i);
+    const int hij = plane_cell(d, inf, i, 0, j);
+    if (cur_op & OP_M) {
+        for (int k = p0; k < p1; ++k) {
+            const int pi = rt.pre_row[k];
+            if (j - 1 < d.info[pi].beg || j - 1 > d.info[pi].end) continue;
+            if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) { i = pi; --j; cur_op = OP_ALL; return CMATCH; }
+        }
+    }
+    if (cur_op & OP_E) {
+        for (int k = p0; k < p1; ++k) {
+            const int pi = rt.pre_row[k];
+            if (j < d.info[pi].beg || j > d.info[pi].end) continue;
+            const int ph = plane_cell(d, inf, pi, 0, j);
+            if (cur_op & OP_E1) {
+                const int pe1 = plane_cell(d, inf, pi, 1, j);
+                const bool ok = (cur_op & OP_M) ? (hij == pe1) : (plane_cell(d, inf, i, 1, j) == pe1 - e1);
+                if (ok) { cur_op = (ph - oe1 == pe1) ? (OP_M | OP_F) : OP_E1; i = pi; return CDEL; }
+            }
+            if (cur_op & OP_E2) {
+                const int pe2 = plane_cell(d, inf, pi, 2, j);
+                const bool ok = (cur_op & OP_M) ? (hij == pe2) : (plane_cell(d, inf, i, 2, j) == pe2 - e2);
+                if (ok) { cur_op = (ph - oe2 == pe2) ? (OP_M | OP_F) : OP_E2; i = pi; return CDEL; }
+            }
+        }
+    }
+    if (cur_op & OP_F) {
+        bool hit = false;
+        if (cur_op & OP_F1) {
+            const int f = plane_cell(d, inf, i, 3, j);
+            if (!(cur_op & OP_M) || hij == f) {
+                if (plane_cell(d, inf, i, 0, j - 1) - oe1 == f) { cur_op = OP_M | OP_E; hit = true; }
+                else if (plane_cell(d, inf, i, 3, j - 1) - e1 == f) { cur_op = OP_F1; hit = true; }
+            }
+        }
+        if (!hit && (cur_op & OP_F2)) {
+            const int f = plane_cell(d, inf, i, 4, j);
+            if (!(cur_op & OP_M) || hij == f) {
+                if (plane_cell(d, inf, i, 0, j - 1) - oe2 == f) { cur_op = OP_M | OP_E; hit = true; }
+                else if (plane_cell(d, inf, i, 4, j - 1) - e2 == f) { cur_op = OP_F2; hit = true; }
+            }
+        }
+        if (hit) { --j; return CINS; }
+    }
+    // (the reference retries M here, :429-446; with put_gap_on_right = 0 that is the test that already failed above)
+    return -1;
+}
+
+// simd_abpoa_cg_backtrack (abpoa_align_simd.c:309-458), serial form. Emits the graph cigar in forward order.
+HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
     d.n_cigar = 0;
     int i = d.best_i, j = d.best_j, cur_op = OP_ALL;
     if (j < L) push_cigar(d, g, CINS, L - j, -1, L - 1);
     while (i > 0 && j > 0 && !g.err) {
-        const int id = g.index_to_node[i];
-        const int s = P.mat[5 * rt.row_base[i] + q[j - 1]];
-        const int p0 = rt.pre_off[i], p1 = rt.pre_off[i + 1];
-        const int hij = plane_cell(d, inf, i, 0, j);
-        bool hit = false;
-        if (cur_op & OP_M) {
-            for (int k = p0; k < p1; ++k) {
-                const int pi = rt.pre_row[k];
-                if (j - 1 < d.dp_beg[pi] || j - 1 > d.dp_end[pi]) continue;
-                if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) {
-                    push_cigar(d, g, CMATCH, 1, id, j - 1); i = pi; --j; hit = true; cur_op = OP_ALL; break;
-                }
-            }
+        const int id = g.index_to_node[i], jq = j - 1;
+        const int op = backtrack_step(g, rt, d, P, q, i, j, cur_op);
+        if (op < 0) {
+#if defined(__CUDA_ARCH__)
+            printf("barb200: backtrack stuck at row %d col %d cur_op %d (band %d..%d, H %d) best %d,%d n_cigar %d\n", i, j, cur_op,
+                   d.info[i].beg, d.info[i].end, plane_cell(d, P.inf_min, i, 0, j), d.best_i, d.best_j, d.n_cigar);
+#endif
+            g.err = JOB_ERR_BACKTRACK; return;
         }
-        if (!hit && (cur_op & OP_E)) {
-            for (int k = p0; k < p1; ++k) {
-                const int pi = rt.pre_row[k];
-                if (j < d.dp_beg[pi] || j > d.dp_end[pi]) continue;
-                const int ph = plane_cell(d, inf, pi, 0, j);
-                if (cur_op & OP_E1) {
-                    const int pe1 = plane_cell(d, inf, pi, 1, j);
-                    const bool ok = (cur_op & OP_M) ? (hij == pe1) : (plane_cell(d, inf, i, 1, j) == pe1 - e1);
-                    if (ok) { cur_op = (ph - oe1 == pe1) ? (OP_M | OP_F) : OP_E1; push_cigar(d, g, CDEL, 1, id, j - 1); i = pi; hit = true; break; }
-                }
-                if (cur_op & OP_E2) {
-                    const int pe2 = plane_cell(d, inf, pi, 2, j);
-                    const bool ok = (cur_op & OP_M) ? (hij == pe2) : (plane_cell(d, inf, i, 2, j) == pe2 - e2);
-                    if (ok) { cur_op = (ph - oe2 == pe2) ? (OP_M | OP_F) : OP_E2; push_cigar(d, g, CDEL, 1, id, j - 1); i = pi; hit = true; break; }
-                }
-            }
-        }
-        if (!hit && (cur_op & OP_F)) {
-            if (cur_op & OP_F1) {
-                const int f = plane_cell(d, inf, i, 3, j);
-                if (!(cur_op & OP_M) || hij == f) {
-                    if (plane_cell(d, inf, i, 0, j - 1) - oe1 == f) { cur_op = OP_M | OP_E; hit = true; }
-                    else if (plane_cell(d, inf, i, 3, j - 1) - e1 == f) { cur_op = OP_F1; hit = true; }
-                }
-            }
-            if (!hit && (cur_op & OP_F2)) {
-                const int f = plane_cell(d, inf, i, 4, j);
-                if (!(cur_op & OP_M) || hij == f) {
-                    if (plane_cell(d, inf, i, 0, j - 1) - oe2 == f) { cur_op = OP_M | OP_E; hit = true; }
-                    else if (plane_cell(d, inf, i, 4, j - 1) - e2 == f) { cur_op = OP_F2; hit = true; }
-                }
-            }
-            if (hit) { push_cigar(d, g, CINS, 1, id, j - 1); --j; }
-        }
-        if (!hit && (cur_op & OP_M)) {
-            for (int k = p0; k < p1; ++k) {
-                const int pi = rt.pre_row[k];
-                if (j - 1 < d.dp_beg[pi] || j - 1 > d.dp_end[pi]) continue;
-                if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) {
-                    push_cigar(d, g, CMATCH, 1, id, j - 1); i = pi; --j; hit = true; cur_op = OP_ALL; break;
-                }
-            }
-        }
-        if (!hit) { g.err = JOB_ERR_BACKTRACK; return; }
+        push_cigar(d, g, op, 1, id, jq);
     }
     if (g.err) return;
     if (j > 0) push_cigar(d, g, CINS, j, -1, j - 1);

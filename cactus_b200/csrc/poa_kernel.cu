@@ -4,27 +4,32 @@
 // it keeps the job's partial-order graph in its slot of device memory, aligns the sequences to it one after the
 // other and never returns to the host in between. CTAs are persistent: each pulls the next job index from a
 // global counter, so a launch of (148 SMs x resident CTAs) blocks streams through thousands of jobs while the
-// strictly sequential phases of some jobs (traceback, graph fusion, topological sort) overlap the bandwidth-bound
-// DP sweeps of the others on the same SM.
+// strictly sequential phases of some jobs (traceback, graph fusion, topological sort) overlap the DP sweeps of
+// the other CTAs resident on the same SM.
 //
 // DP sweep (the hot loop; replaces simd_abpoa_cg_dp + first row + row max + adaptive band,
 // abPOA src/abpoa_align_simd.c:617-688, 935-1130):
 //   * graph rows in topological order, strictly one after the other (the adaptive band of a row needs the argmax
-//     columns of all predecessor rows), columns of a row in parallel: thread t owns 4 adjacent columns per pass;
-//   * predecessor row values come from a double-buffered shared-memory copy of the previous row when the
-//     predecessor is the row just computed (the common case in a near-linear graph), otherwise from the planes in
-//     global memory (L2);
+//     columns of all predecessor rows); the columns of a row in parallel;
+//   * column ownership is FIXED: thread t owns columns [16t, 16t+16) of every row. The H / E1 / E2 values of the
+//     row just computed therefore stay in the owning thread's registers and feed the next row without touching
+//     memory when the predecessor is the previous row (the common case in a near-linear graph); only H[16t-1]
+//     comes from the neighbour thread (warp shuffle; one shared-memory word per warp boundary). Predecessors
+//     further back are read from the planes in global memory (L2), coalesced 16 B per thread;
 //   * the max-plus recurrence of the two insertion states F1/F2 along the row is turned into a plain prefix
-//     maximum by the substitution A[k] = H'[k] - oe + (k+1)*e  =>  F[j] = max_{k<j} A[k] - j*e, done as
-//     4 serial cells per thread, a warp shuffle scan over the 32 thread aggregates and a redux over the warp
-//     aggregates staged in shared memory;
-//   * all five int32 planes (H, E1, E2, F1, F2) of the row's band are written once, coalesced 16 B per thread,
-//     to global memory for the traceback: 20 B/cell of HBM write traffic is what bounds the kernel.
+//     maximum by the substitution A[k] = H'[k] - oe + (k+1)*e  =>  F[j] = max_{k<j} A[k] - j*e: 16 serial cells per
+//     thread, a warp shuffle scan over the 32 thread aggregates, a redux over the warp aggregates staged in
+//     shared memory;
+//   * all five int32 planes (H, E1, E2, F1, F2) of the row's band are written once for the traceback, in a
+//     thread-blocked layout (poa_types.h: DpState) that makes every 16-byte store of a warp one contiguous 512 B
+//     run: 20 B/cell of HBM write traffic is the kernel's only DRAM stream;
+//   * two block barriers per row.
 // Integer DP: no tensor cores. int32 everywhere with the reference's own "minus infinity" so that finite cells
 // are bit-identical to abPOA's AVX2 path.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "poa_graph.cuh"
+#include "poa_cta.cuh"
 #include "poa_kernel.cuh"
 
 namespace barb200 {
@@ -34,183 +39,203 @@ namespace barb200 {
 struct KShared {
     Graph g; RowTables rt; DpState d;
     int job, msa_len_s, abort_s;
-    int smat[25];
-    int wF[2][2][32];      // [pass parity][plane F1/F2][warp] block scan staging
-    int wM[3][32];         // row max / leftmost / rightmost per warp
+    int smat[5 * 8];       // [graph base][query code 0..4, 5 = "no base": column 0 / beyond the query -> 0]
+    int wF[2][2][32];      // [row parity][plane F1/F2][warp] block scan staging
+    int wM[2][4][32];      // [row parity][max, leftmost, rightmost, H of the warp's last column][warp]
 };
 
-__device__ __forceinline__ int4 ld4(const int *p) { return *reinterpret_cast<const int4 *>(p); }
-__device__ __forceinline__ void st4(int *p, int4 v) { *reinterpret_cast<int4 *>(p) = v; }
+__device__ __forceinline__ int4 ld4cg(const int *p) { return __ldcg(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ void st4(int *p, int a, int b, int c, int d) { *reinterpret_cast<int4 *>(p) = make_int4(a, b, c, d); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
 // ---------------------------------------------------------------------------------------------------------
-// banded convex-gap DP of query q[1..L] against the sorted graph. All threads of the CTA.
+// banded convex-gap DP of query q[1..L] against the sorted graph. All threads of the CTA; L + 1 <= 16 * blockDim.x.
 // Returns the number of banded cells (sum of dp_end-dp_beg+1), or -1 if the planes outgrew the slot.
 // ---------------------------------------------------------------------------------------------------------
-__device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__restrict__ qg, int L,
-                              uint8_t *sq, int *rowbuf, int rb_stride, bool use_smem) {
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+__device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__restrict__ qg, int L) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const Graph &g = S.g; const RowTables &rt = S.rt; DpState &d = S.d;
     const int node_n = g.node_n, R = node_n - 1;
     const int NEG = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int w = P.wb + (int)(P.wf * L);                                    // abpoa_align_simd.c:474
     const int pn = reference_lane_count(P, L, node_n);
+    const int j0 = tid * CPT;
 
-    // query bytes to shared memory; sq[j] = q_j for j = 1..L, sq[0] unused (column 0 scores 0, :536)
-    for (int j = tid; j <= L + 4; j += T) sq[j] = (j >= 1 && j <= L) ? qg[j - 1] : 4;
-    int *bufH[2], *bufE1[2], *bufE2[2];
-    for (int b = 0; b < 2; ++b) {
-        bufH[b] = rowbuf + (b * 3 + 0) * rb_stride + 4;     // +4: index -1 is addressable, 16 B alignment kept
-        bufE1[b] = rowbuf + (b * 3 + 1) * rb_stride + 4;
-        bufE2[b] = rowbuf + (b * 3 + 2) * rb_stride + 4;
+    // query codes of my 16 columns, 4 bits each (column j scores against q_j = qg[j-1]; column 0 and columns past the
+    // query score 0, abpoa_align_simd.c:536)
+    uint32_t qc[2] = {0u, 0u};
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+        const int j = j0 + e;
+        const uint32_t c = (j >= 1 && j <= L) ? qg[j - 1] : 5u;
+        qc[e >> 3] |= c << ((e & 7) * 4);
     }
-    __syncthreads();
+
+    int H[CPT], E1[CPT], E2[CPT];          // the previous row's values of my columns (valid iff prev_active)
+    bool prev_active;
+    int prev_beg = 0, prev_end, prev_left = 0, prev_right = 0;
+    long long cur_off = 0, cells = 0;
 
     // ---- row 0 (simd_abpoa_cg_first_dp, :617-688) ----
-    int prev_beg = 0, prev_end, prev_left = 0, prev_right = 0;
-    long long cur_off = 0, prev_off = 0, cells = 0;
     {
-        const int dd = L - rt.row_rd[0];
+        const int dd = L - rt.rec[0].rd;
         prev_end = min(L, max(0, dd) + w);
-        const int wr4 = (prev_end | 3) + 1;
-        if (5LL * wr4 > d.plane_cap) return -1;
-        int *row = d.planes;
-        for (int c0 = tid * 4; c0 <= prev_end; c0 += T * 4) {
-            int h[4], x1[4], x2[4], f1[4], f2[4];
+        const int nT = prev_end / CPT + 1;
+        if (5LL * nT * CPT > d.plane_cap) return -1;
+        prev_active = tid < nT;
+        if (prev_active) {
+            int *row = d.planes; const int PS = nT * CPT;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int j = c0 + t;
-                if (j == 0) { h[t] = 0; x1[t] = -oe1; x2[t] = -oe2; f1[t] = NEG; f2[t] = NEG; }
-                else if (j <= prev_end) { f1[t] = -P.o1 - e1 * j; f2[t] = -P.o2 - e2 * j; h[t] = max(f1[t], f2[t]); x1[t] = NEG; x2[t] = NEG; }
-                else { h[t] = x1[t] = x2[t] = f1[t] = f2[t] = NEG; }
+            for (int q = 0; q < 4; ++q) {
+                int f1[4], f2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = q * 4 + u, j = j0 + e;
+                    if (j == 0) { H[e] = 0; E1[e] = -oe1; E2[e] = -oe2; f1[u] = NEG; f2[u] = NEG; }
+                    else if (j <= prev_end) { f1[u] = -P.o1 - e1 * j; f2[u] = -P.o2 - e2 * j; H[e] = max(f1[u], f2[u]); E1[e] = NEG; E2[e] = NEG; }
+                    else { H[e] = E1[e] = E2[e] = f1[u] = f2[u] = NEG; }
+                }
+                const int o = (q * nT + tid) << 2;
+                st4(row + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
+                st4(row + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
+                st4(row + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
+                st4(row + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
+                st4(row + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
             }
-            st4(row + c0, make_int4(h[0], h[1], h[2], h[3]));
-            st4(row + wr4 + c0, make_int4(x1[0], x1[1], x1[2], x1[3]));
-            st4(row + 2 * wr4 + c0, make_int4(x2[0], x2[1], x2[2], x2[3]));
-            st4(row + 3 * wr4 + c0, make_int4(f1[0], f1[1], f1[2], f1[3]));
-            st4(row + 4 * wr4 + c0, make_int4(f2[0], f2[1], f2[2], f2[3]));
-            if (use_smem) {
-                st4(bufH[0] + c0, make_int4(h[0], h[1], h[2], h[3]));
-                st4(bufE1[0] + c0, make_int4(x1[0], x1[1], x1[2], x1[3]));
-                st4(bufE2[0] + c0, make_int4(x2[0], x2[1], x2[2], x2[3]));
-            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) H[e] = E1[e] = E2[e] = NEG;
         }
-        if (tid == 0) { d.dp_beg[0] = 0; d.dp_end[0] = prev_end; d.row_off[0] = 0; d.row_left[0] = 0; d.row_right[0] = 0; }
-        cur_off = 5LL * wr4; cells = prev_end + 1;
+        if (lane == 31) S.wM[0][3][warp] = prev_active ? H[CPT - 1] : NEG;
+        if (tid == 0) { RowInfo ri; ri.beg = 0; ri.end = prev_end; ri.left = 0; ri.right = 0; d.info[0] = ri; d.row_off[0] = 0; }
+        cur_off = 5LL * nT * CPT; cells = prev_end + 1;
     }
     __syncthreads();
 
-    int cur = 1;                               // shared-memory buffer the current row is written to
-    for (int r = 1; r < R; ++r, cur ^= 1) {
+    RowRec rec = rt.rec[R > 1 ? 1 : 0];
+    for (int r = 1; r < R; ++r) {
+        const int par = r & 1;
+        const RowRec nrec = rt.rec[r + 1 < R ? r + 1 : r];      // next row's record, in flight while this row computes
         // ---- band of the row (GET_AD_DP_BEGIN/END + lane-group snap, :946-960) ----
-        const int b = rt.row_base[r], p0 = rt.pre_off[r], p1 = rt.pre_off[r + 1];
-        const int dd = L - rt.row_rd[r];
+        const int b = rec.base_npre & 0xff, npre = rec.base_npre >> 8;
+        const int dd = L - rec.rd;
         int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
-        for (int k = p0; k < p1; ++k) {
-            const int p = rt.pre_row[k];
+        bool has_prev = false;
+        for (int k = 0; k < npre; ++k) {
+            const int p = k == 0 ? rec.pre0 : rt.pre_row[rec.pre_off + k];
             int pl, pr, pb;
-            if (p == r - 1) { pl = prev_left; pr = prev_right; pb = prev_beg; }
-            else { pl = d.row_left[p]; pr = d.row_right[p]; pb = d.dp_beg[p]; }
+            if (p == r - 1) { pl = prev_left; pr = prev_right; pb = prev_beg; has_prev = true; }
+            else { const RowInfo pi = d.info[p]; pl = pi.left; pr = pi.right; pb = pi.beg; }
             maxL = min(maxL, pl + 1); maxR = max(maxR, pr + 1); min_pre_beg = min(min_pre_beg, pb);
         }
         int beg = max(0, min(maxL, dd) - w);
         const int end = min(L, max(maxR, dd) + w);
         if (beg / pn < min_pre_beg / pn) beg = min_pre_beg;
-        const int beg4 = beg & ~3, wr4 = (end | 3) - beg4 + 1;
-        if (cur_off + 5LL * wr4 > d.plane_cap) return -1;     // uniform across the CTA
-        int *rowp = d.planes + cur_off - beg4;                  // rowp[plane*wr4 + j]
-        const int *mrow = S.smat + 5 * b;
+        const int t0 = beg / CPT, nT = end / CPT - t0 + 1, PS = nT * CPT, tt = tid - t0;
+        if (cur_off + 5LL * PS > d.plane_cap) return -1;        // uniform across the CTA
+        const bool active = tt >= 0 && tt < nT;
+        const bool full = j0 >= beg && j0 + CPT - 1 <= end;     // all 16 of my columns inside the band
+        const int *mrow = S.smat + 8 * b;
 
-        int carry1 = NEG + beg * e1, carry2 = NEG + beg * e2;   // prefix-max carry in "A space"
-        const int id1 = carry1, id2 = carry2;                   // identities of the two scans
-        int tmax = NEG - 1000, tleft = 0x7fffffff, tright = -1; // thread-local row max bookkeeping
-        const int npass = (wr4 + 4 * T - 1) / (4 * T);
-        for (int pass = 0; pass < npass; ++pass) {
-            const int c0 = beg4 + (pass * T + tid) * 4;
-            const bool active = c0 <= end;
-            int hme[4], x1[4], x2[4], A1[4], A2[4];
-            int agg1 = id1, agg2 = id2;
-            if (active) {
-                int m[4];
+        // H of the column left of my first one, previous row
+        int hl = __shfl_up_sync(FULL, prev_active ? H[CPT - 1] : NEG, 1);
+        if (lane == 0) hl = warp > 0 ? S.wM[par ^ 1][3][warp - 1] : NEG;
+
+        const int id1 = NEG + beg * e1, id2 = NEG + beg * e2;   // identities of the two scans ("A space")
+        int agg1 = id1, agg2 = id2;
+        const int c1 = (j0 + 1) * e1 - oe1, c2 = (j0 + 1) * e2 - oe2;     // A[e] = H'[e] + c + e*e_ext
+        if (active) {
+            // M candidates: H[e] <- H_pred[e-1]; E candidates stay in E1/E2 (previous row = predecessor case)
+            if (has_prev && prev_active) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { m[t] = NEG; x1[t] = NEG; x2[t] = NEG; }
-                for (int k = p0; k < p1; ++k) {
-                    const int p = rt.pre_row[k];
-                    int pb, pe; const int *Hs, *E1s, *E2s;
-                    if (p == r - 1) { pb = prev_beg; pe = prev_end; } else { pb = d.dp_beg[p]; pe = d.dp_end[p]; }
-                    if (use_smem && p == r - 1) { Hs = bufH[cur ^ 1]; E1s = bufE1[cur ^ 1]; E2s = bufE2[cur ^ 1]; }
-                    else {
-                        const int pb4 = pb & ~3, pw4 = (pe | 3) - pb4 + 1;
-                        Hs = d.planes + (p == r - 1 ? prev_off : d.row_off[p]) - pb4; E1s = Hs + pw4; E2s = E1s + pw4;
-                    }
-                    if (c0 - 1 >= pb && c0 + 3 <= pe) {       // whole group inside the predecessor's band
-                        const int4 h = ld4(Hs + c0); const int hl = Hs[c0 - 1];
-                        const int4 a = ld4(E1s + c0), c = ld4(E2s + c0);
-                        m[0] = max(m[0], hl); m[1] = max(m[1], h.x); m[2] = max(m[2], h.y); m[3] = max(m[3], h.z);
-                        x1[0] = max(x1[0], a.x); x1[1] = max(x1[1], a.y); x1[2] = max(x1[2], a.z); x1[3] = max(x1[3], a.w);
-                        x2[0] = max(x2[0], c.x); x2[1] = max(x2[1], c.y); x2[2] = max(x2[2], c.z); x2[3] = max(x2[3], c.w);
-                    } else {
+                for (int e = CPT - 1; e >= 1; --e) H[e] = H[e - 1];
+                H[0] = hl;
+            } else {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int j = c0 + t;
-                            if (j - 1 >= pb && j - 1 <= pe) m[t] = max(m[t], Hs[j - 1]);
-                            if (j >= pb && j <= pe) { x1[t] = max(x1[t], E1s[j]); x2[t] = max(x2[t], E2s[j]); }
-                        }
+                for (int e = 0; e < CPT; ++e) { H[e] = NEG; E1[e] = NEG; E2[e] = NEG; }
+                if (has_prev) H[0] = hl;
+            }
+            // predecessors further back: from the planes in global memory
+            for (int k = 0; k < npre; ++k) {
+                const int p = k == 0 ? rec.pre0 : rt.pre_row[rec.pre_off + k];
+                if (p == r - 1) continue;
+                const RowInfo pi = d.info[p];
+                const int pt0 = pi.beg / CPT, pnT = pi.end / CPT - pt0 + 1, pPS = pnT * CPT, ptt = tid - pt0;
+                const int *Hp = d.planes + d.row_off[p];
+                if (ptt >= 0 && ptt < pnT) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int o = (q * pnT + ptt) << 2;
+                        const int4 h = ld4cg(Hp + o), a = ld4cg(Hp + pPS + o), c = ld4cg(Hp + 2 * pPS + o);
+                        H[q * 4 + 1] = max(H[q * 4 + 1], h.x); H[q * 4 + 2] = max(H[q * 4 + 2], h.y); H[q * 4 + 3] = max(H[q * 4 + 3], h.z);
+                        if (q < 3) H[q * 4 + 4] = max(H[q * 4 + 4], h.w);
+                        E1[q * 4] = max(E1[q * 4], a.x); E1[q * 4 + 1] = max(E1[q * 4 + 1], a.y); E1[q * 4 + 2] = max(E1[q * 4 + 2], a.z); E1[q * 4 + 3] = max(E1[q * 4 + 3], a.w);
+                        E2[q * 4] = max(E2[q * 4], c.x); E2[q * 4 + 1] = max(E2[q * 4 + 1], c.y); E2[q * 4 + 2] = max(E2[q * 4 + 2], c.z); E2[q * 4 + 3] = max(E2[q * 4 + 3], c.w);
                     }
                 }
-                const uint32_t q4 = *reinterpret_cast<const uint32_t *>(sq + c0);   // q_{c0..c0+3}
+                if (ptt >= 1 && ptt <= pnT) H[0] = max(H[0], __ldcg(Hp + (((3 * pnT + ptt - 1) << 2) | 3)));
+            }
+            // H' = max(M + s, E1, E2) (:1033,1050) and the thread's scan aggregates
+            if (full) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int j = c0 + t;
-                    const int s = (j == 0) ? 0 : mrow[(q4 >> (8 * t)) & 0xff];
-                    if (j < beg || j > end) { hme[t] = NEG; x1[t] = NEG; x2[t] = NEG; }
-                    else hme[t] = max3(m[t] + s, x1[t], x2[t]);                      // H' = max(M + s, E1, E2), :1033,1050
-                    A1[t] = hme[t] - oe1 + (j + 1) * e1;
-                    A2[t] = hme[t] - oe2 + (j + 1) * e2;
-                    agg1 = max(agg1, A1[t]); agg2 = max(agg2, A2[t]);
+                for (int e = 0; e < CPT; ++e) {
+                    const int s = mrow[(qc[e >> 3] >> ((e & 7) * 4)) & 7];
+                    H[e] = max3(H[e] + s, E1[e], E2[e]);
+                    agg1 = max(agg1, H[e] + c1 + e * e1); agg2 = max(agg2, H[e] + c2 + e * e2);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < CPT; ++e) {
+                    const int j = j0 + e;
+                    const int s = mrow[(qc[e >> 3] >> ((e & 7) * 4)) & 7];
+                    if (j < beg || j > end) { H[e] = NEG; E1[e] = NEG; E2[e] = NEG; }
+                    else H[e] = max3(H[e] + s, E1[e], E2[e]);
+                    agg1 = max(agg1, H[e] + c1 + e * e1); agg2 = max(agg2, H[e] + c2 + e * e2);
                 }
             }
-            // ---- exclusive prefix maximum over the row: warp shuffle scan + redux over warp aggregates ----
-            int inc1 = agg1, inc2 = agg2;
+        }
+        // ---- exclusive prefix maximum over the row: warp shuffle scan + redux over warp aggregates ----
+        int inc1 = agg1, inc2 = agg2;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int n1 = __shfl_up_sync(FULL, inc1, off), n2 = __shfl_up_sync(FULL, inc2, off);
-                if (lane >= off) { inc1 = max(inc1, n1); inc2 = max(inc2, n2); }
-            }
-            int ex1 = __shfl_up_sync(FULL, inc1, 1), ex2 = __shfl_up_sync(FULL, inc2, 1);
-            if (lane == 0) { ex1 = id1; ex2 = id2; }
-            if (lane == 31) { S.wF[pass & 1][0][warp] = inc1; S.wF[pass & 1][1][warp] = inc2; }
-            __syncthreads();
-            const int wv1 = lane < nwarps ? S.wF[pass & 1][0][lane] : id1, wv2 = lane < nwarps ? S.wF[pass & 1][1][lane] : id2;
-            const int before1 = __reduce_max_sync(FULL, lane < warp ? wv1 : id1), before2 = __reduce_max_sync(FULL, lane < warp ? wv2 : id2);
-            const int tot1 = __reduce_max_sync(FULL, wv1), tot2 = __reduce_max_sync(FULL, wv2);
-            int P1 = max3(carry1, before1, ex1), P2 = max3(carry2, before2, ex2);
-            carry1 = max(carry1, tot1); carry2 = max(carry2, tot2);
-            if (active) {
-                int h[4], f1[4], f2[4];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int n1 = __shfl_up_sync(FULL, inc1, off), n2 = __shfl_up_sync(FULL, inc2, off);
+            if (lane >= off) { inc1 = max(inc1, n1); inc2 = max(inc2, n2); }
+        }
+        int ex1 = __shfl_up_sync(FULL, inc1, 1), ex2 = __shfl_up_sync(FULL, inc2, 1);
+        if (lane == 0) { ex1 = id1; ex2 = id2; }
+        if (lane == 31) { S.wF[par][0][warp] = inc1; S.wF[par][1][warp] = inc2; }
+        __syncthreads();
+        int P1, P2;
+        {
+            const int wv1 = lane < warp ? S.wF[par][0][lane] : id1, wv2 = lane < warp ? S.wF[par][1][lane] : id2;
+            P1 = max(__reduce_max_sync(FULL, wv1), ex1); P2 = max(__reduce_max_sync(FULL, wv2), ex2);
+        }
+        int tmax = NEG - 1000, tleft = 0x7fffffff, tright = -1;   // thread-local row max bookkeeping
+        if (active) {
+            int *rowp = d.planes + cur_off;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int j = c0 + t;
-                    f1[t] = P1 - j * e1; f2[t] = P2 - j * e2;                       // F[j] = max_{k<j} A[k] - j*e
-                    P1 = max(P1, A1[t]); P2 = max(P2, A2[t]);
-                    if (j < beg || j > end) { h[t] = NEG; f1[t] = NEG; f2[t] = NEG; }
+            for (int q = 0; q < 4; ++q) {
+                int f1[4], f2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = q * 4 + u, j = j0 + e;
+                    f1[u] = P1 - j * e1; f2[u] = P2 - j * e2;                       // F[j] = max_{k<j} A[k] - j*e
+                    P1 = max(P1, H[e] + c1 + e * e1); P2 = max(P2, H[e] + c2 + e * e2);
+                    if (!full && (j < beg || j > end)) { H[e] = NEG; f1[u] = NEG; f2[u] = NEG; }
                     else {
-                        h[t] = max3(hme[t], f1[t], f2[t]);                           // :1067
-                        x1[t] = max(x1[t] - e1, h[t] - oe1);                         // E for the next rows, :1070-1071
-                        x2[t] = max(x2[t] - e2, h[t] - oe2);
-                        if (h[t] > tmax) { tmax = h[t]; tleft = j; tright = j; } else if (h[t] == tmax) tright = j;
+                        const int h = max3(H[e], f1[u], f2[u]);                      // :1067
+                        H[e] = h;
+                        E1[e] = max(E1[e] - e1, h - oe1);                            // E for the next rows, :1070-1071
+                        E2[e] = max(E2[e] - e2, h - oe2);
+                        if (h > tmax) { tmax = h; tleft = j; tright = j; } else if (h == tmax) tright = j;
                     }
                 }
-                st4(rowp + c0, make_int4(h[0], h[1], h[2], h[3]));
-                st4(rowp + wr4 + c0, make_int4(x1[0], x1[1], x1[2], x1[3]));
-                st4(rowp + 2 * wr4 + c0, make_int4(x2[0], x2[1], x2[2], x2[3]));
-                st4(rowp + 3 * wr4 + c0, make_int4(f1[0], f1[1], f1[2], f1[3]));
-                st4(rowp + 4 * wr4 + c0, make_int4(f2[0], f2[1], f2[2], f2[3]));
-                if (use_smem) {
-                    st4(bufH[cur] + c0, make_int4(h[0], h[1], h[2], h[3]));
-                    st4(bufE1[cur] + c0, make_int4(x1[0], x1[1], x1[2], x1[3]));
-                    st4(bufE2[cur] + c0, make_int4(x2[0], x2[1], x2[2], x2[3]));
-                }
+                const int o = (q * nT + tt) << 2;
+                st4(rowp + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
+                st4(rowp + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
+                st4(rowp + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
+                st4(rowp + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
+                st4(rowp + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
             }
         }
         // ---- left/right-most argmax of H over the band (simd_abpoa_max_in_row, :1107-1119) ----
@@ -218,19 +243,21 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
             const int wmax = __reduce_max_sync(FULL, tmax);
             const int wl = __reduce_min_sync(FULL, tmax == wmax ? tleft : 0x7fffffff);
             const int wr = __reduce_max_sync(FULL, tmax == wmax ? tright : -1);
-            if (lane == 0) { S.wM[0][warp] = wmax; S.wM[1][warp] = wl; S.wM[2][warp] = wr; }
+            if (lane == 0) { S.wM[par][0][warp] = wmax; S.wM[par][1][warp] = wl; S.wM[par][2][warp] = wr; }
+            if (lane == 31) S.wM[par][3][warp] = active ? H[CPT - 1] : NEG;
         }
         __syncthreads();
         {
-            const int v = lane < nwarps ? S.wM[0][lane] : NEG - 1000;
+            const int v = lane < nwarps ? S.wM[par][0][lane] : NEG - 1000;
             const int bmax = __reduce_max_sync(FULL, v);
-            const int l = (lane < nwarps && v == bmax) ? S.wM[1][lane] : 0x7fffffff;
-            const int rr = (lane < nwarps && v == bmax) ? S.wM[2][lane] : -1;
+            const int l = (lane < nwarps && v == bmax) ? S.wM[par][1][lane] : 0x7fffffff;
+            const int rr = (lane < nwarps && v == bmax) ? S.wM[par][2][lane] : -1;
             prev_left = __reduce_min_sync(FULL, l); prev_right = __reduce_max_sync(FULL, rr);
         }
-        prev_beg = beg; prev_end = end;
-        if (tid == 0) { d.dp_beg[r] = beg; d.dp_end[r] = end; d.row_off[r] = cur_off; d.row_left[r] = prev_left; d.row_right[r] = prev_right; }
-        prev_off = cur_off; cur_off += 5LL * wr4; cells += end - beg + 1;
+        prev_beg = beg; prev_end = end; prev_active = active;
+        if (tid == 0) { RowInfo ri; ri.beg = beg; ri.end = end; ri.left = prev_left; ri.right = prev_right; d.info[r] = ri; d.row_off[r] = cur_off; }
+        cur_off += 5LL * PS; cells += end - beg + 1;
+        rec = nrec;
     }
     __syncthreads();
     return cells;
@@ -249,40 +276,21 @@ __device__ __forceinline__ void carve(KShared &S, const BatchArgs &A, int slot) 
     g.index_to_node = (int *)(b + Y.o_index_to_node); g.node_to_index = (int *)(b + Y.o_node_to_index);
     g.remain = (int *)(b + Y.o_remain); g.msa_rank = (int *)(b + Y.o_msa_rank);
     g.tmp0 = (int *)(b + Y.o_tmp0); g.tmp1 = (int *)(b + Y.o_tmp1);
-    rt.row_base = b + Y.o_row_base; rt.row_rd = (int *)(b + Y.o_row_rd);
-    rt.pre_off = (int *)(b + Y.o_pre_off); rt.pre_row = (int *)(b + Y.o_pre_row);
+    rt.rec = (RowRec *)(b + Y.o_row_rec); rt.pre_row = (int *)(b + Y.o_pre_row);
     d.planes = A.planes + (int64_t)slot * Y.plane_cap; d.plane_cap = Y.plane_cap;
-    d.row_off = (int64_t *)(b + Y.o_row_off); d.dp_beg = (int *)(b + Y.o_dp_beg); d.dp_end = (int *)(b + Y.o_dp_end);
-    d.row_left = (int *)(b + Y.o_row_left); d.row_right = (int *)(b + Y.o_row_right);
+    d.row_off = (int64_t *)(b + Y.o_row_off); d.info = (RowInfo *)(b + Y.o_row_info);
     d.cigar = (uint64_t *)(b + Y.o_cigar); d.cigar_cap = Y.cigar_cap; d.n_cigar = 0;
-}
-
-// abpoa_topological_sort (abpoa_graph.c:322-357): BFS index (serial), edge sort (one node per thread),
-// max_remain + row tables (serial).
-__device__ void topo_sort_cta(KShared &S) {
-    Graph &g = S.g;
-    if (threadIdx.x == 0) graph_bfs_index(g);
-    __syncthreads();
-    if (g.err) return;
-    for (int v = threadIdx.x; v < g.node_n; v += blockDim.x) graph_sort_node_edges(g, v);
-    __syncthreads();
-    if (threadIdx.x == 0) { graph_bfs_remain(g); if (!g.err) graph_build_rows(g, S.rt); }
-    __syncthreads();
 }
 
 #define PHASE_TICK(ph) do { if (A.phase_clk && threadIdx.x == 0) { unsigned long long _n = clock64(); A.phase_clk[(size_t)blockIdx.x * PH_N + (ph)] += _n - t_last; t_last = _n; } } while (0)
 
-extern "C" __global__ void __launch_bounds__(512, 2) poa_msa_kernel(const BatchArgs A) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+__device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];    // scratch of the topological sort (poa_cta.cuh)
     __shared__ KShared S;
     const int tid = threadIdx.x;
+    int *ws = &S.wF[0][0][0];
     if (tid == 0) carve(S, A, blockIdx.x);
-    if (tid < 25) S.smat[tid] = A.P.mat[tid];
-    // dynamic shared memory: query bytes, then the double-buffered previous-row cache
-    const int qbytes = (A.q_cols + 8 + 15) & ~15;
-    uint8_t *sq = dyn_smem;
-    int *rowbuf = reinterpret_cast<int *>(dyn_smem + qbytes);
-    const int rb_stride = A.smem_cols + 8;
+    for (int k = tid; k < 40; k += blockDim.x) S.smat[k] = (k & 7) < 5 ? A.P.mat[(k >> 3) * 5 + (k & 7)] : 0;
     unsigned long long t_last = A.phase_clk ? clock64() : 0ULL, t_start = t_last;
     __syncthreads();
 
@@ -303,24 +311,28 @@ extern "C" __global__ void __launch_bounds__(512, 2) poa_msa_kernel(const BatchA
             const int read = order[a], L = lens[read];
             const uint8_t *q = seqs + soff[read];
             if (a == 0) {
-                if (tid == 0) graph_add_first_sequence(S.g, q, L, read);
+                if (A.serial_phases) { if (tid == 0) graph_add_first_sequence(S.g, q, L, read); }
+                else cta_add_first_sequence(S.g, q, L, read);
                 PHASE_TICK(PH_FUSE);
             } else {
-                // queries longer than the shared-memory row cache read their predecessors from global memory (L2)
-                const bool fits = L + 1 <= A.smem_cols;
-                long long c = dp_sweep(S, A.P, q, L, sq, rowbuf, rb_stride, fits);
-                if (c < 0) { if (tid == 0) S.g.err = JOB_ERR_PLANE_CAP; c = 0; }
+                long long c = -2;
+                if (L + 1 <= CPT * (int)blockDim.x) c = dp_sweep(S, A.P, q, L);
+                if (c < 0) { if (tid == 0) S.g.err = c == -2 ? JOB_ERR_QUERY_LEN : JOB_ERR_PLANE_CAP; c = 0; }
                 cells += c;
                 __syncthreads();
                 PHASE_TICK(PH_DP);
-                if (tid == 0 && !S.g.err) { dp_best_cell(S.g, S.rt, S.d, A.P, L); dp_backtrack(S.g, S.rt, S.d, A.P, q, L); }
+                if (A.serial_phases) { if (tid == 0 && !S.g.err) { dp_best_cell(S.g, S.rt, S.d, A.P, L); dp_backtrack(S.g, S.rt, S.d, A.P, q, L); } }
+                else if (tid < 32 && !S.g.err) warp_backtrack(S.g, S.rt, S.d, A.P, S.smat, q, L);
                 PHASE_TICK(PH_BACKTRACK);
-                if (tid == 0 && !S.g.err) graph_fuse_alignment(S.g, q, S.d.cigar, S.d.n_cigar, read);
+                __syncthreads();
+                if (A.serial_phases) { if (tid == 0 && !S.g.err) graph_fuse_alignment(S.g, q, S.d.cigar, S.d.n_cigar, read); }
+                else if (!S.g.err) cta_fuse_alignment(S.g, q, L, S.d.cigar, S.d.n_cigar, read, ws);
                 PHASE_TICK(PH_FUSE);
             }
             __syncthreads();
             if (S.g.err) break;
-            topo_sort_cta(S);
+            if (A.serial_phases) { if (tid == 0) graph_topo_sort_serial(S.g, S.rt); __syncthreads(); }
+            else cta_topo_sort(S.g, S.rt, dyn_smem, A.scratch_bytes, ws);
             PHASE_TICK(PH_TOPO);
             if (S.g.err) break;
         }
@@ -345,5 +357,16 @@ extern "C" __global__ void __launch_bounds__(512, 2) poa_msa_kernel(const BatchA
     }
     if (A.phase_clk && tid == 0) A.phase_clk[(size_t)blockIdx.x * PH_N + PH_TOTAL] += clock64() - t_start;
 }
+
+// One entry point per CTA-size class (the register budget per thread follows from the launch bounds):
+//   queries up to 511 bases -> one warp, 16 CTAs per SM;  up to 1023 -> 64 threads;
+//   up to 2047 -> 128 threads, 4 CTAs per SM;  up to 4095 -> 256 threads, 2 per SM;
+//   up to 10239 (covers Cactus' 10 kbp window) -> 640 threads;  up to 16383 -> 1024 threads.
+extern "C" __global__ void __launch_bounds__(32, 16) poa_msa_kernel_t32(const BatchArgs A) { poa_msa_body(A); }
+extern "C" __global__ void __launch_bounds__(64, 8) poa_msa_kernel_t64(const BatchArgs A) { poa_msa_body(A); }
+extern "C" __global__ void __launch_bounds__(128, 4) poa_msa_kernel_t128(const BatchArgs A) { poa_msa_body(A); }
+extern "C" __global__ void __launch_bounds__(256, 2) poa_msa_kernel_t256(const BatchArgs A) { poa_msa_body(A); }
+extern "C" __global__ void __launch_bounds__(640, 1) poa_msa_kernel_t640(const BatchArgs A) { poa_msa_body(A); }
+extern "C" __global__ void __launch_bounds__(1024, 1) poa_msa_kernel_t1024(const BatchArgs A) { poa_msa_body(A); }
 
 }  // namespace barb200

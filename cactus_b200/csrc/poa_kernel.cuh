@@ -12,8 +12,8 @@ struct SlotLayout {
     int64_t o_base, o_aln_n, o_aln_id, o_in_off, o_in_n, o_in_cap, o_out_off, o_out_n, o_out_cap;
     int64_t o_in_id, o_in_w, o_out_id, o_out_w, o_out_rid;
     int64_t o_index_to_node, o_node_to_index, o_remain, o_msa_rank, o_tmp0, o_tmp1;
-    int64_t o_row_base, o_row_rd, o_pre_off, o_pre_row;
-    int64_t o_row_off, o_dp_beg, o_dp_end, o_row_left, o_row_right, o_cigar;
+    int64_t o_row_rec, o_pre_row;
+    int64_t o_row_off, o_row_info, o_cigar;
 };
 
 enum { PH_DP = 0, PH_BACKTRACK = 1, PH_FUSE = 2, PH_TOPO = 3, PH_MSA = 4, PH_TOTAL = 5, PH_N = 8 };
@@ -28,8 +28,8 @@ struct BatchArgs {
     uint8_t *slots; int *planes;
     int *next_job;              // work queue head
     unsigned long long *phase_clk;   // [gridDim.x * PH_N] clock64 per phase, or nullptr
-    int q_cols;                 // >= longest query + 1: bytes reserved in shared memory for the query
-    int smem_cols;              // columns the shared-memory row cache can hold (0: read predecessors from global)
+    int serial_phases;          // debugging aid: 1 = run the graph phases in their serial reference form
+    int scratch_bytes;          // dynamic shared memory per CTA (topological sort scratch)
     SlotLayout lay;
     PoaParams P;
 };

@@ -31,7 +31,8 @@ enum JobStatus : int {
     JOB_ERR_MSA_CAP = 5,     // msa_len larger than the job's output stride (host retries)
     JOB_ERR_TOPO = 6,        // "Failed to set node index" in the reference (abpoa_graph.c:265)
     JOB_ERR_BACKTRACK = 7,   // "Error in cg_backtrack" in the reference (abpoa_align_simd.c:448)
-    JOB_ERR_ALIGNED_CAP = 8
+    JOB_ERR_ALIGNED_CAP = 8,
+    JOB_ERR_QUERY_LEN = 9    // query longer than 16 x threads per CTA (host sizing bug)
 };
 
 // Scoring / banding parameters: what abpoaParamaters_constructFromCactusParams builds
@@ -75,25 +76,47 @@ struct Graph {
     int *tmp0, *tmp1;                   // [node_cap] scratch: degree counters, queues
 };
 
-// Row-major view of the sorted graph that the DP sweeps (built after every topological sort).
+// Row-major view of the sorted graph that the DP sweeps (built after every topological sort): one 16-byte record
+// per topological index r, fetched with a single load per row.
+struct alignas(16) RowRec {
+    int base_npre;       // base of the node at index r | (number of predecessors << 8)
+    int rd;              // remain[v] - remain[SINK] - 1  (GET_AD_DP_BEGIN/END, abpoa_align.h:34-35)
+    int pre_off;         // CSR offset into pre_row
+    int pre0;            // first predecessor row (the only one for ~90 % of rows), -1 if none
+};
 struct RowTables {
-    uint8_t *row_base;   // [node_cap]  base of the node at topological index r
-    int *row_rd;         // [node_cap]  remain[v] - remain[SINK] - 1  (GET_AD_DP_BEGIN/END, abpoa_align.h:34-35)
-    int *pre_off;        // [node_cap+1] CSR into pre_row
+    RowRec *rec;         // [node_cap]
     int *pre_row;        // [in_pool]   predecessor rows in in_id order (abpoa_align_simd.c:550-558)
 };
 
-// Banded DP planes of the current alignment + per-row band bookkeeping.
-// Row r occupies 5 consecutive planes (H, E1, E2, F1, F2) of wr4 ints each at planes + row_off[r],
-// wr4 = (dp_end|3) - (dp_beg&~3) + 1; column j of a plane is at [j - (dp_beg&~3)].
+// Per-row band bookkeeping of the current alignment.
+struct alignas(16) RowInfo {
+    int beg, end;        // dp_beg / dp_end (abpoa_align_simd.c:946-960)
+    int left, right;     // left/right-most argmax of H in the row (abpoa_align_simd.c:1107-1119)
+};
+
+// Banded DP planes of the current alignment.
+// Column ownership is fixed: thread t of the CTA owns columns [CPT*t, CPT*t + CPT) of EVERY row, so the values of the
+// previous row stay in that thread's registers. A row with band [beg, end] is stored for the threads
+// t0 = beg/CPT .. t1 = end/CPT only (nT = t1-t0+1), as 5 consecutive planes (H, E1, E2, F1, F2) of nT*CPT ints at
+// planes + row_off[r]. Inside a plane the layout is "thread-blocked": quad q (4 adjacent columns) of thread t is at
+// int offset ((q*nT + (t-t0)) << 2), so that the 16-byte store of quad q by consecutive threads is one contiguous
+// run (full 32 B sectors, 512 B per warp instruction). Cells of the stored threads outside [beg, end] hold inf_min.
+constexpr int CPT = 16;
 struct DpState {
     int *planes; int64_t plane_cap;     // ints
     int64_t *row_off;                   // [node_cap]
-    int *dp_beg, *dp_end;               // [node_cap]
-    int *row_left, *row_right;          // [node_cap] left/right-most argmax of H in the row (abpoa_align_simd.c:1107-1119)
+    RowInfo *info;                      // [node_cap]
     uint64_t *cigar; int n_cigar, cigar_cap;
     int best_i, best_j, best_score;
 };
+
+// int offset of column j of `plane` inside the row's block (see DpState); j must lie in a stored thread's range
+HD int64_t plane_index(int beg, int end, int plane, int j) {
+    const int t0 = beg / CPT, nT = end / CPT - t0 + 1, t = j / CPT, e = j % CPT;
+    return (int64_t)plane * nT * CPT + ((((e >> 2) * nT + (t - t0)) << 2) | (e & 3));
+}
+HD int64_t row_ints(int beg, int end) { return 5LL * (end / CPT - beg / CPT + 1) * CPT; }
 
 HD int imax(int a, int b) { return a > b ? a : b; }
 HD int imin(int a, int b) { return a < b ? a : b; }

@@ -20,53 +20,50 @@ static long long emulate_sweep(const Graph &g, const RowTables &rt, DpState &d, 
     const int node_n = g.node_n, R = node_n - 1, NEG = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int w = P.wb + (int)(P.wf * L), pn = reference_lane_count(P, L, node_n);
     long long cur_off = 0, cells = 0;
-    {
-        const int end = std::min(L, std::max(0, L - rt.row_rd[0]) + w), wr4 = (end | 3) + 1;
-        if (5LL * wr4 > d.plane_cap) return -1;
-        int *row = d.planes;
-        for (int j = 0; j < wr4; ++j) {
+    for (int r = 0; r < R; ++r) {
+        int beg, end;
+        const int b = row_base(rt, r), p0 = rt.rec[r].pre_off, p1 = p0 + row_npre(rt, r), dd = L - rt.rec[r].rd;
+        if (r == 0) { beg = 0; end = std::min(L, std::max(0, dd) + w); }
+        else {
+            int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
+            for (int k = p0; k < p1; ++k) { const int p = rt.pre_row[k]; maxL = std::min(maxL, d.info[p].left + 1); maxR = std::max(maxR, d.info[p].right + 1); min_pre_beg = std::min(min_pre_beg, d.info[p].beg); }
+            beg = std::max(0, std::min(maxL, dd) - w); end = std::min(L, std::max(maxR, dd) + w);
+            if (beg / pn < min_pre_beg / pn) beg = min_pre_beg;
+        }
+        if (cur_off + row_ints(beg, end) > d.plane_cap) return -1;
+        int *rowp = d.planes + cur_off;
+        int P1 = NEG + beg * e1, P2 = NEG + beg * e2, tmax = NEG - 1000, tl = 0, tr = r == 0 ? 0 : -1;
+        for (int j = beg / CPT * CPT; j <= (end / CPT) * CPT + CPT - 1; ++j) {
             int h, x1, x2, f1, f2;
-            if (j == 0) { h = 0; x1 = -oe1; x2 = -oe2; f1 = f2 = NEG; }
-            else if (j <= end) { f1 = -P.o1 - e1 * j; f2 = -P.o2 - e2 * j; h = std::max(f1, f2); x1 = x2 = NEG; }
-            else h = x1 = x2 = f1 = f2 = NEG;
-            row[j] = h; row[wr4 + j] = x1; row[2 * wr4 + j] = x2; row[3 * wr4 + j] = f1; row[4 * wr4 + j] = f2;
-        }
-        d.dp_beg[0] = 0; d.dp_end[0] = end; d.row_off[0] = 0; d.row_left[0] = 0; d.row_right[0] = 0;
-        cur_off = 5LL * wr4; cells = end + 1;
-    }
-    for (int r = 1; r < R; ++r) {
-        const int b = rt.row_base[r], p0 = rt.pre_off[r], p1 = rt.pre_off[r + 1], dd = L - rt.row_rd[r];
-        int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
-        for (int k = p0; k < p1; ++k) { const int p = rt.pre_row[k]; maxL = std::min(maxL, d.row_left[p] + 1); maxR = std::max(maxR, d.row_right[p] + 1); min_pre_beg = std::min(min_pre_beg, d.dp_beg[p]); }
-        int beg = std::max(0, std::min(maxL, dd) - w); const int end = std::min(L, std::max(maxR, dd) + w);
-        if (beg / pn < min_pre_beg / pn) beg = min_pre_beg;
-        const int beg4 = beg & ~3, wr4 = (end | 3) - beg4 + 1;
-        if (cur_off + 5LL * wr4 > d.plane_cap) return -1;
-        int *rowp = d.planes + cur_off - beg4;
-        int P1 = NEG + beg * e1, P2 = NEG + beg * e2, tmax = NEG - 1000, tl = 0, tr = -1;
-        d.dp_beg[r] = beg; d.dp_end[r] = end; d.row_off[r] = cur_off;
-        for (int j = beg4; j <= (end | 3); ++j) {
-            int m = NEG, x1 = NEG, x2 = NEG;
-            for (int k = p0; k < p1; ++k) {
-                const int p = rt.pre_row[k];
-                m = std::max(m, plane_cell(d, NEG, p, 0, j - 1)); x1 = std::max(x1, plane_cell(d, NEG, p, 1, j)); x2 = std::max(x2, plane_cell(d, NEG, p, 2, j));
+            if (r == 0) {
+                if (j == 0) { h = 0; x1 = -oe1; x2 = -oe2; f1 = f2 = NEG; }
+                else if (j <= end) { f1 = -P.o1 - e1 * j; f2 = -P.o2 - e2 * j; h = std::max(f1, f2); x1 = x2 = NEG; }
+                else h = x1 = x2 = f1 = f2 = NEG;
+            } else {
+                int m = NEG; x1 = NEG; x2 = NEG;
+                for (int k = p0; k < p1; ++k) {
+                    const int p = rt.pre_row[k];
+                    m = std::max(m, plane_cell(d, NEG, p, 0, j - 1)); x1 = std::max(x1, plane_cell(d, NEG, p, 1, j)); x2 = std::max(x2, plane_cell(d, NEG, p, 2, j));
+                }
+                const int s = (j >= 1 && j <= L) ? P.mat[5 * b + q[j - 1]] : 0;
+                int hme;
+                if (j < beg || j > end) { hme = NEG; x1 = NEG; x2 = NEG; } else hme = std::max(std::max(m + s, x1), x2);
+                const int A1 = hme - oe1 + (j + 1) * e1, A2 = hme - oe2 + (j + 1) * e2;
+                f1 = P1 - j * e1; f2 = P2 - j * e2;
+                P1 = std::max(P1, A1); P2 = std::max(P2, A2);
+                if (j < beg || j > end) { h = NEG; f1 = NEG; f2 = NEG; }
+                else {
+                    h = std::max(std::max(hme, f1), f2);
+                    x1 = std::max(x1 - e1, h - oe1); x2 = std::max(x2 - e2, h - oe2);
+                    if (h > tmax) { tmax = h; tl = tr = j; } else if (h == tmax) tr = j;
+                }
             }
-            const int s = j == 0 ? 0 : (j <= L ? P.mat[5 * b + q[j - 1]] : 0);
-            int hme;
-            if (j < beg || j > end) { hme = NEG; x1 = NEG; x2 = NEG; } else hme = std::max(std::max(m + s, x1), x2);
-            const int A1 = hme - oe1 + (j + 1) * e1, A2 = hme - oe2 + (j + 1) * e2;
-            int f1 = P1 - j * e1, f2 = P2 - j * e2, h;
-            P1 = std::max(P1, A1); P2 = std::max(P2, A2);
-            if (j < beg || j > end) { h = NEG; f1 = NEG; f2 = NEG; }
-            else {
-                h = std::max(std::max(hme, f1), f2);
-                x1 = std::max(x1 - e1, h - oe1); x2 = std::max(x2 - e2, h - oe2);
-                if (h > tmax) { tmax = h; tl = tr = j; } else if (h == tmax) tr = j;
-            }
-            rowp[j] = h; rowp[wr4 + j] = x1; rowp[2 * wr4 + j] = x2; rowp[3 * wr4 + j] = f1; rowp[4 * wr4 + j] = f2;
+            rowp[plane_index(beg, end, 0, j)] = h; rowp[plane_index(beg, end, 1, j)] = x1; rowp[plane_index(beg, end, 2, j)] = x2;
+            rowp[plane_index(beg, end, 3, j)] = f1; rowp[plane_index(beg, end, 4, j)] = f2;
         }
-        d.row_left[r] = tl; d.row_right[r] = tr;
-        cur_off += 5LL * wr4; cells += end - beg + 1;
+        RowInfo ri; ri.beg = beg; ri.end = end; ri.left = r == 0 ? 0 : tl; ri.right = r == 0 ? 0 : tr;
+        d.info[r] = ri; d.row_off[r] = cur_off;
+        cur_off += row_ints(beg, end); cells += end - beg + 1;
     }
     return cells;
 }
@@ -84,21 +81,22 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
     guide_tree_order(hpp, hp->progressive, n_seq, seqs.data(), lens, order.data());
     const int N = (int)sum + 2, EP = (int)(4 * (sum + n_seq) + 64), W = 1 + ((n_seq - 1) >> 6);
     Graph g; RowTables rt; DpState d;
-    std::vector<uint8_t> base(N), aln_n(N), row_base(N);
+    std::vector<uint8_t> base(N), aln_n(N);
     std::vector<int> aln_id(4 * N), in_off(N), in_n(N), in_cap(N), out_off(N), out_n(N), out_cap(N), in_id(EP), in_w(EP), out_id(EP), out_w(EP),
-        i2n(N), n2i(N), remain(N), rank(N), t0(N), t1(N), row_rd(N), pre_off(N + 1), pre_row(EP), dp_beg(N), dp_end(N), rl(N), rr(N);
+        i2n(N), n2i(N), remain(N), rank(N), t0(N), t1(N), pre_row(EP);
+    std::vector<RowRec> rrec(N); std::vector<RowInfo> rinfo(N);
     std::vector<uint64_t> rid((size_t)EP * W), cigar(maxl + N + 16);
     std::vector<int64_t> row_off(N);
-    const int64_t plane_cap = (int64_t)N * 5 * (maxl + 8);
+    const int64_t plane_cap = (int64_t)N * 5 * (maxl + 2 * CPT);
     std::vector<int> planes((size_t)std::min<int64_t>(plane_cap, (int64_t)1 << 31));
     g.node_cap = N; g.in_pool = EP; g.out_pool = EP;
     g.base = base.data(); g.aln_n = aln_n.data(); g.aln_id = aln_id.data(); g.in_off = in_off.data(); g.in_n = in_n.data(); g.in_cap = in_cap.data();
     g.out_off = out_off.data(); g.out_n = out_n.data(); g.out_cap = out_cap.data(); g.in_id = in_id.data(); g.in_w = in_w.data();
     g.out_id = out_id.data(); g.out_w = out_w.data(); g.out_rid = rid.data(); g.index_to_node = i2n.data(); g.node_to_index = n2i.data();
     g.remain = remain.data(); g.msa_rank = rank.data(); g.tmp0 = t0.data(); g.tmp1 = t1.data();
-    rt.row_base = row_base.data(); rt.row_rd = row_rd.data(); rt.pre_off = pre_off.data(); rt.pre_row = pre_row.data();
-    d.planes = planes.data(); d.plane_cap = (int64_t)planes.size(); d.row_off = row_off.data(); d.dp_beg = dp_beg.data(); d.dp_end = dp_end.data();
-    d.row_left = rl.data(); d.row_right = rr.data(); d.cigar = cigar.data(); d.cigar_cap = (int)cigar.size(); d.n_cigar = 0;
+    rt.rec = rrec.data(); rt.pre_row = pre_row.data();
+    d.planes = planes.data(); d.plane_cap = (int64_t)planes.size(); d.row_off = row_off.data(); d.info = rinfo.data();
+    d.cigar = cigar.data(); d.cigar_cap = (int)cigar.size(); d.n_cigar = 0;
     graph_reset(g, n_seq);
     std::vector<int64_t> w;
     w.push_back(n_seq); w.push_back(0); w.push_back(0);
@@ -116,8 +114,8 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
         }
         w.push_back(read); w.push_back(L); w.push_back(node_n); w.push_back(d.n_cigar); w.push_back(a == 0 ? 0 : d.best_score); w.push_back(n_rows);
         for (int c = 0; c < d.n_cigar; ++c) w.push_back((int64_t)d.cigar[c]);
-        for (int r = 0; r < n_rows; ++r) w.push_back(d.dp_beg[r]);
-        for (int r = 0; r < n_rows; ++r) w.push_back(d.dp_end[r]);
+        for (int r = 0; r < n_rows; ++r) w.push_back(d.info[r].beg);
+        for (int r = 0; r < n_rows; ++r) w.push_back(d.info[r].end);
         if (g.err) break;
         if (a > 0) graph_fuse_alignment(g, q, d.cigar, d.n_cigar, read);
         if (g.err) break;
