@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libabpoa_ref.so")
 BAR_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbar_ref.so")
+BAR_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libbar_shim.so")
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libpoa_oracle.so")
 
 # Cactus defaults, src/cactus/cactus_progressive_config.xml:307-325
@@ -57,6 +58,10 @@ def have_ref():
 
 def have_bar_ref():
     return os.path.exists(BAR_REF_SO)
+
+
+def have_bar_shim():
+    return os.path.exists(BAR_SHIM_SO)
 
 
 def build_oracle():
@@ -175,8 +180,8 @@ def _msa_make(libname, strs, window_size, max_prog_rows, max_prog_length_diff, p
     p = p or cactus_params()
     arr, lens = _cstrings(strs)
     n = len(strs)
-    if libname == "ref":
-        lib = _load(BAR_REF_SO)
+    if libname in ("ref", "shim"):
+        lib = _load(BAR_REF_SO if libname == "ref" else BAR_SHIM_SO)
         f = lib.bar_ref_msa_make_partial_order_alignment
         f.restype = C.c_int64
         f.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
@@ -204,6 +209,11 @@ def ref_msa_make_partial_order_alignment(strs, window_size=10000, max_prog_rows=
     return _msa_make("ref", strs, window_size, max_prog_rows, max_prog_length_diff, p)
 
 
+def shim_msa_make_partial_order_alignment(strs, window_size=10000, max_prog_rows=5000, max_prog_length_diff=1.0, p=None):
+    """the reference's msa_make_partial_order_alignment SYMBOL as re-exported by shim/cactus_bar_shim.c (GPU needed)"""
+    return _msa_make("shim", strs, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
 def oracle_msa_make_partial_order_alignment(strs, window_size=10000, max_prog_rows=5000, max_prog_length_diff=1.0, p=None):
     return _msa_make("oracle", strs, window_size, max_prog_rows, max_prog_length_diff, p)
 
@@ -229,8 +239,8 @@ def _consistent(libname, ends, right_end_indexes, right_end_row_indexes, overlap
         es[i], el[i] = C.cast(arr, C.c_void_p), C.cast(lens, C.c_void_p)
         ri[i], rr[i], ov[i] = C.cast(a, C.c_void_p), C.cast(b, C.c_void_p), C.cast(c, C.c_void_p)
     out = []
-    if libname == "ref":
-        lib = _load(BAR_REF_SO)
+    if libname in ("ref", "shim"):
+        lib = _load(BAR_REF_SO if libname == "ref" else BAR_SHIM_SO)
         f = lib.bar_ref_make_consistent_partial_order_alignments
         f.restype = None
         f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -265,6 +275,12 @@ def _consistent(libname, ends, right_end_indexes, right_end_row_indexes, overlap
 def ref_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,
                                                  max_prog_length_diff=1.0, p=None):
     return _consistent("ref", ends, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, p)
+
+
+def shim_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,
+                                                  max_prog_length_diff=1.0, p=None):
+    """the reference's make_consistent_partial_order_alignments SYMBOL as re-exported by the shim (GPU needed)"""
+    return _consistent("shim", ends, ri, rr, ov, window_size, max_prog_rows, max_prog_length_diff, p)
 
 
 def oracle_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_size=10000, max_prog_rows=5000,

@@ -1,0 +1,47 @@
+"""Drop-in check (B200): the reference's OWN compiled bar/impl/poaBarAligner.o, relinked so that its two MSA entry
+points are the ones shim/cactus_bar_shim.c exports on top of libbarb200 (oracle/Makefile: libbar_shim.so), must return
+the same Msa matrices as the unmodified reference library. This is the link a Cactus build makes.
+Both libraries are built in the CPU container (they need /root/reference) and travel to the GPU box prebuilt; the
+test is skipped only when they were never built."""
+import numpy as np
+import pytest
+
+import _golden as G
+import _reflib as R
+from _synth import family, to_ascii, two_end_problem
+
+pytestmark = pytest.mark.gpu
+
+needs_libs = pytest.mark.skipif(not (R.have_bar_shim() and R.have_bar_ref()),
+                                reason="oracle/_ref/libbar_shim.so / libbar_ref.so not built (needs /root/reference at build time)")
+
+
+@needs_libs
+def test_shim_golden_windows_and_two_ends():
+    for c in G.window_cases():
+        m = R.shim_msa_make_partial_order_alignment(c["strs"], window_size=c["win"])
+        assert m.shape == c["msa"].shape and np.array_equal(m, c["msa"]), c["id"]
+    for c in G.two_end_cases():
+        ms = R.shim_make_consistent_partial_order_alignments(c["ends"], c["ri"], c["rr"], c["ov"], window_size=c["win"])
+        for a, b in zip(ms, c["msas"]):
+            assert a.shape == b.shape and np.array_equal(a, b), c["id"]
+
+
+@needs_libs
+def test_shim_vs_reference_library():
+    rng = np.random.default_rng(314)
+    for it in range(10):
+        K = int(rng.integers(1, 9))
+        L = int(rng.choice([10, 80, 300, 900]))
+        strs = [to_ascii(s) for s in family(rng, K, L, sub=0.05, ins=0.02, dele=0.02, nfrac=0.01)]
+        for win in (50, 10000):
+            a = R.shim_msa_make_partial_order_alignment(strs, window_size=win)
+            b = R.ref_msa_make_partial_order_alignment(strs, window_size=win)
+            assert a.shape == b.shape and np.array_equal(a, b), (it, win)
+    for it in range(4):
+        K = int(rng.integers(1, 8))
+        ends, ri, rr, ov = two_end_problem(rng, K, int(rng.choice([20, 150])), sub=0.05, ins=0.02, dele=0.02)
+        a = R.shim_make_consistent_partial_order_alignments(ends, ri, rr, ov)
+        b = R.ref_make_consistent_partial_order_alignments(ends, ri, rr, ov)
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y), it
