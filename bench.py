@@ -79,10 +79,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """host threads the box really gives us: affinity mask capped by the cgroup CPU quota (the GPU boxes show 128
+    logical CPUs but run the container under a 16-CPU quota; oversubscribing them makes the CPU arm slower, not faster)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
 def cpu_baseline(n_seq, lens, flat, cells, budget_s=20.0):
     """reference CPU path on the host cores, bounded sample (about budget_s seconds of wall time)"""
     import _reflib as R
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     K = K_SEQS
     # calibrate on a few ends, then size the sample
     n0 = min(len(n_seq), max(2, threads))
@@ -125,7 +138,7 @@ def main():
             return 0
         import _reflib as R
         n_seq, lens, flat = cb.synth_ends(0, E, K_SEQS, L_BP)
-        threads = os.cpu_count() or 1
+        threads = usable_cores()
         # cells of the sample from the oracle/reference itself (bounded): per-end count through the trace is slow, so
         # use the port's cell counter on the sample actually timed
         K = K_SEQS
@@ -266,7 +279,7 @@ def main():
             cpu, n_cpu, secs = cpu_baseline(n_seq, lens, flat, cells, args.cpu_budget)
             line["cpu_baseline"] = cpu
         except Exception as e:  # noqa: BLE001
-            line["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+            line["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": usable_cores(), "kind": "unavailable", "sample": str(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -40,18 +40,71 @@ struct barb200_ctx {
     HostParams hp;
     int device = 0, sm_count = 0;
     size_t smem_optin = 0;
-    std::mutex mu;
+    std::mutex mu;                      // serialises device batches (one kernel owns the slot arena at a time)
+    std::mutex err_mu, cache_mu;
     std::string err;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // kernels + result copies
+    cudaStream_t copy_stream = nullptr; // uploads of the NEXT chunk while a kernel runs
+    // grow-only cache of device blocks for the per-stage buffers (cudaMalloc / cudaFree per call cost milliseconds
+    // and cudaFree synchronises the device, which would stall the upload / kernel overlap)
+    std::vector<std::pair<void *, size_t>> free_blocks; size_t cached_bytes = 0;
+    uint8_t *h_pinned = nullptr; size_t h_pinned_bytes = 0;   // pinned staging buffer for the MSA download
     uint8_t *d_slots = nullptr; size_t slots_bytes = 0;
     int *d_planes = nullptr; size_t planes_bytes = 0;
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
 };
 
 namespace barb200 {
-void set_error(barb200_ctx *ctx, const std::string &msg) { if (ctx) ctx->err = msg; }
-int host_threads(barb200_ctx *ctx) { return ctx->p.host_threads > 0 ? ctx->p.host_threads : omp_get_max_threads(); }
+void set_error(barb200_ctx *ctx, const std::string &msg) { if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = msg; } }
+// threads for host-side work: the OpenMP default capped by the cgroup CPU quota (containers on big hosts often see
+// all logical CPUs but may only use a few; oversubscribing them slows the packing / guide-tree loops down)
+static int usable_host_threads() {
+    int n = omp_get_max_threads();
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char q[64]; long long period = 0;
+        if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            const long long quota = atoll(q);
+            const int lim = (int)((quota + period / 2) / period);
+            if (lim >= 1 && lim < n) n = lim;
+        }
+        fclose(f);
+    }
+    return n;
+}
+int host_threads(barb200_ctx *ctx) {
+    static const int dflt = usable_host_threads();
+    return ctx->p.host_threads > 0 ? ctx->p.host_threads : dflt;
+}
 int default_progressive(barb200_ctx *ctx) { return ctx->p.progressive_poa; }
+}
+
+static cudaError_t ctx_alloc(barb200_ctx *ctx, void **p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    {
+        std::lock_guard<std::mutex> lk(ctx->cache_mu);
+        int best = -1;
+        for (size_t i = 0; i < ctx->free_blocks.size(); ++i)
+            if (ctx->free_blocks[i].second >= bytes && ctx->free_blocks[i].second <= 2 * bytes + (1 << 20) &&
+                (best < 0 || ctx->free_blocks[i].second < ctx->free_blocks[best].second)) best = (int)i;
+        if (best >= 0) { *p = ctx->free_blocks[best].first; ctx->cached_bytes -= ctx->free_blocks[best].second; ctx->free_blocks.erase(ctx->free_blocks.begin() + best); return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {       // give the cache back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(ctx->cache_mu);
+        for (auto &b : ctx->free_blocks) cudaFree(b.first);
+        ctx->free_blocks.clear(); ctx->cached_bytes = 0;
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+static size_t block_size_of(size_t bytes) { return (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; }
+static void ctx_free(barb200_ctx *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(ctx->cache_mu);
+    if (ctx->cached_bytes + block_size_of(bytes) > ((size_t)4 << 30) || ctx->free_blocks.size() >= 64) { cudaFree(p); return; }
+    ctx->free_blocks.emplace_back(p, block_size_of(bytes)); ctx->cached_bytes += block_size_of(bytes);
 }
 
 #define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
@@ -99,6 +152,7 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     P.inf_min = std::max(std::max(INT32_MIN + P.min_mis, INT32_MIN + oe1), INT32_MIN + oe2) + 512 * std::max(P.e1, P.e2);
     ctx->hp = HostParams{p->k, p->w, p->min_w, p->progressive_poa};
     for (int i = 0; i < kNumKernels; ++i) cudaFuncSetAttribute(kKernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kKernels[i].scratch);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
     return ctx;
 }
@@ -109,6 +163,9 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
     if (ctx->d_slots) cudaFree(ctx->d_slots);
     if (ctx->d_planes) cudaFree(ctx->d_planes);
     if (ctx->d_clk) cudaFree(ctx->d_clk);
+    for (auto &b : ctx->free_blocks) cudaFree(b.first);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -140,22 +197,22 @@ struct barb200_stage {
     std::vector<JobDesc> desc;
     int64_t msa_bytes = 0;
     bool worst_case = false;
-    // device
+    // device: one block from the context's cache holds all per-stage arrays
+    void *d_block = nullptr; size_t d_block_bytes = 0;
     uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr, *d_order = nullptr; int64_t *d_soff = nullptr;
     JobDesc *d_desc = nullptr; int *d_msa_len = nullptr, *d_status = nullptr, *d_next = nullptr; long long *d_cells = nullptr;
     // sizing
     SlotLayout lay; int T = 0, slots = 0, kernel_class = 0; size_t dyn_smem = 0;
     // results of the last run
     std::vector<int> status, msa_len; std::vector<long long> cells;
-    std::vector<uint8_t> h_msa;
     barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;
     int64_t launches = 0; bool ran = false;
     uint64_t clk[6] = {0, 0, 0, 0, 0, 0};
 };
 
 static void stage_free_device(barb200_stage *st) {
-    cudaFree(st->d_seqs); cudaFree(st->d_msa); cudaFree(st->d_lens); cudaFree(st->d_order); cudaFree(st->d_soff);
-    cudaFree(st->d_desc); cudaFree(st->d_msa_len); cudaFree(st->d_status); cudaFree(st->d_next); cudaFree(st->d_cells);
+    ctx_free(st->ctx, st->d_block, st->d_block_bytes);
+    st->d_block = nullptr; st->d_block_bytes = 0;
     st->d_seqs = st->d_msa = nullptr; st->d_lens = st->d_order = nullptr; st->d_soff = nullptr; st->d_desc = nullptr;
     st->d_msa_len = st->d_status = st->d_next = nullptr; st->d_cells = nullptr;
 }
@@ -304,18 +361,22 @@ static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const
     if (n_jobs == 0) { *out = st; return BARB200_OK; }
     int rc = plan_stage(st);
     if (rc) { delete st; return rc; }
-    // device buffers + upload
-    auto dalloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16); };
-    cudaError_t e = cudaSuccess;
-    if ((e = dalloc((void **)&st->d_seqs, nb)) != cudaSuccess || (e = dalloc((void **)&st->d_lens, ns * 4)) != cudaSuccess ||
-        (e = dalloc((void **)&st->d_order, ns * 4)) != cudaSuccess || (e = dalloc((void **)&st->d_soff, ns * 8)) != cudaSuccess ||
-        (e = dalloc((void **)&st->d_desc, n_jobs * sizeof(JobDesc))) != cudaSuccess || (e = dalloc((void **)&st->d_msa, st->msa_bytes)) != cudaSuccess ||
-        (e = dalloc((void **)&st->d_msa_len, n_jobs * 4)) != cudaSuccess || (e = dalloc((void **)&st->d_status, n_jobs * 4)) != cudaSuccess ||
-        (e = dalloc((void **)&st->d_cells, n_jobs * 8)) != cudaSuccess || (e = dalloc((void **)&st->d_next, 4)) != cudaSuccess) {
+    // device buffers (one cached block) + upload on the copy stream, so that it overlaps a running kernel
+    size_t off = 0;
+    auto sub = [&](size_t bytes) { size_t r = off; off = (off + std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return r; };
+    const size_t o_seqs = sub(nb), o_lens = sub(ns * 4), o_order = sub(ns * 4), o_soff = sub(ns * 8), o_desc = sub(n_jobs * sizeof(JobDesc)),
+                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4);
+    cudaError_t e = ctx_alloc(ctx, &st->d_block, off);
+    if (e != cudaSuccess) {
         cudaGetLastError(); set_error(ctx, std::string("cudaMalloc(stage) failed: ") + cudaGetErrorString(e));
-        stage_free_device(st); delete st; return BARB200_ENOMEM;
+        delete st; return BARB200_ENOMEM;
     }
-    cudaStream_t s = ctx->stream;
+    st->d_block_bytes = off;
+    uint8_t *blk = (uint8_t *)st->d_block;
+    st->d_seqs = blk + o_seqs; st->d_lens = (int *)(blk + o_lens); st->d_order = (int *)(blk + o_order); st->d_soff = (int64_t *)(blk + o_soff);
+    st->d_desc = (JobDesc *)(blk + o_desc); st->d_msa = blk + o_msa; st->d_msa_len = (int *)(blk + o_msa_len); st->d_status = (int *)(blk + o_status);
+    st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next);
+    cudaStream_t s = ctx->copy_stream;
     if ((e = cudaMemcpyAsync(st->d_seqs, seqs, nb, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_order, st->order.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
@@ -428,12 +489,7 @@ static int stage_fetch_locked(barb200_stage *st, uint8_t **msa_out, int *msa_len
     if (!st->ran) { set_error(ctx, "stage_fetch before stage_run"); return BARB200_EINVAL; }
     if (st->n_jobs == 0) return BARB200_OK;
     cudaSetDevice(ctx->device);
-    st->msa_len.resize(st->n_jobs); st->cells.resize(st->n_jobs); st->h_msa.resize(st->msa_bytes);
-    cudaStream_t s = ctx->stream;
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->msa_len.data(), st->d_msa_len, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->cells.data(), st->d_cells, st->n_jobs * 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->h_msa.data(), st->d_msa, st->msa_bytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    // the retry stage first: it shares the context's pinned staging buffer
     std::vector<uint8_t *> r_out; std::vector<int> r_len; std::vector<int64_t> r_cells;
     if (st->retry) {
         const size_t n = st->retry_jobs.size();
@@ -441,6 +497,20 @@ static int stage_fetch_locked(barb200_stage *st, uint8_t **msa_out, int *msa_len
         int rc = stage_fetch_locked(st->retry, r_out.data(), r_len.data(), r_cells.data());
         if (rc) return rc;
     }
+    st->msa_len.resize(st->n_jobs); st->cells.resize(st->n_jobs);
+    if ((size_t)st->msa_bytes > ctx->h_pinned_bytes) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
+        const size_t want = (size_t)st->msa_bytes + ((size_t)st->msa_bytes >> 2);
+        if (cudaMallocHost((void **)&ctx->h_pinned, want) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMallocHost failed"); return BARB200_ENOMEM; }
+        ctx->h_pinned_bytes = want;
+    }
+    uint8_t *h_msa = ctx->h_pinned;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->msa_len.data(), st->d_msa_len, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->cells.data(), st->d_cells, st->n_jobs * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_msa, st->d_msa, st->msa_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
     std::vector<int64_t> redo_pos(st->n_jobs, -1);
     for (size_t i = 0; i < st->retry_jobs.size(); ++i) redo_pos[st->retry_jobs[i]] = (int64_t)i;
     int oom = 0;
@@ -460,7 +530,7 @@ static int stage_fetch_locked(barb200_stage *st, uint8_t **msa_out, int *msa_len
         if (msa_out) {
             uint8_t *o = (uint8_t *)malloc((size_t)K * (ml > 0 ? ml : 1));
             if (!o) { oom = 1; msa_out[j] = nullptr; continue; }
-            const uint8_t *src = st->h_msa.data() + st->desc[j].msa_off;
+            const uint8_t *src = h_msa + st->desc[j].msa_off;
             for (int i = 0; i < K; ++i) memcpy(o + (size_t)i * ml, src + (size_t)i * st->desc[j].msa_stride, ml);
             msa_out[j] = o;
         }

@@ -48,6 +48,75 @@ __device__ __forceinline__ int4 ld4cg(const int *p) { return __ldcg(reinterpret_
 __device__ __forceinline__ void st4(int *p, int a, int b, int c, int d) { *reinterpret_cast<int4 *>(p) = make_int4(a, b, c, d); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
+
+// ---- the two per-thread passes over a row's 16 cells, in a branch-free form -------------------------------------
+// "A space" of the F scans: A1'[k] = H'[k] + k*e1 (the constant -o1 is applied when F is read back), so
+// F1[j] = max_{k<j} A1'[k] - o1 - j*e1 and the scan identity is inf_min + beg*e1 + o1. MASKED = some of the thread's
+// columns lie outside [beg, end] (they must come out as exactly inf_min).
+template <bool MASKED>
+__device__ __forceinline__ void row_pass1(int (&H)[CPT], int (&E1)[CPT], int (&E2)[CPT], const int *mrow, const uint32_t (&qc)[2],
+                                          int j0, int beg, int end, int NEG, int je1, int je2, int e1, int e2, int &agg1, int &agg2) {
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+        const int s = mrow[(qc[e >> 3] >> ((e & 7) * 4)) & 7];
+        int h = __vimax3_s32(H[e] + s, E1[e], E2[e]);                    // H' = max(M + s, E1, E2), :1033,1050
+        if (MASKED) {
+            const bool inb = (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
+            h = inb ? h : NEG; E1[e] = inb ? E1[e] : NEG; E2[e] = inb ? E2[e] : NEG;
+        }
+        H[e] = h;
+        agg1 = __viaddmax_s32(h, je1 + e * e1, agg1); agg2 = __viaddmax_s32(h, je2 + e * e2, agg2);
+    }
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E2)[CPT], int P1, int P2, int j0, int beg, int end, int NEG,
+                                          int je1, int je2, int e1, int e2, int o1, int o2, int *rowp, int PS, int nT, int tt, int &tmax) {
+    const int oe1 = o1 + e1, oe2 = o2 + e2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int f1[4], f2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = q * 4 + u, u1 = je1 + e * e1, u2 = je2 + e * e2;
+            f1[u] = P1 - o1 - u1; f2[u] = P2 - o2 - u2;                  // F[j] = max_{k<j} A'[k] - o - j*e
+            P1 = __viaddmax_s32(H[e], u1, P1); P2 = __viaddmax_s32(H[e], u2, P2);
+            int h = __vimax3_s32(H[e], f1[u], f2[u]);                    // :1067
+            int x1 = __viaddmax_s32(E1[e], -e1, h - oe1);                // E for the next rows, :1070-1071
+            int x2 = __viaddmax_s32(E2[e], -e2, h - oe2);
+            if (MASKED) {
+                const bool inb = (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
+                h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG; f1[u] = inb ? f1[u] : NEG; f2[u] = inb ? f2[u] : NEG;
+            }
+            H[e] = h; E1[e] = x1; E2[e] = x2;
+            tmax = max(tmax, h);
+        }
+        const int o = (q * nT + tt) << 2;
+        st4(rowp + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
+        st4(rowp + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
+        st4(rowp + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
+        st4(rowp + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
+        st4(rowp + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
+    }
+}
+
+// left/right-most column of the thread's cells that attain v (only in-band cells count)
+template <bool MASKED>
+__device__ __forceinline__ void row_argmax(const int (&H)[CPT], int v, int j0, int beg, int end, int &tl, int &tr) {
+#pragma unroll
+    for (int e = CPT - 1; e >= 0; --e) {
+        bool eq = H[e] == v;
+        if (MASKED) eq = eq && (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
+        tl = eq ? j0 + e : tl;
+    }
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+        bool eq = H[e] == v;
+        if (MASKED) eq = eq && (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
+        tr = eq ? j0 + e : tr;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // banded convex-gap DP of query q[1..L] against the sorted graph. All threads of the CTA; L + 1 <= 16 * blockDim.x.
 // Returns the number of banded cells (sum of dp_end-dp_beg+1), or -1 if the planes outgrew the slot.
@@ -59,7 +128,7 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
     const int NEG = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int w = P.wb + (int)(P.wf * L);                                    // abpoa_align_simd.c:474
     const int pn = reference_lane_count(P, L, node_n);
-    const int j0 = tid * CPT;
+    const int j0 = tid * CPT, je1 = j0 * e1, je2 = j0 * e2;
 
     // query codes of my 16 columns, 4 bits each (column j scores against q_j = qg[j-1]; column 0 and columns past the
     // query score 0, abpoa_align_simd.c:536)
@@ -134,16 +203,17 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
         const int t0 = beg / CPT, nT = end / CPT - t0 + 1, PS = nT * CPT, tt = tid - t0;
         if (cur_off + 5LL * PS > d.plane_cap) return -1;        // uniform across the CTA
         const bool active = tt >= 0 && tt < nT;
-        const bool full = j0 >= beg && j0 + CPT - 1 <= end;     // all 16 of my columns inside the band
+        // masking is decided per WARP (no divergent double execution): a warp whose active threads all lie inside the band
+        // runs the unmasked passes
+        const bool wfull = __all_sync(FULL, !active || (j0 >= beg && j0 + CPT - 1 <= end));
         const int *mrow = S.smat + 8 * b;
 
         // H of the column left of my first one, previous row
         int hl = __shfl_up_sync(FULL, prev_active ? H[CPT - 1] : NEG, 1);
         if (lane == 0) hl = warp > 0 ? S.wM[par ^ 1][3][warp - 1] : NEG;
 
-        const int id1 = NEG + beg * e1, id2 = NEG + beg * e2;   // identities of the two scans ("A space")
+        const int id1 = NEG + beg * e1 + P.o1, id2 = NEG + beg * e2 + P.o2;   // identities of the two scans ("A space")
         int agg1 = id1, agg2 = id2;
-        const int c1 = (j0 + 1) * e1 - oe1, c2 = (j0 + 1) * e2 - oe2;     // A[e] = H'[e] + c + e*e_ext
         if (active) {
             // M candidates: H[e] <- H_pred[e-1]; E candidates stay in E1/E2 (previous row = predecessor case)
             if (has_prev && prev_active) {
@@ -175,24 +245,8 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
                 }
                 if (ptt >= 1 && ptt <= pnT) H[0] = max(H[0], __ldcg(Hp + (((3 * pnT + ptt - 1) << 2) | 3)));
             }
-            // H' = max(M + s, E1, E2) (:1033,1050) and the thread's scan aggregates
-            if (full) {
-#pragma unroll
-                for (int e = 0; e < CPT; ++e) {
-                    const int s = mrow[(qc[e >> 3] >> ((e & 7) * 4)) & 7];
-                    H[e] = max3(H[e] + s, E1[e], E2[e]);
-                    agg1 = max(agg1, H[e] + c1 + e * e1); agg2 = max(agg2, H[e] + c2 + e * e2);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < CPT; ++e) {
-                    const int j = j0 + e;
-                    const int s = mrow[(qc[e >> 3] >> ((e & 7) * 4)) & 7];
-                    if (j < beg || j > end) { H[e] = NEG; E1[e] = NEG; E2[e] = NEG; }
-                    else H[e] = max3(H[e] + s, E1[e], E2[e]);
-                    agg1 = max(agg1, H[e] + c1 + e * e1); agg2 = max(agg2, H[e] + c2 + e * e2);
-                }
-            }
+            if (wfull) row_pass1<false>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
+            else row_pass1<true>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
         }
         // ---- exclusive prefix maximum over the row: warp shuffle scan + redux over warp aggregates ----
         int inc1 = agg1, inc2 = agg2;
@@ -210,39 +264,19 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
             const int wv1 = lane < warp ? S.wF[par][0][lane] : id1, wv2 = lane < warp ? S.wF[par][1][lane] : id2;
             P1 = max(__reduce_max_sync(FULL, wv1), ex1); P2 = max(__reduce_max_sync(FULL, wv2), ex2);
         }
-        int tmax = NEG - 1000, tleft = 0x7fffffff, tright = -1;   // thread-local row max bookkeeping
+        int tmax = NEG - 1000;
         if (active) {
-            int *rowp = d.planes + cur_off;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int f1[4], f2[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = q * 4 + u, j = j0 + e;
-                    f1[u] = P1 - j * e1; f2[u] = P2 - j * e2;                       // F[j] = max_{k<j} A[k] - j*e
-                    P1 = max(P1, H[e] + c1 + e * e1); P2 = max(P2, H[e] + c2 + e * e2);
-                    if (!full && (j < beg || j > end)) { H[e] = NEG; f1[u] = NEG; f2[u] = NEG; }
-                    else {
-                        const int h = max3(H[e], f1[u], f2[u]);                      // :1067
-                        H[e] = h;
-                        E1[e] = max(E1[e] - e1, h - oe1);                            // E for the next rows, :1070-1071
-                        E2[e] = max(E2[e] - e2, h - oe2);
-                        if (h > tmax) { tmax = h; tleft = j; tright = j; } else if (h == tmax) tright = j;
-                    }
-                }
-                const int o = (q * nT + tt) << 2;
-                st4(rowp + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
-                st4(rowp + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
-                st4(rowp + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
-                st4(rowp + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
-                st4(rowp + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
-            }
+            if (wfull) row_pass2<false>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, d.planes + cur_off, PS, nT, tt, tmax);
+            else row_pass2<true>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, d.planes + cur_off, PS, nT, tt, tmax);
         }
         // ---- left/right-most argmax of H over the band (simd_abpoa_max_in_row, :1107-1119) ----
         {
             const int wmax = __reduce_max_sync(FULL, tmax);
-            const int wl = __reduce_min_sync(FULL, tmax == wmax ? tleft : 0x7fffffff);
-            const int wr = __reduce_max_sync(FULL, tmax == wmax ? tright : -1);
+            int tleft = 0x7fffffff, tright = -1;
+            if (active && tmax == wmax) {
+                if (wfull) row_argmax<false>(H, wmax, j0, beg, end, tleft, tright); else row_argmax<true>(H, wmax, j0, beg, end, tleft, tright);
+            }
+            const int wl = __reduce_min_sync(FULL, tleft), wr = __reduce_max_sync(FULL, tright);
             if (lane == 0) { S.wM[par][0][warp] = wmax; S.wM[par][1][warp] = wl; S.wM[par][2][warp] = wr; }
             if (lane == 31) S.wM[par][3][warp] = active ? H[CPT - 1] : NEG;
         }
