@@ -25,7 +25,8 @@ class BarB200Error(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libbarb200.so")
+    # BARB200_LIB: development aid (A/B runs of differently tuned builds); the product loads the in-tree library
+    return os.environ.get("BARB200_LIB") or os.path.join(_HERE, "libbarb200.so")
 
 
 class _CParams(C.Structure):

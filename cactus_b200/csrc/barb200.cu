@@ -11,7 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include "host_api.h"
@@ -43,14 +45,14 @@ struct barb200_ctx {
     std::mutex mu;                      // serialises device batches (one kernel owns the slot arena at a time)
     std::mutex err_mu, cache_mu;
     std::string err;
-    cudaStream_t stream = nullptr;      // kernels + result copies
     cudaStream_t copy_stream = nullptr; // uploads of the NEXT chunk while a kernel runs
+    // two slot arenas with a stream each: chunk k+1's kernel is queued (and its CTAs move in as chunk k's retire) while
+    // chunk k's results are downloaded and unpacked
+    struct Arena { uint8_t *d_slots = nullptr; size_t slots_bytes = 0; int *d_planes = nullptr; size_t planes_bytes = 0; cudaStream_t stream = nullptr; } ar[2];
     // grow-only cache of device blocks for the per-stage buffers (cudaMalloc / cudaFree per call cost milliseconds
     // and cudaFree synchronises the device, which would stall the upload / kernel overlap)
     std::vector<std::pair<void *, size_t>> free_blocks; size_t cached_bytes = 0;
     uint8_t *h_pinned = nullptr; size_t h_pinned_bytes = 0;   // pinned staging buffer for the MSA download
-    uint8_t *d_slots = nullptr; size_t slots_bytes = 0;
-    int *d_planes = nullptr; size_t planes_bytes = 0;
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
 };
 
@@ -153,20 +155,23 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     ctx->hp = HostParams{p->k, p->w, p->min_w, p->progressive_poa};
     for (int i = 0; i < kNumKernels; ++i) cudaFuncSetAttribute(kKernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kKernels[i].scratch);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
+    for (int a = 0; a < 2; ++a)
+        if (cudaStreamCreateWithFlags(&ctx->ar[a].stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
     return ctx;
 }
 
 extern "C" void barb200_destroy(barb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->d_slots) cudaFree(ctx->d_slots);
-    if (ctx->d_planes) cudaFree(ctx->d_planes);
+    for (int a = 0; a < 2; ++a) {
+        if (ctx->ar[a].d_slots) cudaFree(ctx->ar[a].d_slots);
+        if (ctx->ar[a].d_planes) cudaFree(ctx->ar[a].d_planes);
+        if (ctx->ar[a].stream) cudaStreamDestroy(ctx->ar[a].stream);
+    }
     if (ctx->d_clk) cudaFree(ctx->d_clk);
     for (auto &b : ctx->free_blocks) cudaFree(b.first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -207,6 +212,7 @@ struct barb200_stage {
     std::vector<int> status, msa_len; std::vector<long long> cells;
     barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;
     int64_t launches = 0; bool ran = false;
+    int arena = 0; double mem_share = 1.0; cudaEvent_t e0 = nullptr, e1 = nullptr; bool launched = false;
     uint64_t clk[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -221,6 +227,7 @@ extern "C" void barb200_stage_destroy(barb200_stage *st) {
     if (!st) return;
     cudaSetDevice(st->ctx->device);
     if (st->retry) barb200_stage_destroy(st->retry);
+    if (st->e0) { cudaEventDestroy(st->e0); cudaEventDestroy(st->e1); }
     stage_free_device(st);
     delete st;
 }
@@ -266,6 +273,7 @@ static int plan_stage(barb200_stage *st) {
     for (int i = 0; i < kNumKernels; ++i) if ((int64_t)kKernels[i].T * CPT >= max_len + 1 && kKernels[i].T >= ctx->p.threads_per_block) { cls = i; break; }
     if (cls < 0) { set_error(ctx, "a sequence is longer than the device engine's row limit (16383 bases per window)"); return BARB200_EINVAL; }
     st->T = kKernels[cls].T; st->kernel_class = cls; st->dyn_smem = kKernels[cls].scratch;
+    if (getenv("BARB200_SCRATCH_KB")) st->dyn_smem = (size_t)atoi(getenv("BARB200_SCRATCH_KB")) * 1024;   // tuning aid
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kKernels[cls].fn, st->T, st->dyn_smem));
     if (per_sm < 1) { set_error(ctx, "kernel does not fit on an SM with the requested configuration"); return BARB200_EINVAL; }
@@ -274,7 +282,8 @@ static int plan_stage(barb200_stage *st) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
     const double frac = ctx->p.mem_fraction > 0 ? ctx->p.mem_fraction : 0.85;
-    const double budget = (double)(free_b + ctx->slots_bytes + ctx->planes_bytes) * frac;
+    const barb200_ctx::Arena &AR = ctx->ar[st->arena];
+    const double budget = (double)(free_b + AR.slots_bytes + AR.planes_bytes) * frac * st->mem_share;
     const double per_slot = (double)Y.slot_bytes + (double)Y.plane_cap * 4.0;
     if (per_slot > budget) { set_error(ctx, "a single job needs more device memory than is available"); return BARB200_ENOMEM; }
     slots = std::max<int64_t>(1, std::min<int64_t>(slots, (int64_t)(budget / per_slot)));
@@ -282,18 +291,19 @@ static int plan_stage(barb200_stage *st) {
     return BARB200_OK;
 }
 
-static int ensure_arena(barb200_ctx *ctx, size_t slots_bytes, size_t planes_bytes, size_t clk_entries) {
-    if (slots_bytes > ctx->slots_bytes) {
-        if (ctx->d_slots) cudaFree(ctx->d_slots);
-        ctx->d_slots = nullptr; ctx->slots_bytes = 0;
-        if (cudaMalloc(&ctx->d_slots, slots_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(slots) failed"); return BARB200_ENOMEM; }
-        ctx->slots_bytes = slots_bytes;
+static int ensure_arena(barb200_ctx *ctx, int a, size_t slots_bytes, size_t planes_bytes, size_t clk_entries) {
+    barb200_ctx::Arena &AR = ctx->ar[a];
+    if (slots_bytes > AR.slots_bytes) {
+        if (AR.d_slots) cudaFree(AR.d_slots);
+        AR.d_slots = nullptr; AR.slots_bytes = 0;
+        if (cudaMalloc(&AR.d_slots, slots_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(slots) failed"); return BARB200_ENOMEM; }
+        AR.slots_bytes = slots_bytes;
     }
-    if (planes_bytes > ctx->planes_bytes) {
-        if (ctx->d_planes) cudaFree(ctx->d_planes);
-        ctx->d_planes = nullptr; ctx->planes_bytes = 0;
-        if (cudaMalloc(&ctx->d_planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(planes) failed"); return BARB200_ENOMEM; }
-        ctx->planes_bytes = planes_bytes;
+    if (planes_bytes > AR.planes_bytes) {
+        if (AR.d_planes) cudaFree(AR.d_planes);
+        AR.d_planes = nullptr; AR.planes_bytes = 0;
+        if (cudaMalloc(&AR.d_planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(planes) failed"); return BARB200_ENOMEM; }
+        AR.planes_bytes = planes_bytes;
     }
     if (clk_entries > ctx->clk_entries) {
         if (ctx->d_clk) cudaFree(ctx->d_clk);
@@ -305,11 +315,11 @@ static int ensure_arena(barb200_ctx *ctx, size_t slots_bytes, size_t planes_byte
 }
 
 static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
-                       const int *progressive, bool worst_case, barb200_stage **out) {
+                       const int *progressive, bool worst_case, barb200_stage **out, int arena = 0, double mem_share = 1.0) {
     if (!ctx || n_jobs < 0 || (n_jobs > 0 && (!n_seq || !seq_lens || !seqs))) { set_error(ctx, "bad arguments"); return BARB200_EINVAL; }
     cudaSetDevice(ctx->device);
     barb200_stage *st = new barb200_stage();
-    st->ctx = ctx; st->n_jobs = n_jobs; st->worst_case = worst_case;
+    st->ctx = ctx; st->n_jobs = n_jobs; st->worst_case = worst_case; st->arena = arena; st->mem_share = mem_share;
     st->n_seq.assign(n_seq, n_seq + n_jobs);
     st->job_len_off.resize(n_jobs + 1); st->job_seq_off.resize(n_jobs + 1);
     st->job_sum_len.resize(n_jobs); st->job_max_len.resize(n_jobs);
@@ -396,39 +406,55 @@ extern "C" int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int 
     return stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, out);
 }
 
-static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
+static int stage_run_locked(barb200_stage *st, float *kernel_ms);
+
+// queue the stage's kernel (+ the download of the job statuses) on its arena's stream; returns without waiting
+static int stage_launch(barb200_stage *st) {
     barb200_ctx *ctx = st->ctx;
     cudaSetDevice(ctx->device);
-    st->launches = 0; st->ran = false;
-    if (kernel_ms) *kernel_ms = 0.f;
-    if (st->n_jobs == 0) { st->ran = true; return BARB200_OK; }
+    st->launches = 0; st->ran = false; st->launched = false;
+    if (st->n_jobs == 0) return BARB200_OK;
     if (st->retry) { barb200_stage_destroy(st->retry); st->retry = nullptr; st->retry_jobs.clear(); }
     const size_t clk_n = ctx->p.collect_phase_clocks ? (size_t)st->slots * PH_N : 0;
-    int rc = ensure_arena(ctx, (size_t)st->lay.slot_bytes * st->slots, (size_t)st->lay.plane_cap * 4 * st->slots, clk_n);
+    int rc = ensure_arena(ctx, st->arena, (size_t)st->lay.slot_bytes * st->slots, (size_t)st->lay.plane_cap * 4 * st->slots, clk_n);
     if (rc) return rc;
-    cudaStream_t s = ctx->stream;
+    barb200_ctx::Arena &AR = ctx->ar[st->arena];
+    cudaStream_t s = AR.stream;
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4, s));
     if (clk_n) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_clk, 0, clk_n * sizeof(unsigned long long), s));
     BatchArgs A;
     A.jobs = st->d_desc; A.n_jobs = (int)st->n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff; A.order = st->d_order;
     A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
-    A.slots = ctx->d_slots; A.planes = ctx->d_planes; A.next_job = st->d_next;
+    A.slots = AR.d_slots; A.planes = AR.d_planes; A.next_job = st->d_next;
     A.phase_clk = clk_n ? ctx->d_clk : nullptr;
     A.serial_phases = getenv("BARB200_DEBUG_SERIAL") ? 1 : 0;
+    A.bfs_order = getenv("BARB200_DEBUG_BFS") ? 1 : 0;
     A.scratch_bytes = (int)st->dyn_smem; A.lay = st->lay; A.P = ctx->P;
-    cudaEvent_t e0, e1;
-    CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
-    CUDA_TRY(ctx, cudaEventRecord(e0, s));
+    if (!st->e0) { CUDA_TRY(ctx, cudaEventCreate(&st->e0)); CUDA_TRY(ctx, cudaEventCreate(&st->e1)); }
+    CUDA_TRY(ctx, cudaEventRecord(st->e0, s));
     kKernels[st->kernel_class].fn<<<st->slots, st->T, st->dyn_smem, s>>>(A);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { set_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; }
-    CUDA_TRY(ctx, cudaEventRecord(e1, s));
+    CUDA_TRY(ctx, cudaEventRecord(st->e1, s));
     st->status.resize(st->n_jobs);
     CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    st->launched = true;
+    return BARB200_OK;
+}
+
+// wait for the stage's kernel, collect its device time, re-run capacity misses in a worst-case-sized stage
+static int stage_finish(barb200_stage *st, float *kernel_ms) {
+    barb200_ctx *ctx = st->ctx;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (st->n_jobs == 0) { st->ran = true; return BARB200_OK; }
+    if (!st->launched) { set_error(ctx, "stage_finish without stage_launch"); return BARB200_EINVAL; }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->ar[st->arena].stream;
     cudaError_t se = cudaStreamSynchronize(s);
     if (se != cudaSuccess) { set_error(ctx, std::string("kernel execution: ") + cudaGetErrorString(se)); return BARB200_ECUDA; }
-    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
-    st->launches = 1;
+    float ms = 0.f; cudaEventElapsedTime(&ms, st->e0, st->e1);
+    st->launches = 1; st->launched = false;
+    const size_t clk_n = ctx->p.collect_phase_clocks ? (size_t)st->slots * PH_N : 0;
     if (clk_n) {
         std::vector<unsigned long long> h(clk_n);
         CUDA_TRY(ctx, cudaMemcpy(h.data(), ctx->d_clk, clk_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -457,7 +483,7 @@ static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
             r_seqs.insert(r_seqs.end(), h_seqs.begin() + st->job_seq_off[j], h_seqs.begin() + st->job_seq_off[j + 1]);
         }
         barb200_stage *rs = nullptr;
-        rc = stage_build(ctx, (int64_t)redo.size(), r_nseq.data(), r_lens.data(), r_seqs.data(), r_prog.data(), true, &rs);
+        int rc = stage_build(ctx, (int64_t)redo.size(), r_nseq.data(), r_lens.data(), r_seqs.data(), r_prog.data(), true, &rs, st->arena, st->mem_share);
         if (rc) return rc;
         float rms = 0.f;
         rc = stage_run_locked(rs, &rms);
@@ -468,6 +494,12 @@ static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
     if (kernel_ms) *kernel_ms = ms;
     st->ran = true;
     return BARB200_OK;
+}
+
+static int stage_run_locked(barb200_stage *st, float *kernel_ms) {
+    int rc = stage_launch(st);
+    if (rc) return rc;
+    return stage_finish(st, kernel_ms);
 }
 
 extern "C" int barb200_stage_run(barb200_stage *st, float *kernel_ms) {
@@ -506,7 +538,7 @@ static int stage_fetch_locked(barb200_stage *st, uint8_t **msa_out, int *msa_len
         ctx->h_pinned_bytes = want;
     }
     uint8_t *h_msa = ctx->h_pinned;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->ar[st->arena].stream;
     CUDA_TRY(ctx, cudaMemcpyAsync(st->msa_len.data(), st->d_msa_len, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->cells.data(), st->d_cells, st->n_jobs * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_msa, st->d_msa, st->msa_bytes, cudaMemcpyDeviceToHost, s));
@@ -545,11 +577,74 @@ extern "C" int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *ms
     return stage_fetch_locked(st, msa_out, msa_len, cells);
 }
 
+// Large batches are cut into chunks that flow through a two-deep pipeline: a producer thread packs chunk k+1, computes
+// its guide trees and uploads it on the copy stream while chunk k's kernel runs; chunk k+1's kernel is queued on the
+// other arena's stream before chunk k's results are downloaded and unpacked. The chunk size keeps several waves of
+// resident CTAs per launch so that launch tails stay small.
+static int batch_pipelined(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
+                           const int *progressive, uint8_t **msa_out, int *msa_len, int64_t *cells, int64_t chunk) {
+    const int64_t n_chunks = (n_jobs + chunk - 1) / chunk;
+    std::vector<int64_t> first(n_chunks + 1), len_off(n_chunks + 1), seq_off(n_chunks + 1);
+    {
+        int64_t ns = 0, nb = 0;
+        for (int64_t j = 0, c = 0; j <= n_jobs; ++j) {
+            if (j == c * chunk || j == n_jobs) { first[c] = j; len_off[c] = ns; seq_off[c] = nb; ++c; }
+            if (j < n_jobs) for (int i = 0; i < n_seq[j]; ++i) { nb += seq_lens[ns]; ++ns; }
+        }
+    }
+    struct Item { barb200_stage *st = nullptr; int rc = 0; };
+    std::vector<Item> items(n_chunks);
+    std::mutex qmu; std::condition_variable qcv; int64_t produced = 0, consumed = 0; bool abort = false;
+    std::thread producer([&]() {
+        cudaSetDevice(ctx->device);
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            { std::unique_lock<std::mutex> lk(qmu); qcv.wait(lk, [&] { return abort || produced - consumed < 2; }); if (abort) return; }
+            Item it;
+            it.rc = stage_build(ctx, first[c + 1] - first[c], n_seq + first[c], seq_lens + len_off[c], seqs + seq_off[c],
+                                progressive ? progressive + first[c] : nullptr, false, &it.st, (int)(c & 1), 0.5);
+            { std::lock_guard<std::mutex> lk(qmu); items[c] = it; ++produced; }
+            qcv.notify_all();
+            if (it.rc) return;
+        }
+    });
+    auto wait_for = [&](int64_t c) { std::unique_lock<std::mutex> lk(qmu); qcv.wait(lk, [&] { return produced > c; }); return items[c]; };
+    int rc = 0;
+    Item cur = wait_for(0);
+    rc = cur.rc;
+    if (!rc) rc = stage_launch(cur.st);
+    for (int64_t c = 0; c < n_chunks && !rc; ++c) {
+        Item nxt;
+        if (c + 1 < n_chunks) { nxt = wait_for(c + 1); rc = nxt.rc; if (!rc) rc = stage_launch(nxt.st); }
+        if (!rc) rc = stage_finish(cur.st, nullptr);
+        if (!rc) rc = stage_fetch_locked(cur.st, msa_out ? msa_out + first[c] : nullptr, msa_len ? msa_len + first[c] : nullptr, cells ? cells + first[c] : nullptr);
+        if (cur.st) { barb200_stage_destroy(cur.st); items[c].st = nullptr; }
+        { std::lock_guard<std::mutex> lk(qmu); ++consumed; }
+        qcv.notify_all();
+        cur = nxt;
+    }
+    { std::lock_guard<std::mutex> lk(qmu); abort = true; }
+    qcv.notify_all();
+    producer.join();
+    if (rc) {   // drain: wait for queued kernels, release whatever was built or returned
+        cudaDeviceSynchronize();
+        for (auto &it : items) if (it.st) { barb200_stage_destroy(it.st); it.st = nullptr; }
+        if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) { free(msa_out[j]); msa_out[j] = nullptr; }
+    }
+    return rc;
+}
+
 extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
                                      const uint8_t *seqs, const int *progressive, uint8_t **msa_out, int *msa_len,
                                      int64_t *cells) {
     if (!ctx) return BARB200_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) msa_out[j] = nullptr;
+    // chunking: at least ~2 waves of the densest CTA class per chunk, at most 8 chunks; profiling runs stay single-stage
+    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
+    if (n_jobs >= 2 * min_chunk && !ctx->p.collect_phase_clocks && !getenv("BARB200_NO_PIPELINE")) {
+        const int64_t n_chunks = std::min<int64_t>(8, n_jobs / min_chunk);
+        return batch_pipelined(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, msa_out, msa_len, cells, (n_jobs + n_chunks - 1) / n_chunks);
+    }
     barb200_stage *st = nullptr;
     int rc = stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, &st);
     if (rc) return rc;

@@ -39,6 +39,25 @@ __device__ int cta_excl_scan(int *a, int n, int *ws) {
     return total;
 }
 
+// inclusive prefix maximum of a[0..n) in place. All threads of the CTA. ws: >= 32 ints of shared memory.
+__device__ void cta_incl_max_scan(int *a, int n, int *ws) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    const int chunk = (n + T - 1) / T, b = min(n, tid * chunk), e = min(n, b + chunk);
+    int s = INT32_MIN;
+    for (int i = b; i < e; ++i) s = max(s, a[i]);
+    int inc = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc = max(inc, v); }
+    int run = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) run = INT32_MIN;
+    __syncthreads();
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    for (int k = 0; k < nw; ++k) if (k < warp) run = max(run, ws[k]);
+    for (int i = b; i < e; ++i) { run = max(run, a[i]); a[i] = run; }
+    __syncthreads();
+}
+
 // ---- edge lists with atomic pool allocation (same lists as graph_add_edge; chunk placement in the pool differs) ----
 __device__ __forceinline__ bool grow_in_par(Graph &g, int t) {
     if (g.in_n[t] < g.in_cap[t]) return true;
@@ -94,7 +113,10 @@ __device__ void cta_add_first_sequence(Graph &g, const uint8_t *seq, int len, in
         g.out_off[from] = 2 * i; g.out_n[from] = 1; g.out_cap[from] = 2; g.out_id[2 * i] = to; g.out_w[2 * i] = 1;
         for (int w = 0; w < W; ++w) { g.out_rid[(int64_t)(2 * i) * W + w] = w == rw ? rb : 0; g.out_rid[(int64_t)(2 * i + 1) * W + w] = 0; }
         if (i < len) { g.base[to] = seq[i]; g.aln_n[to] = 0; }
+        // topological order of the chain: SRC, 2, 3, ..., len+1, SINK
+        g.index_to_node[i + 1] = to; g.node_to_index[to] = i + 1;
     }
+    if (tid == 0) { g.index_to_node[0] = SRC_ID; g.node_to_index[SRC_ID] = 0; }
     if (tid == 0) { g.node_n = len + 2; g.in_used = 2 * (len + 1); g.out_used = 2 * (len + 1); }
     __syncthreads();
 }
@@ -140,10 +162,39 @@ __device__ void cta_fuse_alignment(Graph &g, const uint8_t *seq, int L, const ui
     if (tid == 0) g.node_n = first_new + n_new;
     __syncthreads();
     if (g.err) return;
+    // (3b) topological order WITHOUT re-running abPOA's BFS (abpoa_graph.c:221-266): the DP, the traceback and the MSA
+    // do not depend on which topological order the rows are swept in (bands, scores and tie-breaks are per node / per
+    // in-edge order; tests/test_host_graph_code.py pins this against the reference), so the previous order is kept for
+    // the old nodes and the new ones are spliced in: a new node aligned to x goes to the end of x's block of aligned
+    // nodes (blocks stay contiguous, so the order stays topological for the quotient by aligned groups, which later
+    // fusions rely on when they move a path onto an aligned sibling), an inserted new node opens a block right after
+    // the block of the previous path node. Anchors are non-decreasing along the path, so the new node with rank m
+    // (in query order) and anchor A lands at A + 1 + m, and old index i moves up by the number of anchors < i.
+    {
+        int *anc = g.remain, *cnt = g.msa_rank, *new_i2n = g.tmp1;
+        const int n_old = first_new;
+        for (int q = tid; q < L; q += T) {
+            const int v = node_of[q];
+            int e = v < first_new ? g.node_to_index[v] : -1;
+            for (int k = 0; k < g.aln_n[v]; ++k) { const int a = g.aln_id[v * 4 + k]; if (a < first_new) e = max(e, g.node_to_index[a]); }
+            anc[q] = e;
+        }
+        for (int i = tid; i < n_old; i += T) cnt[i] = 0;
+        __syncthreads();
+        cta_incl_max_scan(anc, L, ws);
+        for (int q = tid; q < L; q += T) if (node_of[q] >= first_new) atomicAdd(&cnt[max(anc[q], 0)], 1);
+        __syncthreads();
+        cta_excl_scan(cnt, n_old, ws);                                   // cnt[i] = number of new nodes anchored before old index i
+        for (int i = tid; i < n_old; i += T) new_i2n[i + cnt[i]] = g.index_to_node[i];
+        for (int q = tid; q < L; q += T) { const int v = node_of[q]; if (v >= first_new) new_i2n[max(anc[q], 0) + 1 + (v - first_new)] = v; }
+        __syncthreads();
+        for (int k = tid; k < first_new + n_new; k += T) { const int v = new_i2n[k]; g.index_to_node[k] = v; g.node_to_index[v] = k; }
+        __syncthreads();
+    }
     // (4) the L+1 edges of the path; check_edge = neither end is new (abpoa_graph.c:731-766)
     for (int q = tid; q <= L; q += T) {
         const int from = q == 0 ? SRC_ID : node_of[q - 1], to = q == L ? SINK_ID : node_of[q];
-        const int fresh = (q > 0 && is_new[q - 1]) || (q < L && is_new[q]);
+        const int fresh = (q > 0 && from >= first_new) || (q < L && to >= first_new);
         graph_add_edge_par(g, from, to, fresh ? 0 : 1, read_id);
     }
     __syncthreads();
@@ -264,8 +315,14 @@ __device__ void bfs_index_smem(Graph &g, const BfsScratch &B) {      // one thre
 }
 
 // All threads. scr/scr_bytes: dynamic shared memory scratch; ws: >= 32 ints shared.
-__device__ void cta_topo_sort(Graph &g, RowTables &rt, unsigned char *scr, int scr_bytes, int *ws) {
+// have_order: index_to_node / node_to_index already hold a valid topological order (cta_fuse_alignment keeps it up to
+// date), so only the edge sort, max_remain and the row tables are (re)built.
+__device__ void cta_topo_sort(Graph &g, RowTables &rt, unsigned char *scr, int scr_bytes, int *ws, bool have_order) {
     const int tid = threadIdx.x, T = blockDim.x, n = g.node_n;
+    if (have_order) {
+        for (int v = tid; v < n; v += T) graph_sort_node_edges(g, v);
+        __syncthreads();
+    } else {
     // ---- (1) BFS index + edge sort ----
     for (int v = tid; v < n; v += T) g.tmp0[v] = g.out_n[v];
     __syncthreads();
@@ -304,6 +361,7 @@ __device__ void cta_topo_sort(Graph &g, RowTables &rt, unsigned char *scr, int s
         for (int v = tid; v < n; v += T) graph_sort_node_edges(g, v);
     }
     __syncthreads();
+    }
     // ---- (2) max_remain by pointer jumping: d[v] = #steps to SINK along the first heaviest out edge ----
     int *nx[2] = {g.tmp0, g.tmp1}, *dd[2] = {g.remain, g.msa_rank};
     for (int v = tid; v < n; v += T) {
@@ -334,6 +392,69 @@ __device__ void cta_topo_sort(Graph &g, RowTables &rt, unsigned char *scr, int s
     __syncthreads();
     cta_excl_scan(g.tmp0, n, ws);
     for (int r = tid; r < n; r += T) graph_build_row(g, rt, r, g.tmp0[r]);
+    __syncthreads();
+}
+
+
+// abpoa_DFS_set_msa_rank (abpoa_graph.c:359-410) + msa_len (abpoa_output.c:157) on a shared-memory copy of the out-edge
+// CSR (one thread walks; the rest stage and write back). Falls back to the global-memory walk when the graph does not
+// fit the scratch. All threads; *msa_len_out is in shared memory.
+__device__ void cta_msa_rank(Graph &g, unsigned char *scr, int scr_bytes, int *ws, int *msa_len_out) {
+    const int tid = threadIdx.x, T = blockDim.x, n = g.node_n;
+    for (int v = tid; v < n; v += T) g.tmp0[v] = g.out_n[v];
+    __syncthreads();
+    const int E = cta_excl_scan(g.tmp0, n, ws);
+    if (n < 65535 && bfs_scratch_bytes(n, E) + 2 * (size_t)n <= (size_t)scr_bytes) {
+        BfsScratch B;
+        B.optr = reinterpret_cast<uint32_t *>(scr);
+        B.odst = reinterpret_cast<uint16_t *>(B.optr + n + 1);
+        B.queue = B.odst + E; B.indeg = B.queue + n;
+        uint16_t *rk = B.indeg + n;
+        B.alnn = reinterpret_cast<uint8_t *>(rk + n);
+        for (int v = tid; v < n; v += T) {
+            const uint32_t o = (uint32_t)g.tmp0[v];
+            B.optr[v] = o;
+            const int oo = g.out_off[v], on = g.out_n[v];
+            for (int i = 0; i < on; ++i) B.odst[o + i] = (uint16_t)g.out_id[oo + i];
+            B.indeg[v] = (uint16_t)g.in_n[v]; B.alnn[v] = g.aln_n[v];
+        }
+        if (tid == 0) B.optr[n] = (uint32_t)E;
+        __syncthreads();
+        if (tid == 0) {
+            uint16_t *st = B.queue;
+            int sp = 0, rank = 0, len = -1;
+            st[sp++] = SRC_ID; rk[SRC_ID] = 0xffff;
+            while (sp > 0) {
+                const int cur = st[--sp];
+                if (rk[cur] == 0xffff) {
+                    rk[cur] = (uint16_t)rank;
+                    for (int i = 0; i < B.alnn[cur]; ++i) rk[g.aln_id[cur * 4 + i]] = (uint16_t)rank;
+                    ++rank;
+                }
+                if (cur == SINK_ID) { len = (int)rk[SINK_ID] - 1; break; }
+                const uint32_t o0 = B.optr[cur], o1 = B.optr[cur + 1];
+                for (uint32_t i = o0; i < o1; ++i) {
+                    const int o = B.odst[i];
+                    const int left = (int)B.indeg[o] - 1; B.indeg[o] = (uint16_t)left;
+                    if (left == 0) {
+                        const int an = B.alnn[o];
+                        bool ok = true;
+                        for (int j = 0; j < an; ++j) if (B.indeg[g.aln_id[o * 4 + j]] != 0) { ok = false; break; }
+                        if (!ok) continue;
+                        st[sp++] = (uint16_t)o; rk[o] = 0xffff;
+                        for (int j = 0; j < an; ++j) { const int a = g.aln_id[o * 4 + j]; st[sp++] = (uint16_t)a; rk[a] = 0xffff; }
+                    }
+                }
+            }
+            if (len < 0) g.err = JOB_ERR_TOPO;
+            *msa_len_out = len;
+        }
+        __syncthreads();
+        if (g.err) return;
+        for (int v = tid; v < n; v += T) g.msa_rank[v] = rk[v];
+    } else {
+        if (tid == 0) *msa_len_out = graph_msa_rank(g);
+    }
     __syncthreads();
 }
 

@@ -47,6 +47,16 @@ struct KShared {
 __device__ __forceinline__ int4 ld4cg(const int *p) { return __ldcg(reinterpret_cast<const int4 *>(p)); }
 __device__ __forceinline__ void st4(int *p, int a, int b, int c, int d) { *reinterpret_cast<int4 *>(p) = make_int4(a, b, c, d); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
+// 256-bit global accesses (sm_100: STG.E.256 / LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void st8(int *p, int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+struct int8v { int v[8]; };
+__device__ __forceinline__ int8v ld8cg(const int *p) {
+    int8v r;
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p) : "memory");
+    return r;
+}
 
 
 // ---- the two per-thread passes over a row's 16 cells, in a branch-free form -------------------------------------
@@ -71,14 +81,14 @@ __device__ __forceinline__ void row_pass1(int (&H)[CPT], int (&E1)[CPT], int (&E
 
 template <bool MASKED>
 __device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E2)[CPT], int P1, int P2, int j0, int beg, int end, int NEG,
-                                          int je1, int je2, int e1, int e2, int o1, int o2, int *rowp, int PS, int nT, int tt, int &tmax) {
+                                          int je1, int je2, int e1, int e2, int o1, int o2, int *tp, int &tmax) {
     const int oe1 = o1 + e1, oe2 = o2 + e2;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        int f1[4], f2[4];
+    for (int oc = 0; oc < 2; ++oc) {
+        int f1[8], f2[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = q * 4 + u, u1 = je1 + e * e1, u2 = je2 + e * e2;
+        for (int u = 0; u < 8; ++u) {
+            const int e = oc * 8 + u, u1 = je1 + e * e1, u2 = je2 + e * e2;
             f1[u] = P1 - o1 - u1; f2[u] = P2 - o2 - u2;                  // F[j] = max_{k<j} A'[k] - o - j*e
             P1 = __viaddmax_s32(H[e], u1, P1); P2 = __viaddmax_s32(H[e], u2, P2);
             int h = __vimax3_s32(H[e], f1[u], f2[u]);                    // :1067
@@ -91,43 +101,51 @@ __device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E
             H[e] = h; E1[e] = x1; E2[e] = x2;
             tmax = max(tmax, h);
         }
-        const int o = (q * nT + tt) << 2;
-        st4(rowp + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
-        st4(rowp + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
-        st4(rowp + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
-        st4(rowp + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
-        st4(rowp + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
+        st8(tp + 3 * CPT + oc * 8, f1[0], f1[1], f1[2], f1[3], f1[4], f1[5], f1[6], f1[7]);
+        st8(tp + 4 * CPT + oc * 8, f2[0], f2[1], f2[2], f2[3], f2[4], f2[5], f2[6], f2[7]);
+    }
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc) {
+        st8(tp + oc * 8, H[oc * 8], H[oc * 8 + 1], H[oc * 8 + 2], H[oc * 8 + 3], H[oc * 8 + 4], H[oc * 8 + 5], H[oc * 8 + 6], H[oc * 8 + 7]);
+        st8(tp + CPT + oc * 8, E1[oc * 8], E1[oc * 8 + 1], E1[oc * 8 + 2], E1[oc * 8 + 3], E1[oc * 8 + 4], E1[oc * 8 + 5], E1[oc * 8 + 6], E1[oc * 8 + 7]);
+        st8(tp + 2 * CPT + oc * 8, E2[oc * 8], E2[oc * 8 + 1], E2[oc * 8 + 2], E2[oc * 8 + 3], E2[oc * 8 + 4], E2[oc * 8 + 5], E2[oc * 8 + 6], E2[oc * 8 + 7]);
     }
 }
 
 // left/right-most column of the thread's cells that attain v (only in-band cells count)
 template <bool MASKED>
 __device__ __forceinline__ void row_argmax(const int (&H)[CPT], int v, int j0, int beg, int end, int &tl, int &tr) {
+    unsigned m = 0;
 #pragma unroll
-    for (int e = CPT - 1; e >= 0; --e) {
-        bool eq = H[e] == v;
-        if (MASKED) eq = eq && (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
-        tl = eq ? j0 + e : tl;
+    for (int e = 0; e < CPT; ++e) m |= H[e] == v ? 1u << e : 0u;
+    if (MASKED) {
+        const int lo = max(beg - j0, 0), hi = min(end - j0, CPT - 1);
+        m &= (2u << hi) - (1u << lo);
     }
-#pragma unroll
-    for (int e = 0; e < CPT; ++e) {
-        bool eq = H[e] == v;
-        if (MASKED) eq = eq && (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
-        tr = eq ? j0 + e : tr;
-    }
+    if (m) { tl = j0 + __ffs(m) - 1; tr = j0 + 31 - __clz(m); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // banded convex-gap DP of query q[1..L] against the sorted graph. All threads of the CTA; L + 1 <= 16 * blockDim.x.
 // Returns the number of banded cells (sum of dp_end-dp_beg+1), or -1 if the planes outgrew the slot.
 // ---------------------------------------------------------------------------------------------------------
-__device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__restrict__ qg, int L) {
+__device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__restrict__ qg, int L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const Graph &g = S.g; const RowTables &rt = S.rt; DpState &d = S.d;
-    const int node_n = g.node_n, R = node_n - 1;
+    const PoaParams &P = A.P;
+    // slot arrays addressed from the kernel parameters (not through the pointers cached in shared memory), so that the
+    // compiler knows they are global memory and emits LDG/STG instead of generic accesses
+    uint8_t *const sb = A.slots + (int64_t)blockIdx.x * A.lay.slot_bytes;
+    const RowRec *const rec_tab = reinterpret_cast<const RowRec *>(sb + A.lay.o_row_rec);
+    const int *const pre_row = reinterpret_cast<const int *>(sb + A.lay.o_pre_row);
+    RowInfo *const info = reinterpret_cast<RowInfo *>(sb + A.lay.o_row_info);
+    int64_t *const row_off = reinterpret_cast<int64_t *>(sb + A.lay.o_row_off);
+    int *const planes = A.planes + (int64_t)blockIdx.x * A.lay.plane_cap;
+    const int64_t plane_cap = A.lay.plane_cap;
+    const int node_n = S.g.node_n, R = node_n - 1;
     const int NEG = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int w = P.wb + (int)(P.wf * L);                                    // abpoa_align_simd.c:474
-    const int pn = reference_lane_count(P, L, node_n);
+    const int pn_shift = reference_lane_count(P, L, node_n) == 16 ? 4 : 3;
+    static_assert(CPT == 16, "shifts below assume 16 columns per thread");
     const int j0 = tid * CPT, je1 = j0 * e1, je2 = j0 * e2;
 
     // query codes of my 16 columns, 4 bits each (column j scores against q_j = qg[j-1]; column 0 and columns past the
@@ -147,61 +165,66 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
 
     // ---- row 0 (simd_abpoa_cg_first_dp, :617-688) ----
     {
-        const int dd = L - rt.rec[0].rd;
+        const int dd = L - rec_tab[0].rd;
         prev_end = min(L, max(0, dd) + w);
         const int nT = prev_end / CPT + 1;
-        if (5LL * nT * CPT > d.plane_cap) return -1;
+        if ((int64_t)nT * TB > plane_cap) return -1;
         prev_active = tid < nT;
         if (prev_active) {
-            int *row = d.planes; const int PS = nT * CPT;
+            int *tp = planes + tid * TB;
+            int f1[CPT], f2[CPT];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int f1[4], f2[4];
+            for (int e = 0; e < CPT; ++e) {
+                const int j = j0 + e;
+                if (j == 0) { H[e] = 0; E1[e] = -oe1; E2[e] = -oe2; f1[e] = NEG; f2[e] = NEG; }
+                else if (j <= prev_end) { f1[e] = -P.o1 - e1 * j; f2[e] = -P.o2 - e2 * j; H[e] = max(f1[e], f2[e]); E1[e] = NEG; E2[e] = NEG; }
+                else { H[e] = E1[e] = E2[e] = f1[e] = f2[e] = NEG; }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = q * 4 + u, j = j0 + e;
-                    if (j == 0) { H[e] = 0; E1[e] = -oe1; E2[e] = -oe2; f1[u] = NEG; f2[u] = NEG; }
-                    else if (j <= prev_end) { f1[u] = -P.o1 - e1 * j; f2[u] = -P.o2 - e2 * j; H[e] = max(f1[u], f2[u]); E1[e] = NEG; E2[e] = NEG; }
-                    else { H[e] = E1[e] = E2[e] = f1[u] = f2[u] = NEG; }
-                }
-                const int o = (q * nT + tid) << 2;
-                st4(row + o, H[q * 4], H[q * 4 + 1], H[q * 4 + 2], H[q * 4 + 3]);
-                st4(row + PS + o, E1[q * 4], E1[q * 4 + 1], E1[q * 4 + 2], E1[q * 4 + 3]);
-                st4(row + 2 * PS + o, E2[q * 4], E2[q * 4 + 1], E2[q * 4 + 2], E2[q * 4 + 3]);
-                st4(row + 3 * PS + o, f1[0], f1[1], f1[2], f1[3]);
-                st4(row + 4 * PS + o, f2[0], f2[1], f2[2], f2[3]);
+            for (int oc = 0; oc < 2; ++oc) {
+                st8(tp + oc * 8, H[oc * 8], H[oc * 8 + 1], H[oc * 8 + 2], H[oc * 8 + 3], H[oc * 8 + 4], H[oc * 8 + 5], H[oc * 8 + 6], H[oc * 8 + 7]);
+                st8(tp + CPT + oc * 8, E1[oc * 8], E1[oc * 8 + 1], E1[oc * 8 + 2], E1[oc * 8 + 3], E1[oc * 8 + 4], E1[oc * 8 + 5], E1[oc * 8 + 6], E1[oc * 8 + 7]);
+                st8(tp + 2 * CPT + oc * 8, E2[oc * 8], E2[oc * 8 + 1], E2[oc * 8 + 2], E2[oc * 8 + 3], E2[oc * 8 + 4], E2[oc * 8 + 5], E2[oc * 8 + 6], E2[oc * 8 + 7]);
+                st8(tp + 3 * CPT + oc * 8, f1[oc * 8], f1[oc * 8 + 1], f1[oc * 8 + 2], f1[oc * 8 + 3], f1[oc * 8 + 4], f1[oc * 8 + 5], f1[oc * 8 + 6], f1[oc * 8 + 7]);
+                st8(tp + 4 * CPT + oc * 8, f2[oc * 8], f2[oc * 8 + 1], f2[oc * 8 + 2], f2[oc * 8 + 3], f2[oc * 8 + 4], f2[oc * 8 + 5], f2[oc * 8 + 6], f2[oc * 8 + 7]);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < CPT; ++e) H[e] = E1[e] = E2[e] = NEG;
         }
         if (lane == 31) S.wM[0][3][warp] = prev_active ? H[CPT - 1] : NEG;
-        if (tid == 0) { RowInfo ri; ri.beg = 0; ri.end = prev_end; ri.left = 0; ri.right = 0; d.info[0] = ri; d.row_off[0] = 0; }
-        cur_off = 5LL * nT * CPT; cells = prev_end + 1;
+        if (tid == 0) { RowInfo ri; ri.beg = 0; ri.end = prev_end; ri.left = 0; ri.right = 0; info[0] = ri; row_off[0] = 0; }
+        cur_off = (int64_t)nT * TB; cells = prev_end + 1;
     }
     __syncthreads();
 
-    RowRec rec = rt.rec[R > 1 ? 1 : 0];
+    RowRec rec = rec_tab[R > 1 ? 1 : 0];
     for (int r = 1; r < R; ++r) {
         const int par = r & 1;
-        const RowRec nrec = rt.rec[r + 1 < R ? r + 1 : r];      // next row's record, in flight while this row computes
+        const RowRec nrec = rec_tab[r + 1 < R ? r + 1 : r];      // next row's record, in flight while this row computes
         // ---- band of the row (GET_AD_DP_BEGIN/END + lane-group snap, :946-960) ----
         const int b = rec.base_npre & 0xff, npre = rec.base_npre >> 8;
         const int dd = L - rec.rd;
         int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
         bool has_prev = false;
-        for (int k = 0; k < npre; ++k) {
-            const int p = k == 0 ? rec.pre0 : rt.pre_row[rec.pre_off + k];
-            int pl, pr, pb;
-            if (p == r - 1) { pl = prev_left; pr = prev_right; pb = prev_beg; has_prev = true; }
-            else { const RowInfo pi = d.info[p]; pl = pi.left; pr = pi.right; pb = pi.beg; }
-            maxL = min(maxL, pl + 1); maxR = max(maxR, pr + 1); min_pre_beg = min(min_pre_beg, pb);
+        if (npre == 1 && rec.pre0 == r - 1) {                       // the linear-chain case: everything is in registers
+            maxL = prev_left + 1; maxR = prev_right + 1; min_pre_beg = prev_beg; has_prev = true;
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < npre; ++k) {
+                const int p = k == 0 ? rec.pre0 : pre_row[rec.pre_off + k];
+                int pl, pr, pb;
+                if (p == r - 1) { pl = prev_left; pr = prev_right; pb = prev_beg; has_prev = true; }
+                else { const RowInfo pi = info[p]; pl = pi.left; pr = pi.right; pb = pi.beg; }
+                maxL = min(maxL, pl + 1); maxR = max(maxR, pr + 1); min_pre_beg = min(min_pre_beg, pb);
+            }
         }
+        const bool only_prev = npre == 1 && has_prev;
         int beg = max(0, min(maxL, dd) - w);
         const int end = min(L, max(maxR, dd) + w);
-        if (beg / pn < min_pre_beg / pn) beg = min_pre_beg;
-        const int t0 = beg / CPT, nT = end / CPT - t0 + 1, PS = nT * CPT, tt = tid - t0;
-        if (cur_off + 5LL * PS > d.plane_cap) return -1;        // uniform across the CTA
+        if ((beg >> pn_shift) < (min_pre_beg >> pn_shift)) beg = min_pre_beg;
+        const int t0 = beg >> 4, nT = (end >> 4) - t0 + 1, tt = tid - t0;
+        if (cur_off + (int64_t)nT * TB > plane_cap) return -1;        // uniform across the CTA
         const bool active = tt >= 0 && tt < nT;
         // masking is decided per WARP (no divergent double execution): a warp whose active threads all lie inside the band
         // runs the unmasked passes
@@ -226,24 +249,26 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
                 if (has_prev) H[0] = hl;
             }
             // predecessors further back: from the planes in global memory
-            for (int k = 0; k < npre; ++k) {
-                const int p = k == 0 ? rec.pre0 : rt.pre_row[rec.pre_off + k];
+#pragma unroll 1
+            for (int k = only_prev ? npre : 0; k < npre; ++k) {
+                const int p = k == 0 ? rec.pre0 : pre_row[rec.pre_off + k];
                 if (p == r - 1) continue;
-                const RowInfo pi = d.info[p];
-                const int pt0 = pi.beg / CPT, pnT = pi.end / CPT - pt0 + 1, pPS = pnT * CPT, ptt = tid - pt0;
-                const int *Hp = d.planes + d.row_off[p];
+                const RowInfo pi = info[p];
+                const int pt0 = pi.beg >> 4, pnT = (pi.end >> 4) - pt0 + 1, ptt = tid - pt0;
+                const int *Hp = planes + row_off[p] + (int64_t)ptt * TB;      // my block of row p (if stored)
                 if (ptt >= 0 && ptt < pnT) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int o = (q * pnT + ptt) << 2;
-                        const int4 h = ld4cg(Hp + o), a = ld4cg(Hp + pPS + o), c = ld4cg(Hp + 2 * pPS + o);
-                        H[q * 4 + 1] = max(H[q * 4 + 1], h.x); H[q * 4 + 2] = max(H[q * 4 + 2], h.y); H[q * 4 + 3] = max(H[q * 4 + 3], h.z);
-                        if (q < 3) H[q * 4 + 4] = max(H[q * 4 + 4], h.w);
-                        E1[q * 4] = max(E1[q * 4], a.x); E1[q * 4 + 1] = max(E1[q * 4 + 1], a.y); E1[q * 4 + 2] = max(E1[q * 4 + 2], a.z); E1[q * 4 + 3] = max(E1[q * 4 + 3], a.w);
-                        E2[q * 4] = max(E2[q * 4], c.x); E2[q * 4 + 1] = max(E2[q * 4 + 1], c.y); E2[q * 4 + 2] = max(E2[q * 4 + 2], c.z); E2[q * 4 + 3] = max(E2[q * 4 + 3], c.w);
+                    for (int oc = 0; oc < 2; ++oc) {
+                        const int8v h = ld8cg(Hp + oc * 8), a = ld8cg(Hp + CPT + oc * 8), c = ld8cg(Hp + 2 * CPT + oc * 8);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int e = oc * 8 + u;
+                            if (e + 1 < CPT) H[e + 1] = max(H[e + 1], h.v[u]);
+                            E1[e] = max(E1[e], a.v[u]); E2[e] = max(E2[e], c.v[u]);
+                        }
                     }
                 }
-                if (ptt >= 1 && ptt <= pnT) H[0] = max(H[0], __ldcg(Hp + (((3 * pnT + ptt - 1) << 2) | 3)));
+                if (ptt >= 1 && ptt <= pnT) H[0] = max(H[0], __ldcg(Hp - TB + CPT - 1));    // H[16*tid - 1]: last H of the left neighbour's block
             }
             if (wfull) row_pass1<false>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
             else row_pass1<true>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
@@ -266,8 +291,8 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
         }
         int tmax = NEG - 1000;
         if (active) {
-            if (wfull) row_pass2<false>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, d.planes + cur_off, PS, nT, tt, tmax);
-            else row_pass2<true>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, d.planes + cur_off, PS, nT, tt, tmax);
+            if (wfull) row_pass2<false>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, planes + cur_off + (int64_t)tt * TB, tmax);
+            else row_pass2<true>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, planes + cur_off + (int64_t)tt * TB, tmax);
         }
         // ---- left/right-most argmax of H over the band (simd_abpoa_max_in_row, :1107-1119) ----
         {
@@ -289,8 +314,8 @@ __device__ long long dp_sweep(KShared &S, const PoaParams &P, const uint8_t *__r
             prev_left = __reduce_min_sync(FULL, l); prev_right = __reduce_max_sync(FULL, rr);
         }
         prev_beg = beg; prev_end = end; prev_active = active;
-        if (tid == 0) { RowInfo ri; ri.beg = beg; ri.end = end; ri.left = prev_left; ri.right = prev_right; d.info[r] = ri; d.row_off[r] = cur_off; }
-        cur_off += 5LL * PS; cells += end - beg + 1;
+        if (tid == 0) { RowInfo ri; ri.beg = beg; ri.end = end; ri.left = prev_left; ri.right = prev_right; info[r] = ri; row_off[r] = cur_off; }
+        cur_off += (int64_t)nT * TB; cells += end - beg + 1;
         rec = nrec;
     }
     __syncthreads();
@@ -350,7 +375,7 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
                 PHASE_TICK(PH_FUSE);
             } else {
                 long long c = -2;
-                if (L + 1 <= CPT * (int)blockDim.x) c = dp_sweep(S, A.P, q, L);
+                if (L + 1 <= CPT * (int)blockDim.x) c = dp_sweep(S, A, q, L);
                 if (c < 0) { if (tid == 0) S.g.err = c == -2 ? JOB_ERR_QUERY_LEN : JOB_ERR_PLANE_CAP; c = 0; }
                 cells += c;
                 __syncthreads();
@@ -366,15 +391,16 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
             __syncthreads();
             if (S.g.err) break;
             if (A.serial_phases) { if (tid == 0) graph_topo_sort_serial(S.g, S.rt); __syncthreads(); }
-            else cta_topo_sort(S.g, S.rt, dyn_smem, A.scratch_bytes, ws);
+            else cta_topo_sort(S.g, S.rt, dyn_smem, A.scratch_bytes, ws, A.bfs_order == 0);
             PHASE_TICK(PH_TOPO);
             if (S.g.err) break;
         }
         __syncthreads();
         // ---- MSA (abpoa_generate_rc_msa, abpoa_output.c:149-176) ----
-        if (tid == 0 && !S.g.err) {
-            S.msa_len_s = graph_msa_rank(S.g);
-            if (!S.g.err && S.msa_len_s > jd.msa_stride) S.g.err = JOB_ERR_MSA_CAP;
+        if (!S.g.err) {
+            if (A.serial_phases) { if (tid == 0) S.msa_len_s = graph_msa_rank(S.g); __syncthreads(); }
+            else cta_msa_rank(S.g, dyn_smem, A.scratch_bytes, ws, &S.msa_len_s);
+            if (tid == 0 && !S.g.err && S.msa_len_s > jd.msa_stride) S.g.err = JOB_ERR_MSA_CAP;
         }
         __syncthreads();
         if (!S.g.err) {
@@ -398,7 +424,10 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
 //   up to 10239 (covers Cactus' 10 kbp window) -> 640 threads;  up to 16383 -> 1024 threads.
 extern "C" __global__ void __launch_bounds__(32, 16) poa_msa_kernel_t32(const BatchArgs A) { poa_msa_body(A); }
 extern "C" __global__ void __launch_bounds__(64, 8) poa_msa_kernel_t64(const BatchArgs A) { poa_msa_body(A); }
-extern "C" __global__ void __launch_bounds__(128, 4) poa_msa_kernel_t128(const BatchArgs A) { poa_msa_body(A); }
+#ifndef BARB200_T128_MINB
+#define BARB200_T128_MINB 4
+#endif
+extern "C" __global__ void __launch_bounds__(128, BARB200_T128_MINB) poa_msa_kernel_t128(const BatchArgs A) { poa_msa_body(A); }
 extern "C" __global__ void __launch_bounds__(256, 2) poa_msa_kernel_t256(const BatchArgs A) { poa_msa_body(A); }
 extern "C" __global__ void __launch_bounds__(640, 1) poa_msa_kernel_t640(const BatchArgs A) { poa_msa_body(A); }
 extern "C" __global__ void __launch_bounds__(1024, 1) poa_msa_kernel_t1024(const BatchArgs A) { poa_msa_body(A); }

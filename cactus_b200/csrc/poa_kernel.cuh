@@ -29,6 +29,7 @@ struct BatchArgs {
     int *next_job;              // work queue head
     unsigned long long *phase_clk;   // [gridDim.x * PH_N] clock64 per phase, or nullptr
     int serial_phases;          // debugging aid: 1 = run the graph phases in their serial reference form
+    int bfs_order;              // debugging aid: 1 = recompute abPOA's BFS order after every fusion instead of splicing
     int scratch_bytes;          // dynamic shared memory per CTA (topological sort scratch)
     SlotLayout lay;
     PoaParams P;

@@ -98,10 +98,11 @@ struct alignas(16) RowInfo {
 // Banded DP planes of the current alignment.
 // Column ownership is fixed: thread t of the CTA owns columns [CPT*t, CPT*t + CPT) of EVERY row, so the values of the
 // previous row stay in that thread's registers. A row with band [beg, end] is stored for the threads
-// t0 = beg/CPT .. t1 = end/CPT only (nT = t1-t0+1), as 5 consecutive planes (H, E1, E2, F1, F2) of nT*CPT ints at
-// planes + row_off[r]. Inside a plane the layout is "thread-blocked": quad q (4 adjacent columns) of thread t is at
-// int offset ((q*nT + (t-t0)) << 2), so that the 16-byte store of quad q by consecutive threads is one contiguous
-// run (full 32 B sectors, 512 B per warp instruction). Cells of the stored threads outside [beg, end] hold inf_min.
+// t0 = beg/CPT .. t1 = end/CPT only (nT = t1-t0+1), at planes + row_off[r], "thread-major": thread t's block of
+// 5*CPT ints = [H(16) | E1(16) | E2(16) | F1(16) | F2(16)] sits at int offset (t-t0)*5*CPT. A thread therefore writes its
+// 320 bytes of a row with ten 256-bit stores at immediate offsets from one pointer (full 32 B sectors; a warp covers one
+// contiguous 10 KB run), and reads a far predecessor's H/E1/E2 for its own columns with six 256-bit loads.
+// Cells of the stored threads outside [beg, end] hold inf_min.
 constexpr int CPT = 16;
 struct DpState {
     int *planes; int64_t plane_cap;     // ints
@@ -112,9 +113,10 @@ struct DpState {
 };
 
 // int offset of column j of `plane` inside the row's block (see DpState); j must lie in a stored thread's range
+constexpr int TB = 5 * CPT;   // ints per thread block of a row
 HD int64_t plane_index(int beg, int end, int plane, int j) {
-    const int t0 = beg / CPT, nT = end / CPT - t0 + 1, t = j / CPT, e = j % CPT;
-    return (int64_t)plane * nT * CPT + ((((e >> 2) * nT + (t - t0)) << 2) | (e & 3));
+    (void)end;
+    return (int64_t)(j / CPT - beg / CPT) * TB + plane * CPT + j % CPT;
 }
 HD int64_t row_ints(int beg, int end) { return 5LL * (end / CPT - beg / CPT + 1) * CPT; }
 

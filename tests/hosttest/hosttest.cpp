@@ -68,6 +68,53 @@ static long long emulate_sweep(const Graph &g, const RowTables &rt, DpState &d, 
     return cells;
 }
 
+
+// TEST-ONLY serial statement of the incremental topological order the device uses instead of re-running the BFS
+// (poa_cta.cuh: cta_fuse_alignment): the previous order stays valid for old nodes; a new node aligned to x is appended
+// to x's block of aligned nodes, an inserted (unaligned) new node opens a block right after the block of the previous
+// path node. Called AFTER graph_fuse_alignment; replays the cigar to find the node of every query base.
+static void incremental_order(Graph &g, const uint8_t *seq, const uint64_t *cigar, int n_cigar, int first_new, int n_old) {
+    std::vector<int> path;                                   // node of query base q
+    int next_new = first_new;
+    for (int c = 0; c < n_cigar; ++c) {
+        const int op = (int)(cigar[c] & 0xf);
+        if (op == CMATCH) {
+            const int node_id = (int)((cigar[c] >> 34) & 0x3fffffff), q = (int)((cigar[c] >> 4) & 0x3fffffff);
+            int v = node_id;
+            if (g.base[node_id] != seq[q]) v = graph_aligned_with_base(g, node_id, seq[q]);
+            if (v >= first_new) ++next_new;
+            path.push_back(v);
+        } else if (op == CINS) {
+            const int len = (int)((cigar[c] >> 4) & 0x3fffffff);
+            for (int k = 0; k < len; ++k) path.push_back(next_new++);
+        }
+    }
+    auto block_end = [&](int v) {                            // last old index of v's block of aligned nodes, -1 if none
+        int e = v < first_new ? g.node_to_index[v] : -1;
+        for (int k = 0; k < g.aln_n[v]; ++k) { const int a = g.aln_id[v * 4 + k]; if (a < first_new) e = std::max(e, g.node_to_index[a]); }
+        return e;
+    };
+    std::vector<std::vector<int>> after(n_old);              // new nodes to place after old index i, in path order
+    int anchor = 0;                                          // SRC's index
+    for (size_t q = 0; q < path.size(); ++q) {
+        const int v = path[q], e = block_end(v);
+        if (e >= 0) anchor = std::max(anchor, e);
+        if (v >= first_new) after[anchor].push_back(v);
+    }
+    std::vector<int> order;
+    for (int i = 0; i < n_old; ++i) { order.push_back(g.index_to_node[i]); for (int v : after[i]) order.push_back(v); }
+    for (size_t k = 0; k < order.size(); ++k) { g.index_to_node[k] = order[k]; g.node_to_index[order[k]] = (int)k; }
+    // the order must be topological for every edge AND for the quotient by aligned groups (a later fusion may move a
+    // path onto an aligned sibling): all members of a block are contiguous
+    if ((int)order.size() != g.node_n) g.err = JOB_ERR_TOPO;
+    for (int v = 0; v < g.node_n; ++v) {
+        for (int k = 0; k < g.out_n[v]; ++k) if (g.node_to_index[v] >= g.node_to_index[g.out_id[g.out_off[v] + k]]) g.err = JOB_ERR_TOPO;
+        int lo = g.node_to_index[v], hi = lo;
+        for (int k = 0; k < g.aln_n[v]; ++k) { lo = std::min(lo, g.node_to_index[g.aln_id[v * 4 + k]]); hi = std::max(hi, g.node_to_index[g.aln_id[v * 4 + k]]); }
+        if (hi - lo != g.aln_n[v]) g.err = JOB_ERR_TOPO;
+    }
+}
+
 // same word layout as oracle/ref_harness.c:ref_poa_msa_trace; returns malloc'd words
 extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const int *lens, const uint8_t *flat, int64_t *n_words, int *status) {
     PoaParams P; memcpy(P.mat, hp->mat, sizeof(P.mat));
@@ -117,9 +164,16 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
         for (int r = 0; r < n_rows; ++r) w.push_back(d.info[r].beg);
         for (int r = 0; r < n_rows; ++r) w.push_back(d.info[r].end);
         if (g.err) break;
+        const int n_old = g.node_n;
         if (a > 0) graph_fuse_alignment(g, q, d.cigar, d.n_cigar, read);
         if (g.err) break;
-        graph_topo_sort_serial(g, rt);
+        if (a > 0 && getenv("HOSTTEST_INCREMENTAL_ORDER")) {
+            // keep the previous order, splice the new nodes in; then the order independent parts of the sort
+            incremental_order(g, q, d.cigar, d.n_cigar, n_old, n_old);
+            for (int v = 0; v < g.node_n; ++v) graph_sort_node_edges(g, v);
+            graph_bfs_remain(g);
+            if (!g.err) graph_build_rows(g, rt);
+        } else graph_topo_sort_serial(g, rt);
     }
     *status = g.err;
     int msa_len = 0; std::vector<uint8_t> msa;

@@ -179,3 +179,26 @@ def test_errors_are_loud(engine):
         engine.poa_msa_batch([[np.array([], np.uint8), np.array([0, 1], np.uint8)]])
     with pytest.raises(cb.BarB200Error):
         cb.Engine(cb.PoaParams(partialOrderAlignmentGapOpenPenalty2=0))
+
+
+def test_pipelined_batch_equals_single_stage(engine, oracle_built):
+    """a batch large enough to be cut into pipelined chunks (producer thread, two slot arenas, two streams) returns
+    exactly what one single-stage launch returns; spot-checked against the oracle"""
+    rng = np.random.default_rng(46)
+    jobs = []
+    for it in range(2600):
+        K = int(rng.integers(2, 6))
+        L = int(rng.choice([8, 30, 70, 120]))
+        jobs.append(family(rng, K, L, sub=0.05, ins=0.02, dele=0.02))
+    msas, cells = engine.poa_msa_batch(jobs, return_cells=True)          # pipelined path (>= 2 * 8 * SMs jobs)
+    st = engine.stage(jobs)
+    st.run()
+    msas1, cells1 = st.fetch()
+    st.close()
+    assert len(msas) == len(msas1) == len(jobs)
+    for j in range(len(jobs)):
+        assert msas[j].shape == msas1[j].shape and np.array_equal(msas[j], msas1[j]), j
+    assert np.array_equal(np.asarray(cells), np.asarray(cells1))
+    for j in range(0, len(jobs), 173):
+        tr = R.oracle_poa_msa_trace(jobs[j])
+        assert np.array_equal(msas[j], tr["msa"]) and int(cells[j]) == tr["cells"], j
