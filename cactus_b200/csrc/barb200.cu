@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -436,8 +437,8 @@ static int stage_launch(barb200_stage *st) {
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { set_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; }
     CUDA_TRY(ctx, cudaEventRecord(st->e1, s));
-    st->status.resize(st->n_jobs);
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    // (no device-to-host copy here: into pageable memory it would block the host until the kernel is done and
+    // serialise the chunk pipeline; stage_finish fetches the statuses after its synchronisation)
     st->launched = true;
     return BARB200_OK;
 }
@@ -454,6 +455,9 @@ static int stage_finish(barb200_stage *st, float *kernel_ms) {
     if (se != cudaSuccess) { set_error(ctx, std::string("kernel execution: ") + cudaGetErrorString(se)); return BARB200_ECUDA; }
     float ms = 0.f; cudaEventElapsedTime(&ms, st->e0, st->e1);
     st->launches = 1; st->launched = false;
+    st->status.resize(st->n_jobs);
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
     const size_t clk_n = ctx->p.collect_phase_clocks ? (size_t)st->slots * PH_N : 0;
     if (clk_n) {
         std::vector<unsigned long long> h(clk_n);
@@ -581,6 +585,9 @@ extern "C" int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *ms
 // its guide trees and uploads it on the copy stream while chunk k's kernel runs; chunk k+1's kernel is queued on the
 // other arena's stream before chunk k's results are downloaded and unpacked. The chunk size keeps several waves of
 // resident CTAs per launch so that launch tails stay small.
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool timing_on() { static const bool on = getenv("BARB200_TIMING") != nullptr; return on; }
+
 static int batch_pipelined(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
                            const int *progressive, uint8_t **msa_out, int *msa_len, int64_t *cells, int64_t chunk) {
     const int64_t n_chunks = (n_jobs + chunk - 1) / chunk;
@@ -600,8 +607,10 @@ static int batch_pipelined(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, c
         for (int64_t c = 0; c < n_chunks; ++c) {
             { std::unique_lock<std::mutex> lk(qmu); qcv.wait(lk, [&] { return abort || produced - consumed < 2; }); if (abort) return; }
             Item it;
+            const double tb0 = now_ms();
             it.rc = stage_build(ctx, first[c + 1] - first[c], n_seq + first[c], seq_lens + len_off[c], seqs + seq_off[c],
                                 progressive ? progressive + first[c] : nullptr, false, &it.st, (int)(c & 1), 0.5);
+            if (timing_on()) fprintf(stderr, "barb200 timing: chunk %lld built in %.1f ms\n", (long long)c, now_ms() - tb0);
             { std::lock_guard<std::mutex> lk(qmu); items[c] = it; ++produced; }
             qcv.notify_all();
             if (it.rc) return;
@@ -615,8 +624,11 @@ static int batch_pipelined(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, c
     for (int64_t c = 0; c < n_chunks && !rc; ++c) {
         Item nxt;
         if (c + 1 < n_chunks) { nxt = wait_for(c + 1); rc = nxt.rc; if (!rc) rc = stage_launch(nxt.st); }
-        if (!rc) rc = stage_finish(cur.st, nullptr);
+        const double tf0 = now_ms(); float kms = 0.f;
+        if (!rc) rc = stage_finish(cur.st, &kms);
+        const double tf1 = now_ms();
         if (!rc) rc = stage_fetch_locked(cur.st, msa_out ? msa_out + first[c] : nullptr, msa_len ? msa_len + first[c] : nullptr, cells ? cells + first[c] : nullptr);
+        if (timing_on()) fprintf(stderr, "barb200 timing: chunk %lld waited %.1f ms for its kernel (%.1f ms on the device), fetched in %.1f ms\n", (long long)c, tf1 - tf0, kms, now_ms() - tf1);
         if (cur.st) { barb200_stage_destroy(cur.st); items[c].st = nullptr; }
         { std::lock_guard<std::mutex> lk(qmu); ++consumed; }
         qcv.notify_all();
@@ -640,17 +652,22 @@ extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) msa_out[j] = nullptr;
     // chunking: at least ~2 waves of the densest CTA class per chunk, at most 8 chunks; profiling runs stay single-stage
-    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
+    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;   // >= 2 waves of 128-thread CTAs per chunk
     if (n_jobs >= 2 * min_chunk && !ctx->p.collect_phase_clocks && !getenv("BARB200_NO_PIPELINE")) {
         const int64_t n_chunks = std::min<int64_t>(8, n_jobs / min_chunk);
         return batch_pipelined(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, msa_out, msa_len, cells, (n_jobs + n_chunks - 1) / n_chunks);
     }
     barb200_stage *st = nullptr;
+    const double t0 = now_ms();
     int rc = stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, &st);
     if (rc) return rc;
-    rc = stage_run_locked(st, nullptr);
+    const double t1 = now_ms(); float kms = 0.f;
+    rc = stage_run_locked(st, &kms);
+    const double t2 = now_ms();
     if (!rc) rc = stage_fetch_locked(st, msa_out, msa_len, cells);
+    const double t3 = now_ms();
     barb200_stage_destroy(st);
+    if (timing_on()) fprintf(stderr, "barb200 timing: single stage: build %.1f ms, run %.1f ms (%.1f on the device), fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, kms, t3 - t2, now_ms() - t3);
     return rc;
 }
 

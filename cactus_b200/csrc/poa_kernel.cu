@@ -79,10 +79,14 @@ __device__ __forceinline__ void row_pass1(int (&H)[CPT], int (&E1)[CPT], int (&E
     }
 }
 
-template <bool MASKED>
+// MODE 0: all of the warp's active columns are inside the band; 1: some lie left (or left and right) of it -- every value
+// of an outside cell is forced to inf_min; 2: some lie right of it only -- nothing in the band depends on those cells
+// and the traceback never reads the F planes outside the band, so only H / E1 / E2 are forced (they feed later rows).
+template <int MODE>
 __device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E2)[CPT], int P1, int P2, int j0, int beg, int end, int NEG,
                                           int je1, int je2, int e1, int e2, int o1, int o2, int *tp, int &tmax) {
     const int oe1 = o1 + e1, oe2 = o2 + e2;
+    // (256-bit stores of whole 32-byte sectors: 128-bit halves cost ~20 % of the kernel's throughput in L2 write merging)
 #pragma unroll
     for (int oc = 0; oc < 2; ++oc) {
         int f1[8], f2[8];
@@ -94,9 +98,12 @@ __device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E
             int h = __vimax3_s32(H[e], f1[u], f2[u]);                    // :1067
             int x1 = __viaddmax_s32(E1[e], -e1, h - oe1);                // E for the next rows, :1070-1071
             int x2 = __viaddmax_s32(E2[e], -e2, h - oe2);
-            if (MASKED) {
+            if (MODE == 1) {
                 const bool inb = (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
                 h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG; f1[u] = inb ? f1[u] : NEG; f2[u] = inb ? f2[u] : NEG;
+            } else if (MODE == 2) {
+                const bool inb = j0 + e <= end;
+                h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG;
             }
             H[e] = h; E1[e] = x1; E2[e] = x2;
             tmax = max(tmax, h);
@@ -161,7 +168,7 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
     int H[CPT], E1[CPT], E2[CPT];          // the previous row's values of my columns (valid iff prev_active)
     bool prev_active;
     int prev_beg = 0, prev_end, prev_left = 0, prev_right = 0;
-    long long cur_off = 0, cells = 0;
+    int cur_blk = 0, cells = 0;               // row blocks (of TB ints) written so far; banded cells so far
 
     // ---- row 0 (simd_abpoa_cg_first_dp, :617-688) ----
     {
@@ -194,7 +201,7 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
         }
         if (lane == 31) S.wM[0][3][warp] = prev_active ? H[CPT - 1] : NEG;
         if (tid == 0) { RowInfo ri; ri.beg = 0; ri.end = prev_end; ri.left = 0; ri.right = 0; info[0] = ri; row_off[0] = 0; }
-        cur_off = (int64_t)nT * TB; cells = prev_end + 1;
+        cur_blk = nT; cells = prev_end + 1;
     }
     __syncthreads();
 
@@ -208,7 +215,7 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
         int maxL = node_n, maxR = 0, min_pre_beg = 0x7fffffff;
         bool has_prev = false;
         if (npre == 1 && rec.pre0 == r - 1) {                       // the linear-chain case: everything is in registers
-            maxL = prev_left + 1; maxR = prev_right + 1; min_pre_beg = prev_beg; has_prev = true;
+            maxL = min(node_n, prev_left + 1); maxR = prev_right + 1; min_pre_beg = prev_beg; has_prev = true;   // max_pos_left starts at node_n (abpoa_graph.c:347-352)
         } else {
 #pragma unroll 1
             for (int k = 0; k < npre; ++k) {
@@ -224,11 +231,11 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
         const int end = min(L, max(maxR, dd) + w);
         if ((beg >> pn_shift) < (min_pre_beg >> pn_shift)) beg = min_pre_beg;
         const int t0 = beg >> 4, nT = (end >> 4) - t0 + 1, tt = tid - t0;
-        if (cur_off + (int64_t)nT * TB > plane_cap) return -1;        // uniform across the CTA
+        if ((int64_t)(cur_blk + nT) * TB > plane_cap) return -1;        // uniform across the CTA
         const bool active = tt >= 0 && tt < nT;
-        // masking is decided per WARP (no divergent double execution): a warp whose active threads all lie inside the band
-        // runs the unmasked passes
-        const bool wfull = __all_sync(FULL, !active || (j0 >= beg && j0 + CPT - 1 <= end));
+        // masking is decided per WARP (no divergent double execution): 0 = all active threads inside the band,
+        // 1 = some columns left of the band, 2 = some columns right of it only
+        const int wmode = __any_sync(FULL, active && j0 < beg) ? 1 : __any_sync(FULL, active && j0 + CPT - 1 > end) ? 2 : 0;
         const int *mrow = S.smat + 8 * b;
 
         // H of the column left of my first one, previous row
@@ -270,7 +277,7 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
                 }
                 if (ptt >= 1 && ptt <= pnT) H[0] = max(H[0], __ldcg(Hp - TB + CPT - 1));    // H[16*tid - 1]: last H of the left neighbour's block
             }
-            if (wfull) row_pass1<false>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
+            if (wmode != 1) row_pass1<false>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
             else row_pass1<true>(H, E1, E2, mrow, qc, j0, beg, end, NEG, je1, je2, e1, e2, agg1, agg2);
         }
         // ---- exclusive prefix maximum over the row: warp shuffle scan + redux over warp aggregates ----
@@ -291,15 +298,17 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
         }
         int tmax = NEG - 1000;
         if (active) {
-            if (wfull) row_pass2<false>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, planes + cur_off + (int64_t)tt * TB, tmax);
-            else row_pass2<true>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, planes + cur_off + (int64_t)tt * TB, tmax);
+            int *tp = planes + (int64_t)(cur_blk + tt) * TB;
+            if (wmode == 0) row_pass2<0>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, tp, tmax);
+            else if (wmode == 2) row_pass2<2>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, tp, tmax);
+            else row_pass2<1>(H, E1, E2, P1, P2, j0, beg, end, NEG, je1, je2, e1, e2, P.o1, P.o2, tp, tmax);
         }
         // ---- left/right-most argmax of H over the band (simd_abpoa_max_in_row, :1107-1119) ----
         {
             const int wmax = __reduce_max_sync(FULL, tmax);
             int tleft = 0x7fffffff, tright = -1;
             if (active && tmax == wmax) {
-                if (wfull) row_argmax<false>(H, wmax, j0, beg, end, tleft, tright); else row_argmax<true>(H, wmax, j0, beg, end, tleft, tright);
+                if (wmode == 0) row_argmax<false>(H, wmax, j0, beg, end, tleft, tright); else row_argmax<true>(H, wmax, j0, beg, end, tleft, tright);
             }
             const int wl = __reduce_min_sync(FULL, tleft), wr = __reduce_max_sync(FULL, tright);
             if (lane == 0) { S.wM[par][0][warp] = wmax; S.wM[par][1][warp] = wl; S.wM[par][2][warp] = wr; }
@@ -314,8 +323,8 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
             prev_left = __reduce_min_sync(FULL, l); prev_right = __reduce_max_sync(FULL, rr);
         }
         prev_beg = beg; prev_end = end; prev_active = active;
-        if (tid == 0) { RowInfo ri; ri.beg = beg; ri.end = end; ri.left = prev_left; ri.right = prev_right; info[r] = ri; row_off[r] = cur_off; }
-        cur_off += (int64_t)nT * TB; cells += end - beg + 1;
+        if (tid == 0) { RowInfo ri; ri.beg = beg; ri.end = end; ri.left = prev_left; ri.right = prev_right; info[r] = ri; row_off[r] = (int64_t)cur_blk * TB; }
+        cur_blk += nT; cells += end - beg + 1;
         rec = nrec;
     }
     __syncthreads();
