@@ -214,15 +214,29 @@ def main():
     my_cells = float(cells.sum())
 
     # ---- e2e through the host-buffer C-ABI call ----
-    jobs_packed = (n_seq, lens, flat)
+    # inputs in PINNED host memory; per step: pack + guide trees + H2D + kernels + D2H + unpack (all inside
+    # barb200_poa_msa_batch), and for N > 1 the gather of every rank's MSA bytes on rank 0 over NCCL (the only data-path
+    # exchange the reference-facing call needs: alignments come back to the process that owns the flowers).
     import ctypes as C
+    pin = [torch.from_numpy(a).pin_memory() for a in (n_seq, lens, flat)]
+    p_nseq, p_lens, p_flat = [t.numpy() for t in pin]
+
     def e2e_once():
         outs = (C.c_void_p * n_ends)()
         ml = np.zeros(n_ends, np.int32)
         cc = np.zeros(n_ends, np.int64)
-        eng._check(eng.lib.barb200_poa_msa_batch(eng.ctx, n_ends, n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, None,
+        eng._check(eng.lib.barb200_poa_msa_batch(eng.ctx, n_ends, p_nseq.ctypes.data, p_lens.ctypes.data, p_flat.ctypes.data, None,
                                                  outs, ml.ctypes.data, cc.ctypes.data))
         d2h = int((ml.astype(np.int64) * K_SEQS).sum())
+        if world > 1:
+            # concatenate this rank's MSA rows and send them to rank 0
+            buf = np.empty(d2h, np.uint8)
+            o = 0
+            for i in range(n_ends):
+                nb = int(ml[i]) * K_SEQS
+                C.memmove(buf.ctypes.data + o, outs[i], nb)
+                o += nb
+            D.gather_bytes(torch.from_numpy(buf), dev)
         for i in range(n_ends):
             eng.lib.barb200_free(outs[i])
         return d2h

@@ -54,6 +54,7 @@ struct barb200_ctx {
     // and cudaFree synchronises the device, which would stall the upload / kernel overlap)
     std::vector<std::pair<void *, size_t>> free_blocks; size_t cached_bytes = 0;
     uint8_t *h_pinned = nullptr; size_t h_pinned_bytes = 0;   // pinned staging buffer for the MSA download
+    int *h_ready = nullptr; unsigned ready_slot = 0;          // pinned ring of "jobs released" values (copied to the device by the copy engine)
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
 };
 
@@ -156,6 +157,7 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     ctx->hp = HostParams{p->k, p->w, p->min_w, p->progressive_poa};
     for (int i = 0; i < kNumKernels; ++i) cudaFuncSetAttribute(kKernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kKernels[i].scratch);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
+    if (cudaMallocHost((void **)&ctx->h_ready, 1024 * sizeof(int)) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaMallocHost failed"); delete ctx; return nullptr; }
     for (int a = 0; a < 2; ++a)
         if (cudaStreamCreateWithFlags(&ctx->ar[a].stream, cudaStreamNonBlocking) != cudaSuccess) { fail(errbuf, errbuf_len, "cudaStreamCreate failed"); delete ctx; return nullptr; }
     return ctx;
@@ -172,6 +174,7 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
     if (ctx->d_clk) cudaFree(ctx->d_clk);
     for (auto &b : ctx->free_blocks) cudaFree(b.first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_ready) cudaFreeHost(ctx->h_ready);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -214,6 +217,7 @@ struct barb200_stage {
     barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;
     int64_t launches = 0; bool ran = false;
     int arena = 0; double mem_share = 1.0; cudaEvent_t e0 = nullptr, e1 = nullptr; bool launched = false;
+    int *d_ready = nullptr; const uint8_t *host_seqs = nullptr; int64_t orders_done = 0;   // streamed guide trees (see stage_stream_orders)
     uint64_t clk[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -315,8 +319,33 @@ static int ensure_arena(barb200_ctx *ctx, int a, size_t slots_bytes, size_t plan
     return BARB200_OK;
 }
 
+// tell the device that jobs [0, n) may start: a 4-byte copy from a pinned ring by the COPY ENGINE (a kernel could not
+// be used for this: the persistent POA kernel owns every SM while its CTAs wait for the value)
+static cudaError_t post_ready(barb200_stage *st, int64_t n) {
+    barb200_ctx *ctx = st->ctx;
+    if (ctx->ready_slot && (ctx->ready_slot & 1023) == 0) { cudaError_t e = cudaStreamSynchronize(ctx->copy_stream); if (e != cudaSuccess) return e; }
+    int *slot = ctx->h_ready + (ctx->ready_slot++ & 1023);
+    *slot = (int)n;
+    return cudaMemcpyAsync(st->d_ready, slot, 4, cudaMemcpyHostToDevice, ctx->copy_stream);
+}
+
+// guide-tree orders (abpoa_seed.c:85-156, 232-325 via guide_tree.cpp) of jobs [j0, j1) into st->order
+static void host_orders(barb200_stage *st, int64_t j0, int64_t j1) {
+    barb200_ctx *ctx = st->ctx;
+    const int nthreads = host_threads(ctx);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t j = j0; j < j1; ++j) {
+        const int K = st->n_seq[j];
+        std::vector<const uint8_t *> ptr(K);
+        const uint8_t *base = st->host_seqs + st->job_seq_off[j];
+        for (int i = 0; i < K; ++i) ptr[i] = base + st->soff[st->job_len_off[j] + i];
+        guide_tree_order(ctx->hp, st->progressive[j], K, ptr.data(), st->lens.data() + st->job_len_off[j], st->order.data() + st->job_len_off[j]);
+    }
+}
+
 static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
-                       const int *progressive, bool worst_case, barb200_stage **out, int arena = 0, double mem_share = 1.0) {
+                       const int *progressive, bool worst_case, barb200_stage **out, int arena = 0, double mem_share = 1.0,
+                       bool defer_orders = false) {
     if (!ctx || n_jobs < 0 || (n_jobs > 0 && (!n_seq || !seq_lens || !seqs))) { set_error(ctx, "bad arguments"); return BARB200_EINVAL; }
     cudaSetDevice(ctx->device);
     barb200_stage *st = new barb200_stage();
@@ -355,20 +384,22 @@ static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const
         msa_off += stride * n_seq[j];
     }
     st->msa_bytes = msa_off;
-    // guide-tree orders on host threads
+    // input validation (codes 0..4), then the guide-tree orders on host threads -- unless the caller streams them in
+    // behind the running kernel (stage_stream_orders)
     const int nthreads = host_threads(ctx);
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(| : bad)
-    for (int64_t j = 0; j < n_jobs; ++j) {
-        const int K = n_seq[j];
-        std::vector<const uint8_t *> ptr(K);
-        const uint8_t *base = seqs + st->job_seq_off[j];
-        for (int i = 0; i < K; ++i) {
-            ptr[i] = base + st->soff[st->job_len_off[j] + i];
-            for (int t = 0; t < seq_lens[st->job_len_off[j] + i]; ++t) if (ptr[i][t] > 4) bad = 1;
-        }
-        guide_tree_order(ctx->hp, st->progressive[j], K, ptr.data(), seq_lens + st->job_len_off[j], st->order.data() + st->job_len_off[j]);
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : bad)
+    for (int64_t b = 0; b < (nb + 65535) / 65536; ++b) {
+        const int64_t e = std::min<int64_t>(nb, (b + 1) * 65536);
+        uint8_t m = 0;
+        for (int64_t t = b * 65536; t < e; ++t) m |= seqs[t] > 4;
+        bad |= m;
     }
     if (bad) { set_error(ctx, "sequence code > 4"); delete st; return BARB200_EINVAL; }
+    st->host_seqs = seqs;
+    if (!defer_orders) {
+        host_orders(st, 0, n_jobs);
+        st->orders_done = n_jobs;
+    }
     if (n_jobs == 0) { *out = st; return BARB200_OK; }
     int rc = plan_stage(st);
     if (rc) { delete st; return rc; }
@@ -376,7 +407,7 @@ static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const
     size_t off = 0;
     auto sub = [&](size_t bytes) { size_t r = off; off = (off + std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return r; };
     const size_t o_seqs = sub(nb), o_lens = sub(ns * 4), o_order = sub(ns * 4), o_soff = sub(ns * 8), o_desc = sub(n_jobs * sizeof(JobDesc)),
-                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4);
+                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4), o_ready = sub(4);
     cudaError_t e = ctx_alloc(ctx, &st->d_block, off);
     if (e != cudaSuccess) {
         cudaGetLastError(); set_error(ctx, std::string("cudaMalloc(stage) failed: ") + cudaGetErrorString(e));
@@ -386,11 +417,12 @@ static int stage_build(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const
     uint8_t *blk = (uint8_t *)st->d_block;
     st->d_seqs = blk + o_seqs; st->d_lens = (int *)(blk + o_lens); st->d_order = (int *)(blk + o_order); st->d_soff = (int64_t *)(blk + o_soff);
     st->d_desc = (JobDesc *)(blk + o_desc); st->d_msa = blk + o_msa; st->d_msa_len = (int *)(blk + o_msa_len); st->d_status = (int *)(blk + o_status);
-    st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next);
+    st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next); st->d_ready = (int *)(blk + o_ready);
     cudaStream_t s = ctx->copy_stream;
     if ((e = cudaMemcpyAsync(st->d_seqs, seqs, nb, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(st->d_order, st->order.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (st->orders_done && (e = cudaMemcpyAsync(st->d_order, st->order.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) ||
+        (e = post_ready(st, st->orders_done)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_soff, st->soff.data(), ns * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_desc, st->desc.data(), n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaStreamSynchronize(s)) != cudaSuccess) {
@@ -409,6 +441,27 @@ extern "C" int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int 
 
 static int stage_run_locked(barb200_stage *st, float *kernel_ms);
 
+// Guide trees behind the running kernel: the stage was built with defer_orders, its kernel is already queued and its
+// CTAs wait for `ready`. Jobs are released chunk by chunk as soon as their read orders have been computed and uploaded.
+static int stage_stream_orders(barb200_stage *st) {
+    barb200_ctx *ctx = st->ctx;
+    const int64_t chunk = std::max<int64_t>(256, st->slots);
+    while (st->orders_done < st->n_jobs) {
+        const int64_t j0 = st->orders_done, j1 = std::min<int64_t>(st->n_jobs, j0 + chunk);
+        host_orders(st, j0, j1);
+        const int64_t a = st->job_len_off[j0], b = st->job_len_off[j1];
+        cudaError_t e = cudaMemcpyAsync(st->d_order + a, st->order.data() + a, (b - a) * 4, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = post_ready(st, j1);
+        if (e != cudaSuccess) {
+            // release everything so that the kernel can drain, then report
+            post_ready(st, st->n_jobs); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->ar[st->arena].stream);
+            set_error(ctx, std::string("streaming guide trees: ") + cudaGetErrorString(e)); return BARB200_ECUDA;
+        }
+        st->orders_done = j1;
+    }
+    return BARB200_OK;
+}
+
 // queue the stage's kernel (+ the download of the job statuses) on its arena's stream; returns without waiting
 static int stage_launch(barb200_stage *st) {
     barb200_ctx *ctx = st->ctx;
@@ -426,7 +479,7 @@ static int stage_launch(barb200_stage *st) {
     BatchArgs A;
     A.jobs = st->d_desc; A.n_jobs = (int)st->n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff; A.order = st->d_order;
     A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
-    A.slots = AR.d_slots; A.planes = AR.d_planes; A.next_job = st->d_next;
+    A.slots = AR.d_slots; A.planes = AR.d_planes; A.next_job = st->d_next; A.ready = st->d_ready;
     A.phase_clk = clk_n ? ctx->d_clk : nullptr;
     A.serial_phases = getenv("BARB200_DEBUG_SERIAL") ? 1 : 0;
     A.bfs_order = getenv("BARB200_DEBUG_BFS") ? 1 : 0;
@@ -581,69 +634,8 @@ extern "C" int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *ms
     return stage_fetch_locked(st, msa_out, msa_len, cells);
 }
 
-// Large batches are cut into chunks that flow through a two-deep pipeline: a producer thread packs chunk k+1, computes
-// its guide trees and uploads it on the copy stream while chunk k's kernel runs; chunk k+1's kernel is queued on the
-// other arena's stream before chunk k's results are downloaded and unpacked. The chunk size keeps several waves of
-// resident CTAs per launch so that launch tails stay small.
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool timing_on() { static const bool on = getenv("BARB200_TIMING") != nullptr; return on; }
-
-static int batch_pipelined(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs,
-                           const int *progressive, uint8_t **msa_out, int *msa_len, int64_t *cells, int64_t chunk) {
-    const int64_t n_chunks = (n_jobs + chunk - 1) / chunk;
-    std::vector<int64_t> first(n_chunks + 1), len_off(n_chunks + 1), seq_off(n_chunks + 1);
-    {
-        int64_t ns = 0, nb = 0;
-        for (int64_t j = 0, c = 0; j <= n_jobs; ++j) {
-            if (j == c * chunk || j == n_jobs) { first[c] = j; len_off[c] = ns; seq_off[c] = nb; ++c; }
-            if (j < n_jobs) for (int i = 0; i < n_seq[j]; ++i) { nb += seq_lens[ns]; ++ns; }
-        }
-    }
-    struct Item { barb200_stage *st = nullptr; int rc = 0; };
-    std::vector<Item> items(n_chunks);
-    std::mutex qmu; std::condition_variable qcv; int64_t produced = 0, consumed = 0; bool abort = false;
-    std::thread producer([&]() {
-        cudaSetDevice(ctx->device);
-        for (int64_t c = 0; c < n_chunks; ++c) {
-            { std::unique_lock<std::mutex> lk(qmu); qcv.wait(lk, [&] { return abort || produced - consumed < 2; }); if (abort) return; }
-            Item it;
-            const double tb0 = now_ms();
-            it.rc = stage_build(ctx, first[c + 1] - first[c], n_seq + first[c], seq_lens + len_off[c], seqs + seq_off[c],
-                                progressive ? progressive + first[c] : nullptr, false, &it.st, (int)(c & 1), 0.5);
-            if (timing_on()) fprintf(stderr, "barb200 timing: chunk %lld built in %.1f ms\n", (long long)c, now_ms() - tb0);
-            { std::lock_guard<std::mutex> lk(qmu); items[c] = it; ++produced; }
-            qcv.notify_all();
-            if (it.rc) return;
-        }
-    });
-    auto wait_for = [&](int64_t c) { std::unique_lock<std::mutex> lk(qmu); qcv.wait(lk, [&] { return produced > c; }); return items[c]; };
-    int rc = 0;
-    Item cur = wait_for(0);
-    rc = cur.rc;
-    if (!rc) rc = stage_launch(cur.st);
-    for (int64_t c = 0; c < n_chunks && !rc; ++c) {
-        Item nxt;
-        if (c + 1 < n_chunks) { nxt = wait_for(c + 1); rc = nxt.rc; if (!rc) rc = stage_launch(nxt.st); }
-        const double tf0 = now_ms(); float kms = 0.f;
-        if (!rc) rc = stage_finish(cur.st, &kms);
-        const double tf1 = now_ms();
-        if (!rc) rc = stage_fetch_locked(cur.st, msa_out ? msa_out + first[c] : nullptr, msa_len ? msa_len + first[c] : nullptr, cells ? cells + first[c] : nullptr);
-        if (timing_on()) fprintf(stderr, "barb200 timing: chunk %lld waited %.1f ms for its kernel (%.1f ms on the device), fetched in %.1f ms\n", (long long)c, tf1 - tf0, kms, now_ms() - tf1);
-        if (cur.st) { barb200_stage_destroy(cur.st); items[c].st = nullptr; }
-        { std::lock_guard<std::mutex> lk(qmu); ++consumed; }
-        qcv.notify_all();
-        cur = nxt;
-    }
-    { std::lock_guard<std::mutex> lk(qmu); abort = true; }
-    qcv.notify_all();
-    producer.join();
-    if (rc) {   // drain: wait for queued kernels, release whatever was built or returned
-        cudaDeviceSynchronize();
-        for (auto &it : items) if (it.st) { barb200_stage_destroy(it.st); it.st = nullptr; }
-        if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) { free(msa_out[j]); msa_out[j] = nullptr; }
-    }
-    return rc;
-}
 
 extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, const int *seq_lens,
                                      const uint8_t *seqs, const int *progressive, uint8_t **msa_out, int *msa_len,
@@ -651,23 +643,21 @@ extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int
     if (!ctx) return BARB200_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) msa_out[j] = nullptr;
-    // chunking: at least ~2 waves of the densest CTA class per chunk, at most 8 chunks; profiling runs stay single-stage
-    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;   // >= 2 waves of 128-thread CTAs per chunk
-    if (n_jobs >= 2 * min_chunk && !ctx->p.collect_phase_clocks && !getenv("BARB200_NO_PIPELINE")) {
-        const int64_t n_chunks = std::min<int64_t>(8, n_jobs / min_chunk);
-        return batch_pipelined(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, msa_out, msa_len, cells, (n_jobs + n_chunks - 1) / n_chunks);
-    }
     barb200_stage *st = nullptr;
     const double t0 = now_ms();
-    int rc = stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, &st);
+    // one launch; the guide trees are computed behind it and jobs are released to the kernel as their orders arrive
+    const bool stream = n_jobs >= 512 && !getenv("BARB200_NO_PIPELINE");
+    int rc = stage_build(ctx, n_jobs, n_seq, seq_lens, seqs, progressive, false, &st, 0, 1.0, stream);
     if (rc) return rc;
     const double t1 = now_ms(); float kms = 0.f;
-    rc = stage_run_locked(st, &kms);
+    rc = stage_launch(st);
+    if (!rc && stream) rc = stage_stream_orders(st);
+    if (!rc) rc = stage_finish(st, &kms);
     const double t2 = now_ms();
     if (!rc) rc = stage_fetch_locked(st, msa_out, msa_len, cells);
     const double t3 = now_ms();
     barb200_stage_destroy(st);
-    if (timing_on()) fprintf(stderr, "barb200 timing: single stage: build %.1f ms, run %.1f ms (%.1f on the device), fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, kms, t3 - t2, now_ms() - t3);
+    if (timing_on()) fprintf(stderr, "barb200 timing: build %.1f ms, run %.1f ms (%.1f on the device), fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, kms, t3 - t2, now_ms() - t3);
     return rc;
 }
 

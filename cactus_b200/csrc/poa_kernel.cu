@@ -363,7 +363,14 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
     __syncthreads();
 
     while (true) {
-        if (tid == 0) S.job = atomicAdd(A.next_job, 1);
+        if (tid == 0) {
+            const int j = atomicAdd(A.next_job, 1);
+            if (j < A.n_jobs) {                                  // wait until the host has released the job (its read order is uploaded)
+                while (*reinterpret_cast<const volatile int *>(A.ready) <= j) __nanosleep(2000);
+                __threadfence();
+            }
+            S.job = j;
+        }
         __syncthreads();
         const int job = S.job;
         if (job >= A.n_jobs) break;

@@ -27,6 +27,7 @@ struct BatchArgs {
     uint8_t *msa; int *msa_len; int *status; long long *cells;
     uint8_t *slots; int *planes;
     int *next_job;              // work queue head
+    const int *ready;           // jobs [0, *ready) may start (the host streams guide-tree orders in behind the launch)
     unsigned long long *phase_clk;   // [gridDim.x * PH_N] clock64 per phase, or nullptr
     int serial_phases;          // debugging aid: 1 = run the graph phases in their serial reference form
     int bfs_order;              // debugging aid: 1 = recompute abPOA's BFS order after every fusion instead of splicing

@@ -49,3 +49,22 @@ def gather_checksums(value, device):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())] if dist.get_rank() == 0 else None
     dist.gather(t, out, dst=0)
     return [float(x[0]) for x in out] if out is not None else None
+
+
+def gather_bytes(host_bytes, device):
+    """gather a variable-length uint8 tensor per rank on rank 0 (device buffers over the backend's transport; returns
+    the list of host tensors on rank 0, None elsewhere). Lengths travel first, payloads are padded to the longest."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [host_bytes]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([host_bytes.numel()], dtype=torch.int64, device=device)
+    lens = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(lens, n)
+    mx = max(int(x.item()) for x in lens)
+    pad = torch.zeros(mx, dtype=torch.uint8, device=device)
+    pad[: host_bytes.numel()].copy_(host_bytes, non_blocking=True)
+    out = [torch.empty(mx, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, out, dst=0)
+    if rank != 0:
+        return None
+    return [out[r][: int(lens[r].item())].cpu() for r in range(world)]

@@ -16,7 +16,8 @@ def _worker(rank, world, port, q):
     first, n = D.scatter_end_ranges(ranges, dev)
     mx, sm = D.reduce_stats([10.0 + rank, float(n)], dev)
     ck = D.gather_checksums(first * 1000 + n, dev)
-    q.put((rank, first, n, mx, sm, ck))
+    gb = D.gather_bytes(torch.arange(3 + 2 * rank, dtype=torch.uint8) + 10 * rank, dev)
+    q.put((rank, first, n, mx, sm, ck, None if gb is None else [t.tolist() for t in gb]))
     dist.destroy_process_group()
 
 
@@ -31,7 +32,8 @@ def test_scatter_reduce_gather_two_ranks():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, f0, n0, mx0, sm0, ck0), (r1, f1, n1, mx1, sm1, ck1) = res
+    (r0, f0, n0, mx0, sm0, ck0, gb0), (r1, f1, n1, mx1, sm1, ck1, gb1) = res
+    assert gb0 == [[0, 1, 2], [10, 11, 12, 13, 14]] and gb1 is None
     assert (f0, n0) == (0, 51) and (f1, n1) == (51, 50)
     assert mx0 == mx1 == [11.0, 51.0] and sm0 == sm1 == [21.0, 101.0]
     assert ck0 == [51.0, 51050.0] and ck1 is None
