@@ -37,6 +37,12 @@ class _CParams(C.Structure):
                 ("host_threads", C.c_int), ("collect_phase_clocks", C.c_int)]
 
 
+class _CPecanParams(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("min_diags_between_traceback", C.c_int64), ("traceback_diagonals", C.c_int64),
+                ("diagonal_expansion", C.c_int64), ("split_matrix_bigger_than_this", C.c_int64),
+                ("dynamic_anchor_expansion", C.c_int)]
+
+
 class _CMsa(C.Structure):
     _fields_ = [("seq_no", C.c_int64), ("column_no", C.c_int64), ("seq_lens", C.POINTER(C.c_int)),
                 ("msa", C.POINTER(C.c_uint8))]
@@ -89,6 +95,27 @@ def load_library():
     lib.barb200_device_info.restype = ci
     lib.barb200_free.argtypes = [vp]
     lib.barb200_free.restype = None
+    pp = C.POINTER(_CPecanParams)
+    lib.barb200_pecan_params_default.argtypes = [pp]
+    lib.barb200_pecan_params_default.restype = None
+    lib.barb200_pecan_aligned_pairs_batch.argtypes = [vp, pp, i64] + [vp] * 12
+    lib.barb200_pecan_aligned_pairs_batch.restype = ci
+    lib.barb200_pecan_stage_create.argtypes = [vp, pp, i64] + [vp] * 8 + [C.POINTER(vp)]
+    lib.barb200_pecan_stage_create.restype = ci
+    lib.barb200_pecan_stage_run.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.barb200_pecan_stage_run.restype = ci
+    lib.barb200_pecan_stage_fetch.argtypes = [vp, vp, vp, vp, vp]
+    lib.barb200_pecan_stage_fetch.restype = ci
+    lib.barb200_pecan_stage_cells.argtypes = [vp]
+    lib.barb200_pecan_stage_cells.restype = i64
+    lib.barb200_pecan_stage_launches.argtypes = [vp]
+    lib.barb200_pecan_stage_launches.restype = i64
+    lib.barb200_pecan_stage_destroy.argtypes = [vp]
+    lib.barb200_pecan_stage_destroy.restype = None
+    lib.barb200_pecan_band.argtypes = [i64, i64, vp, i64, i64, vp, vp]
+    lib.barb200_pecan_band.restype = ci
+    lib.barb200_pecan_split_points.argtypes = [i64, i64, vp, i64, i64, ci, ci, C.POINTER(vp)]
+    lib.barb200_pecan_split_points.restype = i64
     _LIB = lib
     return lib
 
@@ -136,6 +163,79 @@ class PoaParams:
         c.device, c.threads_per_block, c.ctas_per_sm = device, threads_per_block, ctas_per_sm
         c.mem_fraction, c.host_threads, c.collect_phase_clocks = mem_fraction, host_threads, collect_phase_clocks
         self.c = c
+
+
+class PairwiseAlignmentParameters:
+    """The PairwiseAlignmentParameters fields the posterior path reads (submodules/cPecan/impl/pairwiseAligner.c:1369-1391;
+    the <bar><pecan> keys of bar/impl/bar.c:20-37: diagonalExpansion, splitMatrixBiggerThanThis -- the XML value is the
+    side length, squared here as bar.c:23-24 does)."""
+
+    def __init__(self, threshold=0.01, minDiagsBetweenTraceBack=1000, traceBackDiagonals=40, diagonalExpansion=20,
+                 splitMatrixBiggerThanThis=3000, dynamicAnchorExpansion=0):
+        self.c = _CPecanParams(threshold, minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion,
+                               int(splitMatrixBiggerThanThis) * int(splitMatrixBiggerThanThis), dynamicAnchorExpansion)
+
+
+class _PairTable:
+    """argument arrays of the barb200_pecan_* calls for a list of (sX, sY, anchorPairs, raggedLeft, raggedRight)"""
+
+    def __init__(self, pairs):
+        n = len(pairs)
+        self.n = n
+        m = max(n, 1)
+        self.sx_b = [_as_bytes(q[0]) for q in pairs]
+        self.sy_b = [_as_bytes(q[1]) for q in pairs]
+        self.sx = (C.c_char_p * m)(*self.sx_b)
+        self.sy = (C.c_char_p * m)(*self.sy_b)
+        self.lx = np.array([len(b) for b in self.sx_b] or [0], np.int64)
+        self.ly = np.array([len(b) for b in self.sy_b] or [0], np.int64)
+        self.anch = [np.ascontiguousarray(np.asarray(q[2] if len(q) > 2 and q[2] is not None else [], np.int64).reshape(-1, 2)) for q in pairs]
+        self.ap = (C.c_void_p * m)(*[a.ctypes.data if len(a) else None for a in self.anch])
+        self.na = np.array([len(a) for a in self.anch] or [0], np.int64)
+        self.rl = np.array([1 if (len(q) > 3 and q[3]) else 0 for q in pairs] or [0], np.uint8)
+        self.rr = np.array([1 if (len(q) > 4 and q[4]) else 0 for q in pairs] or [0], np.uint8)
+
+    def args(self):
+        return [self.sx, self.lx.ctypes.data, self.sy, self.ly.ctypes.data, self.ap, self.na.ctypes.data,
+                self.rl.ctypes.data, self.rr.ctypes.data]
+
+
+class PecanStage:
+    """Pair-HMM inputs resident in HBM: create (split + band + pack + H2D) once, run any number of times, fetch."""
+
+    def __init__(self, engine, handle, table):
+        self.engine, self.h, self.table = engine, handle, table
+
+    def run(self):
+        ms = C.c_float()
+        self.engine._check(self.engine.lib.barb200_pecan_stage_run(self.h, C.byref(ms)))
+        return ms.value
+
+    def cells(self):
+        return int(self.engine.lib.barb200_pecan_stage_cells(self.h))
+
+    def launches(self):
+        return int(self.engine.lib.barb200_pecan_stage_launches(self.h))
+
+    def fetch(self, return_posteriors=False):
+        n = self.table.n
+        m = max(n, 1)
+        trip, post = (C.c_void_p * m)(), (C.c_void_p * m)()
+        n_out, cells = np.zeros(m, np.int64), np.zeros(m, np.int64)
+        self.engine._check(self.engine.lib.barb200_pecan_stage_fetch(self.h, trip, n_out.ctypes.data,
+                                                                     post if return_posteriors else None, cells.ctypes.data))
+        return self.engine._take_pairs(trip, post if return_posteriors else None, n_out, cells, n)
+
+    def close(self):
+        if self.h:
+            self.engine.lib.barb200_pecan_stage_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Msa:
@@ -284,6 +384,47 @@ class Engine:
                                                   C.byref(h)))
         return Stage(self, h, n_seq)
 
+    # ---- cPecan mode: pairwiseAligner.h level -----------------------------------------------------------------
+    def _take_pairs(self, trip, post, n_out, cells, n):
+        res = []
+        for i in range(n):
+            k = int(n_out[i])
+            t = np.ctypeslib.as_array(C.cast(trip[i], C.POINTER(C.c_int64)), shape=(max(3 * k, 1),))[: 3 * k].reshape(k, 3).copy()
+            self.lib.barb200_free(trip[i])
+            if post is not None:
+                p = np.ctypeslib.as_array(C.cast(post[i], C.POINTER(C.c_double)), shape=(max(k, 1),))[:k].copy()
+                self.lib.barb200_free(post[i])
+                res.append((t, p, int(cells[i])))
+            else:
+                res.append((t, int(cells[i])))
+        return res
+
+    def get_aligned_pairs_using_anchors_batch(self, pairs, params=None, return_posteriors=False):
+        """getAlignedPairsUsingAnchors (submodules/cPecan/impl/pairwiseAligner.c:1477-1495) for many sequence pairs.
+        pairs: list of (sX, sY, anchorPairs[n, 2], alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd).
+        Returns per pair (triples int64 [k, 3] = (score, x, y) in the reference's order, [posteriors,] banded cells)."""
+        params = params or PairwiseAlignmentParameters()
+        t = _PairTable(pairs)
+        m = max(t.n, 1)
+        trip, post = (C.c_void_p * m)(), (C.c_void_p * m)()
+        n_out, cells = np.zeros(m, np.int64), np.zeros(m, np.int64)
+        self._check(self.lib.barb200_pecan_aligned_pairs_batch(self.ctx, C.byref(params.c), t.n, *t.args(), trip, n_out.ctypes.data,
+                                                               post if return_posteriors else None, cells.ctypes.data))
+        return self._take_pairs(trip, post if return_posteriors else None, n_out, cells, t.n)
+
+    def get_aligned_pairs_using_anchors(self, sX, sY, anchorPairs=(), params=None, alignmentHasRaggedLeftEnd=False,
+                                        alignmentHasRaggedRightEnd=False):
+        """single-pair form with the reference's argument order; returns the (score, x, y) triples"""
+        return self.get_aligned_pairs_using_anchors_batch(
+            [(sX, sY, anchorPairs, alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd)], params)[0][0]
+
+    def pecan_stage(self, pairs, params=None):
+        params = params or PairwiseAlignmentParameters()
+        t = _PairTable(pairs)
+        h = C.c_void_p()
+        self._check(self.lib.barb200_pecan_stage_create(self.ctx, C.byref(params.c), t.n, *t.args(), C.byref(h)))
+        return PecanStage(self, h, t)
+
     # ---- poaBarAligner.h level --------------------------------------------------------------------------------
     def _wrap(self, cm):
         m = cm.contents
@@ -326,6 +467,30 @@ class Engine:
         out = [self._wrap(ms[i]) for i in range(n)]
         self.lib.barb200_free(C.cast(ms, C.c_void_p))
         return out
+
+
+def pecan_band(lx, ly, anchors, expansion=20):
+    """Host only: (xmyL, xmyR) of the diagonals 0..lx+ly as the engine builds them (band_construct, pairwiseAligner.c:193-244)."""
+    lib = load_library()
+    a = np.ascontiguousarray(np.asarray(anchors, np.int64).reshape(-1, 2))
+    L, R = np.zeros(lx + ly + 1, np.int64), np.zeros(lx + ly + 1, np.int64)
+    if lib.barb200_pecan_band(lx, ly, a.ctypes.data if len(a) else None, len(a), expansion, L.ctypes.data, R.ctypes.data) != 0:
+        raise BarB200Error("barb200_pecan_band: bad arguments")
+    return L, R
+
+
+def pecan_split_points(lx, ly, anchors, split_matrix_bigger_than_this, ragged_left=False, ragged_right=False):
+    """Host only: getSplitPoints (pairwiseAligner.c:1265-1292) as the engine computes it -> int64 [n, 4] (x1, y1, x2, y2)."""
+    lib = load_library()
+    a = np.ascontiguousarray(np.asarray(anchors, np.int64).reshape(-1, 2))
+    o = C.c_void_p()
+    n = lib.barb200_pecan_split_points(lx, ly, a.ctypes.data if len(a) else None, len(a), split_matrix_bigger_than_this,
+                                       int(ragged_left), int(ragged_right), C.byref(o))
+    if n < 0:
+        raise BarB200Error("barb200_pecan_split_points: bad arguments")
+    out = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_int64)), shape=(max(4 * n, 1),))[: 4 * n].reshape(n, 4).copy()
+    lib.barb200_free(o)
+    return out
 
 
 def synth_ends(first_end, n_ends, K, L, seed=0xBA5E0000, sub=0.02, ins=0.005, dele=0.005):

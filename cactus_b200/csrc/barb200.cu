@@ -81,6 +81,10 @@ int host_threads(barb200_ctx *ctx) {
     return ctx->p.host_threads > 0 ? ctx->p.host_threads : dflt;
 }
 int default_progressive(barb200_ctx *ctx) { return ctx->p.progressive_poa; }
+std::mutex &device_mutex(barb200_ctx *ctx) { return ctx->mu; }
+int ctx_device(barb200_ctx *ctx) { return ctx->device; }
+int ctx_sm_count(barb200_ctx *ctx) { return ctx->sm_count; }
+double ctx_mem_fraction(barb200_ctx *ctx) { return ctx->p.mem_fraction > 0 ? ctx->p.mem_fraction : 0.85; }
 }
 
 static cudaError_t ctx_alloc(barb200_ctx *ctx, void **p, size_t bytes) {

@@ -1,6 +1,7 @@
 // host_api.h -- internal C++ interfaces between the host-side translation units of libbarb200.
 #pragma once
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/barb200.h"
@@ -33,5 +34,10 @@ int run_jobs(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<Job
 void set_error(barb200_ctx *ctx, const std::string &msg);
 int host_threads(barb200_ctx *ctx);
 int default_progressive(barb200_ctx *ctx);
+// context facts for the other translation units (pecan.cu)
+std::mutex &device_mutex(barb200_ctx *ctx);    // serialises device batches on one context
+int ctx_device(barb200_ctx *ctx);
+int ctx_sm_count(barb200_ctx *ctx);
+double ctx_mem_fraction(barb200_ctx *ctx);
 
 }  // namespace barb200

@@ -1,0 +1,496 @@
+// pecan.cu -- cPecan mode of libbarb200: the batched banded pair-HMM kernel (one warp per job, pecan_warp.cuh), its
+// host orchestration and the C ABI declared in include/barb200.h (barb200_pecan_*).
+//
+// A *stage* takes n sequence pairs with their anchors, splits each pair at large anchor gaps, builds the anchor band of
+// every sub-matrix and the traceback schedule on host threads (pecan_plan.cpp), packs everything, uploads it once and
+// launches persistent warps that pull jobs (largest first) from a device counter. Each warp owns a scratch slot in HBM:
+// the forward ring, three backward diagonals and one reduction buffer. Jobs are grouped by the ring size they need so
+// that the common case (narrow anchored bands) runs with every SM full and rare wide jobs run with fewer, larger slots.
+// Candidate pairs (x, y, log posterior) are written in the reference's order of emission, compacted on the device, copied
+// back once and finished on the host with libm's exp (the same function the reference calls), threshold and floor.
+// There is no CPU fallback: the DP only exists as the CUDA kernel below.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "host_api.h"
+#include "pecan_plan.h"
+#include "pecan_warp.cuh"
+
+using namespace barb200;
+using namespace barb200::pecan;
+
+namespace barb200 {
+namespace pecan {
+
+struct KernelArgs {
+    const Job *jobs;
+    const int *order;          // job indices of this launch, largest first
+    int n_jobs;
+    int n_warps;
+    const uint8_t *sym;
+    const int *bandL, *coff;
+    Pair *out;
+    int *out_n;
+    unsigned *counter;
+    const double *consts;
+    double *scratch;
+    size_t slot_doubles;       // per warp: ring (fmask + 1) + 16 * ringW
+    unsigned fmask;
+    int ringW;
+    Params P;
+};
+
+constexpr int kWarpsPerCta = 4;
+
+extern "C" __global__ void __launch_bounds__(32 * kWarpsPerCta) pecan_posterior_kernel(const KernelArgs A) {
+    __shared__ double K[K_TOTAL];
+    for (int i = threadIdx.x; i < K_TOTAL; i += blockDim.x) K[i] = A.consts[i];
+    __syncthreads();
+    const int warp = blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    if (warp >= A.n_warps) return;
+    WarpMem wm;
+    wm.F = A.scratch + (size_t)warp * A.slot_doubles;
+    wm.fmask = A.fmask;
+    wm.B = wm.F + (size_t)A.fmask + 1;
+    wm.ringW = A.ringW;
+    wm.tbuf = wm.B + 15 * (size_t)A.ringW;
+    for (;;) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(A.counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= (unsigned)A.n_jobs) break;
+        const int j = A.order[idx];
+        const Job J = A.jobs[j];
+        const int n = run_job(J, A.sym, A.bandL, A.coff, wm, A.P, K, A.out, nullptr);
+        if (lane == 0) A.out_n[j] = n;
+        __syncwarp();
+    }
+}
+
+// one CTA per job: copy its records to their place in the compact array
+extern "C" __global__ void pecan_compact_kernel(const Job *jobs, const int *out_n, const long long *dst_off, const Pair *out, Pair *dst, int n_jobs) {
+    for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
+        const long long d0 = dst_off[j], n = dst_off[j + 1] - d0;
+        const Pair *src = out + jobs[j].out_off;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[d0 + i] = src[i];
+    }
+}
+
+}  // namespace pecan
+}  // namespace barb200
+
+#define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
+    set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(_e)); return BARB200_ECUDA; } } while (0)
+
+struct PecanGroup {
+    std::vector<int> jobs;       // largest first
+    unsigned fcap = 0;           // ring doubles (power of two)
+    int ringW = 0;
+    int warps = 0;
+    size_t slot_doubles = 0;
+    int order_off = 0;           // into d_order
+};
+
+struct barb200_pecan_stage {
+    barb200_ctx *ctx = nullptr;
+    PlanParams P;
+    Params devP;
+    int64_t n_pairs = 0;
+    bool full_cap = false;                       // retry stage: room for every cell
+    std::vector<SubJob> subs;                    // in pair order
+    std::vector<int64_t> pair_first;             // subs of pair i: [pair_first[i], pair_first[i+1])
+    std::vector<Job> jobs;
+    std::vector<uint8_t> h_sym;                  // packed symbols 0..4 (kept for re-runs of overflowed jobs)
+    std::vector<PecanGroup> groups;
+    int64_t cells = 0, launches = 0, out_total = 0;
+    // device
+    uint8_t *d_sym = nullptr; int *d_bandL = nullptr, *d_coff = nullptr, *d_order = nullptr, *d_out_n = nullptr;
+    Job *d_jobs = nullptr; Pair *d_out = nullptr; unsigned *d_counter = nullptr; double *d_consts = nullptr, *d_scratch = nullptr;
+    cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ran = false;
+};
+
+extern "C" void barb200_pecan_params_default(barb200_pecan_params *p) {
+    memset(p, 0, sizeof(*p));            // pairwiseAlignmentBandingParameters_construct, pairwiseAligner.c:1369-1391
+    p->threshold = 0.01; p->min_diags_between_traceback = 1000; p->traceback_diagonals = 40; p->diagonal_expansion = 20;
+    p->split_matrix_bigger_than_this = (int64_t)3000 * 3000; p->dynamic_anchor_expansion = 0;
+}
+
+static inline int sym_of(char c) {       // symbol_convertCharToSymbol, pairwiseAligner.c:327-344
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+
+static unsigned pow2ceil(uint64_t v) { uint64_t p = 1024; while (p < v) p <<= 1; return (unsigned)p; }
+
+extern "C" void barb200_pecan_stage_destroy(barb200_pecan_stage *st) {
+    if (!st) return;
+    cudaSetDevice(ctx_device(st->ctx));
+    void *ptrs[] = {st->d_sym, st->d_bandL, st->d_coff, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (st->ev0) cudaEventDestroy(st->ev0);
+    if (st->ev1) cudaEventDestroy(st->ev1);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    delete st;
+}
+
+static int plan_params(barb200_ctx *ctx, const barb200_pecan_params *p, PlanParams &P) {
+    if (!p) { set_error(ctx, "null pecan params"); return BARB200_EINVAL; }
+    if (p->dynamic_anchor_expansion) { set_error(ctx, "dynamicAnchorExpansion is not supported (Cactus never sets it)"); return BARB200_EINVAL; }
+    P.threshold = p->threshold; P.min_diags = p->min_diags_between_traceback; P.tb_diags = p->traceback_diagonals;
+    P.expansion = p->diagonal_expansion; P.split_bigger = p->split_matrix_bigger_than_this;
+    const std::string e = check_params(P);
+    if (!e.empty()) { set_error(ctx, e); return BARB200_EINVAL; }
+    return BARB200_OK;
+}
+
+// build the device side of a stage from st->subs (already split, not yet planned unless bandL is filled)
+// symbols come either from the caller's strings (sx, sy) or, for a retry stage, from the parent stage's packed copy
+static int stage_build(barb200_pecan_stage *st, const char *const *sx, const char *const *sy,
+                       const barb200_pecan_stage *parent, const std::vector<int64_t> *parent_idx) {
+    barb200_ctx *ctx = st->ctx;
+    const int64_t ns = (int64_t)st->subs.size();
+    std::string err;
+    const int nthr = host_threads(ctx);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
+    for (int64_t i = 0; i < ns; ++i) {
+        if (!st->subs[i].bandL.empty()) continue;
+        const std::string e = plan_subjob(st->P, st->subs[i]);
+        if (!e.empty()) {
+#pragma omp critical
+            err = e;
+        }
+    }
+    if (!err.empty()) { set_error(ctx, err); return BARB200_EINVAL; }
+    // offsets
+    st->jobs.resize(ns);
+    int64_t sym_off = 0, band_off = 0, out_off = 0, cells = 0;
+    for (int64_t i = 0; i < ns; ++i) {
+        SubJob &s = st->subs[i];
+        Job &J = st->jobs[i];
+        J.sx_off = sym_off; sym_off += s.lx; J.sy_off = sym_off; sym_off += s.ly;
+        J.band_off = band_off; band_off += (int64_t)s.lx + s.ly + 2;
+        J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged;
+        const int64_t cap = st->full_cap ? s.cells : std::min<int64_t>(s.cells, (int64_t)s.lx + s.ly + 64);
+        s.out_cap = (int)cap; J.out_cap = (int)cap; J.out_off = out_off; out_off += cap;
+        cells += s.cells;
+    }
+    st->cells = cells; st->out_total = out_off;
+    // pack
+    std::vector<uint8_t> &sym = st->h_sym;
+    sym.assign((size_t)std::max<int64_t>(sym_off, 1), 4);
+    std::vector<int> bandL((size_t)band_off + 1), coff((size_t)band_off + 1);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
+    for (int64_t i = 0; i < ns; ++i) {
+        const SubJob &s = st->subs[i];
+        const Job &J = st->jobs[i];
+        if (parent) {
+            const Job &PJ = parent->jobs[(*parent_idx)[i]];
+            if (s.lx) memcpy(&sym[J.sx_off], &parent->h_sym[PJ.sx_off], s.lx);
+            if (s.ly) memcpy(&sym[J.sy_off], &parent->h_sym[PJ.sy_off], s.ly);
+        } else {
+            const char *px = sx[s.pair] + s.x1, *py = sy[s.pair] + s.y1;
+            for (int k = 0; k < s.lx; ++k) sym[J.sx_off + k] = (uint8_t)sym_of(px[k]);
+            for (int k = 0; k < s.ly; ++k) sym[J.sy_off + k] = (uint8_t)sym_of(py[k]);
+        }
+        const int D = s.lx + s.ly;
+        memcpy(&bandL[J.band_off], s.bandL.data(), sizeof(int) * (D + 1)); bandL[J.band_off + D + 1] = 0;
+        memcpy(&coff[J.band_off], s.coff.data(), sizeof(int) * (D + 2));
+    }
+    // groups by forward-ring size
+    cudaSetDevice(ctx_device(ctx));
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const size_t fixed = (size_t)sym_off + (size_t)band_off * 8 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
+    if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
+    const size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
+    const int full_warps = ctx_sm_count(ctx) * 32;
+    std::vector<unsigned> need(ns);
+    for (int64_t i = 0; i < ns; ++i) need[i] = pow2ceil((uint64_t)5 * (uint64_t)std::max<int64_t>(st->subs[i].span_cells, 1));
+    std::vector<int> by_need(ns);
+    for (int64_t i = 0; i < ns; ++i) by_need[i] = (int)i;
+    std::sort(by_need.begin(), by_need.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] < need[b] : a < b; });
+    // main group: the largest prefix (by need) that still lets every SM be full
+    st->groups.clear();
+    int64_t taken = 0;
+    {
+        int64_t best = 0; int rw = 0;
+        for (int64_t i = 0; i < ns; ++i) {
+            rw = std::max(rw, st->subs[by_need[i]].max_w);
+            const size_t slot = ((size_t)need[by_need[i]] + 16 * (size_t)rw) * 8;
+            const int64_t warps = std::min<int64_t>(full_warps, i + 1);
+            if (slot * (size_t)warps <= budget) best = i + 1; else break;
+        }
+        if (best > 0) {
+            PecanGroup g; g.jobs.assign(by_need.begin(), by_need.begin() + best);
+            st->groups.push_back(std::move(g)); taken = best;
+        }
+    }
+    while (taken < ns) {          // rest: one group per ring size, as many warps as memory allows
+        PecanGroup g; const unsigned nd = need[by_need[taken]];
+        while (taken < ns && need[by_need[taken]] == nd) g.jobs.push_back(by_need[taken++]);
+        st->groups.push_back(std::move(g));
+    }
+    size_t scratch_bytes = 0; int order_off = 0;
+    std::vector<int> order((size_t)std::max<int64_t>(ns, 1));
+    for (PecanGroup &g : st->groups) {
+        unsigned fc = 1024; int rw = 1;
+        for (int j : g.jobs) { fc = std::max(fc, need[j]); rw = std::max(rw, st->subs[j].max_w); }
+        g.fcap = fc; g.ringW = (rw + 31) & ~31; g.slot_doubles = (size_t)fc + 16 * (size_t)g.ringW;
+        const size_t slot = g.slot_doubles * 8;
+        int64_t warps = std::min<int64_t>({(int64_t)full_warps, (int64_t)g.jobs.size(), (int64_t)(budget / slot)});
+        if (warps < 1) { set_error(ctx, "a pair-HMM job needs more device memory than is available"); return BARB200_ENOMEM; }
+        g.warps = (int)warps;
+        scratch_bytes = std::max(scratch_bytes, slot * (size_t)warps);
+        std::sort(g.jobs.begin(), g.jobs.end(), [&](int a, int b) { return st->subs[a].cells != st->subs[b].cells ? st->subs[a].cells > st->subs[b].cells : a < b; });
+        g.order_off = order_off;
+        for (int j : g.jobs) order[order_off++] = j;
+    }
+    // device arrays
+    Consts C; fill_constants(C);
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_sym, sym.size()));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_bandL, bandL.size() * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_coff, coff.size() * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_order, order.size() * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out_n, (size_t)std::max<int64_t>(ns, 1) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_jobs, (size_t)std::max<int64_t>(ns, 1) * sizeof(Job)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out, (size_t)std::max<int64_t>(out_off, 1) * sizeof(Pair)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_counter, sizeof(unsigned) * (st->groups.size() + 1)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_consts, sizeof(Consts)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_scratch, std::max<size_t>(scratch_bytes, 8)));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreate(&st->ev0)); CUDA_TRY(ctx, cudaEventCreate(&st->ev1));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_sym, sym.data(), sym.size(), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_bandL, bandL.data(), bandL.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_coff, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
+    if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(st->d_jobs, st->jobs.data(), (size_t)ns * sizeof(Job), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_consts, &C, sizeof(C), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st->stream));
+    st->devP.log_thr_lo = st->P.threshold > 0 ? log(st->P.threshold) - 1e-9 : -INFINITY;
+    st->devP.min_diags = (int)st->P.min_diags; st->devP.tb_diags = (int)st->P.tb_diags; st->devP.expansion = (int)st->P.expansion;
+    return BARB200_OK;
+}
+
+extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                                          const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                                          const int64_t *const *anchors, const int64_t *n_anchor,
+                                          const uint8_t *ragged_left, const uint8_t *ragged_right, barb200_pecan_stage **out) {
+    if (!ctx || !out || n_pairs < 0 || (n_pairs > 0 && (!sx || !sy || !lx || !ly))) { if (ctx) set_error(ctx, "bad argument"); return BARB200_EINVAL; }
+    PlanParams P;
+    int rc = plan_params(ctx, p, P);
+    if (rc) return rc;
+    barb200_pecan_stage *st = new barb200_pecan_stage();
+    st->ctx = ctx; st->P = P; st->n_pairs = n_pairs;
+    st->pair_first.assign(n_pairs + 1, 0);
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        const int64_t na = n_anchor ? n_anchor[i] : 0;
+        const int64_t *a = (anchors && na) ? anchors[i] : nullptr;
+        if (lx[i] < 0 || ly[i] < 0 || lx[i] > 0x3fffffff || ly[i] > 0x3fffffff || (na && !a)) { set_error(ctx, "bad sequence length or anchors"); delete st; return BARB200_EINVAL; }
+        const std::string e = check_anchors(a, na, lx[i], ly[i]);
+        if (!e.empty()) { set_error(ctx, e); delete st; return BARB200_EINVAL; }
+        st->pair_first[i] = (int64_t)st->subs.size();
+        split_pair(P, i, lx[i], ly[i], a, na, ragged_left && ragged_left[i], ragged_right && ragged_right[i], st->subs);
+    }
+    st->pair_first[n_pairs] = (int64_t)st->subs.size();
+    std::lock_guard<std::mutex> lk(device_mutex(ctx));
+    rc = stage_build(st, sx, sy, nullptr, nullptr);
+    if (rc) { barb200_pecan_stage_destroy(st); return rc; }
+    *out = st;
+    return BARB200_OK;
+}
+
+static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
+    barb200_ctx *ctx = st->ctx;
+    cudaSetDevice(ctx_device(ctx));
+    CUDA_TRY(ctx, cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned) * (st->groups.size() + 1), st->stream));
+    CUDA_TRY(ctx, cudaEventRecord(st->ev0, st->stream));
+    st->launches = 0;
+    for (size_t gi = 0; gi < st->groups.size(); ++gi) {
+        const PecanGroup &g = st->groups[gi];
+        KernelArgs A;
+        A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size(); A.n_warps = g.warps;
+        A.sym = st->d_sym; A.bandL = st->d_bandL; A.coff = st->d_coff; A.out = st->d_out; A.out_n = st->d_out_n;
+        A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch; A.slot_doubles = g.slot_doubles;
+        A.fmask = g.fcap - 1; A.ringW = g.ringW; A.P = st->devP;
+        const int ctas = (g.warps + kWarpsPerCta - 1) / kWarpsPerCta;
+        pecan_posterior_kernel<<<ctas, 32 * kWarpsPerCta, 0, st->stream>>>(A);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ++st->launches;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(st->ev1, st->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st->stream));
+    if (kernel_ms) CUDA_TRY(ctx, cudaEventElapsedTime(kernel_ms, st->ev0, st->ev1));
+    st->ran = true;
+    return BARB200_OK;
+}
+
+extern "C" int barb200_pecan_stage_run(barb200_pecan_stage *st, float *kernel_ms) {
+    if (!st) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(device_mutex(st->ctx));
+    return stage_run_locked(st, kernel_ms);
+}
+
+extern "C" int64_t barb200_pecan_stage_cells(barb200_pecan_stage *st) { return st ? st->cells : 0; }
+extern "C" int64_t barb200_pecan_stage_launches(barb200_pecan_stage *st) { return st ? st->launches : 0; }
+
+// candidates of every sub-job, in emission order (host copies); overflowed jobs are re-run with room for every cell
+static int stage_collect(barb200_pecan_stage *st, std::vector<std::vector<Pair>> &per_sub) {
+    barb200_ctx *ctx = st->ctx;
+    const int64_t ns = (int64_t)st->subs.size();
+    per_sub.assign(ns, std::vector<Pair>());
+    if (ns == 0) return BARB200_OK;
+    cudaSetDevice(ctx_device(ctx));
+    std::vector<int> out_n(ns);
+    CUDA_TRY(ctx, cudaMemcpy(out_n.data(), st->d_out_n, sizeof(int) * ns, cudaMemcpyDeviceToHost));
+    std::vector<long long> dst_off(ns + 1, 0);
+    std::vector<int64_t> retry;
+    for (int64_t i = 0; i < ns; ++i) {
+        const bool over = out_n[i] > st->subs[i].out_cap;
+        if (over) retry.push_back(i);
+        dst_off[i + 1] = dst_off[i] + (over ? 0 : out_n[i]);
+    }
+    const long long total = dst_off[ns];
+    std::vector<Pair> flat((size_t)std::max<long long>(total, 1));
+    if (total > 0) {
+        long long *d_dst_off = nullptr; Pair *d_flat = nullptr;
+        CUDA_TRY(ctx, cudaMalloc((void **)&d_dst_off, sizeof(long long) * (ns + 1)));
+        cudaError_t e = cudaMalloc((void **)&d_flat, sizeof(Pair) * (size_t)total);
+        if (e != cudaSuccess) { cudaFree(d_dst_off); set_error(ctx, "cudaMalloc (compact output) failed"); return BARB200_ENOMEM; }
+        cudaMemcpyAsync(d_dst_off, dst_off.data(), sizeof(long long) * (ns + 1), cudaMemcpyHostToDevice, st->stream);
+        const int grid = (int)std::min<int64_t>(ns, (int64_t)ctx_sm_count(ctx) * 16);
+        pecan_compact_kernel<<<grid, 128, 0, st->stream>>>(st->d_jobs, st->d_out_n, d_dst_off, st->d_out, d_flat, (int)ns);
+        ++st->launches;
+        cudaMemcpyAsync(flat.data(), d_flat, sizeof(Pair) * (size_t)total, cudaMemcpyDeviceToHost, st->stream);
+        e = cudaStreamSynchronize(st->stream);
+        cudaFree(d_dst_off); cudaFree(d_flat);
+        if (e != cudaSuccess) { set_error(ctx, std::string("pecan compaction: ") + cudaGetErrorString(e)); return BARB200_ECUDA; }
+    }
+    const int nthr = host_threads(ctx);
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (int64_t i = 0; i < ns; ++i) per_sub[i].assign(flat.begin() + dst_off[i], flat.begin() + dst_off[i + 1]);
+    if (!retry.empty()) {
+        if (st->full_cap) { set_error(ctx, "pecan: output overflow with full capacity (internal error)"); return BARB200_EJOB; }
+        barb200_pecan_stage *rs = new barb200_pecan_stage();
+        rs->ctx = ctx; rs->P = st->P; rs->n_pairs = st->n_pairs; rs->full_cap = true;
+        for (int64_t i : retry) rs->subs.push_back(st->subs[i]);
+        int rc = stage_build(rs, nullptr, nullptr, st, &retry);
+        if (rc == BARB200_OK) rc = stage_run_locked(rs, nullptr);
+        std::vector<std::vector<Pair>> sub2;
+        if (rc == BARB200_OK) rc = stage_collect(rs, sub2);
+        st->launches += rs->launches;
+        barb200_pecan_stage_destroy(rs);
+        if (rc) return rc;
+        for (size_t k = 0; k < retry.size(); ++k) per_sub[retry[k]] = std::move(sub2[k]);
+    }
+    return BARB200_OK;
+}
+
+// exp / threshold / floor on the host with the reference's own libm (addPosteriorProb, pairwiseAligner.c:665-674) and the
+// coordinate shift of convertAlignedPairs (:1294-1306)
+static int finish_pairs(barb200_pecan_stage *st, const std::vector<std::vector<Pair>> &per_sub, int64_t **triples_out, int64_t *n_out,
+                        double **posteriors_out, int64_t *cells_out) {
+    barb200_ctx *ctx = st->ctx;
+    const int nthr = host_threads(ctx);
+    const double thr = st->P.threshold;
+    bool oom = false;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthr)
+    for (int64_t i = 0; i < st->n_pairs; ++i) {
+        int64_t cand = 0, cells = 0;
+        for (int64_t s = st->pair_first[i]; s < st->pair_first[i + 1]; ++s) { cand += (int64_t)per_sub[s].size(); cells += st->subs[s].cells; }
+        int64_t *tr = (int64_t *)malloc(sizeof(int64_t) * 3 * (size_t)std::max<int64_t>(cand, 1));
+        double *po = posteriors_out ? (double *)malloc(sizeof(double) * (size_t)std::max<int64_t>(cand, 1)) : nullptr;
+        if (!tr || (posteriors_out && !po)) { oom = true; free(tr); free(po); triples_out[i] = nullptr; if (posteriors_out) posteriors_out[i] = nullptr; n_out[i] = 0; continue; }
+        int64_t n = 0;
+        for (int64_t s = st->pair_first[i]; s < st->pair_first[i + 1]; ++s) {
+            const SubJob &sj = st->subs[s];
+            // alignedPairCoordinateCorrectionFn moves a region's pairs over with stList_pop: reverse order of emission (:1457-1464)
+            for (int64_t q = (int64_t)per_sub[s].size() - 1; q >= 0; --q) {
+                const Pair &c = per_sub[s][q];
+                double pp = exp(c.lp);
+                if (!(pp >= thr)) continue;
+                if (po) po[n] = pp;
+                if (pp > 1.0) pp = 1.0;
+                tr[3 * n] = (int64_t)floor(pp * 10000000.0);       // PAIR_ALIGNMENT_PROB_1
+                tr[3 * n + 1] = c.x + sj.x1; tr[3 * n + 2] = c.y + sj.y1;
+                ++n;
+            }
+        }
+        triples_out[i] = tr; n_out[i] = n;
+        if (posteriors_out) posteriors_out[i] = po;
+        if (cells_out) cells_out[i] = cells;
+    }
+    if (oom) { set_error(ctx, "host allocation failed"); return BARB200_ENOMEM; }
+    return BARB200_OK;
+}
+
+extern "C" int barb200_pecan_stage_fetch(barb200_pecan_stage *st, int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out) {
+    if (!st || !triples_out || !n_out) return BARB200_EINVAL;
+    if (!st->ran) { set_error(st->ctx, "barb200_pecan_stage_fetch before barb200_pecan_stage_run"); return BARB200_EINVAL; }
+    std::vector<std::vector<Pair>> per_sub;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(device_mutex(st->ctx));
+        rc = stage_collect(st, per_sub);
+    }
+    if (rc) return rc;
+    return finish_pairs(st, per_sub, triples_out, n_out, posteriors_out, cells_out);
+}
+
+extern "C" int barb200_pecan_aligned_pairs_batch(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                                                 const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                                                 const int64_t *const *anchors, const int64_t *n_anchor,
+                                                 const uint8_t *ragged_left, const uint8_t *ragged_right,
+                                                 int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out) {
+    if (!ctx || !triples_out || !n_out) { if (ctx) set_error(ctx, "bad argument"); return BARB200_EINVAL; }
+    // chunks bounded by the output room a stage reserves (16 B per candidate, ~ (lx + ly) candidates per pair)
+    const int64_t kChunkRecords = (int64_t)128 << 20;
+    int64_t i0 = 0;
+    while (i0 < n_pairs || (n_pairs == 0 && i0 == 0)) {
+        int64_t i1 = i0, rec = 0;
+        while (i1 < n_pairs && (i1 == i0 || rec + lx[i1] + ly[i1] + 64 <= kChunkRecords)) { rec += lx[i1] + ly[i1] + 64; ++i1; }
+        barb200_pecan_stage *st = nullptr;
+        int rc = barb200_pecan_stage_create(ctx, p, i1 - i0, sx + i0, lx + i0, sy + i0, ly + i0, anchors ? anchors + i0 : nullptr,
+                                            n_anchor ? n_anchor + i0 : nullptr, ragged_left ? ragged_left + i0 : nullptr,
+                                            ragged_right ? ragged_right + i0 : nullptr, &st);
+        if (rc == BARB200_OK) rc = barb200_pecan_stage_run(st, nullptr);
+        if (rc == BARB200_OK) rc = barb200_pecan_stage_fetch(st, triples_out + i0, n_out + i0, posteriors_out ? posteriors_out + i0 : nullptr,
+                                                            cells_out ? cells_out + i0 : nullptr);
+        barb200_pecan_stage_destroy(st);
+        if (rc) return rc;
+        if (n_pairs == 0) break;
+        i0 = i1;
+    }
+    return BARB200_OK;
+}
+
+extern "C" int barb200_pecan_band(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor, int64_t expansion, int64_t *xmy_l, int64_t *xmy_r) {
+    if (lx < 0 || ly < 0 || lx > 0x3fffffff || ly > 0x3fffffff || expansion < 0 || expansion % 2 || !xmy_l || !xmy_r) return BARB200_EINVAL;
+    if (!check_anchors(anchors, n_anchor, lx, ly).empty()) return BARB200_EINVAL;
+    PlanParams P{0.01, 1000, 40, expansion, (int64_t)1 << 60};
+    SubJob s; s.lx = (int)lx; s.ly = (int)ly;
+    s.anchors.assign(anchors, anchors + 2 * n_anchor);
+    if (!plan_subjob(P, s).empty()) return BARB200_EINVAL;
+    for (int64_t d = 0; d <= lx + ly; ++d) { xmy_l[d] = s.bandL[d]; xmy_r[d] = s.bandL[d] + 2 * (int64_t)(s.coff[d + 1] - s.coff[d] - 1); }
+    return BARB200_OK;
+}
+
+extern "C" int64_t barb200_pecan_split_points(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor, int64_t split_bigger,
+                                              int ragged_left, int ragged_right, int64_t **splits_out) {
+    if (lx < 0 || ly < 0 || !splits_out || split_bigger < 1) return BARB200_EINVAL;
+    if (!check_anchors(anchors, n_anchor, lx, ly).empty()) return BARB200_EINVAL;
+    PlanParams P{0.01, 1000, 40, 20, split_bigger};
+    std::vector<SubJob> subs;
+    split_pair(P, 0, lx, ly, anchors, n_anchor, ragged_left != 0, ragged_right != 0, subs);
+    int64_t *o = (int64_t *)malloc(sizeof(int64_t) * 4 * std::max<size_t>(subs.size(), 1));
+    if (!o) return BARB200_ENOMEM;
+    for (size_t i = 0; i < subs.size(); ++i) { o[4 * i] = subs[i].x1; o[4 * i + 1] = subs[i].y1; o[4 * i + 2] = subs[i].x1 + subs[i].lx; o[4 * i + 3] = subs[i].y1 + subs[i].ly; }
+    *splits_out = o;
+    return (int64_t)subs.size();
+}

@@ -1,0 +1,46 @@
+// pecan_plan.h -- host-side planning of pair-HMM jobs: splitting a sequence pair at large anchor gaps, the anchor band,
+// and the forward/traceback schedule (which only depends on the band geometry) that sizes the device buffers.
+// Re-stated from submodules/cPecan/impl/pairwiseAligner.c: getSplitPoints :1241-1292, the sub-anchor selection of
+// getPosteriorProbsWithBandingSplittingAlignmentsByLargeGaps :1308-1363, band_construct :193-244 with
+// band_setCurrentDiagonal :104-132, and the traceback conditions of getPosteriorProbsWithBanding :798-803, 817.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+namespace barb200 {
+namespace pecan {
+
+struct PlanParams {
+    double threshold;
+    int64_t min_diags, tb_diags, expansion, split_bigger;
+};
+
+struct SubJob {
+    int64_t pair = 0;              // index of the sequence pair this sub-matrix belongs to
+    int64_t x1 = 0, y1 = 0;        // offset of the sub-matrix in the pair
+    int lx = 0, ly = 0;
+    int ragged = 0;                // bit 0 left, bit 1 right
+    std::vector<int64_t> anchors;  // (x, y) relative to (x1, y1)
+    // plan
+    std::vector<int> bandL;        // xmyL of diagonals 0..D
+    std::vector<int> coff;         // cells before diagonal d, D+2 entries
+    int64_t cells = 0;             // sum of diagonal widths
+    int64_t span_cells = 0;        // most forward cells alive at once (between two tracebacks)
+    int max_w = 0;
+    int out_cap = 0;
+};
+
+// Returns "" or an error message (the reference asserts on the same conditions).
+std::string check_params(const PlanParams &P);
+std::string check_anchors(const int64_t *anchors, int64_t n, int64_t lx, int64_t ly);
+
+// getSplitPoints + sub-anchor lists: appends the sub-jobs of one pair (anchors: n (x, y) pairs, 0-based).
+void split_pair(const PlanParams &P, int64_t pair, int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor,
+                bool ragged_left, bool ragged_right, std::vector<SubJob> &out);
+
+// band_construct: fills bandL / coff / cells / max_w; then the schedule: span_cells. Returns "" or an error.
+std::string plan_subjob(const PlanParams &P, SubJob &j);
+
+}  // namespace pecan
+}  // namespace barb200

@@ -124,6 +124,65 @@ barb200_msa **barb200_make_consistent_partial_order_alignments(barb200_ctx *ctx,
 int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
                           uint8_t *codes_out, int *lens_out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * cPecan mode (bar/partialOrderAlignment="0"): the banded five-state pair-HMM posteriors.
+ *
+ *   - barb200_pecan_aligned_pairs_batch replaces getAlignedPairsUsingAnchors
+ *     (submodules/cPecan/inc/pairwiseAligner.h, impl/pairwiseAligner.c:1477-1495), the call
+ *     addMultipleAlignedPairs makes once per chosen sequence pair (impl/multipleAligner.c:660, via getAlignedPairs
+ *     :1527-1534), for MANY sequence pairs at once: split at large anchor gaps (getSplitPoints :1265-1292), banded
+ *     forward / backward / posterior match probabilities (getPosteriorProbsWithBanding :766-887), coordinates shifted
+ *     back (:1457-1464). Anchors stay the caller's (getAnchorPairsForPairwiseAlignmentParameters :1222-1233).
+ *   - barb200_pecan_params are the PairwiseAlignmentParameters fields that path reads
+ *     (pairwiseAlignmentBandingParameters_construct :1369-1391; bar/impl/bar.c:20-37 for the <bar><pecan> keys).
+ *   The state machine is the reference's fiveState machine with its built-in constants (stateMachine.c:482-521).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    double threshold;                      /* 0.01 */
+    int64_t min_diags_between_traceback;   /* 1000 */
+    int64_t traceback_diagonals;           /* 40 */
+    int64_t diagonal_expansion;            /* 20; <bar><pecan diagonalExpansion> */
+    int64_t split_matrix_bigger_than_this; /* 3000*3000; <bar><pecan splitMatrixBiggerThanThis> SQUARED as bar.c:23-24 does */
+    int dynamic_anchor_expansion;          /* must be 0 (band_constructDynamic is not used by Cactus) */
+} barb200_pecan_params;
+void barb200_pecan_params_default(barb200_pecan_params *p);
+
+/* For pair i: NUL-free ASCII strings sx[i] (length lx[i]) and sy[i] (ly[i]); anchors[i] = n_anchor[i] (x, y) pairs of
+ * 0-based sequence coordinates, strictly increasing in both (may be NULL when n_anchor[i] == 0); ragged_left[i] /
+ * ragged_right[i] as alignmentHasRaggedLeftEnd / RightEnd. Outputs per pair: triples_out[i] = malloc'd n_out[i] x 3
+ * int64 (score = floor(posterior * PAIR_ALIGNMENT_PROB_1), x, y) in the order the reference returns them;
+ * posteriors_out (may be NULL) receives malloc'd doubles, the pre-floor posteriors exp(f_M + b_M - total);
+ * cells_out (may be NULL) the banded DP cells of the pair (sum of diagonal widths over its sub-matrices).
+ * Release every array with barb200_free. */
+int barb200_pecan_aligned_pairs_batch(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                                      const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                                      const int64_t *const *anchors, const int64_t *n_anchor,
+                                      const uint8_t *ragged_left, const uint8_t *ragged_right,
+                                      int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out);
+
+/* Staged form (inputs resident in HBM; used by bench.py): create = split + band + pack + H2D; run = kernels only
+ * (repeatable); fetch = compaction + D2H + exp/threshold/floor on the host. */
+typedef struct barb200_pecan_stage barb200_pecan_stage;
+int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                               const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                               const int64_t *const *anchors, const int64_t *n_anchor,
+                               const uint8_t *ragged_left, const uint8_t *ragged_right, barb200_pecan_stage **out);
+int barb200_pecan_stage_run(barb200_pecan_stage *st, float *kernel_ms);
+int barb200_pecan_stage_fetch(barb200_pecan_stage *st, int64_t **triples_out, int64_t *n_out, double **posteriors_out,
+                              int64_t *cells_out);
+int64_t barb200_pecan_stage_cells(barb200_pecan_stage *st);      /* banded cells of the whole stage */
+int64_t barb200_pecan_stage_launches(barb200_pecan_stage *st);   /* kernels launched by the last run */
+void barb200_pecan_stage_destroy(barb200_pecan_stage *st);
+
+/* Host-only planning helper (no device work): the band of one sub-matrix as the engine builds it -- xmyL / xmyR of the
+ * diagonals 0..lx+ly (band_construct, pairwiseAligner.c:193-244). Returns 0 or BARB200_EINVAL. */
+int barb200_pecan_band(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor, int64_t expansion,
+                       int64_t *xmy_l, int64_t *xmy_r);
+/* Host-only: getSplitPoints (pairwiseAligner.c:1265-1292). splits_out = malloc'd n x 4 (x1, y1, x2, y2); returns n or <0. */
+int64_t barb200_pecan_split_points(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor,
+                                   int64_t split_matrix_bigger_than_this, int ragged_left, int ragged_right,
+                                   int64_t **splits_out);
+
 /* Device facts for reports. */
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);
 

@@ -215,3 +215,67 @@ int64_t oracle_pecan_posteriors(const char *csx, int64_t lX, const char *csy, in
 }
 
 void oracle_pecan_free(void *p) { free(p); }
+
+/* ---- getAlignedPairsUsingAnchors (pairwiseAligner.c:1477-1495): split at large anchor gaps (getSplitPoints :1241-1292),
+ * posteriors of every sub-matrix (:1308-1363), floor(p * PAIR_ALIGNMENT_PROB_1) (addPosteriorProb :665-674), coordinates
+ * shifted back (:1294-1306, 1457-1464). Output: n x 3 int64 (score, x, y) in the reference's order (each region's
+ * pairs in REVERSE order of emission, because they are moved over with stList_pop). ------------------- */
+typedef struct { int64_t *v; int64_t n, m; } vec_t;
+static void vpush4(vec_t *s, int64_t a, int64_t b, int64_t c, int64_t d) {
+    if (s->n + 4 > s->m) { s->m = s->m ? 2 * s->m : 64; s->v = realloc(s->v, 8 * s->m); }
+    s->v[s->n++] = a; s->v[s->n++] = b; s->v[s->n++] = c; s->v[s->n++] = d;
+}
+static int split_p(int64_t *x1, int64_t *y1, int64_t x2, int64_t y2, int64_t x3, int64_t y3, vec_t *sp, int64_t bigger, int skip) {
+    int64_t lX2 = x3 - x2, lY2 = y3 - y2;
+    if (lX2 * lY2 > bigger) {
+        int64_t maxLen = sqrt(bigger);
+        int64_t hX = lX2 / 2 > maxLen ? maxLen : lX2 / 2, hY = lY2 / 2 > maxLen ? maxLen : lY2 / 2;
+        if (!skip) vpush4(sp, *x1, *y1, x2 + hX, y2 + hY);
+        *x1 = x3 - hX; *y1 = y3 - hY;
+        return 1;
+    }
+    return 0;
+}
+/* returns the number of split regions; *out = malloc'd n x 4 (x1, y1, x2, y2) */
+int64_t oracle_pecan_split_points(const int64_t *anchors, int64_t n_anchor, int64_t lX, int64_t lY, int64_t bigger, int ragged_left, int ragged_right, int64_t **out) {
+    vec_t sp; memset(&sp, 0, sizeof(sp));
+    int64_t x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    for (int64_t i = 0; i < n_anchor; ++i) {
+        int64_t x3 = anchors[2 * i], y3 = anchors[2 * i + 1];
+        split_p(&x1, &y1, x2, y2, x3, y3, &sp, bigger, ragged_left && i == 0);
+        x2 = x3 + 1; y2 = y3 + 1;
+    }
+    if (!split_p(&x1, &y1, x2, y2, lX, lY, &sp, bigger, ragged_left && n_anchor == 0) || !ragged_right) vpush4(&sp, x1, y1, lX, lY);
+    *out = sp.v;
+    return sp.n / 4;
+}
+
+int64_t oracle_pecan_aligned_pairs(const char *csx, int64_t lX, const char *csy, int64_t lY, const int64_t *anchors, int64_t n_anchor,
+                                   int ragged_left, int ragged_right, const pecan_params_t *pp, int64_t split_bigger, int64_t **trip, double **post) {
+    int64_t *sp = NULL;
+    const int64_t nsp = oracle_pecan_split_points(anchors, n_anchor, lX, lY, split_bigger, ragged_left, ragged_right, &sp);
+    int64_t n = 0, m = 0, *t = NULL, j = 0; double *po = NULL;
+    for (int64_t i = 0; i < nsp; ++i) {
+        const int64_t x1 = sp[4 * i], y1 = sp[4 * i + 1], x2 = sp[4 * i + 2], y2 = sp[4 * i + 3];
+        int64_t *sub = malloc(16 * (n_anchor > 0 ? n_anchor : 1)), ns = 0;
+        while (j < n_anchor) {
+            const int64_t x = anchors[2 * j], y = anchors[2 * j + 1];
+            if (x + y >= x2 + y2) break;
+            sub[2 * ns] = x - x1; sub[2 * ns + 1] = y - y1; ++ns; ++j;
+        }
+        int64_t *xs, *ys; double *ps;
+        const int64_t k = oracle_pecan_posteriors(csx + x1, x2 - x1, csy + y1, y2 - y1, sub, ns, ragged_left || i > 0, ragged_right || i < nsp - 1, pp, &xs, &ys, &ps);
+        if (n + k > m) { m = 2 * (n + k) + 16; t = realloc(t, 24 * m); po = realloc(po, 8 * m); }
+        for (int64_t q = k - 1; q >= 0; --q) {      /* alignedPairCoordinateCorrectionFn POPS the sub-list: reversed per region (:1457-1464) */
+            double p = ps[q];
+            po[n] = p;
+            if (p > 1.0) p = 1.0;
+            t[3 * n] = (int64_t)floor(p * 10000000.0); t[3 * n + 1] = xs[q] + x1; t[3 * n + 2] = ys[q] + y1; ++n;
+        }
+        free(xs); free(ys); free(ps); free(sub);
+    }
+    free(sp);
+    if (!t) { t = malloc(24); po = malloc(8); }
+    *trip = t; *post = po;
+    return n;
+}

@@ -59,7 +59,7 @@ int64_t pecan_ref_posteriors(const char *sx, int64_t lx, const char *sy, int64_t
     p->threshold = pp->threshold; p->minDiagsBetweenTraceBack = pp->minDiagsBetweenTraceBack;
     p->traceBackDiagonals = pp->traceBackDiagonals; p->diagonalExpansion = pp->diagonalExpansion;
     stList *anchorPairs = stList_construct3(0, (void (*)(void *))stIntTuple_destruct);
-    for (int64_t i = 0; i < n_anchor; ++i) stList_append(anchorPairs, stIntTuple_construct2(anchors[2 * i], anchors[2 * i + 1]));
+    for (int64_t i = 0; i < n_anchor; ++i) stList_append(anchorPairs, stIntTuple_construct3(anchors[2 * i], anchors[2 * i + 1], p->diagonalExpansion));
     SymbolString sX = symbolString_construct(sx, lx), sY = symbolString_construct(sy, ly);
     sink_t s; memset(&s, 0, sizeof(s));
     s.band = band_construct(anchorPairs, lx, ly, p->diagonalExpansion); s.lXalY = lx + ly; s.threshold = p->threshold;
@@ -75,14 +75,15 @@ int64_t pecan_ref_posteriors(const char *sx, int64_t lx, const char *sy, int64_t
 
 /* the reference's own integer triples through its public entry point (getAlignedPairsUsingAnchors,
  * pairwiseAligner.c) -- used to check the harness itself against the code path Cactus calls */
-int64_t pecan_ref_aligned_pairs(const char *sx, int64_t lx, const char *sy, int64_t ly, const int64_t *anchors, int64_t n_anchor,
-                                int ragged_left, int ragged_right, const pecan_params_t *pp, int64_t **trip) {
+int64_t pecan_ref_aligned_pairs2(const char *sx, int64_t lx, const char *sy, int64_t ly, const int64_t *anchors, int64_t n_anchor,
+                                 int ragged_left, int ragged_right, const pecan_params_t *pp, int64_t split_bigger, int64_t **trip) {
     StateMachine *sM = stateMachine5_construct(fiveState);
     PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
+    if (split_bigger > 0) p->splitMatrixBiggerThanThis = split_bigger;
     p->threshold = pp->threshold; p->minDiagsBetweenTraceBack = pp->minDiagsBetweenTraceBack;
     p->traceBackDiagonals = pp->traceBackDiagonals; p->diagonalExpansion = pp->diagonalExpansion;
     stList *anchorPairs = stList_construct3(0, (void (*)(void *))stIntTuple_destruct);
-    for (int64_t i = 0; i < n_anchor; ++i) stList_append(anchorPairs, stIntTuple_construct2(anchors[2 * i], anchors[2 * i + 1]));
+    for (int64_t i = 0; i < n_anchor; ++i) stList_append(anchorPairs, stIntTuple_construct3(anchors[2 * i], anchors[2 * i + 1], p->diagonalExpansion));
     char *cx = malloc(lx + 1), *cy = malloc(ly + 1);
     memcpy(cx, sx, lx); cx[lx] = 0; memcpy(cy, sy, ly); cy[ly] = 0;
     stList *pairs = getAlignedPairsUsingAnchors(sM, cx, cy, anchorPairs, p, ragged_left, ragged_right);
@@ -95,6 +96,11 @@ int64_t pecan_ref_aligned_pairs(const char *sx, int64_t lx, const char *sy, int6
     stateMachine_destruct(sM);
     *trip = t;
     return n;
+}
+
+int64_t pecan_ref_aligned_pairs(const char *sx, int64_t lx, const char *sy, int64_t ly, const int64_t *anchors, int64_t n_anchor,
+                                int ragged_left, int ragged_right, const pecan_params_t *pp, int64_t **trip) {
+    return pecan_ref_aligned_pairs2(sx, lx, sy, ly, anchors, n_anchor, ragged_left, ragged_right, pp, 0, trip);
 }
 
 void pecan_ref_free(void *p) { free(p); }

@@ -39,3 +39,17 @@ def two_end_cases():
         yield dict(id=m, ends=ends, ri=[[1] * K, [0] * K], rr=rr,
                    ov=[[len(s) for s in ends[0]], [len(s) for s in ends[1]]], win=int(z[f"t{m}_win"][0]),
                    msas=[z[f"t{m}_msa{e}"] for e in range(2)])
+
+
+def pecan_cases():
+    """outputs of the reference's getAlignedPairsUsingAnchors / getPosteriorProbsWithBanding (scripts/make_golden_pecan.py);
+    case 0 is the reference's own known-answer input (submodules/cPecan/tests/pairwiseAlignerTest.c:243-322)"""
+    z = np.load(os.path.join(GOLD, "pecan_golden.npz"))
+    for ci in range(int(z["n_cases"][0])):
+        fl = z[f"c{ci}_flags"]
+        c = dict(id=ci, sx=z[f"c{ci}_sx"].tobytes(), sy=z[f"c{ci}_sy"].tobytes(), anchors=z[f"c{ci}_anchors"],
+                 rl=bool(fl[0]), rr=bool(fl[1]), min_diags=int(fl[2]), tb_diags=int(fl[3]), expansion=int(fl[4]),
+                 split=int(fl[5]), threshold=float(z[f"c{ci}_thr"][0]), triples=z[f"c{ci}_triples"])
+        if f"c{ci}_post" in z:
+            c.update(post_x=z[f"c{ci}_post_x"], post_y=z[f"c{ci}_post_y"], post=z[f"c{ci}_post"])
+        yield c

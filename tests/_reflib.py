@@ -332,3 +332,156 @@ def cpu_poa_msa_many(n_seq, lens, flat, threads=0, p=None, prefer_ref=True):
     ck = C.c_uint64()
     secs = f(C.byref(p), len(n_seq), n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, threads, None, C.byref(ck))
     return secs, kind, ck.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# cPecan mode checkers: the compiled reference (oracle/_ref/libpecan_ref.so, oracle/pecan_ref_harness.c), the plain-C
+# oracle (oracle/pecan_oracle.c) and the host emulation of the product's warp program (tests/hosttest)
+# ---------------------------------------------------------------------------------------------------
+PECAN_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libpecan_ref.so")
+
+
+class PecanParams(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("minDiagsBetweenTraceBack", C.c_int64), ("traceBackDiagonals", C.c_int64),
+                ("diagonalExpansion", C.c_int64)]
+
+
+def pecan_params(threshold=0.01, min_diags=1000, tb_diags=40, expansion=20):
+    return PecanParams(threshold, min_diags, tb_diags, expansion)
+
+
+def have_pecan_ref():
+    return os.path.exists(PECAN_REF_SO)
+
+
+def _anch(anchors):
+    a = np.ascontiguousarray(np.asarray(anchors, dtype=np.int64).reshape(-1, 2))
+    return a, len(a)
+
+
+def _take(lib_free, ptr, n, ctype, dtype, width=1):
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(n * width, 1),))[: n * width].astype(dtype).copy()
+    lib_free(ptr)
+    return arr.reshape(n, width) if width > 1 else arr
+
+
+def _posteriors(lib, fname, freename, sx, sy, anchors, rl, rr, p):
+    f = getattr(lib, fname)
+    f.restype = C.c_int64
+    f.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(PecanParams),
+                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    fr = getattr(lib, freename)
+    fr.argtypes = [C.c_void_p]
+    fr.restype = None
+    a, na = _anch(anchors)
+    xs, ys, ps = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = f(sx, len(sx), sy, len(sy), a.ctypes.data, na, int(rl), int(rr), C.byref(p), C.byref(xs), C.byref(ys), C.byref(ps))
+    if n == 0:
+        for q in (xs, ys, ps):
+            if q.value:
+                fr(q)
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64)
+    return (_take(fr, xs, n, C.c_int64, np.int64), _take(fr, ys, n, C.c_int64, np.int64), _take(fr, ps, n, C.c_double, np.float64))
+
+
+def ref_pecan_posteriors(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None):
+    """pre-floor match posteriors of ONE sub-matrix from the unmodified reference getPosteriorProbsWithBanding"""
+    return _posteriors(_load(PECAN_REF_SO), "pecan_ref_posteriors", "pecan_ref_free", sx, sy, anchors, ragged_left, ragged_right, p or pecan_params())
+
+
+def oracle_pecan_posteriors(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None):
+    return _posteriors(_load(build_oracle()), "oracle_pecan_posteriors", "oracle_pecan_free", sx, sy, anchors, ragged_left, ragged_right, p or pecan_params())
+
+
+def ref_pecan_aligned_pairs(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None, split_bigger=3000 * 3000):
+    """integer triples (score, x, y) from the reference's public getAlignedPairsUsingAnchors"""
+    lib = _load(PECAN_REF_SO)
+    f = lib.pecan_ref_aligned_pairs2
+    f.restype = C.c_int64
+    f.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(PecanParams), C.c_int64,
+                  C.POINTER(C.c_void_p)]
+    lib.pecan_ref_free.argtypes = [C.c_void_p]
+    lib.pecan_ref_free.restype = None
+    a, na = _anch(anchors)
+    t = C.c_void_p()
+    p = p or pecan_params()
+    n = f(sx, len(sx), sy, len(sy), a.ctypes.data, na, int(ragged_left), int(ragged_right), C.byref(p), split_bigger, C.byref(t))
+    return _take(lib.pecan_ref_free, t, n, C.c_int64, np.int64, 3) if n else (lib.pecan_ref_free(t), np.zeros((0, 3), np.int64))[1]
+
+
+def _aligned_pairs(lib, fname, freename, sx, sy, anchors, rl, rr, p, split_bigger, with_cells):
+    f = getattr(lib, fname)
+    f.restype = C.c_int64
+    args = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(PecanParams), C.c_int64,
+            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    if with_cells:
+        args.append(C.POINTER(C.c_int64))
+    f.argtypes = args
+    fr = getattr(lib, freename)
+    fr.argtypes = [C.c_void_p]
+    fr.restype = None
+    a, na = _anch(anchors)
+    t, po, cells = C.c_void_p(), C.c_void_p(), C.c_int64()
+    extra = [C.byref(cells)] if with_cells else []
+    n = f(sx, len(sx), sy, len(sy), a.ctypes.data, na, int(rl), int(rr), C.byref(p), split_bigger, C.byref(t), C.byref(po), *extra)
+    assert n >= 0, "%s failed: %d" % (fname, n)
+    if n == 0:
+        fr(t), fr(po)
+        return np.zeros((0, 3), np.int64), np.zeros(0, np.float64), cells.value
+    return _take(fr, t, n, C.c_int64, np.int64, 3), _take(fr, po, n, C.c_double, np.float64), cells.value
+
+
+def oracle_pecan_aligned_pairs(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None, split_bigger=3000 * 3000):
+    """(triples, pre-floor posteriors) of the plain-C restatement of getAlignedPairsUsingAnchors"""
+    t, po, _ = _aligned_pairs(_load(build_oracle()), "oracle_pecan_aligned_pairs", "oracle_pecan_free", sx, sy, anchors, ragged_left,
+                              ragged_right, p or pecan_params(), split_bigger, False)
+    return t, po
+
+
+def hosttest_pecan_aligned_pairs(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None, split_bigger=3000 * 3000):
+    """the product's warp program emulated on the host (tests/hosttest): (triples, posteriors, banded cells)"""
+    return _aligned_pairs(_load(build_hosttest()), "hosttest_pecan_aligned_pairs", "hosttest_free", sx, sy, anchors, ragged_left,
+                          ragged_right, p or pecan_params(), split_bigger, True)
+
+
+def oracle_pecan_band(lx, ly, anchors, expansion):
+    lib = _load(build_oracle())
+    f = lib.oracle_pecan_band
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    a, na = _anch(anchors)
+    L, R = np.zeros(lx + ly + 1, np.int64), np.zeros(lx + ly + 1, np.int64)
+    f(a.ctypes.data, na, lx, ly, expansion, L.ctypes.data, R.ctypes.data)
+    return L, R
+
+
+def oracle_pecan_split_points(lx, ly, anchors, split_bigger, ragged_left, ragged_right):
+    lib = _load(build_oracle())
+    f = lib.oracle_pecan_split_points
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.oracle_pecan_free.argtypes = [C.c_void_p]
+    a, na = _anch(anchors)
+    o = C.c_void_p()
+    n = f(a.ctypes.data, na, lx, ly, split_bigger, int(ragged_left), int(ragged_right), C.byref(o))
+    return _take(lib.oracle_pecan_free, o, n, C.c_int64, np.int64, 4) if n else np.zeros((0, 4), np.int64)
+
+
+def cpu_pecan_many(pairs, threads=0, p=None, prefer_ref=True):
+    """Time getAlignedPairsUsingAnchors over many pairs on the host cores. pairs: list of (sx, sy, anchors, rl, rr).
+    Returns (seconds, kind). Python-level loop over a thread pool of ctypes calls (the libraries release the GIL)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    p = p or pecan_params()
+    use_ref = prefer_ref and have_pecan_ref()
+    fn = (lambda q: ref_pecan_aligned_pairs(q[0], q[1], q[2], q[3], q[4], p)) if use_ref else \
+        (lambda q: oracle_pecan_aligned_pairs(q[0], q[1], q[2], q[3], q[4], p))
+    fn(pairs[0])
+    t0 = time.perf_counter()
+    if threads and threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(fn, pairs))
+    else:
+        for q in pairs:
+            fn(q)
+    return time.perf_counter() - t0, ("reference" if use_ref else "port")

@@ -60,3 +60,50 @@ def two_end_problem(rng, K, L, **kw):
     right_row = [perm, inv]
     overlaps = [[len(s) for s in s1], [len(s) for s in s2]]
     return ends, right_end, right_row, overlaps
+
+
+def evolve_with_map(parent, rng, sub=0.02, ins=0.005, dele=0.005, nfrac=0.0):
+    """like evolve(), also returning for every output base the parent position it descends from (-1 for insertions)
+    and whether it was copied unchanged"""
+    out, src, same = [], [], []
+    for i, b in enumerate(parent):
+        r = rng.random()
+        if r >= dele:
+            if r < dele + sub:
+                out.append((int(b) + int(rng.integers(1, 4))) % 4 if b < 4 else int(rng.integers(0, 4)))
+                same.append(False)
+            else:
+                out.append(int(b))
+                same.append(True)
+            src.append(i)
+        if rng.random() < ins:
+            out.append(int(rng.integers(0, 4)))
+            src.append(-1)
+            same.append(False)
+    out = np.array(out, dtype=np.uint8)
+    if nfrac > 0 and len(out):
+        nm = rng.random(len(out)) < nfrac
+        out[nm] = 4
+        same = list(np.asarray(same) & ~nm)
+    return out, np.array(src, dtype=np.int64), np.array(same, dtype=bool)
+
+
+def pecan_pair(rng, L, k_anchor=12, keep=1.0, **kw):
+    """Two descendants of a random parent as ASCII plus anchor pairs the way cPecan's MUM anchoring would place them:
+    every position of every run of >= k_anchor identical, co-linear bases of the true alignment (a fraction `keep` of
+    the runs is used). Returns (sx, sy, anchors[n, 2])."""
+    parent = rng.integers(0, 4, L).astype(np.uint8)
+    x, sx_src, sx_same = evolve_with_map(parent, rng, **kw)
+    y, sy_src, sy_same = evolve_with_map(parent, rng, **kw)
+    ypos = {int(s): j for j, s in enumerate(sy_src) if s >= 0 and sy_same[j]}
+    cols = [(i, ypos[int(s)]) for i, s in enumerate(sx_src) if s >= 0 and sx_same[i] and int(s) in ypos and x[i] < 4]
+    anchors, run = [], []
+    for c in cols + [(-10, -10)]:
+        if run and c[0] == run[-1][0] + 1 and c[1] == run[-1][1] + 1:
+            run.append(c)
+            continue
+        if len(run) >= k_anchor and rng.random() < keep:
+            anchors.extend(run)
+        run = [c]
+    a = np.array(anchors, dtype=np.int64).reshape(-1, 2)
+    return to_ascii(x), to_ascii(y), a

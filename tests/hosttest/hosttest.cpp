@@ -193,3 +193,65 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
 }
 
 extern "C" void hosttest_free(void *p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// cPecan mode: the product's warp program (cactus_b200/csrc/pecan_warp.cuh) with the 32 lanes of every phase run one
+// after the other, on top of the product's host planning (pecan_plan.cpp). The exp / threshold / floor step mirrors
+// finish_pairs in pecan.cu. Same output as oracle_pecan_aligned_pairs.
+// ---------------------------------------------------------------------------------------------------------
+#include <math.h>
+#include "../../cactus_b200/csrc/pecan_plan.h"
+#include "../../cactus_b200/csrc/pecan_warp.cuh"
+
+struct HtPecanParams { double threshold; int64_t minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion; };
+
+extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, const char *csy, int64_t lY, const int64_t *anchors, int64_t n_anchor,
+                                                int ragged_left, int ragged_right, const HtPecanParams *pp, int64_t split_bigger,
+                                                int64_t **trip, double **post, int64_t *cells_out) {
+    namespace pc = barb200::pecan;
+    pc::PlanParams P{pp->threshold, pp->minDiagsBetweenTraceBack, pp->traceBackDiagonals, pp->diagonalExpansion, split_bigger};
+    *trip = nullptr; *post = nullptr;
+    if (!pc::check_params(P).empty() || !pc::check_anchors(anchors, n_anchor, lX, lY).empty()) return -1;
+    std::vector<pc::SubJob> subs;
+    pc::split_pair(P, 0, lX, lY, anchors, n_anchor, ragged_left != 0, ragged_right != 0, subs);
+    pc::Consts C; pc::fill_constants(C);
+    pc::Params dp; dp.log_thr_lo = P.threshold > 0 ? log(P.threshold) - 1e-9 : -INFINITY;
+    dp.min_diags = (int)P.min_diags; dp.tb_diags = (int)P.tb_diags; dp.expansion = (int)P.expansion;
+    std::vector<int64_t> t; std::vector<double> po;
+    int64_t cells = 0;
+    for (pc::SubJob &s : subs) {
+        if (!pc::plan_subjob(P, s).empty()) return -2;
+        cells += s.cells;
+        std::vector<uint8_t> sym((size_t)s.lx + s.ly + 1);
+        auto code = [](char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
+        for (int k = 0; k < s.lx; ++k) sym[k] = (uint8_t)code(csx[s.x1 + k]);
+        for (int k = 0; k < s.ly; ++k) sym[s.lx + k] = (uint8_t)code(csy[s.y1 + k]);
+        unsigned fcap = 1024; while (fcap < 5 * (uint64_t)std::max<int64_t>(s.span_cells, 1)) fcap <<= 1;
+        const int ringW = (s.max_w + 31) & ~31;
+        std::vector<double> scratch((size_t)fcap + 16 * (size_t)ringW, NAN);
+        pc::WarpMem wm; wm.F = scratch.data(); wm.fmask = fcap - 1; wm.B = wm.F + fcap; wm.ringW = ringW; wm.tbuf = wm.B + 15 * (size_t)ringW;
+        pc::Job J; J.sx_off = 0; J.sy_off = s.lx; J.band_off = 0; J.out_off = 0; J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged;
+        J.out_cap = (int)std::min<int64_t>(s.cells, (int64_t)s.lx + s.ly + 64);
+        std::vector<int> bl(s.bandL); bl.push_back(0);
+        std::vector<pc::Pair> out((size_t)std::max(J.out_cap, 1));
+        int n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), wm, dp, C.v, out.data(), nullptr);
+        if (n > J.out_cap) {              // the product's retry: room for every cell
+            J.out_cap = (int)s.cells; out.assign((size_t)std::max(J.out_cap, 1), pc::Pair());
+            n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), wm, dp, C.v, out.data(), nullptr);
+            if (n > J.out_cap) return -3;
+        }
+        for (int q = n - 1; q >= 0; --q) {
+            double p = exp(out[q].lp);
+            if (!(p >= P.threshold)) continue;
+            po.push_back(p);
+            if (p > 1.0) p = 1.0;
+            t.push_back((int64_t)floor(p * 10000000.0)); t.push_back(out[q].x + s.x1); t.push_back(out[q].y + s.y1);
+        }
+    }
+    const int64_t n = (int64_t)po.size();
+    *trip = (int64_t *)malloc(sizeof(int64_t) * 3 * (size_t)std::max<int64_t>(n, 1));
+    *post = (double *)malloc(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
+    if (n) { memcpy(*trip, t.data(), sizeof(int64_t) * 3 * n); memcpy(*post, po.data(), sizeof(double) * n); }
+    if (cells_out) *cells_out = cells;
+    return n;
+}
