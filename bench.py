@@ -109,6 +109,82 @@ def cpu_baseline(n_seq, lens, flat, cells, budget_s=20.0):
             "sample": "first %d of the step's ends (8 x 2 kbp each), %.1f s wall, OpenMP schedule(dynamic,1) over ends" % (n, secs)}, n, secs
 
 
+PECAN_BYTES_PER_CELL = 120.0   # 5 fp64 states x (forward write + forward read at the traceback + backward write)
+
+
+def pecan_bench(cb, local_rank, world, rank, first_pair, n_pairs, steps, warmup, cpu_budget, want_cpu, barrier, reduce_stats, dev, no_e2e=False):
+    """cPecan mode (BASELINE.json configs[3]): banded pair-HMM posteriors of n_pairs synthetic
+    2 kbp pairs per GPU per step with MUM-like anchors (k = 50, Cactus' setting). Returns the "pecan" object of the JSON
+    line (rank 0) or None."""
+    import ctypes as C
+    eng = cb.Engine(cb.PoaParams(device=local_rank))
+    pairs = cb.synth_pairs(first_pair, n_pairs, L_BP, k_anchor=50)
+    st = eng.pecan_stage(pairs)
+    cells = float(st.cells())
+    for _ in range(warmup):
+        st.run()
+    barrier()
+    dev_ms, launches = 0.0, 0
+    for _ in range(steps):
+        dev_ms += st.run()
+        launches += st.launches()
+    barrier()
+    res = st.fetch(True)
+    n_trip = int(sum(len(r[0]) for r in res))
+    st.close()
+    # e2e: host strings + anchors in, integer triples out, everything inside the timed region
+    if no_e2e:
+        e2e_ms, same = float("nan"), True
+    else:
+        eng.get_aligned_pairs_using_anchors_batch(pairs[: max(1, n_pairs // 8)])
+        barrier()
+        t0 = time.time()
+        res2 = eng.get_aligned_pairs_using_anchors_batch(pairs)
+        barrier()
+        e2e_ms = (time.time() - t0) * 1e3
+        same = all(np.array_equal(a[0], b[0]) for a, b in zip(res, res2))
+    h2d = int(sum(len(q[0]) + len(q[1]) + q[2].nbytes for q in pairs)) + 8 * int(sum(len(q[0]) + len(q[1]) + 2 for q in pairs))
+    d2h = n_trip * 16
+    mx, sm = reduce_stats([dev_ms, e2e_ms, cells, float(n_pairs), float(launches)], dev)
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        tot_cells, tot_pairs = float(sm[2]), float(sm[3])
+        launch_ms = dev_ms / max(1, launches)
+        achieved = cells * (steps / max(1, launches)) * PECAN_BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
+        out = {"metric": "cPecan banded pair-HMM forward/backward/posterior Gcell/s (cells = sum of band diagonal widths)",
+               "value": tot_cells * steps / float(mx[0]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs * steps / float(mx[0]) * 1e3,
+               "ms_per_step": float(mx[0]) / steps, "dtype": "f64",
+               "config": {"workload": "synthetic %d pairs x %d bp per GPU per step, 2%% sub / 0.5%% ins / 0.5%% del, anchors = exact co-linear "
+                                      "runs >= 50 bp (MUM-like), diagonalExpansion 20, threshold 0.01" % (n_pairs, L_BP),
+                          "cells_per_pair": cells / n_pairs},
+               "e2e": {"value": tot_cells / float(mx[1]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs / float(mx[1]) * 1e3, "ms_per_step": float(mx[1]),
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "barb200_pecan_aligned_pairs_batch (host strings + anchors -> (score, x, y) triples)",
+                       "same_as_staged": bool(same)},
+               "gpu_launches": int(sm[4]),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "kernel": "pecan_posterior_kernel", "bytes_per_cell_algorithmic": PECAN_BYTES_PER_CELL}}
+        if want_cpu:
+            try:
+                import _reflib as R
+                threads = usable_cores()
+                samp = [(q[0], q[1], q[2], False, False) for q in pairs[: max(2, threads)]]
+                s0, kind = R.cpu_pecan_many(samp, threads)
+                n = int(min(n_pairs, max(len(samp), cpu_budget / max(s0 / len(samp), 1e-6))))
+                samp = [(q[0], q[1], q[2], False, False) for q in pairs[:n]]
+                secs, kind = R.cpu_pecan_many(samp, threads)
+                c = float(sum(r[2] for r in res[:n]))
+                # parity on the sample actually timed: the reference's triples must equal the engine's
+                chk = R.ref_pecan_aligned_pairs(*samp[0], R.pecan_params()) if kind == "reference" else R.oracle_pecan_aligned_pairs(*samp[0], R.pecan_params())[0]
+                out["cpu_baseline"] = {"value": c / secs / 1e9, "unit": "Gcell/s", "pairs_per_s": n / secs, "cores": threads, "kind": kind,
+                                       "sample": "first %d of the step's pairs, %.1f s wall, one getAlignedPairsUsingAnchors call per pair on a pool of %d threads" % (n, secs, threads),
+                                       "bit_identical_on_first_pair": bool(np.array_equal(chk, res[0][0]))}
+            except Exception as e:  # noqa: BLE001
+                out["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": usable_cores(), "kind": "unavailable", "sample": str(e)}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -119,6 +195,10 @@ def main():
                     help="ends per GPU per step (default 16 x 148 SMs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (for runs under ncu: the streamed e2e path releases jobs "
+                    "to a RUNNING kernel from the host, which deadlocks under ncu's kernel serialisation)")
+    ap.add_argument("--pecan-pairs-per-step", type=int, default=int(os.environ.get("BARB200_PECAN_PAIRS_PER_STEP", "4736")),
+                    help="cPecan-mode pairs per GPU per step (default 32 x 148 SMs); 0 skips the cPecan section")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -240,21 +320,29 @@ def main():
         for i in range(n_ends):
             eng.lib.barb200_free(outs[i])
         return d2h
-    e2e_once()
-    barrier()
-    t1 = time.time()
-    e2e_steps = max(1, min(args.steps, 3))
-    d2h = 0
-    for _ in range(e2e_steps):
-        d2h = e2e_once()
-    barrier()
-    e2e_ms = (time.time() - t1) * 1e3 / e2e_steps
+    d2h, e2e_ms = 0, float("nan")
+    if not args.no_e2e:
+        e2e_once()
+        barrier()
+        t1 = time.time()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            d2h = e2e_once()
+        barrier()
+        e2e_ms = (time.time() - t1) * 1e3 / e2e_steps
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     # ---- reduce over ranks: max time, sum cells; gather alignment checksums on rank 0 ----
     mx, sm = D.reduce_stats([dev_ms, wall_ms, e2e_ms, my_cells, float(n_ends), float(launches)], dev)
     checksums = D.gather_checksums(float(sum(int(m.sum()) for m in msas[:64])), dev)
+    # ---- cPecan mode (its own context: the POA arenas are released first) ----
+    pecan = None
+    if args.pecan_pairs_per_step > 0:
+        stage.close()
+        eng.close()
+        pecan = pecan_bench(cb, local_rank, world, rank, rank * args.pecan_pairs_per_step, args.pecan_pairs_per_step, max(1, min(args.steps, 3)),
+                            max(1, min(args.warmup, 2)), min(args.cpu_budget, 12.0), not args.no_cpu_baseline, barrier, D.reduce_stats, dev, args.no_e2e)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -288,6 +376,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "poa_msa_kernel",
                          "bytes_per_cell_algorithmic": ALGO_BYTES_PER_CELL},
             "clocks": sampler.summary(), "rank_checksums": checksums}
+    if pecan is not None:
+        line["pecan"] = pecan
     if not args.no_cpu_baseline:
         try:
             cpu, n_cpu, secs = cpu_baseline(n_seq, lens, flat, cells, args.cpu_budget)

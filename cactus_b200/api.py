@@ -91,6 +91,8 @@ def load_library():
     lib.barb200_make_consistent_partial_order_alignments.restype = C.POINTER(C.POINTER(_CMsa))
     lib.barb200_synth_end.argtypes = [C.c_uint64, C.c_uint64, ci, ci, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.barb200_synth_end.restype = i64
+    lib.barb200_synth_pair.argtypes = [C.c_uint64, C.c_uint64, ci, C.c_double, C.c_double, C.c_double, ci, vp, vp, vp, vp, vp]
+    lib.barb200_synth_pair.restype = i64
     lib.barb200_device_info.argtypes = [vp, C.POINTER(ci), C.POINTER(i64), C.POINTER(i64), C.c_char_p, ci]
     lib.barb200_device_info.restype = ci
     lib.barb200_free.argtypes = [vp]
@@ -467,6 +469,21 @@ class Engine:
         out = [self._wrap(ms[i]) for i in range(n)]
         self.lib.barb200_free(C.cast(ms, C.c_void_p))
         return out
+
+
+def synth_pairs(first_pair, n_pairs, L, k_anchor=50, seed=0xBA5E0000, sub=0.02, ins=0.005, dele=0.005):
+    """Seeded synthetic sequence pairs with MUM-like anchors -> list of (sX, sY, anchors[n, 2], False, False). Host only."""
+    lib = load_library()
+    bx, by = C.create_string_buffer(2 * L + 16), C.create_string_buffer(2 * L + 16)
+    an = np.zeros((2 * L, 2), np.int64)
+    lx, ly = C.c_int64(), C.c_int64()
+    out = []
+    for i in range(n_pairs):
+        na = lib.barb200_synth_pair(seed, first_pair + i, L, sub, ins, dele, k_anchor, bx, C.byref(lx), by, C.byref(ly), an.ctypes.data)
+        if na < 0:
+            raise BarB200Error("barb200_synth_pair failed")
+        out.append((bx.raw[:lx.value], by.raw[:ly.value], an[:na].copy(), False, False))
+    return out
 
 
 def pecan_band(lx, ly, anchors, expansion=20):

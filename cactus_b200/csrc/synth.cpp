@@ -56,3 +56,46 @@ extern "C" int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, i
     }
     return o;
 }
+
+// Seeded synthetic sequence PAIR for the cPecan-mode benchmark: two descendants of one random parent (same event model as
+// above) as ASCII, plus anchor pairs placed the way cPecan's MUM anchoring places them on similar sequences: every
+// position of every run of >= k_anchor identical, co-linear bases of the true alignment (getAlignedMums emits one anchor
+// per base of each maximal unique match of length >= k, submodules/cPecan/impl/pairwiseAligner.c:2032-2059; Cactus
+// configures k = 50, :1389). sx_out / sy_out: at least 2*L+16 bytes each; anchors_out: at least 2*L (x, y) int64 pairs.
+extern "C" int64_t barb200_synth_pair(uint64_t seed, uint64_t pair_index, int L, double sub, double ins, double del, int k_anchor,
+                                      char *sx_out, int64_t *lx_out, char *sy_out, int64_t *ly_out, int64_t *anchors_out) {
+    if (L <= 0 || k_anchor <= 0 || !sx_out || !sy_out || !lx_out || !ly_out || !anchors_out) return -1;
+    Xoshiro rng(seed * 0x9e3779b97f4a7c15ULL + pair_index + 0x5eed);
+    std::vector<uint8_t> parent((size_t)L);
+    for (int i = 0; i < L; ++i) parent[i] = (uint8_t)(rng.next() >> 62);
+    static const char B[4] = {'A', 'C', 'G', 'T'};
+    // pos[s][i] = position in descendant s of the unchanged copy of parent base i, or -1
+    std::vector<int> pos[2] = {std::vector<int>((size_t)L, -1), std::vector<int>((size_t)L, -1)};
+    char *outs[2] = {sx_out, sy_out};
+    int64_t lens[2] = {0, 0};
+    for (int s = 0; s < 2; ++s) {
+        int64_t n = 0;
+        for (int i = 0; i < L && n < 2 * (int64_t)L + 8; ++i) {
+            const double u = rng.uniform();
+            if (u >= del) {
+                if (u < del + sub) outs[s][n++] = B[(parent[i] + 1 + rng.next() % 3) & 3];
+                else { pos[s][i] = (int)n; outs[s][n++] = B[parent[i]]; }
+            }
+            if (rng.uniform() < ins) outs[s][n++] = B[rng.next() >> 62];
+        }
+        if (n == 0) outs[s][n++] = B[parent[0]];
+        lens[s] = n;
+    }
+    *lx_out = lens[0]; *ly_out = lens[1];
+    int64_t na = 0, run0 = 0, runlen = 0;     // runs of consecutive (x+1, y+1) columns among the shared unchanged bases
+    std::vector<std::pair<int, int>> cols;
+    for (int i = 0; i < L; ++i) if (pos[0][i] >= 0 && pos[1][i] >= 0) cols.emplace_back(pos[0][i], pos[1][i]);
+    for (size_t c = 0; c <= cols.size(); ++c) {
+        const bool cont = c < cols.size() && runlen > 0 && cols[c].first == cols[c - 1].first + 1 && cols[c].second == cols[c - 1].second + 1;
+        if (cont) { ++runlen; continue; }
+        if (runlen >= k_anchor)
+            for (int64_t q = 0; q < runlen; ++q) { anchors_out[2 * na] = cols[run0 + q].first; anchors_out[2 * na + 1] = cols[run0 + q].second; ++na; }
+        run0 = (int64_t)c; runlen = c < cols.size() ? 1 : 0;
+    }
+    return na;
+}

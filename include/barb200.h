@@ -183,6 +183,13 @@ int64_t barb200_pecan_split_points(int64_t lx, int64_t ly, const int64_t *anchor
                                    int64_t split_matrix_bigger_than_this, int ragged_left, int ragged_right,
                                    int64_t **splits_out);
 
+/* Seeded synthetic sequence pair for the cPecan-mode benchmark: two descendants (ASCII) of a random parent of length L
+ * and the anchor pairs MUM anchoring would give on them (every base of every exact co-linear run of >= k_anchor bases of
+ * the true alignment). Buffers: sx_out / sy_out >= 2*L+16 bytes, anchors_out >= 2*L int64 pairs. Returns the number of
+ * anchor pairs. Host only; deterministic in (seed, pair_index). */
+int64_t barb200_synth_pair(uint64_t seed, uint64_t pair_index, int L, double sub, double ins, double del, int k_anchor,
+                           char *sx_out, int64_t *lx_out, char *sy_out, int64_t *ly_out, int64_t *anchors_out);
+
 /* Device facts for reports. */
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);
 

@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "pairwiseAligner.h"
+#include "multipleAligner.h"
 
 typedef struct {
     double threshold;
@@ -101,6 +102,28 @@ int64_t pecan_ref_aligned_pairs2(const char *sx, int64_t lx, const char *sy, int
 int64_t pecan_ref_aligned_pairs(const char *sx, int64_t lx, const char *sy, int64_t ly, const int64_t *anchors, int64_t n_anchor,
                                 int ragged_left, int ragged_right, const pecan_params_t *pp, int64_t **trip) {
     return pecan_ref_aligned_pairs2(sx, lx, sy, ly, anchors, n_anchor, ragged_left, ragged_right, pp, 0, trip);
+}
+
+/* makeAllPairwiseAlignments (multipleAligner.c:667-680): all pairs of n_seq fragments with the reference's default
+ * PairwiseAlignmentParameters (MUM anchors for matrices > 500 x 500). tuples5 = n x 5 (score, seq1, pos1, seq2, pos2),
+ * scores = npairs x 3 (similarity, seq1, seq2). */
+int64_t pecan_ref_make_all_pairwise(int64_t n_seq, const char **seqs, const int64_t *left_end, const int64_t *right_end,
+                                    int64_t **tuples5, int64_t **scores, int64_t *n_scores) {
+    StateMachine *sM = stateMachine5_construct(fiveState);
+    PairwiseAlignmentParameters *p = pairwiseAlignmentBandingParameters_construct();
+    stList *seqFrags = stList_construct3(0, (void (*)(void *))seqFrag_destruct);
+    for (int64_t i = 0; i < n_seq; ++i) stList_append(seqFrags, seqFrag_construct(seqs[i], left_end[i], right_end[i]));
+    stList *sc = NULL;
+    stList *mp = makeAllPairwiseAlignments(sM, seqFrags, p, &sc);
+    int64_t n = stList_length(mp), m = stList_length(sc);
+    int64_t *t = malloc(sizeof(int64_t) * 5 * (n > 0 ? n : 1)), *s = malloc(sizeof(int64_t) * 3 * (m > 0 ? m : 1));
+    for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 5; ++k) t[5 * i + k] = stIntTuple_get(stList_get(mp, i), k);
+    for (int64_t i = 0; i < m; ++i) for (int k = 0; k < 3; ++k) s[3 * i + k] = stIntTuple_get(stList_get(sc, i), k);
+    stList_destruct(mp); stList_destruct(sc); stList_destruct(seqFrags);
+    pairwiseAlignmentBandingParameters_destruct(p);
+    stateMachine_destruct(sM);
+    *tuples5 = t; *scores = s; *n_scores = m;
+    return n;
 }
 
 void pecan_ref_free(void *p) { free(p); }

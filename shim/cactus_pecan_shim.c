@@ -1,0 +1,183 @@
+/*
+ * cactus_pecan_shim.c -- the thin C host shim between cPecan's multiple aligner (used by Cactus' BAR phase when
+ * bar/partialOrderAlignment="0") and libbarb200's pair-HMM engine (include/barb200.h, barb200_pecan_*).
+ *
+ * Compiled AGAINST THE CACTUS TREE (submodules/cPecan/inc + sonLib) and linked into cPecanLib.a in place of the two
+ * reference functions it re-exports with their reference signatures:
+ *
+ *   stList *getAlignedPairsUsingAnchors(StateMachine*, const char *sX, const char *sY, stList *anchorPairs,
+ *                                       PairwiseAlignmentParameters*, bool raggedLeft, bool raggedRight)
+ *        submodules/cPecan/inc/pairwiseAligner.h, impl/pairwiseAligner.c:1477-1495 -- one pair per call (a batch of one:
+ *        correct, but a single warp of the GPU works);
+ *   stList *makeAllPairwiseAlignments(StateMachine*, stList *seqFrags, PairwiseAlignmentParameters*, stList **scores)
+ *        inc/multipleAligner.h:75, impl/multipleAligner.c:667-680 -- ALL sequence pairs of an end in one device batch
+ *        (this is the call makeAlignmentUsingAllPairs issues, multipleAligner.c:690, i.e. what makeAlignment does
+ *        whenever spanningTrees * (n-1) >= n(n-1)/2, :893-895).
+ *
+ * Anchors stay the reference's code (getAnchorPairsForPairwiseAlignmentParameters, pairwiseAligner.c:1222-1233: MUM
+ * chains on the host), and so does everything above: makeAlignment's pair selection, the poset alignment, endAligner.c,
+ * flowerAligner.c, bar(). The state machine must be the reference's five-state machine with its built-in constants
+ * (stateMachine5_construct(fiveState), the one bar() builds at bar/impl/bar.c:66); anything else aborts.
+ *
+ * Error convention as the reference's: st_errAbort. No CPU fallback.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sonLib.h"
+#include "pairwiseAligner.h"
+#include "multipleAligner.h"
+#include "stateMachine.h"
+#include "barb200.h"
+
+/* defined in impl/pairwiseAligner.c:1222-1233 (not static) but missing from pairwiseAligner.h */
+stList *getAnchorPairsForPairwiseAlignmentParameters(const char *sX, const char *sY, const int64_t lX, const int64_t lY,
+                                                    PairwiseAlignmentParameters *p);
+
+static pthread_mutex_t shim_mutex = PTHREAD_MUTEX_INITIALIZER;
+static barb200_ctx *shim_ctx = NULL;
+
+static barb200_ctx *shim_context(void) {
+    pthread_mutex_lock(&shim_mutex);
+    if (shim_ctx == NULL) {
+        barb200_params p;
+        char err[256];
+        barb200_params_default(&p);                       /* the POA fields are not used by the pair-HMM path */
+        const char *dev = getenv("BARB200_DEVICE");
+        if (dev) p.device = atoi(dev);
+        shim_ctx = barb200_create(&p, err, (int)sizeof(err));
+        if (shim_ctx == NULL) {
+            pthread_mutex_unlock(&shim_mutex);
+            st_errAbort("barb200: cannot create the GPU engine: %s", err);
+        }
+    }
+    pthread_mutex_unlock(&shim_mutex);
+    return shim_ctx;
+}
+
+static void params_from_pecan(const PairwiseAlignmentParameters *p, barb200_pecan_params *q) {
+    barb200_pecan_params_default(q);
+    q->threshold = p->threshold;
+    q->min_diags_between_traceback = p->minDiagsBetweenTraceBack;
+    q->traceback_diagonals = p->traceBackDiagonals;
+    q->diagonal_expansion = p->diagonalExpansion;
+    q->split_matrix_bigger_than_this = p->splitMatrixBiggerThanThis;
+    q->dynamic_anchor_expansion = p->dynamicAnchorExpansion;
+}
+
+static void check_state_machine(StateMachine *sM) {
+    if (sM->type != fiveState) st_errAbort("barb200: only the five-state pair-HMM (stateMachine5_construct(fiveState)) is supported");
+}
+
+static int64_t *flatten_anchors(stList *anchorPairs, int64_t *n) {
+    *n = stList_length(anchorPairs);
+    int64_t *a = st_malloc(sizeof(int64_t) * 2 * (*n > 0 ? *n : 1));
+    for (int64_t i = 0; i < *n; i++) {
+        stIntTuple *t = stList_get(anchorPairs, i);
+        a[2 * i] = stIntTuple_get(t, 0);
+        a[2 * i + 1] = stIntTuple_get(t, 1);
+    }
+    return a;
+}
+
+static stList *triples_to_list(int64_t *trip, int64_t n) {
+    stList *l = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    for (int64_t i = 0; i < n; i++) {
+        stList_append(l, stIntTuple_construct3(trip[3 * i], trip[3 * i + 1], trip[3 * i + 2]));
+    }
+    return l;
+}
+
+stList *getAlignedPairsUsingAnchors(StateMachine *sM, const char *sX, const char *sY, stList *anchorPairs, PairwiseAlignmentParameters *p,
+                                    bool alignmentHasRaggedLeftEnd, bool alignmentHasRaggedRightEnd) {
+    check_state_machine(sM);
+    barb200_ctx *ctx = shim_context();
+    barb200_pecan_params q;
+    params_from_pecan(p, &q);
+    int64_t lX = strlen(sX), lY = strlen(sY), nA, nOut = 0, *trip = NULL;
+    int64_t *anchors = flatten_anchors(anchorPairs, &nA);
+    const int64_t *ap = anchors;
+    uint8_t rl = alignmentHasRaggedLeftEnd, rr = alignmentHasRaggedRightEnd;
+    if (barb200_pecan_aligned_pairs_batch(ctx, &q, 1, &sX, &lX, &sY, &lY, &ap, &nA, &rl, &rr, &trip, &nOut, NULL, NULL) != BARB200_OK) {
+        st_errAbort("barb200: pair-HMM batch failed: %s", barb200_last_error(ctx));
+    }
+    stList *alignedPairs = triples_to_list(trip, nOut);
+    barb200_free(trip);
+    free(anchors);
+    return alignedPairs;
+}
+
+/* getAlignmentScore, multipleAligner.c:603-617 (static there) */
+static int64_t alignment_score(int64_t *trip, int64_t n, int64_t seqLength1, int64_t seqLength2) {
+    int64_t alignmentScore = 0;
+    for (int64_t i = 0; i < n; i++) {
+        alignmentScore += trip[3 * i];
+    }
+    int64_t j = seqLength1 < seqLength2 ? seqLength1 : seqLength2;
+    j = j == 0 ? 1 : j;
+    double d = (double) alignmentScore / (j * PAIR_ALIGNMENT_PROB_1);
+    d = d > 1.0 ? 1.0 : d;
+    d = d < 0.0 ? 0.0 : d;
+    return d * PAIR_ALIGNMENT_PROB_1;
+}
+
+stList *makeAllPairwiseAlignments(StateMachine *sM, stList *seqFrags, PairwiseAlignmentParameters *p, stList **seqPairSimilarityScores) {
+    check_state_machine(sM);
+    barb200_ctx *ctx = shim_context();
+    barb200_pecan_params q;
+    params_from_pecan(p, &q);
+    *seqPairSimilarityScores = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    stList *multipleAlignedPairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    const int64_t seqNo = stList_length(seqFrags), pairNo = seqNo * (seqNo - 1) / 2;
+    if (pairNo <= 0) {
+        return multipleAlignedPairs;
+    }
+    const char **sx = st_malloc(sizeof(char *) * pairNo), **sy = st_malloc(sizeof(char *) * pairNo);
+    int64_t *lx = st_malloc(8 * pairNo), *ly = st_malloc(8 * pairNo), *na = st_malloc(8 * pairNo), *nOut = st_malloc(8 * pairNo);
+    int64_t **anchors = st_malloc(sizeof(int64_t *) * pairNo), **trip = st_malloc(sizeof(int64_t *) * pairNo);
+    uint8_t *rl = st_malloc(pairNo), *rr = st_malloc(pairNo);
+    int64_t k = 0;
+    for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {            /* the pairs in the reference's order, multipleAligner.c:675-679 */
+        for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
+            SeqFrag *f1 = stList_get(seqFrags, seq1), *f2 = stList_get(seqFrags, seq2);
+            sx[k] = f1->seq; sy[k] = f2->seq; lx[k] = strlen(f1->seq); ly[k] = strlen(f2->seq);
+            /* anchors: the reference's host code (getAlignedPairs, pairwiseAligner.c:1527-1534) */
+            stList *anchorPairs = getAnchorPairsForPairwiseAlignmentParameters(f1->seq, f2->seq, lx[k], ly[k], p);
+            anchors[k] = flatten_anchors(anchorPairs, &na[k]);
+            stList_destruct(anchorPairs);
+            rl[k] = f1->leftEndId != f2->leftEndId;            /* addMultipleAlignedPairs, multipleAligner.c:660-661 */
+            rr[k] = f1->rightEndId != f2->rightEndId;
+        }
+    }
+    if (barb200_pecan_aligned_pairs_batch(ctx, &q, pairNo, sx, lx, sy, ly, (const int64_t *const *) anchors, na, rl, rr, trip, nOut, NULL, NULL) != BARB200_OK) {
+        st_errAbort("barb200: pair-HMM batch failed: %s", barb200_last_error(ctx));
+    }
+    k = 0;
+    for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {
+        for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
+            SeqFrag *f1 = stList_get(seqFrags, seq1), *f2 = stList_get(seqFrags, seq2);
+            stList *alignedPairs = reweightAlignedPairs2(triples_to_list(trip[k], nOut[k]), f1->length, f2->length, p->gapGamma);
+            int64_t distance;
+            if (p->gapGamma <= 0.0) {
+                distance = alignment_score(trip[k], nOut[k], f1->length, f2->length);
+            } else {                                           /* scores were reweighted: sum them from the list */
+                int64_t n = stList_length(alignedPairs), *t2 = st_malloc(24 * (n > 0 ? n : 1));
+                for (int64_t i = 0; i < n; i++) { t2[3 * i] = stIntTuple_get(stList_get(alignedPairs, i), 0); }
+                distance = alignment_score(t2, n, f1->length, f2->length);
+                free(t2);
+            }
+            /* convertAlignedPairsToMultipleAlignedPairs, multipleAligner.c:619-633 (static there): pops, i.e. reverses */
+            while (stList_length(alignedPairs) > 0) {
+                stIntTuple *aP = stList_pop(alignedPairs);
+                stList_append(multipleAlignedPairs, stIntTuple_construct5(stIntTuple_get(aP, 0), seq1, stIntTuple_get(aP, 1), seq2, stIntTuple_get(aP, 2)));
+                stIntTuple_destruct(aP);
+            }
+            stList_destruct(alignedPairs);
+            stList_append(*seqPairSimilarityScores, stIntTuple_construct3(distance, seq1, seq2));
+            barb200_free(trip[k]);
+            free(anchors[k]);
+        }
+    }
+    free(sx); free(sy); free(lx); free(ly); free(na); free(nOut); free(anchors); free(trip); free(rl); free(rr);
+    return multipleAlignedPairs;
+}

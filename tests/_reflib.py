@@ -485,3 +485,31 @@ def cpu_pecan_many(pairs, threads=0, p=None, prefer_ref=True):
         for q in pairs:
             fn(q)
     return time.perf_counter() - t0, ("reference" if use_ref else "port")
+
+
+PECAN_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libpecan_shim.so")
+
+
+def have_pecan_shim():
+    return os.path.exists(PECAN_SHIM_SO)
+
+
+def make_all_pairwise(seqs, left_end, right_end, libname="ref"):
+    """makeAllPairwiseAlignments (multipleAligner.c:667-680) of the unmodified reference ("ref") or of the shim library, where
+    the reference symbol is served by libbarb200 (GPU needed). Returns (tuples [n, 5], scores [npairs, 3])."""
+    lib = _load(PECAN_REF_SO if libname == "ref" else PECAN_SHIM_SO)
+    f = lib.pecan_ref_make_all_pairwise
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.pecan_ref_free.argtypes = [C.c_void_p]
+    lib.pecan_ref_free.restype = None
+    n = len(seqs)
+    arr = (C.c_char_p * n)(*seqs)
+    le, re_ = np.asarray(left_end, np.int64), np.asarray(right_end, np.int64)
+    t, s, ns = C.c_void_p(), C.c_void_p(), C.c_int64()
+    k = f(n, arr, le.ctypes.data, re_.ctypes.data, C.byref(t), C.byref(s), C.byref(ns))
+    tup = np.ctypeslib.as_array(C.cast(t, C.POINTER(C.c_int64)), shape=(max(5 * k, 1),))[: 5 * k].reshape(k, 5).copy()
+    sc = np.ctypeslib.as_array(C.cast(s, C.POINTER(C.c_int64)), shape=(max(3 * ns.value, 1),))[: 3 * ns.value].reshape(ns.value, 3).copy()
+    lib.pecan_ref_free(t)
+    lib.pecan_ref_free(s)
+    return tup, sc

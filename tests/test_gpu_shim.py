@@ -45,3 +45,44 @@ def test_shim_vs_reference_library():
         b = R.ref_make_consistent_partial_order_alignments(ends, ri, rr, ov)
         for x, y in zip(a, b):
             assert x.shape == y.shape and np.array_equal(x, y), it
+
+
+# ---- cPecan mode: shim/cactus_pecan_shim.c linked with the reference's own pairwiseAligner.o / multipleAligner.o --------
+needs_pecan_libs = pytest.mark.skipif(not (R.have_pecan_shim() and R.have_pecan_ref()),
+                                      reason="oracle/_ref/libpecan_shim.so / libpecan_ref.so not built (needs /root/reference at build time)")
+
+
+@needs_pecan_libs
+def test_pecan_shim_get_aligned_pairs_golden():
+    """the reference's getAlignedPairsUsingAnchors SYMBOL, served by libbarb200, against the golden triples"""
+    import ctypes as C
+    lib = R._load(R.PECAN_SHIM_SO)
+    f = lib.pecan_ref_aligned_pairs2
+    f.restype = C.c_int64
+    f.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(R.PecanParams), C.c_int64,
+                  C.POINTER(C.c_void_p)]
+    lib.pecan_ref_free.argtypes = [C.c_void_p]
+    for c in G.pecan_cases():
+        p = R.pecan_params(c["threshold"], c["min_diags"], c["tb_diags"], c["expansion"])
+        a = np.ascontiguousarray(c["anchors"], np.int64)
+        t = C.c_void_p()
+        n = f(c["sx"], len(c["sx"]), c["sy"], len(c["sy"]), a.ctypes.data, len(a), int(c["rl"]), int(c["rr"]), C.byref(p), c["split"], C.byref(t))
+        got = np.ctypeslib.as_array(C.cast(t, C.POINTER(C.c_int64)), shape=(max(3 * n, 1),))[: 3 * n].reshape(n, 3).copy()
+        lib.pecan_ref_free(t)
+        assert np.array_equal(got, c["triples"]), c["id"]
+
+
+@needs_pecan_libs
+def test_pecan_shim_make_all_pairwise_alignments():
+    """makeAllPairwiseAlignments (multipleAligner.c:667-680): one device batch for all pairs of an end, against the
+    unmodified reference library -- incl. the reference's own MUM anchoring for matrices larger than 500 x 500"""
+    from _synth import evolve
+    rng = np.random.default_rng(2718)
+    for K, L in [(2, 60), (4, 300), (3, 900), (5, 150)]:
+        parent = rng.integers(0, 4, L).astype(np.uint8)
+        seqs = [to_ascii(evolve(parent, rng, sub=0.05, ins=0.01, dele=0.01)) for _ in range(K)]
+        le = [int(x) for x in rng.integers(0, 2, K)]
+        re_ = [int(x) for x in rng.integers(0, 2, K)]
+        a, sa = R.make_all_pairwise(seqs, le, re_, "shim")
+        b, sb = R.make_all_pairwise(seqs, le, re_, "ref")
+        assert np.array_equal(a, b) and np.array_equal(sa, sb), (K, L)
