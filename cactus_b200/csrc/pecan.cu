@@ -1,14 +1,15 @@
-// pecan.cu -- cPecan mode of libbarb200: the batched banded pair-HMM kernel (one warp per job, pecan_warp.cuh), its
-// host orchestration and the C ABI declared in include/barb200.h (barb200_pecan_*).
+// pecan.cu -- cPecan mode of libbarb200: the batched banded pair-HMM kernel (one thread block per job, pecan_cta.cuh),
+// its host orchestration and the C ABI declared in include/barb200.h (barb200_pecan_*).
 //
 // A *stage* takes n sequence pairs with their anchors, splits each pair at large anchor gaps, builds the anchor band of
 // every sub-matrix and the traceback schedule on host threads (pecan_plan.cpp), packs everything, uploads it once and
-// launches persistent warps that pull jobs (largest first) from a device counter. Each warp owns a scratch slot in HBM:
-// the forward ring, three backward diagonals and one reduction buffer. Jobs are grouped by the ring size they need so
-// that the common case (narrow anchored bands) runs with every SM full and rare wide jobs run with fewer, larger slots.
-// Candidate pairs (x, y, log posterior) are written in the reference's order of emission, compacted on the device, copied
-// back once and finished on the host with libm's exp (the same function the reference calls), threshold and floor.
-// There is no CPU fallback: the DP only exists as the CUDA kernel below.
+// launches persistent blocks that pull jobs (largest first) from a device counter. Jobs fall into four classes by their
+// widest diagonal: <= 96 cells -> 32-thread blocks (16 per SM), <= 640 -> 128 threads (2 per SM), <= 1280 -> 256 threads
+// (1 per SM), all with the diagonal ring in shared memory; wider -> 256 threads with the ring in HBM/L2. The classes run
+// concurrently on their own streams. Each resident block owns a slot in HBM for the forward MATCH ring and the ring of
+// complete forward cells. Candidate pairs (x, y, log posterior) are written in the reference's order of emission,
+// compacted on the device, copied back once and finished on the host with libm's exp (the same function the reference
+// calls), threshold and floor. There is no CPU fallback: the DP only exists as the CUDA kernel below.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <omp.h>
@@ -21,7 +22,7 @@
 #include <vector>
 #include "host_api.h"
 #include "pecan_plan.h"
-#include "pecan_warp.cuh"
+#include "pecan_cta.cuh"
 
 using namespace barb200;
 using namespace barb200::pecan;
@@ -33,44 +34,43 @@ struct KernelArgs {
     const Job *jobs;
     const int *order;          // job indices of this launch, largest first
     int n_jobs;
-    int n_warps;
     const uint8_t *sym;
-    const int *bandL, *coff;
+    const int *bandL, *coff, *foff;
     Pair *out;
     int *out_n;
     unsigned *counter;
     const double *consts;
-    double *scratch;
-    size_t slot_doubles;       // per warp: ring (fmask + 1) + 16 * ringW
-    unsigned fmask;
-    int ringW;
+    double *scratch;           // per block: FM ring (maskM + 1), FF ring (maskF + 1) [, ring 15 * RW + tbuf RW when not in smem]
+    size_t slot_doubles;
+    unsigned maskM, maskF;
+    int RW;
+    int ring_in_smem;
     Params P;
 };
 
-constexpr int kWarpsPerCta = 4;
-
-extern "C" __global__ void __launch_bounds__(32 * kWarpsPerCta) pecan_posterior_kernel(const KernelArgs A) {
-    __shared__ double K[K_TOTAL];
+// dynamic shared memory: constants | total | [ring 15 * RW | tbuf RW]
+extern "C" __global__ void __launch_bounds__(256) pecan_posterior_kernel(const KernelArgs A) {
+    extern __shared__ double smem[];
+    double *K = smem;
     for (int i = threadIdx.x; i < K_TOTAL; i += blockDim.x) K[i] = A.consts[i];
-    __syncthreads();
-    const int warp = blockIdx.x * kWarpsPerCta + (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
-    if (warp >= A.n_warps) return;
-    WarpMem wm;
-    wm.F = A.scratch + (size_t)warp * A.slot_doubles;
-    wm.fmask = A.fmask;
-    wm.B = wm.F + (size_t)A.fmask + 1;
-    wm.ringW = A.ringW;
-    wm.tbuf = wm.B + 15 * (size_t)A.ringW;
+    __shared__ unsigned next_job;
+    CtaMem cm;
+    cm.total = smem + K_TOTAL;
+    cm.RW = A.RW; cm.T = (int)blockDim.x;
+    cm.FM = A.scratch + (size_t)blockIdx.x * A.slot_doubles; cm.maskM = A.maskM;
+    cm.FF = cm.FM + (size_t)A.maskM + 1; cm.maskF = A.maskF;
+    if (A.ring_in_smem) { cm.ring = smem + K_TOTAL + 2; cm.tbuf = cm.ring + 15 * (size_t)A.RW; }
+    else { cm.ring = cm.FF + (size_t)A.maskF + 1; cm.tbuf = cm.ring + 15 * (size_t)A.RW; }
     for (;;) {
-        unsigned idx = 0;
-        if (lane == 0) idx = atomicAdd(A.counter, 1u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) next_job = atomicAdd(A.counter, 1u);
+        __syncthreads();
+        const unsigned idx = next_job;
         if (idx >= (unsigned)A.n_jobs) break;
         const int j = A.order[idx];
         const Job J = A.jobs[j];
-        const int n = run_job(J, A.sym, A.bandL, A.coff, wm, A.P, K, A.out, nullptr);
-        if (lane == 0) A.out_n[j] = n;
-        __syncwarp();
+        const int n = run_job(J, A.sym, A.bandL, A.coff, A.foff, cm, A.P, K, A.out);
+        if (threadIdx.x == 0) A.out_n[j] = n;
     }
 }
 
@@ -89,13 +89,16 @@ extern "C" __global__ void pecan_compact_kernel(const Job *jobs, const int *out_
 #define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
     set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(_e)); return BARB200_ECUDA; } } while (0)
 
-struct PecanGroup {
+struct PecanGroup {              // one launch: a class of jobs with one block shape
     std::vector<int> jobs;       // largest first
-    unsigned fcap = 0;           // ring doubles (power of two)
-    int ringW = 0;
-    int warps = 0;
-    size_t slot_doubles = 0;
+    int threads = 32;            // block size
+    int ctas = 0;                // resident blocks = slots
+    int RW = 32;                 // ring width (cells)
+    bool ring_in_smem = true;
+    unsigned capM = 1024, capF = 1024;   // ring doubles (powers of two)
+    size_t slot_doubles = 0, smem_bytes = 0, scratch_off = 0;
     int order_off = 0;           // into d_order
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 };
 
 struct barb200_pecan_stage {
@@ -111,7 +114,7 @@ struct barb200_pecan_stage {
     std::vector<PecanGroup> groups;
     int64_t cells = 0, launches = 0, out_total = 0;
     // device
-    uint8_t *d_sym = nullptr; int *d_bandL = nullptr, *d_coff = nullptr, *d_order = nullptr, *d_out_n = nullptr;
+    uint8_t *d_sym = nullptr; int *d_bandL = nullptr, *d_coff = nullptr, *d_foff = nullptr, *d_order = nullptr, *d_out_n = nullptr;
     Job *d_jobs = nullptr; Pair *d_out = nullptr; unsigned *d_counter = nullptr; double *d_consts = nullptr, *d_scratch = nullptr;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ran = false;
@@ -132,8 +135,9 @@ static unsigned pow2ceil(uint64_t v) { uint64_t p = 1024; while (p < v) p <<= 1;
 extern "C" void barb200_pecan_stage_destroy(barb200_pecan_stage *st) {
     if (!st) return;
     cudaSetDevice(ctx_device(st->ctx));
-    void *ptrs[] = {st->d_sym, st->d_bandL, st->d_coff, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
+    void *ptrs[] = {st->d_sym, st->d_bandL, st->d_coff, st->d_foff, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (PecanGroup &g : st->groups) { if (g.stream) cudaStreamDestroy(g.stream); if (g.done) cudaEventDestroy(g.done); }
     if (st->ev0) cudaEventDestroy(st->ev0);
     if (st->ev1) cudaEventDestroy(st->ev1);
     if (st->stream) cudaStreamDestroy(st->stream);
@@ -185,7 +189,7 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     // pack
     std::vector<uint8_t> &sym = st->h_sym;
     sym.assign((size_t)std::max<int64_t>(sym_off, 1), 4);
-    std::vector<int> bandL((size_t)band_off + 1), coff((size_t)band_off + 1);
+    std::vector<int> bandL((size_t)band_off + 1), coff((size_t)band_off + 1), foff((size_t)band_off + 1);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
     for (int64_t i = 0; i < ns; ++i) {
         const SubJob &s = st->subs[i];
@@ -202,61 +206,58 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         const int D = s.lx + s.ly;
         memcpy(&bandL[J.band_off], s.bandL.data(), sizeof(int) * (D + 1)); bandL[J.band_off + D + 1] = 0;
         memcpy(&coff[J.band_off], s.coff.data(), sizeof(int) * (D + 2));
+        memcpy(&foff[J.band_off], s.foff.data(), sizeof(int) * (D + 2));
     }
-    // groups by forward-ring size
+    // classes by the widest diagonal (see the file header); each class is one launch on its own stream
     cudaSetDevice(ctx_device(ctx));
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const size_t fixed = (size_t)sym_off + (size_t)band_off * 8 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
+    const size_t fixed = (size_t)sym_off + (size_t)band_off * 12 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
-    const size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
-    const int full_warps = ctx_sm_count(ctx) * 32;
-    std::vector<unsigned> need(ns);
-    for (int64_t i = 0; i < ns; ++i) need[i] = pow2ceil((uint64_t)5 * (uint64_t)std::max<int64_t>(st->subs[i].span_cells, 1));
-    std::vector<int> by_need(ns);
-    for (int64_t i = 0; i < ns; ++i) by_need[i] = (int)i;
-    std::sort(by_need.begin(), by_need.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] < need[b] : a < b; });
-    // main group: the largest prefix (by need) that still lets every SM be full
+    size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
+    static const struct { int max_w, threads, ctas_per_sm; bool smem; } kClass[4] = {{96, 32, 16, true}, {640, 128, 2, true}, {1280, 256, 1, true}, {0x7fffffff, 256, 1, false}};
     st->groups.clear();
-    int64_t taken = 0;
-    {
-        int64_t best = 0; int rw = 0;
-        for (int64_t i = 0; i < ns; ++i) {
-            rw = std::max(rw, st->subs[by_need[i]].max_w);
-            const size_t slot = ((size_t)need[by_need[i]] + 16 * (size_t)rw) * 8;
-            const int64_t warps = std::min<int64_t>(full_warps, i + 1);
-            if (slot * (size_t)warps <= budget) best = i + 1; else break;
-        }
-        if (best > 0) {
-            PecanGroup g; g.jobs.assign(by_need.begin(), by_need.begin() + best);
-            st->groups.push_back(std::move(g)); taken = best;
-        }
-    }
-    while (taken < ns) {          // rest: one group per ring size, as many warps as memory allows
-        PecanGroup g; const unsigned nd = need[by_need[taken]];
-        while (taken < ns && need[by_need[taken]] == nd) g.jobs.push_back(by_need[taken++]);
+    for (int c = 0; c < 4; ++c) {
+        PecanGroup g;
+        for (int64_t i = 0; i < ns; ++i) if (st->subs[i].max_w <= kClass[c].max_w && (c == 0 || st->subs[i].max_w > kClass[c - 1].max_w)) g.jobs.push_back((int)i);
+        if (g.jobs.empty()) continue;
+        int64_t spanM = 1, spanF = 1; int rw = 1;
+        for (int j : g.jobs) { spanM = std::max(spanM, st->subs[j].span_cells); spanF = std::max(spanF, st->subs[j].span_full_cells); rw = std::max(rw, st->subs[j].max_w); }
+        g.threads = kClass[c].threads; g.ring_in_smem = kClass[c].smem;
+        g.RW = kClass[c].smem ? kClass[c].max_w : ((rw + 31) & ~31);
+        g.capM = pow2ceil((uint64_t)spanM); g.capF = pow2ceil((uint64_t)5 * (uint64_t)spanF);
+        g.slot_doubles = (size_t)g.capM + g.capF + (g.ring_in_smem ? 0 : 16 * (size_t)g.RW);
+        g.smem_bytes = sizeof(double) * (K_TOTAL + 2 + (g.ring_in_smem ? 16 * (size_t)g.RW : 0));
+        g.ctas = (int)std::min<int64_t>((int64_t)ctx_sm_count(ctx) * kClass[c].ctas_per_sm, (int64_t)g.jobs.size());
+        std::sort(g.jobs.begin(), g.jobs.end(), [&](int a, int b) { return st->subs[a].cells != st->subs[b].cells ? st->subs[a].cells > st->subs[b].cells : a < b; });
         st->groups.push_back(std::move(g));
     }
-    size_t scratch_bytes = 0; int order_off = 0;
+    // the classes run concurrently, so their slots are disjoint; shrink block counts (largest slots first) if memory is short
+    for (;;) {
+        size_t need = 0;
+        for (PecanGroup &g : st->groups) need += g.slot_doubles * 8 * (size_t)g.ctas;
+        if (need <= budget) break;
+        PecanGroup *big = nullptr;
+        for (PecanGroup &g : st->groups) if (g.ctas > 1 && (!big || g.slot_doubles * g.ctas > big->slot_doubles * big->ctas)) big = &g;
+        if (!big) { set_error(ctx, "a pair-HMM job needs more device memory than is available"); return BARB200_ENOMEM; }
+        big->ctas = std::max(1, big->ctas * 3 / 4);
+    }
+    size_t scratch_doubles = 0; int order_off = 0;
     std::vector<int> order((size_t)std::max<int64_t>(ns, 1));
     for (PecanGroup &g : st->groups) {
-        unsigned fc = 1024; int rw = 1;
-        for (int j : g.jobs) { fc = std::max(fc, need[j]); rw = std::max(rw, st->subs[j].max_w); }
-        g.fcap = fc; g.ringW = (rw + 31) & ~31; g.slot_doubles = (size_t)fc + 16 * (size_t)g.ringW;
-        const size_t slot = g.slot_doubles * 8;
-        int64_t warps = std::min<int64_t>({(int64_t)full_warps, (int64_t)g.jobs.size(), (int64_t)(budget / slot)});
-        if (warps < 1) { set_error(ctx, "a pair-HMM job needs more device memory than is available"); return BARB200_ENOMEM; }
-        g.warps = (int)warps;
-        scratch_bytes = std::max(scratch_bytes, slot * (size_t)warps);
-        std::sort(g.jobs.begin(), g.jobs.end(), [&](int a, int b) { return st->subs[a].cells != st->subs[b].cells ? st->subs[a].cells > st->subs[b].cells : a < b; });
+        g.scratch_off = scratch_doubles; scratch_doubles += g.slot_doubles * (size_t)g.ctas;
         g.order_off = order_off;
         for (int j : g.jobs) order[order_off++] = j;
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     }
+    const size_t scratch_bytes = scratch_doubles * 8;
     // device arrays
     Consts C; fill_constants(C);
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_sym, sym.size()));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_bandL, bandL.size() * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_coff, coff.size() * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_foff, foff.size() * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_order, order.size() * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out_n, (size_t)std::max<int64_t>(ns, 1) * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_jobs, (size_t)std::max<int64_t>(ns, 1) * sizeof(Job)));
@@ -269,6 +270,7 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_sym, sym.data(), sym.size(), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_bandL, bandL.data(), bandL.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_coff, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_foff, foff.data(), foff.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
     if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(st->d_jobs, st->jobs.data(), (size_t)ns * sizeof(Job), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_consts, &C, sizeof(C), cudaMemcpyHostToDevice, st->stream));
@@ -309,19 +311,23 @@ extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_
 static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
     barb200_ctx *ctx = st->ctx;
     cudaSetDevice(ctx_device(ctx));
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(pecan_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned) * (st->groups.size() + 1), st->stream));
     CUDA_TRY(ctx, cudaEventRecord(st->ev0, st->stream));
     st->launches = 0;
     for (size_t gi = 0; gi < st->groups.size(); ++gi) {
         const PecanGroup &g = st->groups[gi];
         KernelArgs A;
-        A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size(); A.n_warps = g.warps;
-        A.sym = st->d_sym; A.bandL = st->d_bandL; A.coff = st->d_coff; A.out = st->d_out; A.out_n = st->d_out_n;
-        A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch; A.slot_doubles = g.slot_doubles;
-        A.fmask = g.fcap - 1; A.ringW = g.ringW; A.P = st->devP;
-        const int ctas = (g.warps + kWarpsPerCta - 1) / kWarpsPerCta;
-        pecan_posterior_kernel<<<ctas, 32 * kWarpsPerCta, 0, st->stream>>>(A);
+        A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size();
+        A.sym = st->d_sym; A.bandL = st->d_bandL; A.coff = st->d_coff; A.foff = st->d_foff; A.out = st->d_out; A.out_n = st->d_out_n;
+        A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch + g.scratch_off; A.slot_doubles = g.slot_doubles;
+        A.maskM = g.capM - 1; A.maskF = g.capF - 1; A.RW = g.RW; A.ring_in_smem = g.ring_in_smem ? 1 : 0; A.P = st->devP;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(g.stream, st->ev0, 0));
+        pecan_posterior_kernel<<<g.ctas, g.threads, g.smem_bytes, g.stream>>>(A);
         CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(g.done, g.stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st->stream, g.done, 0));
         ++st->launches;
     }
     CUDA_TRY(ctx, cudaEventRecord(st->ev1, st->stream));

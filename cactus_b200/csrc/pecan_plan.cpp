@@ -107,17 +107,33 @@ std::string plan_subjob(const PlanParams &P, SubJob &s) {
     }
     s.coff[D + 1] = (int)cells;
     s.cells = cells; s.max_w = max_w;
-    // schedule (pairwiseAligner.c:798-803, 817): which spans of forward diagonals are alive together
-    int64_t tb_to = 0, span = 0;
+    // schedule (pairwiseAligner.c:798-803, 817, 840-848): traceback points only depend on the band geometry
+    std::vector<uint8_t> mark((size_t)D + 1, 0);
+    struct Tb { int64_t d, to; };
+    std::vector<Tb> tbs;
+    int64_t tb_to = 0;
     for (int64_t d = 1; d <= D; ++d) {
         const int64_t w = s.coff[d + 1] - s.coff[d];
         const bool at_end = d == D, tb_point = d >= tb_to + P.min_diags && w <= P.expansion * 2 + 1;
         if (!(at_end || tb_point)) continue;
-        span = std::max<int64_t>(span, s.coff[d + 1] - s.coff[tb_to]);
-        tb_to = d - (at_end ? 0 : P.tb_diags + 1);
+        const int64_t tb_from = d - (at_end ? 0 : P.tb_diags + 1);
+        int64_t c = 0;
+        for (int64_t t = tb_from; t > tb_to; --t, ++c)
+            if (c % 10 == 0) { mark[t] = 1; mark[t - 1] = 1; }
+        if (!at_end) { mark[d] = 1; mark[d - 1] = 1; }
+        tbs.push_back(Tb{d, tb_to});
+        tb_to = tb_from;
     }
-    if (D == 0) span = 1;
-    s.span_cells = span;
+    s.foff.assign(D + 2, 0);
+    int64_t fc = 0;
+    for (int64_t d = 0; d <= D; ++d) { s.foff[d] = (int)fc; if (mark[d]) fc += s.coff[d + 1] - s.coff[d]; }
+    s.foff[D + 1] = (int)fc;
+    int64_t span = 1, span_full = 1;
+    for (const Tb &tb : tbs) {
+        span = std::max<int64_t>(span, s.coff[tb.d + 1] - s.coff[tb.to]);
+        span_full = std::max<int64_t>(span_full, s.foff[tb.d + 1] - s.foff[tb.to]);
+    }
+    s.span_cells = span; s.span_full_cells = span_full;
     return "";
 }
 

@@ -25,8 +25,10 @@ struct SubJob {
     // plan
     std::vector<int> bandL;        // xmyL of diagonals 0..D
     std::vector<int> coff;         // cells before diagonal d, D+2 entries
+    std::vector<int> foff;         // cells of MARKED diagonals before diagonal d, D+2 entries (see plan_subjob)
     int64_t cells = 0;             // sum of diagonal widths
     int64_t span_cells = 0;        // most forward cells alive at once (between two tracebacks)
+    int64_t span_full_cells = 0;   // most cells of marked diagonals alive at once
     int max_w = 0;
     int out_cap = 0;
 };
@@ -39,7 +41,10 @@ std::string check_anchors(const int64_t *anchors, int64_t n, int64_t lx, int64_t
 void split_pair(const PlanParams &P, int64_t pair, int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor,
                 bool ragged_left, bool ragged_right, std::vector<SubJob> &out);
 
-// band_construct: fills bandL / coff / cells / max_w; then the schedule: span_cells. Returns "" or an error.
+// band_construct: fills bandL / coff / cells / max_w; then the schedule: which spans of diagonals are alive together
+// (span_cells) and which diagonals a traceback needs COMPLETE forward cells of (marked in foff): the ones the total
+// probability is recomputed on (every 10th posterior diagonal, pairwiseAligner.c:840-848) with their predecessors, and
+// the two diagonals the forward sweep resumes from after an intermediate traceback. Returns "" or an error.
 std::string plan_subjob(const PlanParams &P, SubJob &j);
 
 }  // namespace pecan

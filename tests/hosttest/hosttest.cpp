@@ -195,15 +195,18 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
 extern "C" void hosttest_free(void *p) { free(p); }
 
 // ---------------------------------------------------------------------------------------------------------
-// cPecan mode: the product's warp program (cactus_b200/csrc/pecan_warp.cuh) with the 32 lanes of every phase run one
+// cPecan mode: the product's block program (cactus_b200/csrc/pecan_cta.cuh) with the T threads of every phase run one
 // after the other, on top of the product's host planning (pecan_plan.cpp). The exp / threshold / floor step mirrors
 // finish_pairs in pecan.cu. Same output as oracle_pecan_aligned_pairs.
 // ---------------------------------------------------------------------------------------------------------
 #include <math.h>
 #include "../../cactus_b200/csrc/pecan_plan.h"
-#include "../../cactus_b200/csrc/pecan_warp.cuh"
+#include "../../cactus_b200/csrc/pecan_cta.cuh"
 
 struct HtPecanParams { double threshold; int64_t minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion; };
+
+static int g_pecan_threads = 32;
+extern "C" void hosttest_pecan_set_threads(int t) { g_pecan_threads = t; }
 
 extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, const char *csy, int64_t lY, const int64_t *anchors, int64_t n_anchor,
                                                 int ragged_left, int ragged_right, const HtPecanParams *pp, int64_t split_bigger,
@@ -226,18 +229,21 @@ extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, con
         auto code = [](char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
         for (int k = 0; k < s.lx; ++k) sym[k] = (uint8_t)code(csx[s.x1 + k]);
         for (int k = 0; k < s.ly; ++k) sym[s.lx + k] = (uint8_t)code(csy[s.y1 + k]);
-        unsigned fcap = 1024; while (fcap < 5 * (uint64_t)std::max<int64_t>(s.span_cells, 1)) fcap <<= 1;
-        const int ringW = (s.max_w + 31) & ~31;
-        std::vector<double> scratch((size_t)fcap + 16 * (size_t)ringW, NAN);
-        pc::WarpMem wm; wm.F = scratch.data(); wm.fmask = fcap - 1; wm.B = wm.F + fcap; wm.ringW = ringW; wm.tbuf = wm.B + 15 * (size_t)ringW;
+        unsigned capM = 1024; while (capM < (uint64_t)std::max<int64_t>(s.span_cells, 1)) capM <<= 1;
+        unsigned capF = 1024; while (capF < 5 * (uint64_t)std::max<int64_t>(s.span_full_cells, 1)) capF <<= 1;
+        const int RW = (s.max_w + 31) & ~31;
+        std::vector<double> fm(capM, NAN), ff(capF, NAN), ring(15 * (size_t)RW, NAN), tbuf((size_t)RW, NAN);
+        double total = NAN;
+        pc::CtaMem cm; cm.ring = ring.data(); cm.tbuf = tbuf.data(); cm.total = &total; cm.RW = RW; cm.FM = fm.data(); cm.maskM = capM - 1;
+        cm.FF = ff.data(); cm.maskF = capF - 1; cm.T = g_pecan_threads;
         pc::Job J; J.sx_off = 0; J.sy_off = s.lx; J.band_off = 0; J.out_off = 0; J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged;
         J.out_cap = (int)std::min<int64_t>(s.cells, (int64_t)s.lx + s.ly + 64);
         std::vector<int> bl(s.bandL); bl.push_back(0);
         std::vector<pc::Pair> out((size_t)std::max(J.out_cap, 1));
-        int n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), wm, dp, C.v, out.data(), nullptr);
+        int n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), s.foff.data(), cm, dp, C.v, out.data());
         if (n > J.out_cap) {              // the product's retry: room for every cell
             J.out_cap = (int)s.cells; out.assign((size_t)std::max(J.out_cap, 1), pc::Pair());
-            n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), wm, dp, C.v, out.data(), nullptr);
+            n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), s.foff.data(), cm, dp, C.v, out.data());
             if (n > J.out_cap) return -3;
         }
         for (int q = n - 1; q >= 0; --q) {

@@ -1,6 +1,6 @@
 """cPecan mode, CPU suite: (1) the plain-C oracle against the compiled reference (differential, seeded) and against the
-committed golden vectors, incl. the reference's own known-answer case; (2) the product's warp program
-(cactus_b200/csrc/pecan_warp.cuh) and host planning (pecan_plan.cpp), emulated on the host by tests/hosttest, against the
+committed golden vectors, incl. the reference's own known-answer case; (2) the product's block program
+(cactus_b200/csrc/pecan_cta.cuh) and host planning (pecan_plan.cpp), emulated on the host by tests/hosttest, against the
 oracle -- bit-exact on the integer triples AND on the pre-floor posteriors; (3) the host-only C-ABI helpers
 (barb200_pecan_band / barb200_pecan_split_points) against the oracle. The CUDA kernel itself runs under -m gpu."""
 import numpy as np
@@ -76,8 +76,9 @@ def test_warp_program_vs_oracle_random(oracle_built):
     for it in range(80):
         sx, sy, a, rl, rr, p, sb = _random_case(rng)
         to, po = R.oracle_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb)
-        th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb)
-        assert np.array_equal(to, th) and np.array_equal(po, ph), (it, len(sx), len(sy), len(a))
+        T = int(rng.choice([32, 128, 256]))
+        th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb, threads=T)
+        assert np.array_equal(to, th) and np.array_equal(po, ph), (it, T, len(sx), len(sy), len(a))
 
 
 def test_empty_and_degenerate(oracle_built):
