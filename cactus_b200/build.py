@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbarb200.so")
 SOURCES = ["poa_kernel.cu", "barb200.cu", "guide_tree.cpp", "host_bar.cpp", "synth.cpp", "pecan.cu", "pecan_plan.cpp"]
-HEADERS = ["poa_types.h", "poa_graph.cuh", "poa_kernel.cuh", "host_api.h", "pecan_warp.cuh", "pecan_plan.h", os.path.join("..", "..", "include", "barb200.h")]
+HEADERS = ["poa_types.h", "poa_graph.cuh", "poa_kernel.cuh", "host_api.h", "pecan_cta.cuh", "pecan_plan.h", os.path.join("..", "..", "include", "barb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
          "-Xcompiler", "-fPIC,-fopenmp,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

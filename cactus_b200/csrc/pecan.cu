@@ -35,12 +35,12 @@ struct KernelArgs {
     const int *order;          // job indices of this launch, largest first
     int n_jobs;
     const uint8_t *sym;
-    const int *bandL, *coff, *foff;
+    const DiagMeta *meta;
     Pair *out;
     int *out_n;
     unsigned *counter;
     const double *consts;
-    double *scratch;           // per block: FM ring (maskM + 1), FF ring (maskF + 1) [, ring 15 * RW + tbuf RW when not in smem]
+    double *scratch;           // per block: FM ring (maskM + 1), FF ring (maskF + 1) [, ring 10 * RW + tbuf RW when not in smem]
     size_t slot_doubles;
     unsigned maskM, maskF;
     int RW;
@@ -48,19 +48,21 @@ struct KernelArgs {
     Params P;
 };
 
-// dynamic shared memory: constants | total | [ring 15 * RW | tbuf RW]
-extern "C" __global__ void __launch_bounds__(256) pecan_posterior_kernel(const KernelArgs A) {
+// dynamic shared memory: constants | total | [ring 10 * RW | tbuf RW]
+extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(const KernelArgs A) {
     extern __shared__ double smem[];
     double *K = smem;
     for (int i = threadIdx.x; i < K_TOTAL; i += blockDim.x) K[i] = A.consts[i];
     __shared__ unsigned next_job;
+    __shared__ int n_out;
     CtaMem cm;
     cm.total = smem + K_TOTAL;
+    cm.n_out = &n_out;
     cm.RW = A.RW; cm.T = (int)blockDim.x;
     cm.FM = A.scratch + (size_t)blockIdx.x * A.slot_doubles; cm.maskM = A.maskM;
     cm.FF = cm.FM + (size_t)A.maskM + 1; cm.maskF = A.maskF;
-    if (A.ring_in_smem) { cm.ring = smem + K_TOTAL + 2; cm.tbuf = cm.ring + 15 * (size_t)A.RW; }
-    else { cm.ring = cm.FF + (size_t)A.maskF + 1; cm.tbuf = cm.ring + 15 * (size_t)A.RW; }
+    if (A.ring_in_smem) { cm.ring = smem + K_TOTAL + 2; cm.tbuf = cm.ring + 10 * (size_t)A.RW; }
+    else { cm.ring = cm.FF + (size_t)A.maskF + 1; cm.tbuf = cm.ring + 10 * (size_t)A.RW; }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) next_job = atomicAdd(A.counter, 1u);
@@ -69,7 +71,7 @@ extern "C" __global__ void __launch_bounds__(256) pecan_posterior_kernel(const K
         if (idx >= (unsigned)A.n_jobs) break;
         const int j = A.order[idx];
         const Job J = A.jobs[j];
-        const int n = run_job(J, A.sym, A.bandL, A.coff, A.foff, cm, A.P, K, A.out);
+        const int n = run_job(J, A.sym, A.meta, cm, A.P, K, A.out);
         if (threadIdx.x == 0) A.out_n[j] = n;
     }
 }
@@ -114,7 +116,7 @@ struct barb200_pecan_stage {
     std::vector<PecanGroup> groups;
     int64_t cells = 0, launches = 0, out_total = 0;
     // device
-    uint8_t *d_sym = nullptr; int *d_bandL = nullptr, *d_coff = nullptr, *d_foff = nullptr, *d_order = nullptr, *d_out_n = nullptr;
+    uint8_t *d_sym = nullptr; DiagMeta *d_meta = nullptr; int *d_order = nullptr, *d_out_n = nullptr;
     Job *d_jobs = nullptr; Pair *d_out = nullptr; unsigned *d_counter = nullptr; double *d_consts = nullptr, *d_scratch = nullptr;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ran = false;
@@ -135,7 +137,7 @@ static unsigned pow2ceil(uint64_t v) { uint64_t p = 1024; while (p < v) p <<= 1;
 extern "C" void barb200_pecan_stage_destroy(barb200_pecan_stage *st) {
     if (!st) return;
     cudaSetDevice(ctx_device(st->ctx));
-    void *ptrs[] = {st->d_sym, st->d_bandL, st->d_coff, st->d_foff, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
+    void *ptrs[] = {st->d_sym, st->d_meta, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (PecanGroup &g : st->groups) { if (g.stream) cudaStreamDestroy(g.stream); if (g.done) cudaEventDestroy(g.done); }
     if (st->ev0) cudaEventDestroy(st->ev0);
@@ -189,7 +191,7 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     // pack
     std::vector<uint8_t> &sym = st->h_sym;
     sym.assign((size_t)std::max<int64_t>(sym_off, 1), 4);
-    std::vector<int> bandL((size_t)band_off + 1), coff((size_t)band_off + 1), foff((size_t)band_off + 1);
+    std::vector<DiagMeta> meta((size_t)band_off + 1);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
     for (int64_t i = 0; i < ns; ++i) {
         const SubJob &s = st->subs[i];
@@ -204,20 +206,20 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
             for (int k = 0; k < s.ly; ++k) sym[J.sy_off + k] = (uint8_t)sym_of(py[k]);
         }
         const int D = s.lx + s.ly;
-        memcpy(&bandL[J.band_off], s.bandL.data(), sizeof(int) * (D + 1)); bandL[J.band_off + D + 1] = 0;
-        memcpy(&coff[J.band_off], s.coff.data(), sizeof(int) * (D + 2));
-        memcpy(&foff[J.band_off], s.foff.data(), sizeof(int) * (D + 2));
+        for (int d = 0; d <= D + 1; ++d) meta[J.band_off + d] = DiagMeta{d <= D ? s.bandL[d] : 0, s.coff[d], s.foff[d], 0};
     }
     // classes by the widest diagonal (see the file header); each class is one launch on its own stream
     cudaSetDevice(ctx_device(ctx));
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const size_t fixed = (size_t)sym_off + (size_t)band_off * 12 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
+    const size_t fixed = (size_t)sym_off + (size_t)band_off * 16 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
     size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
-    static const struct { int max_w, threads, ctas_per_sm; bool smem; } kClass[4] = {{96, 32, 16, true}, {640, 128, 2, true}, {1280, 256, 1, true}, {0x7fffffff, 256, 1, false}};
+    // shared memory per block = 8 * (58 + 11 * RW) bytes: 8.9 KB, 28.6 KB, 54 KB, 113 KB; 80 registers per thread
+    static const struct { int max_w, threads, ctas_per_sm; bool smem; } kClass[5] = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true},
+                                                                                   {1280, 256, 2, true}, {0x7fffffff, 256, 2, false}};
     st->groups.clear();
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 5; ++c) {
         PecanGroup g;
         for (int64_t i = 0; i < ns; ++i) if (st->subs[i].max_w <= kClass[c].max_w && (c == 0 || st->subs[i].max_w > kClass[c - 1].max_w)) g.jobs.push_back((int)i);
         if (g.jobs.empty()) continue;
@@ -226,8 +228,8 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         g.threads = kClass[c].threads; g.ring_in_smem = kClass[c].smem;
         g.RW = kClass[c].smem ? kClass[c].max_w : ((rw + 31) & ~31);
         g.capM = pow2ceil((uint64_t)spanM); g.capF = pow2ceil((uint64_t)5 * (uint64_t)spanF);
-        g.slot_doubles = (size_t)g.capM + g.capF + (g.ring_in_smem ? 0 : 16 * (size_t)g.RW);
-        g.smem_bytes = sizeof(double) * (K_TOTAL + 2 + (g.ring_in_smem ? 16 * (size_t)g.RW : 0));
+        g.slot_doubles = (size_t)g.capM + g.capF + (g.ring_in_smem ? 0 : 11 * (size_t)g.RW);
+        g.smem_bytes = sizeof(double) * (K_TOTAL + 2 + (g.ring_in_smem ? 11 * (size_t)g.RW : 0));
         g.ctas = (int)std::min<int64_t>((int64_t)ctx_sm_count(ctx) * kClass[c].ctas_per_sm, (int64_t)g.jobs.size());
         std::sort(g.jobs.begin(), g.jobs.end(), [&](int a, int b) { return st->subs[a].cells != st->subs[b].cells ? st->subs[a].cells > st->subs[b].cells : a < b; });
         st->groups.push_back(std::move(g));
@@ -252,12 +254,14 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     }
     const size_t scratch_bytes = scratch_doubles * 8;
+    if (getenv("BARB200_DEBUG"))
+        for (const PecanGroup &g : st->groups)
+            fprintf(stderr, "[barb200] pecan class: %zu jobs, %d threads x %d blocks, RW %d (%s), FM ring %u, FF ring %u doubles, smem %zu B\n",
+                    g.jobs.size(), g.threads, g.ctas, g.RW, g.ring_in_smem ? "smem" : "global", g.capM, g.capF, g.smem_bytes);
     // device arrays
     Consts C; fill_constants(C);
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_sym, sym.size()));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_bandL, bandL.size() * sizeof(int)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_coff, coff.size() * sizeof(int)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_foff, foff.size() * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_meta, meta.size() * sizeof(DiagMeta)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_order, order.size() * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out_n, (size_t)std::max<int64_t>(ns, 1) * sizeof(int)));
     CUDA_TRY(ctx, cudaMalloc((void **)&st->d_jobs, (size_t)std::max<int64_t>(ns, 1) * sizeof(Job)));
@@ -268,9 +272,7 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaEventCreate(&st->ev0)); CUDA_TRY(ctx, cudaEventCreate(&st->ev1));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_sym, sym.data(), sym.size(), cudaMemcpyHostToDevice, st->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_bandL, bandL.data(), bandL.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_coff, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_foff, foff.data(), foff.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_meta, meta.data(), meta.size() * sizeof(DiagMeta), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
     if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(st->d_jobs, st->jobs.data(), (size_t)ns * sizeof(Job), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_consts, &C, sizeof(C), cudaMemcpyHostToDevice, st->stream));
@@ -320,7 +322,7 @@ static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
         const PecanGroup &g = st->groups[gi];
         KernelArgs A;
         A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size();
-        A.sym = st->d_sym; A.bandL = st->d_bandL; A.coff = st->d_coff; A.foff = st->d_foff; A.out = st->d_out; A.out_n = st->d_out_n;
+        A.sym = st->d_sym; A.meta = st->d_meta; A.out = st->d_out; A.out_n = st->d_out_n;
         A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch + g.scratch_off; A.slot_doubles = g.slot_doubles;
         A.maskM = g.capM - 1; A.maskF = g.capF - 1; A.RW = g.RW; A.ring_in_smem = g.ring_in_smem ? 1 : 0; A.P = st->devP;
         CUDA_TRY(ctx, cudaStreamWaitEvent(g.stream, st->ev0, 0));
@@ -380,7 +382,12 @@ static int stage_collect(barb200_pecan_stage *st, std::vector<std::vector<Pair>>
     }
     const int nthr = host_threads(ctx);
 #pragma omp parallel for schedule(static) num_threads(nthr)
-    for (int64_t i = 0; i < ns; ++i) per_sub[i].assign(flat.begin() + dst_off[i], flat.begin() + dst_off[i + 1]);
+    for (int64_t i = 0; i < ns; ++i) {
+        per_sub[i].assign(flat.begin() + dst_off[i], flat.begin() + dst_off[i + 1]);
+        // the kernel appends the candidates of a diagonal in no particular order: restore the reference's order of emission
+        const SubJob &sj = st->subs[i];
+        std::sort(per_sub[i].begin(), per_sub[i].end(), [&](const Pair &a, const Pair &b) { return emission_key(sj, a.x, a.y) < emission_key(sj, b.x, b.y); });
+    }
     if (!retry.empty()) {
         if (st->full_cap) { set_error(ctx, "pecan: output overflow with full capacity (internal error)"); return BARB200_EJOB; }
         barb200_pecan_stage *rs = new barb200_pecan_stage();

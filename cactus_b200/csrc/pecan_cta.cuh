@@ -9,9 +9,12 @@
 // Formulation (not a translation of the reference's per-cell object code):
 //  * a block of T threads (32, 128 or 256 by the widest diagonal of the job) walks the x+y diagonals; thread t owns the
 //    cells t, t+T, ... of a diagonal (cell index k = (xmy - xmyL) / 2);
-//  * the two previous diagonals every cell needs live in a three-slot RING in shared memory (state-major, so a warp reads
-//    consecutive doubles); the same ring holds the backward diagonals during a traceback -- forward and backward are never
-//    live together, the two forward diagonals the sweep resumes from are re-loaded afterwards;
+//  * the two previous diagonals every cell needs live in a TWO-slot ring in shared memory, one slot per diagonal parity,
+//    indexed by an absolute coordinate a = (xmy + parity) / 2 (mod the ring width): the cell at the same xmy two diagonals
+//    back -- the "middle" neighbour -- then sits at the very position the new cell is written to, so a diagonal is updated
+//    IN PLACE over the one two steps back (each thread only overwrites what it alone has read) and the other slot is
+//    read-only during the step; one barrier per diagonal. The same ring holds the backward diagonals during a traceback
+//    -- forward and backward are never live together, the two forward diagonals the sweep resumes from are re-loaded;
 //  * of the forward matrix only what a traceback reads goes to HBM: the MATCH plane of every cell (the posterior needs
 //    f_M only) plus all five states of the few diagonals the total probability is recomputed on (every 10th, and its
 //    predecessor) and of the two diagonals a sweep resumes from. Which diagonals those are depends only on the band
@@ -36,6 +39,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define PC_HD __host__ __device__ __forceinline__
@@ -110,10 +114,14 @@ struct Job {
 
 struct Pair { int x, y; double lp; };   // 0-based sequence coordinates, log posterior
 
+struct DiagMeta { int L, co, fo, pad; };   // per diagonal: xmyL, cells before it, cells of MARKED diagonals before it (D+2 entries;
+                                            // diagonal d is marked iff fo[d+1] > fo[d])
+
 struct CtaMem {
-    double *ring;         // 3 diagonals x 5 states x RW doubles (shared memory; global scratch for very wide jobs)
-    double *tbuf;         // RW doubles: per-cell terms of a reduction / candidate log posteriors
+    double *ring;         // 2 parity slots x 5 states x RW doubles (shared memory; global scratch for very wide jobs)
+    double *tbuf;         // RW doubles: per-cell terms of a reduction
     double *total;        // 1 double: the running total probability, published by warp 0
+    int *n_out;           // candidates appended so far
     int RW;               // >= widest diagonal of the job
     double *FM;           // HBM ring of forward MATCH values, maskM + 1 doubles
     unsigned maskM;
@@ -143,44 +151,35 @@ PC_HD double d_mul(double a, double b) {
     return a * b;
 #endif
 }
-PC_HD double log_zero() {
+PC_HD unsigned long long d_bits(double v) {
 #if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)0xfff0000000000000ULL);
+    return (unsigned long long)__double_as_longlong(v);
 #else
-    return -INFINITY;
+    unsigned long long b; memcpy(&b, &v, 8); return b;
 #endif
 }
-// "not a candidate" marker in the candidate buffer (a computed NaN never gets there: it fails the threshold test)
-PC_HD double not_a_candidate() {
+PC_HD double bits_d(unsigned long long b) {
 #if defined(__CUDA_ARCH__)
-    return __longlong_as_double(0x7ff8000000000000LL);
+    return __longlong_as_double((long long)b);
 #else
-    return NAN;
+    double v; memcpy(&v, &b, 8); return v;
 #endif
 }
-PC_HD bool is_candidate(double lp) {
-#if defined(__CUDA_ARCH__)
-    return __double_as_longlong(lp) != 0x7ff8000000000000LL;
-#else
-    return lp == lp;
-#endif
-}
+PC_HD double log_zero() { return bits_d(0xfff0000000000000ULL); }
 
-// pairwiseAligner.c:313-317 without branches: big/small by one comparison; the interval of lookup() and the two "return
-// the larger one" conditions are taken from the bit pattern of the (non-negative) difference with integer compares, which
-// keeps them off the FP64 pipe
+// pairwiseAligner.c:313-317 without branches and with one FP64 operation for the ordering: d = x - y gives the order by its
+// sign bit and the (exactly antisymmetric) difference big - small as |d|; the interval of lookup() and the "return the
+// larger one" condition come from the bit pattern of |d| with unsigned integer compares, which keeps them off the FP64
+// pipe. |d| is +inf when small is LOG_ZERO and NaN (either sign) when both are: both compare above 7.5 as unsigned
+// integers, so the larger operand is returned exactly as the reference does.
 PC_HD double log_add(double x, double y, const double *K) {
-    const bool lt = x < y;
+    const unsigned long long db_signed = d_bits(d_sub(x, y));
+    const bool lt = (db_signed >> 63) != 0;                           // x < y (or a NaN / -0 difference, where big == small in value)
     const double big = lt ? y : x, small = lt ? x : y;
-    const double diff = d_sub(big, small);                    // >= +0, +inf (small == LOG_ZERO) or NaN (both LOG_ZERO)
-#if defined(__CUDA_ARCH__)
-    const long long db = __double_as_longlong(diff);
-    const int idx = (int)(db > 0x3FF0000000000000LL) + (int)(db > 0x4004000000000000LL) + (int)(db > 0x4012000000000000LL);   // > 1.0, 2.5, 4.5
-    const bool keep_big = (__double_as_longlong(small) == (long long)0xFFF0000000000000ULL) | (db >= 0x401E000000000000LL);   // small == LOG_ZERO || diff >= 7.5
-#else
-    const int idx = (int)(diff > 1.0) + (int)(diff > 2.5) + (int)(diff > 4.5);
-    const bool keep_big = small == log_zero() || diff >= 7.5;
-#endif
+    const unsigned long long db = db_signed & 0x7fffffffffffffffULL;
+    const double diff = bits_d(db);
+    const int idx = (int)(db > 0x3FF0000000000000ULL) + (int)(db > 0x4004000000000000ULL) + (int)(db > 0x4012000000000000ULL);   // > 1.0, 2.5, 4.5
+    const bool keep_big = db >= 0x401E000000000000ULL;                 // diff >= 7.5, small == LOG_ZERO, or both LOG_ZERO
     const double *c = K + K_LOOKUP + 4 * idx;
     double r = d_add(d_mul(c[0], diff), c[1]);
     r = d_add(d_mul(r, diff), c[2]);
@@ -194,38 +193,47 @@ PC_HD bool chain_inactive(double tot, double t) { return !(tot < t) && (t == log
 
 PC_HD int match_class(int cx, int cy) { return (cx == 4 || cy == 4) ? 3 : (cx == cy ? 0 : (((cx ^ cy) == 2) ? 1 : 2)); }
 
-PC_HD double *slot(const CtaMem &cm, int d) { return cm.ring + (size_t)(d % 3) * (5 * (size_t)cm.RW); }
+PC_HD double *slot(const CtaMem &cm, int d) { return cm.ring + (size_t)(d & 1) * (5 * (size_t)cm.RW); }
+// ring index of cell 0 of a diagonal: a = (xmyL + parity) / 2 + ly >= 0, modulo the ring width
+PC_HD int ring_i0(int L, int d, int ly, int RW) { return (((L + (d & 1)) >> 1) + ly) % RW; }
+PC_HD int wrap(int i, int RW) { return i >= RW ? i - RW : (i < 0 ? i + RW : i); }
 PC_HD double &fm_at(const CtaMem &cm, int cell) { return cm.FM[(unsigned)cell & cm.maskM]; }
 PC_HD double &ff_at(const CtaMem &cm, int base, int w, int s, int k) { return cm.FF[(unsigned)(base + s * w + k) & cm.maskF]; }
 
-struct Band {            // per-diagonal tables of one job
-    const int *L;        // xmyL
-    const int *co;       // cells before diagonal d (D+2 entries)
-    const int *fo;       // cells of MARKED diagonals before diagonal d (D+2 entries); d is marked iff fo[d+1] > fo[d]
-};
+PC_HD void emit_one(const Job &J, const CtaMem &cm, Pair *out, int x, int y, double lp) {
+#if defined(__CUDA_ARCH__)
+    const int pos = atomicAdd(cm.n_out, 1);
+#else
+    const int pos = (*cm.n_out)++;
+#endif
+    if (pos < J.out_cap) { Pair p; p.x = x - 1; p.y = y - 1; p.lp = lp; out[pos] = p; }
+}
 
-// ---- forward: diagonal d from d-1 (lower: xmy-1, upper: xmy+1) and d-2 (middle: xmy) -------------------------------------
-PC_HD void fwd_diag(const uint8_t *sx, const uint8_t *sy, const Band &bd, const CtaMem &cm, const double *K, int d) {
+// ---- forward: diagonal d from d-1 (lower: xmy-1, upper: xmy+1) and d-2 (middle: xmy, updated in place) -------------------
+// md = meta of d, mn = of d+1, m1 = of d-1, m2 = of d-2
+PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const CtaMem &cm, const double *K, int d,
+                    const DiagMeta &md, const DiagMeta &mn, const DiagMeta &m1, const DiagMeta &m2) {
     const double LZ = log_zero();
-    const int Ld = bd.L[d], w = bd.co[d + 1] - bd.co[d], cbase = bd.co[d], RW = cm.RW;
-    const int L1 = bd.L[d - 1], w1 = bd.co[d] - bd.co[d - 1];
-    int L2 = 0, w2 = 0;
-    if (d >= 2) { L2 = bd.L[d - 2]; w2 = bd.co[d - 1] - bd.co[d - 2]; }
-    const int sl = (Ld - L1 - 1) >> 1, sm = (Ld - L2) >> 1;      // both differences are even
-    const bool full = bd.fo[d + 1] > bd.fo[d];
-    const int fbase = 5 * bd.fo[d];
-    double *cur = slot(cm, d);
-    const double *m1 = slot(cm, d - 1), *m2 = slot(cm, d + 1);   // (d - 2) % 3 == (d + 1) % 3
+    const int RW = cm.RW, p = d & 1;
+    const int Ld = md.L, w = mn.co - md.co, cbase = md.co;
+    const int w1 = md.co - m1.co, w2 = d >= 2 ? m1.co - m2.co : 0;
+    const int sl = (Ld - m1.L - 1) >> 1, sm = (Ld - m2.L) >> 1;      // both differences are even
+    const bool full = mn.fo > md.fo;
+    const int fbase = 5 * md.fo;
+    double *cur = slot(cm, d);                                        // also the diagonal two back
+    const double *o1 = slot(cm, d - 1);
+    const int i0 = ring_i0(Ld, d, J.ly, RW);
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
             const int xmy = Ld + 2 * k, x = (d + xmy) >> 1, y = (d - xmy) >> 1;
             const int cx = x > 0 ? sx[x - 1] : 4, cy = y > 0 ? sy[y - 1] : 4;
             const int kl = k + sl, ku = kl + 1, km = k + sm;
+            const int i = wrap(i0 + k, RW), il = wrap(i - p, RW), iu = wrap(i + 1 - p, RW);
             double lM = LZ, lSX = LZ, lLX = LZ, uM = LZ, uSY = LZ, uLY = LZ, mM = LZ, mSX = LZ, mSY = LZ, mLX = LZ, mLY = LZ;
-            if (kl >= 0 && kl < w1) { lM = m1[S_M * RW + kl]; lSX = m1[S_SX * RW + kl]; lLX = m1[S_LX * RW + kl]; }
-            if (ku >= 0 && ku < w1) { uM = m1[S_M * RW + ku]; uSY = m1[S_SY * RW + ku]; uLY = m1[S_LY * RW + ku]; }
+            if (kl >= 0 && kl < w1) { lM = o1[S_M * RW + il]; lSX = o1[S_SX * RW + il]; lLX = o1[S_LX * RW + il]; }
+            if (ku >= 0 && ku < w1) { uM = o1[S_M * RW + iu]; uSY = o1[S_SY * RW + iu]; uLY = o1[S_LY * RW + iu]; }
             if (km >= 0 && km < w2) {
-                mM = m2[S_M * RW + km]; mSX = m2[S_SX * RW + km]; mSY = m2[S_SY * RW + km]; mLX = m2[S_LX * RW + km]; mLY = m2[S_LY * RW + km];
+                mM = cur[S_M * RW + i]; mSX = cur[S_SX * RW + i]; mSY = cur[S_SY * RW + i]; mLX = cur[S_LX * RW + i]; mLY = cur[S_LY * RW + i];
             }
             const double *gx = K + K_GAP + 4 * (cx == 4), *gy = K + K_GAP + 4 * (cy == 4), *mt = K + K_MATCH + 3 * match_class(cx, cy);
             // stateMachine.c:450-480 in its order of transitions; the first transition into a state is an assignment
@@ -236,7 +244,7 @@ PC_HD void fwd_diag(const uint8_t *sx, const uint8_t *sy, const Band &bd, const 
             vM = log_add(vM, d_add(mLX, mt[2]), K); vM = log_add(vM, d_add(mLY, mt[2]), K);
             double vSY = d_add(uM, gy[0]); vSY = log_add(vSY, d_add(uSY, gy[1]), K);
             double vLY = d_add(uM, gy[2]); vLY = log_add(vLY, d_add(uLY, gy[3]), K);
-            cur[S_M * RW + k] = vM; cur[S_SX * RW + k] = vSX; cur[S_SY * RW + k] = vSY; cur[S_LX * RW + k] = vLX; cur[S_LY * RW + k] = vLY;
+            cur[S_M * RW + i] = vM; cur[S_SX * RW + i] = vSX; cur[S_SY * RW + i] = vSY; cur[S_LX * RW + i] = vLX; cur[S_LY * RW + i] = vLY;
             fm_at(cm, cbase + k) = vM;
             if (full) {
                 ff_at(cm, fbase, w, S_M, k) = vM; ff_at(cm, fbase, w, S_SX, k) = vSX; ff_at(cm, fbase, w, S_SY, k) = vSY;
@@ -247,30 +255,39 @@ PC_HD void fwd_diag(const uint8_t *sx, const uint8_t *sy, const Band &bd, const 
     PC_SYNC();
 }
 
-// ---- backward: B[t] gathered from B[t+1] (cells xmy-1 and xmy+1) and B[t+2] (cell xmy); top = diagonal walked from ----------
-// Order of accumulation into the target cell c in the reference's scatter (pairwiseAligner.c:619-634 walking xmy upwards,
-// stateMachine.c:450-480): while diagonal t+2 is processed c is the MIDDLE of the cell at the same xmy (all five states
-// receive from its match state); while t+1 is processed c is first the UPPER of the cell at xmy-1 (M += SY, SY += SY,
-// M += LY, LY += LY) and then the LOWER of the cell at xmy+1 (M += SX, SX += SX, M += LX, LX += LX).
-PC_HD void bwd_diag(const uint8_t *sx, const uint8_t *sy, const Band &bd, const CtaMem &cm, const double *K, int t, int top) {
+// ---- backward: B[t] gathered from B[t+1] (cells xmy-1 and xmy+1) and B[t+2] (cell xmy, updated in place); top = the
+// diagonal walked from. Order of accumulation into the target cell c in the reference's scatter (pairwiseAligner.c:
+// 619-634 walking xmy upwards, stateMachine.c:450-480): while diagonal t+2 is processed c is the MIDDLE of the cell at the
+// same xmy (all five states receive from its match state); while t+1 is processed c is first the UPPER of the cell at
+// xmy-1 (M += SY, SY += SY, M += LY, LY += LY) and then the LOWER of the cell at xmy+1 (M += SX, SX += SX, M += LX, LX += LX).
+// With fuse_emit the posterior candidates of the diagonal (diagonalCalculationPosteriorMatchProbs, :676-699) are produced
+// in the same pass from the total probability already published.
+// mt = meta of t, mt1 = of t+1, mt2 = of t+2, mt3 = of t+3
+PC_HD void bwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const CtaMem &cm, const Params &P, const double *K, int t, int top,
+                    const DiagMeta &mt_, const DiagMeta &mt1, const DiagMeta &mt2, const DiagMeta &mt3, bool fuse_emit, Pair *out) {
     const double LZ = log_zero();
-    const int Lt = bd.L[t], w = bd.co[t + 1] - bd.co[t], RW = cm.RW;
-    const int L1 = bd.L[t + 1], w1 = bd.co[t + 2] - bd.co[t + 1];
+    const int RW = cm.RW, p = t & 1;
+    const int Lt = mt_.L, w = mt1.co - mt_.co, cbase = mt_.co;
+    const int w1 = mt2.co - mt1.co;
     const bool has2 = t + 2 <= top;
-    int L2 = 0, w2 = 0;
-    if (has2) { L2 = bd.L[t + 2]; w2 = bd.co[t + 3] - bd.co[t + 2]; }
-    double *cur = slot(cm, t);
-    const double *b1 = slot(cm, t + 1), *b2 = slot(cm, t + 2);
-    const int s1 = (Lt - 1 - L1) >> 1, s2 = (Lt - L2) >> 1;
+    const int w2 = has2 ? mt3.co - mt2.co : 0;
+    double *cur = slot(cm, t);                                        // also B[t+2]
+    const double *b1 = slot(cm, t + 1);
+    const int s1 = (Lt - 1 - mt1.L) >> 1, s2 = (Lt - mt2.L) >> 1;
+    const int i0 = ring_i0(Lt, t, J.ly, RW);
+    const double total = fuse_emit ? *cm.total : 0.0;
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
             const int xmy = Lt + 2 * k, x = (t + xmy) >> 1, y = (t - xmy) >> 1;
-            const int ku = k + s1, kl = ku + 1, km = k + s2;    // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
+            const bool cand = fuse_emit && x > 0 && y > 0;
+            const double fm = cand ? fm_at(cm, cbase + k) : 0.0;   // issued early: the only HBM read of the step
+            const int ku = k + s1, kl = ku + 1, km = k + s2;       // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
+            const int i = wrap(i0 + k, RW), iu = wrap(i - p, RW), il = wrap(i + 1 - p, RW);
             double mid = LZ, upSY = LZ, upLY = LZ, loSX = LZ, loLX = LZ;
             const double *gx = K + K_GAP, *gy = K + K_GAP, *mt = K + K_MATCH;
-            if (has2 && km >= 0 && km < w2) { mid = b2[S_M * RW + km]; mt = K + K_MATCH + 3 * match_class(sx[x], sy[y]); }   // cell (x+1, y+1)
-            if (ku >= 0 && ku < w1) { upSY = b1[S_SY * RW + ku]; upLY = b1[S_LY * RW + ku]; gy = K + K_GAP + 4 * (sy[y] == 4); }  // cell (x, y+1)
-            if (kl >= 0 && kl < w1) { loSX = b1[S_SX * RW + kl]; loLX = b1[S_LX * RW + kl]; gx = K + K_GAP + 4 * (sx[x] == 4); }  // cell (x+1, y)
+            if (km >= 0 && km < w2) { mid = cur[S_M * RW + i]; mt = K + K_MATCH + 3 * match_class(sx[x], sy[y]); }                      // cell (x+1, y+1)
+            if (ku >= 0 && ku < w1) { upSY = b1[S_SY * RW + iu]; upLY = b1[S_LY * RW + iu]; gy = K + K_GAP + 4 * (sy[y] == 4); }  // cell (x, y+1)
+            if (kl >= 0 && kl < w1) { loSX = b1[S_SX * RW + il]; loLX = b1[S_LX * RW + il]; gx = K + K_GAP + 4 * (sx[x] == 4); }  // cell (x+1, y)
             double vM = d_add(mid, mt[0]);
             vM = log_add(vM, d_add(upSY, gy[0]), K); vM = log_add(vM, d_add(upLY, gy[2]), K);
             vM = log_add(vM, d_add(loSX, gx[0]), K); vM = log_add(vM, d_add(loLX, gx[2]), K);
@@ -278,7 +295,11 @@ PC_HD void bwd_diag(const uint8_t *sx, const uint8_t *sy, const Band &bd, const 
             const double vSY = log_add(d_add(mid, mt[1]), d_add(upSY, gy[1]), K);
             const double vLX = log_add(d_add(mid, mt[2]), d_add(loLX, gx[3]), K);
             const double vLY = log_add(d_add(mid, mt[2]), d_add(upLY, gy[3]), K);
-            cur[S_M * RW + k] = vM; cur[S_SX * RW + k] = vSX; cur[S_SY * RW + k] = vSY; cur[S_LX * RW + k] = vLX; cur[S_LY * RW + k] = vLY;
+            cur[S_M * RW + i] = vM; cur[S_SX * RW + i] = vSX; cur[S_SY * RW + i] = vSY; cur[S_LX * RW + i] = vLX; cur[S_LY * RW + i] = vLY;
+            if (cand) {
+                const double lp = d_sub(d_add(fm, vM), total);
+                if (lp >= P.log_thr_lo) emit_one(J, cm, out, x, y, lp);
+            }
         }
     }
     PC_SYNC();
@@ -327,16 +348,19 @@ PC_HD void chain_warp0(const CtaMem &cm, int w, const double *K, bool accumulate
 
 // diagonalCalculationTotalProbability, pairwiseAligner.c:646-663. Needs the complete forward cells of diagonals t and
 // t-1 (marked by the host). Result in *cm.total (after the final synchronisation).
-PC_HD void total_probability(const uint8_t *sx, const uint8_t *sy, const Band &bd, const CtaMem &cm, const double *K, int t, int top) {
+PC_HD void total_probability(const Job &J, const uint8_t *sx, const uint8_t *sy, const DiagMeta *M, const CtaMem &cm, const double *K, int t, int top) {
     const double LZ = log_zero();
     const int RW = cm.RW;
+    const DiagMeta mt_ = M[t], mt1 = M[t + 1];
     {
-        const int fbase = 5 * bd.fo[t], w = bd.co[t + 1] - bd.co[t];
+        const int fbase = 5 * mt_.fo, w = mt1.co - mt_.co;
         const double *bt = slot(cm, t);
+        const int i0 = ring_i0(mt_.L, t, J.ly, RW);
         PC_THREADS(tid, cm.T) {
             for (int k = tid; k < w; k += cm.T) {
-                double tt = d_add(ff_at(cm, fbase, w, 0, k), bt[k]);                       // cell_dotProduct, pairwiseAligner.c:412-418
-                for (int s = 1; s < NSTATE; ++s) tt = log_add(tt, d_add(ff_at(cm, fbase, w, s, k), bt[s * RW + k]), K);
+                const int i = wrap(i0 + k, RW);
+                double tt = d_add(ff_at(cm, fbase, w, 0, k), bt[i]);                       // cell_dotProduct, pairwiseAligner.c:412-418
+                for (int s = 1; s < NSTATE; ++s) tt = log_add(tt, d_add(ff_at(cm, fbase, w, s, k), bt[s * RW + i]), K);
                 cm.tbuf[k] = tt;
             }
         }
@@ -345,10 +369,12 @@ PC_HD void total_probability(const uint8_t *sx, const uint8_t *sy, const Band &b
         PC_SYNC();
     }
     if (t + 1 <= top) {                                     // matches through t: forward t-1 -> match -> backward t+1
-        const int Lq = bd.L[t + 1], wq = bd.co[t + 2] - bd.co[t + 1];
-        const int Lf = bd.L[t - 1], fbase = 5 * bd.fo[t - 1], wf = bd.co[t] - bd.co[t - 1];
-        const int sm = (Lq - Lf) >> 1;
+        const DiagMeta mf = M[t - 1], mt2 = M[t + 2];
+        const int Lq = mt1.L, wq = mt2.co - mt1.co;
+        const int fbase = 5 * mf.fo, wf = mt_.co - mf.co;
+        const int sm = (Lq - mf.L) >> 1;
         const double *bq = slot(cm, t + 1);
+        const int i0 = ring_i0(Lq, t + 1, J.ly, RW);
         PC_THREADS(tid, cm.T) {
             for (int k = tid; k < wq; k += cm.T) {
                 const int xmy = Lq + 2 * k, x = (t + 1 + xmy) >> 1, y = (t + 1 - xmy) >> 1, km = k + sm;
@@ -362,7 +388,7 @@ PC_HD void total_probability(const uint8_t *sx, const uint8_t *sy, const Band &b
                 double vM = d_add(mM, mt[0]);
                 vM = log_add(vM, d_add(mSX, mt[1]), K); vM = log_add(vM, d_add(mSY, mt[1]), K);
                 vM = log_add(vM, d_add(mLX, mt[2]), K); vM = log_add(vM, d_add(mLY, mt[2]), K);
-                cm.tbuf[k] = d_add(vM, bq[k]);               // the other four states of the match-only diagonal are LOG_ZERO
+                cm.tbuf[k] = d_add(vM, bq[wrap(i0 + k, RW)]);   // the other four states of the match-only diagonal are LOG_ZERO
             }
         }
         PC_SYNC();
@@ -371,108 +397,97 @@ PC_HD void total_probability(const uint8_t *sx, const uint8_t *sy, const Band &b
     }
 }
 
-// diagonalCalculationPosteriorMatchProbs, pairwiseAligner.c:676-699: candidates of diagonal t in xmy order.
-// Phase 1 (all threads): log posterior of every cell, NaN where it is not a candidate; phase 2 (warp 0): ordered append.
-PC_HD void emit_diag(const Job &J, const Band &bd, const CtaMem &cm, const Params &P, int t, Pair *out, int &n_out) {
-    const int Lt = bd.L[t], cbase = bd.co[t], w = bd.co[t + 1] - bd.co[t];
+// diagonalCalculationPosteriorMatchProbs, pairwiseAligner.c:676-699, as a pass of its own (diagonals the total probability
+// was just recomputed on)
+PC_HD void emit_diag(const Job &J, const DiagMeta *M, const CtaMem &cm, const Params &P, int t, Pair *out) {
+    const DiagMeta mt_ = M[t], mt1 = M[t + 1];
+    const int Lt = mt_.L, cbase = mt_.co, w = mt1.co - mt_.co;
     const double *bt = slot(cm, t);
     const double total = *cm.total;
+    const int i0 = ring_i0(Lt, t, J.ly, cm.RW);
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
             const int xmy = Lt + 2 * k, x = (t + xmy) >> 1, y = (t - xmy) >> 1;
-            double lp = not_a_candidate();
             if (x > 0 && y > 0) {
-                const double v = d_sub(d_add(fm_at(cm, cbase + k), bt[k]), total);
-                if (v >= P.log_thr_lo) lp = v;
+                const double lp = d_sub(d_add(fm_at(cm, cbase + k), bt[wrap(i0 + k, cm.RW)]), total);
+                if (lp >= P.log_thr_lo) emit_one(J, cm, out, x, y, lp);
             }
-            cm.tbuf[k] = lp;
         }
     }
-    PC_SYNC();
-#if defined(__CUDA_ARCH__)
-    if (threadIdx.x < 32) {
-        const int lane = (int)threadIdx.x;
-        for (int k0 = 0; k0 < w; k0 += 32) {
-            const int k = k0 + lane;
-            const double lp = k < w ? cm.tbuf[k] : not_a_candidate();
-            const bool pred = is_candidate(lp);
-            const unsigned m = __ballot_sync(0xffffffffu, pred);
-            if (pred) {
-                const int pos = n_out + __popc(m & ((1u << lane) - 1u));
-                if (pos < J.out_cap) { const int xmy = Lt + 2 * k; Pair p; p.x = ((t + xmy) >> 1) - 1; p.y = ((t - xmy) >> 1) - 1; p.lp = lp; out[pos] = p; }
-            }
-            n_out += __popc(m);
-        }
-    }
-#else
-    for (int k = 0; k < w; ++k) {
-        const double lp = cm.tbuf[k];
-        if (is_candidate(lp)) {
-            if (n_out < J.out_cap) { const int xmy = Lt + 2 * k; Pair p; p.x = ((t + xmy) >> 1) - 1; p.y = ((t - xmy) >> 1) - 1; p.lp = lp; out[n_out] = p; }
-            ++n_out;
-        }
-    }
-#endif
 }
 
-// getPosteriorProbsWithBanding, pairwiseAligner.c:766-887. Returns the number of candidate pairs (valid in warp 0; may
-// exceed out_cap: then only out_cap were stored and the job must be re-run with more room).
-PC_HD int run_job(const Job &J, const uint8_t *sym, const int *bandL, const int *coff, const int *foff, const CtaMem &cm, const Params &P,
-                  const double *K, Pair *out_all) {
+// getPosteriorProbsWithBanding, pairwiseAligner.c:766-887. Returns the number of candidate pairs (may exceed out_cap:
+// then only out_cap were stored and the job must be re-run with more room).
+PC_HD int run_job(const Job &J, const uint8_t *sym, const DiagMeta *meta, const CtaMem &cm, const Params &P, const double *K, Pair *out_all) {
     const int D = J.lx + J.ly;
     if (D == 0) return 0;
     const uint8_t *sx = sym + J.sx_off, *sy = sym + J.sy_off;
-    Band bd; bd.L = bandL + J.band_off; bd.co = coff + J.band_off; bd.fo = foff + J.band_off;
+    const DiagMeta *M = meta + J.band_off;
     Pair *out = out_all + J.out_off;
     const int RW = cm.RW;
-    int n_out = 0;
+    DiagMeta m2 = M[0], m1 = M[0], md = M[1], mn = M[2];
     {   // diagonal 0: the single cell (0, 0) holds the start state vector (dpDiagonal_initialiseValues, :785-786)
         const double *st = K + ((J.ragged & 1) ? K_RSTART : K_START);
-        const int w0 = bd.co[1] - bd.co[0];
-        const bool full = bd.fo[1] > bd.fo[0];
+        const int w0 = md.co - m1.co;
+        const bool full = md.fo > m1.fo;
         double *cur = slot(cm, 0);
+        const int i0 = ring_i0(m1.L, 0, J.ly, RW);
         PC_THREADS(tid, cm.T) {
+            if (tid == 0) *cm.n_out = 0;
             for (int k = tid; k < w0; k += cm.T) {
-                for (int s = 0; s < NSTATE; ++s) { cur[s * RW + k] = st[s]; if (full) ff_at(cm, 5 * bd.fo[0], w0, s, k) = st[s]; }
-                fm_at(cm, bd.co[0] + k) = st[S_M];
+                for (int s = 0; s < NSTATE; ++s) { cur[s * RW + wrap(i0 + k, RW)] = st[s]; if (full) ff_at(cm, 5 * m1.fo, w0, s, k) = st[s]; }
+                fm_at(cm, m1.co + k) = st[S_M];
             }
         }
         PC_SYNC();
     }
     int tb_to = 0;
     for (int d = 1; d <= D; ++d) {
-        fwd_diag(sx, sy, bd, cm, K, d);
-        const int w = bd.co[d + 1] - bd.co[d];
+        const DiagMeta mnn = d + 2 <= D + 1 ? M[d + 2] : mn;          // fetched one step ahead
+        fwd_diag(J, sx, sy, cm, K, d, md, mn, m1, m2);
+        const int w = mn.co - md.co;
         const bool at_end = d == D;
         const bool tb_point = d >= tb_to + P.min_diags && w <= P.expansion * 2 + 1;
-        if (!(at_end || tb_point)) continue;
-        {   // the diagonal walked back from holds the end state vector (:806-808)
-            const double *en = K + ((at_end && (J.ragged & 2)) ? K_REND : K_END);
-            double *bt = slot(cm, d);
-            PC_THREADS(tid, cm.T) { for (int k = tid; k < w; k += cm.T) for (int s = 0; s < NSTATE; ++s) bt[s * RW + k] = en[s]; }
-            PC_SYNC();
-        }
-        const int tb_from = d - (at_end ? 0 : P.tb_diags + 1);
-        int ncalc = 0;
-        for (int t = d; t > tb_to; --t) {
-            if (t < d) bwd_diag(sx, sy, bd, cm, K, t, d);
-            if (t <= tb_from) {
-                if (ncalc++ % 10 == 0) total_probability(sx, sy, bd, cm, K, t, d);
-                emit_diag(J, bd, cm, P, t, out, n_out);
+        if (at_end || tb_point) {
+            {   // the diagonal walked back from holds the end state vector (:806-808)
+                const double *en = K + ((at_end && (J.ragged & 2)) ? K_REND : K_END);
+                double *bt = slot(cm, d);
+                const int i0 = ring_i0(md.L, d, J.ly, RW);
+                PC_THREADS(tid, cm.T) { for (int k = tid; k < w; k += cm.T) for (int s = 0; s < NSTATE; ++s) bt[s * RW + wrap(i0 + k, RW)] = en[s]; }
+                PC_SYNC();
+            }
+            const int tb_from = d - (at_end ? 0 : P.tb_diags + 1);
+            int ncalc = 0;
+            DiagMeta b0 = md, b1 = mn, b2 = mn, b3 = mn;               // metas of t, t+1, t+2, t+3
+            for (int t = d; t > tb_to; --t) {
+                const DiagMeta bp = M[t - 1];                           // fetched one step ahead
+                const bool post = t <= tb_from;
+                const bool recompute = post && (ncalc % 10 == 0);
+                if (post) ++ncalc;
+                if (t < d) bwd_diag(J, sx, sy, cm, P, K, t, d, b0, b1, b2, b3, post && !recompute, out);
+                if (recompute) {
+                    total_probability(J, sx, sy, M, cm, K, t, d);
+                    emit_diag(J, M, cm, P, t, out);
+                }
+                b3 = b2; b2 = b1; b1 = b0; b0 = bp;
+            }
+            tb_to = tb_from;
+            if (!at_end) {          // the sweep resumes from the complete forward diagonals d and d-1 (marked by the host)
+                PC_SYNC();
+                for (int q = 0; q < 2; ++q) {
+                    const int dd = d - q;
+                    const DiagMeta a = q ? m1 : md, b = q ? md : mn;
+                    const int wd = b.co - a.co, fbase = 5 * a.fo, i0 = ring_i0(a.L, dd, J.ly, RW);
+                    double *sl = slot(cm, dd);
+                    PC_THREADS(tid, cm.T) { for (int k = tid; k < wd; k += cm.T) for (int s = 0; s < NSTATE; ++s) sl[s * RW + wrap(i0 + k, RW)] = ff_at(cm, fbase, wd, s, k); }
+                }
+                PC_SYNC();
             }
         }
-        tb_to = tb_from;
-        if (!at_end) {          // the sweep resumes from the complete forward diagonals d and d-1 (marked by the host)
-            PC_SYNC();
-            for (int q = 0; q < 2; ++q) {
-                const int dd = d - q, wd = bd.co[dd + 1] - bd.co[dd], fbase = 5 * bd.fo[dd];
-                double *sl = slot(cm, dd);
-                PC_THREADS(tid, cm.T) { for (int k = tid; k < wd; k += cm.T) for (int s = 0; s < NSTATE; ++s) sl[s * RW + k] = ff_at(cm, fbase, wd, s, k); }
-            }
-            PC_SYNC();
-        }
+        m2 = m1; m1 = md; md = mn; mn = mnn;
     }
-    return n_out;
+    PC_SYNC();
+    return *cm.n_out;
 }
 
 }  // namespace pecan

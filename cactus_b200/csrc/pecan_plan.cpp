@@ -109,6 +109,7 @@ std::string plan_subjob(const PlanParams &P, SubJob &s) {
     s.cells = cells; s.max_w = max_w;
     // schedule (pairwiseAligner.c:798-803, 817, 840-848): traceback points only depend on the band geometry
     std::vector<uint8_t> mark((size_t)D + 1, 0);
+    s.tb_from.clear();
     struct Tb { int64_t d, to; };
     std::vector<Tb> tbs;
     int64_t tb_to = 0;
@@ -122,6 +123,7 @@ std::string plan_subjob(const PlanParams &P, SubJob &s) {
             if (c % 10 == 0) { mark[t] = 1; mark[t - 1] = 1; }
         if (!at_end) { mark[d] = 1; mark[d - 1] = 1; }
         tbs.push_back(Tb{d, tb_to});
+        s.tb_from.push_back((int)tb_from);
         tb_to = tb_from;
     }
     s.foff.assign(D + 2, 0);

@@ -6,6 +6,7 @@
 #pragma once
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace barb200 {
@@ -29,6 +30,7 @@ struct SubJob {
     int64_t cells = 0;             // sum of diagonal widths
     int64_t span_cells = 0;        // most forward cells alive at once (between two tracebacks)
     int64_t span_full_cells = 0;   // most cells of marked diagonals alive at once
+    std::vector<int> tb_from;      // the diagonal each traceback starts emitting posteriors from (ascending)
     int max_w = 0;
     int out_cap = 0;
 };
@@ -46,6 +48,16 @@ void split_pair(const PlanParams &P, int64_t pair, int64_t lx, int64_t ly, const
 // probability is recomputed on (every 10th posterior diagonal, pairwiseAligner.c:840-848) with their predecessors, and
 // the two diagonals the forward sweep resumes from after an intermediate traceback. Returns "" or an error.
 std::string plan_subjob(const PlanParams &P, SubJob &j);
+
+// The reference's order of emission inside one sub-matrix (getPosteriorProbsWithBanding): tracebacks in increasing order of
+// their start diagonal, inside a traceback diagonals x+y downwards, inside a diagonal x - y (hence x) upwards.
+// Sort key of the candidate (0-based x, y) of sub-job j; ascending (first, second) = order of emission.
+inline std::pair<uint64_t, uint32_t> emission_key(const SubJob &j, int x, int y) {
+    const uint32_t t = (uint32_t)x + (uint32_t)y + 2u;
+    size_t seg = 0, hi = j.tb_from.size();          // first traceback with tb_from >= t
+    while (seg < hi) { const size_t mid = (seg + hi) / 2; if ((uint32_t)j.tb_from[mid] >= t) hi = mid; else seg = mid + 1; }
+    return std::make_pair(((uint64_t)seg << 32) | (uint64_t)(0xffffffffu - t), (uint32_t)x);
+}
 
 }  // namespace pecan
 }  // namespace barb200

@@ -205,8 +205,9 @@ extern "C" void hosttest_free(void *p) { free(p); }
 
 struct HtPecanParams { double threshold; int64_t minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion; };
 
-static int g_pecan_threads = 32;
+static int g_pecan_threads = 32, g_pecan_ring_w = 0;
 extern "C" void hosttest_pecan_set_threads(int t) { g_pecan_threads = t; }
+extern "C" void hosttest_pecan_set_ring_width(int w) { g_pecan_ring_w = w; }
 
 extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, const char *csy, int64_t lY, const int64_t *anchors, int64_t n_anchor,
                                                 int ragged_left, int ragged_right, const HtPecanParams *pp, int64_t split_bigger,
@@ -231,21 +232,26 @@ extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, con
         for (int k = 0; k < s.ly; ++k) sym[s.lx + k] = (uint8_t)code(csy[s.y1 + k]);
         unsigned capM = 1024; while (capM < (uint64_t)std::max<int64_t>(s.span_cells, 1)) capM <<= 1;
         unsigned capF = 1024; while (capF < 5 * (uint64_t)std::max<int64_t>(s.span_full_cells, 1)) capF <<= 1;
-        const int RW = (s.max_w + 31) & ~31;
-        std::vector<double> fm(capM, NAN), ff(capF, NAN), ring(15 * (size_t)RW, NAN), tbuf((size_t)RW, NAN);
-        double total = NAN;
-        pc::CtaMem cm; cm.ring = ring.data(); cm.tbuf = tbuf.data(); cm.total = &total; cm.RW = RW; cm.FM = fm.data(); cm.maskM = capM - 1;
+        const int RW = g_pecan_ring_w > 0 ? std::max(g_pecan_ring_w, s.max_w) : s.max_w;     // any width >= the widest diagonal
+        std::vector<double> fm(capM, NAN), ff(capF, NAN), ring(10 * (size_t)RW, NAN), tbuf((size_t)RW, NAN);
+        double total = NAN; int n_out = 0;
+        pc::CtaMem cm; cm.ring = ring.data(); cm.tbuf = tbuf.data(); cm.total = &total; cm.n_out = &n_out; cm.RW = RW; cm.FM = fm.data(); cm.maskM = capM - 1;
         cm.FF = ff.data(); cm.maskF = capF - 1; cm.T = g_pecan_threads;
         pc::Job J; J.sx_off = 0; J.sy_off = s.lx; J.band_off = 0; J.out_off = 0; J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged;
         J.out_cap = (int)std::min<int64_t>(s.cells, (int64_t)s.lx + s.ly + 64);
-        std::vector<int> bl(s.bandL); bl.push_back(0);
+        std::vector<pc::DiagMeta> meta((size_t)s.lx + s.ly + 2);
+        for (int d = 0; d <= s.lx + s.ly + 1; ++d) meta[d] = pc::DiagMeta{d <= s.lx + s.ly ? s.bandL[d] : 0, s.coff[d], s.foff[d], 0};
         std::vector<pc::Pair> out((size_t)std::max(J.out_cap, 1));
-        int n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), s.foff.data(), cm, dp, C.v, out.data());
+        int n = pc::run_job(J, sym.data(), meta.data(), cm, dp, C.v, out.data());
         if (n > J.out_cap) {              // the product's retry: room for every cell
             J.out_cap = (int)s.cells; out.assign((size_t)std::max(J.out_cap, 1), pc::Pair());
-            n = pc::run_job(J, sym.data(), bl.data(), s.coff.data(), s.foff.data(), cm, dp, C.v, out.data());
+            n = pc::run_job(J, sym.data(), meta.data(), cm, dp, C.v, out.data());
             if (n > J.out_cap) return -3;
         }
+        // candidates arrive in no particular order within a diagonal (here: scrambled on purpose); restore the order of emission
+        out.resize((size_t)n);
+        for (int q = 0; q + 1 < n; q += 2) std::swap(out[q], out[q + 1]);
+        std::sort(out.begin(), out.end(), [&](const pc::Pair &a, const pc::Pair &b) { return pc::emission_key(s, a.x, a.y) < pc::emission_key(s, b.x, b.y); });
         for (int q = n - 1; q >= 0; --q) {
             double p = exp(out[q].lp);
             if (!(p >= P.threshold)) continue;
