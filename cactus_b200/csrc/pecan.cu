@@ -216,10 +216,21 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
     size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
     // shared memory per block = 8 * (58 + 11 * RW) bytes: 8.9 KB, 28.6 KB, 54 KB, 113 KB; 80 registers per thread
-    static const struct { int max_w, threads, ctas_per_sm; bool smem; } kClass[5] = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true},
-                                                                                   {1280, 256, 2, true}, {0x7fffffff, 256, 2, false}};
+    struct Class { int max_w, threads, ctas_per_sm; bool smem; };
+    std::vector<Class> kClass = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true}, {1280, 256, 2, true}};
+    if (const char *e = getenv("BARB200_PECAN_CLASSES")) {         // tuning aid: "max_w:threads:blocks_per_sm,..." for the shared-memory classes
+        kClass.clear();
+        for (const char *q = e; *q;) {
+            int a = 0, b = 0, c = 0, n = 0;
+            if (sscanf(q, "%d:%d:%d%n", &a, &b, &c, &n) != 3 || a <= 0 || b < 32 || b > 256 || b % 32 || c <= 0) { set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
+            kClass.push_back(Class{a, b, c, true});
+            q += n; if (*q == ',') ++q;
+        }
+        if (kClass.empty() || 8 * (58 + 11 * (size_t)kClass.back().max_w) > 200 * 1024) { set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
+    }
+    kClass.push_back(Class{0x7fffffff, kClass.back().threads, 2, false});       // wider: ring in HBM / L2
     st->groups.clear();
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < (int)kClass.size(); ++c) {
         PecanGroup g;
         for (int64_t i = 0; i < ns; ++i) if (st->subs[i].max_w <= kClass[c].max_w && (c == 0 || st->subs[i].max_w > kClass[c - 1].max_w)) g.jobs.push_back((int)i);
         if (g.jobs.empty()) continue;
@@ -250,7 +261,10 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         g.scratch_off = scratch_doubles; scratch_doubles += g.slot_doubles * (size_t)g.ctas;
         g.order_off = order_off;
         for (int j : g.jobs) order[order_off++] = j;
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        // wider classes hold longer jobs: they are launched first and at higher priority so that they are resident from the start
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, g.ring_in_smem && g.RW <= 608 ? prio_lo : prio_hi));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     }
     const size_t scratch_bytes = scratch_doubles * 8;
@@ -318,7 +332,8 @@ static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned) * (st->groups.size() + 1), st->stream));
     CUDA_TRY(ctx, cudaEventRecord(st->ev0, st->stream));
     st->launches = 0;
-    for (size_t gi = 0; gi < st->groups.size(); ++gi) {
+    for (size_t gq = st->groups.size(); gq-- > 0;) {          // widest class first
+        const size_t gi = gq;
         const PecanGroup &g = st->groups[gi];
         KernelArgs A;
         A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size();

@@ -168,18 +168,22 @@ PC_HD double bits_d(unsigned long long b) {
 PC_HD double log_zero() { return bits_d(0xfff0000000000000ULL); }
 
 // pairwiseAligner.c:313-317 without branches and with one FP64 operation for the ordering: d = x - y gives the order by its
-// sign bit and the (exactly antisymmetric) difference big - small as |d|; the interval of lookup() and the "return the
-// larger one" condition come from the bit pattern of |d| with unsigned integer compares, which keeps them off the FP64
-// pipe. |d| is +inf when small is LOG_ZERO and NaN (either sign) when both are: both compare above 7.5 as unsigned
-// integers, so the larger operand is returned exactly as the reference does.
+// sign bit and the (exactly antisymmetric) difference big - small as |d|. The interval of lookup() and the "return the
+// larger one" condition come from the HIGH WORD of |d| with 32-bit integer arithmetic, which keeps them off the FP64 pipe:
+// the thresholds 1.0, 2.5, 4.5, 7.5 have zero low words, so |d| > T  <=>  hi + (lo != 0) > hi(T)  and  |d| >= T  <=>
+// hi >= hi(T). |d| is +inf when small is LOG_ZERO and NaN (either sign, the sign bit is cleared) when both are: both have
+// a high word above hi(7.5), so the larger operand is returned exactly as the reference does.
 PC_HD double log_add(double x, double y, const double *K) {
     const unsigned long long db_signed = d_bits(d_sub(x, y));
     const bool lt = (db_signed >> 63) != 0;                           // x < y (or a NaN / -0 difference, where big == small in value)
     const double big = lt ? y : x, small = lt ? x : y;
     const unsigned long long db = db_signed & 0x7fffffffffffffffULL;
     const double diff = bits_d(db);
-    const int idx = (int)(db > 0x3FF0000000000000ULL) + (int)(db > 0x4004000000000000ULL) + (int)(db > 0x4012000000000000ULL);   // > 1.0, 2.5, 4.5
-    const bool keep_big = db >= 0x401E000000000000ULL;                 // diff >= 7.5, small == LOG_ZERO, or both LOG_ZERO
+    const int hi = (int)(unsigned)(db >> 32);                          // 0 .. 0x7fffffff
+    const int h2 = hi + (int)((unsigned)db != 0u);
+    // (T - h2) >>> 31 is 1 exactly when h2 > T (no overflow: both are below 2^31)
+    const int idx = (int)(((unsigned)(0x3FF00000 - h2) >> 31) + ((unsigned)(0x40040000 - h2) >> 31) + ((unsigned)(0x40120000 - h2) >> 31));   // > 1.0, 2.5, 4.5
+    const bool keep_big = hi >= 0x401E0000;                            // diff >= 7.5, small == LOG_ZERO, or both LOG_ZERO
     const double *c = K + K_LOOKUP + 4 * idx;
     double r = d_add(d_mul(c[0], diff), c[1]);
     r = d_add(d_mul(r, diff), c[2]);
@@ -209,46 +213,64 @@ PC_HD void emit_one(const Job &J, const CtaMem &cm, Pair *out, int x, int y, dou
     if (pos < J.out_cap) { Pair p; p.x = x - 1; p.y = y - 1; p.lp = lp; out[pos] = p; }
 }
 
+struct Cell5 { double m, sx, sy, lx, ly; };
+
 // ---- forward: diagonal d from d-1 (lower: xmy-1, upper: xmy+1) and d-2 (middle: xmy, updated in place) -------------------
-// md = meta of d, mn = of d+1, m1 = of d-1, m2 = of d-2
+struct FwdDiag {            // per-diagonal uniforms
+    const uint8_t *sx, *sy; const double *K, *o1; double *cur;
+    int d, p, Ld, w, w1, w2, sl, sm, i0, RW;
+};
+PC_HD Cell5 fwd_cell(const FwdDiag &f, int k) {
+    const double LZ = log_zero();
+    const int RW = f.RW;
+    const int xmy = f.Ld + 2 * k, x = (f.d + xmy) >> 1, y = (f.d - xmy) >> 1;
+    const int cx = x > 0 ? f.sx[x - 1] : 4, cy = y > 0 ? f.sy[y - 1] : 4;
+    const int kl = k + f.sl, ku = kl + 1, km = k + f.sm;
+    const int i = wrap(f.i0 + k, RW), il = wrap(i - f.p, RW), iu = wrap(i + 1 - f.p, RW);
+    double lM = LZ, lSX = LZ, lLX = LZ, uM = LZ, uSY = LZ, uLY = LZ, mM = LZ, mSX = LZ, mSY = LZ, mLX = LZ, mLY = LZ;
+    if (kl >= 0 && kl < f.w1) { lM = f.o1[S_M * RW + il]; lSX = f.o1[S_SX * RW + il]; lLX = f.o1[S_LX * RW + il]; }
+    if (ku >= 0 && ku < f.w1) { uM = f.o1[S_M * RW + iu]; uSY = f.o1[S_SY * RW + iu]; uLY = f.o1[S_LY * RW + iu]; }
+    if (km >= 0 && km < f.w2) {
+        mM = f.cur[S_M * RW + i]; mSX = f.cur[S_SX * RW + i]; mSY = f.cur[S_SY * RW + i]; mLX = f.cur[S_LX * RW + i]; mLY = f.cur[S_LY * RW + i];
+    }
+    const double *K = f.K;
+    const double *gx = K + K_GAP + 4 * (cx == 4), *gy = K + K_GAP + 4 * (cy == 4), *mt = K + K_MATCH + 3 * match_class(cx, cy);
+    // stateMachine.c:450-480 in its order of transitions; the first transition into a state is an assignment
+    Cell5 v;
+    v.sx = d_add(lM, gx[0]); v.sx = log_add(v.sx, d_add(lSX, gx[1]), K);
+    v.lx = d_add(lM, gx[2]); v.lx = log_add(v.lx, d_add(lLX, gx[3]), K);
+    v.m = d_add(mM, mt[0]);
+    v.m = log_add(v.m, d_add(mSX, mt[1]), K); v.m = log_add(v.m, d_add(mSY, mt[1]), K);
+    v.m = log_add(v.m, d_add(mLX, mt[2]), K); v.m = log_add(v.m, d_add(mLY, mt[2]), K);
+    v.sy = d_add(uM, gy[0]); v.sy = log_add(v.sy, d_add(uSY, gy[1]), K);
+    v.ly = d_add(uM, gy[2]); v.ly = log_add(v.ly, d_add(uLY, gy[3]), K);
+    return v;
+}
+PC_HD void ring_store(double *slotp, int RW, int i, const Cell5 &v) {
+    slotp[S_M * RW + i] = v.m; slotp[S_SX * RW + i] = v.sx; slotp[S_SY * RW + i] = v.sy; slotp[S_LX * RW + i] = v.lx; slotp[S_LY * RW + i] = v.ly;
+}
+// md = meta of d, mn = of d+1, m1 = of d-1, m2 = of d-2. (Keeping two cells per thread in flight to interleave their
+// dependent logAdd chains was measured SLOWER, 5.6 vs 8.6 Gcell/s: the duplicated work on narrow diagonals and the
+// doubled register footprint cost more than the latency it hides.)
 PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const CtaMem &cm, const double *K, int d,
                     const DiagMeta &md, const DiagMeta &mn, const DiagMeta &m1, const DiagMeta &m2) {
-    const double LZ = log_zero();
-    const int RW = cm.RW, p = d & 1;
-    const int Ld = md.L, w = mn.co - md.co, cbase = md.co;
-    const int w1 = md.co - m1.co, w2 = d >= 2 ? m1.co - m2.co : 0;
-    const int sl = (Ld - m1.L - 1) >> 1, sm = (Ld - m2.L) >> 1;      // both differences are even
+    FwdDiag f;
+    f.sx = sx; f.sy = sy; f.K = K; f.RW = cm.RW; f.d = d; f.p = d & 1;
+    f.Ld = md.L; f.w = mn.co - md.co; f.w1 = md.co - m1.co; f.w2 = d >= 2 ? m1.co - m2.co : 0;
+    f.sl = (f.Ld - m1.L - 1) >> 1; f.sm = (f.Ld - m2.L) >> 1;      // both differences are even
+    f.cur = slot(cm, d);                                           // also the diagonal two back
+    f.o1 = slot(cm, d - 1);
+    f.i0 = ring_i0(f.Ld, d, J.ly, cm.RW);
+    const int w = f.w, cbase = md.co, fbase = 5 * md.fo, RW = cm.RW;
     const bool full = mn.fo > md.fo;
-    const int fbase = 5 * md.fo;
-    double *cur = slot(cm, d);                                        // also the diagonal two back
-    const double *o1 = slot(cm, d - 1);
-    const int i0 = ring_i0(Ld, d, J.ly, RW);
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
-            const int xmy = Ld + 2 * k, x = (d + xmy) >> 1, y = (d - xmy) >> 1;
-            const int cx = x > 0 ? sx[x - 1] : 4, cy = y > 0 ? sy[y - 1] : 4;
-            const int kl = k + sl, ku = kl + 1, km = k + sm;
-            const int i = wrap(i0 + k, RW), il = wrap(i - p, RW), iu = wrap(i + 1 - p, RW);
-            double lM = LZ, lSX = LZ, lLX = LZ, uM = LZ, uSY = LZ, uLY = LZ, mM = LZ, mSX = LZ, mSY = LZ, mLX = LZ, mLY = LZ;
-            if (kl >= 0 && kl < w1) { lM = o1[S_M * RW + il]; lSX = o1[S_SX * RW + il]; lLX = o1[S_LX * RW + il]; }
-            if (ku >= 0 && ku < w1) { uM = o1[S_M * RW + iu]; uSY = o1[S_SY * RW + iu]; uLY = o1[S_LY * RW + iu]; }
-            if (km >= 0 && km < w2) {
-                mM = cur[S_M * RW + i]; mSX = cur[S_SX * RW + i]; mSY = cur[S_SY * RW + i]; mLX = cur[S_LX * RW + i]; mLY = cur[S_LY * RW + i];
-            }
-            const double *gx = K + K_GAP + 4 * (cx == 4), *gy = K + K_GAP + 4 * (cy == 4), *mt = K + K_MATCH + 3 * match_class(cx, cy);
-            // stateMachine.c:450-480 in its order of transitions; the first transition into a state is an assignment
-            double vSX = d_add(lM, gx[0]); vSX = log_add(vSX, d_add(lSX, gx[1]), K);
-            double vLX = d_add(lM, gx[2]); vLX = log_add(vLX, d_add(lLX, gx[3]), K);
-            double vM = d_add(mM, mt[0]);
-            vM = log_add(vM, d_add(mSX, mt[1]), K); vM = log_add(vM, d_add(mSY, mt[1]), K);
-            vM = log_add(vM, d_add(mLX, mt[2]), K); vM = log_add(vM, d_add(mLY, mt[2]), K);
-            double vSY = d_add(uM, gy[0]); vSY = log_add(vSY, d_add(uSY, gy[1]), K);
-            double vLY = d_add(uM, gy[2]); vLY = log_add(vLY, d_add(uLY, gy[3]), K);
-            cur[S_M * RW + i] = vM; cur[S_SX * RW + i] = vSX; cur[S_SY * RW + i] = vSY; cur[S_LX * RW + i] = vLX; cur[S_LY * RW + i] = vLY;
-            fm_at(cm, cbase + k) = vM;
+            const Cell5 a = fwd_cell(f, k);
+            ring_store(f.cur, RW, wrap(f.i0 + k, RW), a);
+            fm_at(cm, cbase + k) = a.m;
             if (full) {
-                ff_at(cm, fbase, w, S_M, k) = vM; ff_at(cm, fbase, w, S_SX, k) = vSX; ff_at(cm, fbase, w, S_SY, k) = vSY;
-                ff_at(cm, fbase, w, S_LX, k) = vLX; ff_at(cm, fbase, w, S_LY, k) = vLY;
+                ff_at(cm, fbase, w, S_M, k) = a.m; ff_at(cm, fbase, w, S_SX, k) = a.sx; ff_at(cm, fbase, w, S_SY, k) = a.sy;
+                ff_at(cm, fbase, w, S_LX, k) = a.lx; ff_at(cm, fbase, w, S_LY, k) = a.ly;
             }
         }
     }
@@ -262,44 +284,52 @@ PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
 // xmy-1 (M += SY, SY += SY, M += LY, LY += LY) and then the LOWER of the cell at xmy+1 (M += SX, SX += SX, M += LX, LX += LX).
 // With fuse_emit the posterior candidates of the diagonal (diagonalCalculationPosteriorMatchProbs, :676-699) are produced
 // in the same pass from the total probability already published.
+struct BwdDiag {            // per-diagonal uniforms
+    const uint8_t *sx, *sy; const double *K, *b1; double *cur;
+    int t, p, Lt, w1, w2, s1, s2, i0, RW;
+};
+PC_HD Cell5 bwd_cell(const BwdDiag &g, int k) {
+    const double LZ = log_zero();
+    const int RW = g.RW;
+    const int xmy = g.Lt + 2 * k, x = (g.t + xmy) >> 1, y = (g.t - xmy) >> 1;
+    const int ku = k + g.s1, kl = ku + 1, km = k + g.s2;       // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
+    const int i = wrap(g.i0 + k, RW), iu = wrap(i - g.p, RW), il = wrap(i + 1 - g.p, RW);
+    double mid = LZ, upSY = LZ, upLY = LZ, loSX = LZ, loLX = LZ;
+    const double *K = g.K;
+    const double *gx = K + K_GAP, *gy = K + K_GAP, *mt = K + K_MATCH;
+    if (km >= 0 && km < g.w2) { mid = g.cur[S_M * RW + i]; mt = K + K_MATCH + 3 * match_class(g.sx[x], g.sy[y]); }                      // cell (x+1, y+1)
+    if (ku >= 0 && ku < g.w1) { upSY = g.b1[S_SY * RW + iu]; upLY = g.b1[S_LY * RW + iu]; gy = K + K_GAP + 4 * (g.sy[y] == 4); }  // cell (x, y+1)
+    if (kl >= 0 && kl < g.w1) { loSX = g.b1[S_SX * RW + il]; loLX = g.b1[S_LX * RW + il]; gx = K + K_GAP + 4 * (g.sx[x] == 4); }  // cell (x+1, y)
+    Cell5 v;
+    v.m = d_add(mid, mt[0]);
+    v.m = log_add(v.m, d_add(upSY, gy[0]), K); v.m = log_add(v.m, d_add(upLY, gy[2]), K);
+    v.m = log_add(v.m, d_add(loSX, gx[0]), K); v.m = log_add(v.m, d_add(loLX, gx[2]), K);
+    v.sx = log_add(d_add(mid, mt[1]), d_add(loSX, gx[1]), K);
+    v.sy = log_add(d_add(mid, mt[1]), d_add(upSY, gy[1]), K);
+    v.lx = log_add(d_add(mid, mt[2]), d_add(loLX, gx[3]), K);
+    v.ly = log_add(d_add(mid, mt[2]), d_add(upLY, gy[3]), K);
+    return v;
+}
 // mt = meta of t, mt1 = of t+1, mt2 = of t+2, mt3 = of t+3
 PC_HD void bwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const CtaMem &cm, const Params &P, const double *K, int t, int top,
                     const DiagMeta &mt_, const DiagMeta &mt1, const DiagMeta &mt2, const DiagMeta &mt3, bool fuse_emit, Pair *out) {
-    const double LZ = log_zero();
-    const int RW = cm.RW, p = t & 1;
-    const int Lt = mt_.L, w = mt1.co - mt_.co, cbase = mt_.co;
-    const int w1 = mt2.co - mt1.co;
-    const bool has2 = t + 2 <= top;
-    const int w2 = has2 ? mt3.co - mt2.co : 0;
-    double *cur = slot(cm, t);                                        // also B[t+2]
-    const double *b1 = slot(cm, t + 1);
-    const int s1 = (Lt - 1 - mt1.L) >> 1, s2 = (Lt - mt2.L) >> 1;
-    const int i0 = ring_i0(Lt, t, J.ly, RW);
+    BwdDiag g;
+    g.sx = sx; g.sy = sy; g.K = K; g.RW = cm.RW; g.t = t; g.p = t & 1;
+    g.Lt = mt_.L; g.w1 = mt2.co - mt1.co; g.w2 = (t + 2 <= top) ? mt3.co - mt2.co : 0;
+    g.cur = slot(cm, t);                                           // also B[t+2]
+    g.b1 = slot(cm, t + 1);
+    g.s1 = (g.Lt - 1 - mt1.L) >> 1; g.s2 = (g.Lt - mt2.L) >> 1;
+    g.i0 = ring_i0(g.Lt, t, J.ly, cm.RW);
+    const int w = mt1.co - mt_.co, cbase = mt_.co, RW = cm.RW, Lt = g.Lt;
     const double total = fuse_emit ? *cm.total : 0.0;
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
-            const int xmy = Lt + 2 * k, x = (t + xmy) >> 1, y = (t - xmy) >> 1;
-            const bool cand = fuse_emit && x > 0 && y > 0;
+            const int xa = (t + Lt + 2 * k) >> 1, ya = (t - Lt - 2 * k) >> 1;
+            const bool cand = fuse_emit && xa > 0 && ya > 0;
             const double fm = cand ? fm_at(cm, cbase + k) : 0.0;   // issued early: the only HBM read of the step
-            const int ku = k + s1, kl = ku + 1, km = k + s2;       // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
-            const int i = wrap(i0 + k, RW), iu = wrap(i - p, RW), il = wrap(i + 1 - p, RW);
-            double mid = LZ, upSY = LZ, upLY = LZ, loSX = LZ, loLX = LZ;
-            const double *gx = K + K_GAP, *gy = K + K_GAP, *mt = K + K_MATCH;
-            if (km >= 0 && km < w2) { mid = cur[S_M * RW + i]; mt = K + K_MATCH + 3 * match_class(sx[x], sy[y]); }                      // cell (x+1, y+1)
-            if (ku >= 0 && ku < w1) { upSY = b1[S_SY * RW + iu]; upLY = b1[S_LY * RW + iu]; gy = K + K_GAP + 4 * (sy[y] == 4); }  // cell (x, y+1)
-            if (kl >= 0 && kl < w1) { loSX = b1[S_SX * RW + il]; loLX = b1[S_LX * RW + il]; gx = K + K_GAP + 4 * (sx[x] == 4); }  // cell (x+1, y)
-            double vM = d_add(mid, mt[0]);
-            vM = log_add(vM, d_add(upSY, gy[0]), K); vM = log_add(vM, d_add(upLY, gy[2]), K);
-            vM = log_add(vM, d_add(loSX, gx[0]), K); vM = log_add(vM, d_add(loLX, gx[2]), K);
-            const double vSX = log_add(d_add(mid, mt[1]), d_add(loSX, gx[1]), K);
-            const double vSY = log_add(d_add(mid, mt[1]), d_add(upSY, gy[1]), K);
-            const double vLX = log_add(d_add(mid, mt[2]), d_add(loLX, gx[3]), K);
-            const double vLY = log_add(d_add(mid, mt[2]), d_add(upLY, gy[3]), K);
-            cur[S_M * RW + i] = vM; cur[S_SX * RW + i] = vSX; cur[S_SY * RW + i] = vSY; cur[S_LX * RW + i] = vLX; cur[S_LY * RW + i] = vLY;
-            if (cand) {
-                const double lp = d_sub(d_add(fm, vM), total);
-                if (lp >= P.log_thr_lo) emit_one(J, cm, out, x, y, lp);
-            }
+            const Cell5 a = bwd_cell(g, k);
+            ring_store(g.cur, RW, wrap(g.i0 + k, RW), a);
+            if (cand) { const double lp = d_sub(d_add(fm, a.m), total); if (lp >= P.log_thr_lo) emit_one(J, cm, out, xa, ya, lp); }
         }
     }
     PC_SYNC();
