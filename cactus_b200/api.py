@@ -406,13 +406,23 @@ class Engine:
         pairs: list of (sX, sY, anchorPairs[n, 2], alignmentHasRaggedLeftEnd, alignmentHasRaggedRightEnd).
         Returns per pair (triples int64 [k, 3] = (score, x, y) in the reference's order, [posteriors,] banded cells)."""
         params = params or PairwiseAlignmentParameters()
-        t = _PairTable(pairs)
-        m = max(t.n, 1)
+        t = pairs if isinstance(pairs, _PairTable) else _PairTable(pairs)
+        raw = self.pecan_batch_raw(t, params, return_posteriors)
+        return self._take_pairs(*raw, t.n)
+
+    def pecan_table(self, pairs):
+        """the C argument arrays of a list of pairs, built once (benchmarks time the C call, not this marshalling)"""
+        return _PairTable(pairs)
+
+    def pecan_batch_raw(self, table, params=None, return_posteriors=False):
+        """barb200_pecan_aligned_pairs_batch on a prepared table; returns the raw output arrays (trip, post, n_out, cells)"""
+        params = params or PairwiseAlignmentParameters()
+        m = max(table.n, 1)
         trip, post = (C.c_void_p * m)(), (C.c_void_p * m)()
         n_out, cells = np.zeros(m, np.int64), np.zeros(m, np.int64)
-        self._check(self.lib.barb200_pecan_aligned_pairs_batch(self.ctx, C.byref(params.c), t.n, *t.args(), trip, n_out.ctypes.data,
+        self._check(self.lib.barb200_pecan_aligned_pairs_batch(self.ctx, C.byref(params.c), table.n, *table.args(), trip, n_out.ctypes.data,
                                                                post if return_posteriors else None, cells.ctypes.data))
-        return self._take_pairs(trip, post if return_posteriors else None, n_out, cells, t.n)
+        return trip, (post if return_posteriors else None), n_out, cells
 
     def get_aligned_pairs_using_anchors(self, sX, sY, anchorPairs=(), params=None, alignmentHasRaggedLeftEnd=False,
                                         alignmentHasRaggedRightEnd=False):

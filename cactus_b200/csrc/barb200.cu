@@ -56,6 +56,8 @@ struct barb200_ctx {
     uint8_t *h_pinned = nullptr; size_t h_pinned_bytes = 0;   // pinned staging buffer for the MSA download
     int *h_ready = nullptr; unsigned ready_slot = 0;          // pinned ring of "jobs released" values (copied to the device by the copy engine)
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
+    void *pecan_scratch = nullptr; size_t pecan_scratch_bytes = 0;   // pecan.cu's batch call (grow-only)
+    void *pecan_pinned[2] = {nullptr, nullptr}; size_t pecan_pinned_bytes[2] = {0, 0};   // pinned staging: 0 upload, 1 download
 };
 
 namespace barb200 {
@@ -114,6 +116,30 @@ static void ctx_free(barb200_ctx *ctx, void *p, size_t bytes) {
     if (ctx->cached_bytes + block_size_of(bytes) > ((size_t)4 << 30) || ctx->free_blocks.size() >= 64) { cudaFree(p); return; }
     ctx->free_blocks.emplace_back(p, block_size_of(bytes)); ctx->cached_bytes += block_size_of(bytes);
 }
+
+namespace barb200 {
+int device_alloc(barb200_ctx *ctx, void **p, size_t bytes) { return ctx_alloc(ctx, p, bytes) == cudaSuccess ? 0 : -1; }
+void device_free(barb200_ctx *ctx, void *p, size_t bytes) { ctx_free(ctx, p, bytes); }
+// grow-only scratch of the pair-HMM batch call (tens of GB of rings: cudaMalloc of that size costs ~0.2 s per call)
+void *pecan_scratch(barb200_ctx *ctx, size_t bytes) {
+    if (ctx->pecan_scratch_bytes >= bytes && ctx->pecan_scratch) return ctx->pecan_scratch;
+    if (ctx->pecan_scratch) { cudaFree(ctx->pecan_scratch); ctx->pecan_scratch = nullptr; ctx->pecan_scratch_bytes = 0; }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->pecan_scratch = p; ctx->pecan_scratch_bytes = bytes;
+    return p;
+}
+// grow-only pinned staging buffers of the pair-HMM batch call (which: 0 upload, 1 download); nullptr on failure
+void *pecan_pinned(barb200_ctx *ctx, int which, size_t bytes) {
+    if (ctx->pecan_pinned_bytes[which] >= bytes && ctx->pecan_pinned[which]) return ctx->pecan_pinned[which];
+    if (ctx->pecan_pinned[which]) { cudaFreeHost(ctx->pecan_pinned[which]); ctx->pecan_pinned[which] = nullptr; ctx->pecan_pinned_bytes[which] = 0; }
+    void *p = nullptr;
+    bytes += bytes / 4;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->pecan_pinned[which] = p; ctx->pecan_pinned_bytes[which] = bytes;
+    return p;
+}
+}  // namespace barb200
 
 #define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
     set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(_e)); return BARB200_ECUDA; } } while (0)
@@ -176,6 +202,8 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
         if (ctx->ar[a].stream) cudaStreamDestroy(ctx->ar[a].stream);
     }
     if (ctx->d_clk) cudaFree(ctx->d_clk);
+    if (ctx->pecan_scratch) cudaFree(ctx->pecan_scratch);
+    for (int i = 0; i < 2; ++i) if (ctx->pecan_pinned[i]) cudaFreeHost(ctx->pecan_pinned[i]);
     for (auto &b : ctx->free_blocks) cudaFree(b.first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_ready) cudaFreeHost(ctx->h_ready);

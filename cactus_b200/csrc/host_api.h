@@ -39,5 +39,10 @@ std::mutex &device_mutex(barb200_ctx *ctx);    // serialises device batches on o
 int ctx_device(barb200_ctx *ctx);
 int ctx_sm_count(barb200_ctx *ctx);
 double ctx_mem_fraction(barb200_ctx *ctx);
+// device blocks from the context's grow-only cache (cudaMalloc / cudaFree per call cost milliseconds); 0 on success
+int device_alloc(barb200_ctx *ctx, void **p, size_t bytes);
+void device_free(barb200_ctx *ctx, void *p, size_t bytes);
+void *pecan_scratch(barb200_ctx *ctx, size_t bytes);
+void *pecan_pinned(barb200_ctx *ctx, int which, size_t bytes);   // grow-only pinned staging (0 upload, 1 download); nullptr on failure   // one grow-only block for the pair-HMM batch call; nullptr on failure
 
 }  // namespace barb200

@@ -4,8 +4,9 @@
 // A *stage* takes n sequence pairs with their anchors, splits each pair at large anchor gaps, builds the anchor band of
 // every sub-matrix and the traceback schedule on host threads (pecan_plan.cpp), packs everything, uploads it once and
 // launches persistent blocks that pull jobs (largest first) from a device counter. Jobs fall into four classes by their
-// widest diagonal: <= 96 cells -> 32-thread blocks (16 per SM), <= 640 -> 128 threads (2 per SM), <= 1280 -> 256 threads
-// (1 per SM), all with the diagonal ring in shared memory; wider -> 256 threads with the ring in HBM/L2. The classes run
+// widest diagonal: <= 96 cells -> 32-thread blocks (24 per SM), <= 320 -> 128 threads (6 per SM), <= 608 -> 128 threads (4 per SM),
+// <= 800 -> 256 threads (3 per SM), <= 1280 -> 256 threads (2 per SM), all with the diagonal ring in shared memory; wider -> 256
+// threads with the ring in HBM/L2. The classes run
 // concurrently on their own streams. Each resident block owns a slot in HBM for the forward MATCH ring and the ring of
 // complete forward cells. Candidate pairs (x, y, log posterior) are written in the reference's order of emission,
 // compacted on the device, copied back once and finished on the host with libm's exp (the same function the reference
@@ -109,6 +110,7 @@ struct barb200_pecan_stage {
     Params devP;
     int64_t n_pairs = 0;
     bool full_cap = false;                       // retry stage: room for every cell
+    bool shared_scratch = false;                 // batch call: rings live in the context's grow-only scratch
     std::vector<SubJob> subs;                    // in pair order
     std::vector<int64_t> pair_first;             // subs of pair i: [pair_first[i], pair_first[i+1])
     std::vector<Job> jobs;
@@ -120,6 +122,8 @@ struct barb200_pecan_stage {
     Job *d_jobs = nullptr; Pair *d_out = nullptr; unsigned *d_counter = nullptr; double *d_consts = nullptr, *d_scratch = nullptr;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ran = false;
+    struct Block { void *p; size_t bytes; };
+    std::vector<Block> blocks;                   // device arrays from the context's block cache
 };
 
 extern "C" void barb200_pecan_params_default(barb200_pecan_params *p) {
@@ -137,8 +141,8 @@ static unsigned pow2ceil(uint64_t v) { uint64_t p = 1024; while (p < v) p <<= 1;
 extern "C" void barb200_pecan_stage_destroy(barb200_pecan_stage *st) {
     if (!st) return;
     cudaSetDevice(ctx_device(st->ctx));
-    void *ptrs[] = {st->d_sym, st->d_meta, st->d_order, st->d_out_n, st->d_jobs, st->d_out, st->d_counter, st->d_consts, st->d_scratch};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &b : st->blocks) device_free(st->ctx, b.p, b.bytes);
+    if (st->d_scratch && !st->shared_scratch) cudaFree(st->d_scratch);
     for (PecanGroup &g : st->groups) { if (g.stream) cudaStreamDestroy(g.stream); if (g.done) cudaEventDestroy(g.done); }
     if (st->ev0) cudaEventDestroy(st->ev0);
     if (st->ev1) cudaEventDestroy(st->ev1);
@@ -191,7 +195,11 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     // pack
     std::vector<uint8_t> &sym = st->h_sym;
     sym.assign((size_t)std::max<int64_t>(sym_off, 1), 4);
-    std::vector<DiagMeta> meta((size_t)band_off + 1);
+    std::vector<DiagMeta> meta_own;
+    DiagMeta *meta = nullptr;
+    const size_t meta_n = (size_t)band_off + 1;
+    if (st->shared_scratch) meta = (DiagMeta *)pecan_pinned(ctx, 0, meta_n * sizeof(DiagMeta));     // pinned: the upload runs at link speed
+    if (!meta) { meta_own.resize(meta_n); meta = meta_own.data(); }
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
     for (int64_t i = 0; i < ns; ++i) {
         const SubJob &s = st->subs[i];
@@ -215,9 +223,10 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     const size_t fixed = (size_t)sym_off + (size_t)band_off * 16 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
     size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
-    // shared memory per block = 8 * (58 + 11 * RW) bytes: 8.9 KB, 28.6 KB, 54 KB, 113 KB; 80 registers per thread
+    // shared memory per block = 8 * (58 + 11 * RW) bytes: 8.9 KB, 28.6 KB, 54 KB, 71 KB, 113 KB; 80 registers per thread
+    // (block shapes from a sweep on the benchmark workload, scripts/pecan_sweep.sh)
     struct Class { int max_w, threads, ctas_per_sm; bool smem; };
-    std::vector<Class> kClass = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true}, {1280, 256, 2, true}};
+    std::vector<Class> kClass = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true}, {800, 256, 3, true}, {1280, 256, 2, true}};
     if (const char *e = getenv("BARB200_PECAN_CLASSES")) {         // tuning aid: "max_w:threads:blocks_per_sm,..." for the shared-memory classes
         kClass.clear();
         for (const char *q = e; *q;) {
@@ -274,19 +283,28 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
                     g.jobs.size(), g.threads, g.ctas, g.RW, g.ring_in_smem ? "smem" : "global", g.capM, g.capF, g.smem_bytes);
     // device arrays
     Consts C; fill_constants(C);
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_sym, sym.size()));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_meta, meta.size() * sizeof(DiagMeta)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_order, order.size() * sizeof(int)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out_n, (size_t)std::max<int64_t>(ns, 1) * sizeof(int)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_jobs, (size_t)std::max<int64_t>(ns, 1) * sizeof(Job)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_out, (size_t)std::max<int64_t>(out_off, 1) * sizeof(Pair)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_counter, sizeof(unsigned) * (st->groups.size() + 1)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_consts, sizeof(Consts)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&st->d_scratch, std::max<size_t>(scratch_bytes, 8)));
+    auto dev_alloc = [&](void **p, size_t bytes) -> bool {
+        if (device_alloc(ctx, p, bytes) != 0) return false;
+        st->blocks.push_back(barb200_pecan_stage::Block{*p, bytes});
+        return true;
+    };
+    const size_t ns1 = (size_t)std::max<int64_t>(ns, 1);
+    if (!dev_alloc((void **)&st->d_sym, sym.size()) || !dev_alloc((void **)&st->d_meta, meta_n * sizeof(DiagMeta)) ||
+        !dev_alloc((void **)&st->d_order, order.size() * sizeof(int)) || !dev_alloc((void **)&st->d_out_n, ns1 * sizeof(int)) ||
+        !dev_alloc((void **)&st->d_jobs, ns1 * sizeof(Job)) || !dev_alloc((void **)&st->d_out, (size_t)std::max<int64_t>(out_off, 1) * sizeof(Pair)) ||
+        !dev_alloc((void **)&st->d_counter, sizeof(unsigned) * (st->groups.size() + 1)) || !dev_alloc((void **)&st->d_consts, sizeof(Consts))) {
+        set_error(ctx, "device allocation failed (pecan stage)"); return BARB200_ENOMEM;
+    }
+    if (st->shared_scratch) {
+        st->d_scratch = (double *)pecan_scratch(ctx, std::max<size_t>(scratch_bytes, 8));
+        if (!st->d_scratch) { set_error(ctx, "device allocation failed (pecan rings)"); return BARB200_ENOMEM; }
+    } else {
+        CUDA_TRY(ctx, cudaMalloc((void **)&st->d_scratch, std::max<size_t>(scratch_bytes, 8)));
+    }
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaEventCreate(&st->ev0)); CUDA_TRY(ctx, cudaEventCreate(&st->ev1));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_sym, sym.data(), sym.size(), cudaMemcpyHostToDevice, st->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_meta, meta.data(), meta.size() * sizeof(DiagMeta), cudaMemcpyHostToDevice, st->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->d_meta, meta, meta_n * sizeof(DiagMeta), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st->stream));
     if (ns) CUDA_TRY(ctx, cudaMemcpyAsync(st->d_jobs, st->jobs.data(), (size_t)ns * sizeof(Job), cudaMemcpyHostToDevice, st->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->d_consts, &C, sizeof(C), cudaMemcpyHostToDevice, st->stream));
@@ -296,16 +314,16 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     return BARB200_OK;
 }
 
-extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
-                                          const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
-                                          const int64_t *const *anchors, const int64_t *n_anchor,
-                                          const uint8_t *ragged_left, const uint8_t *ragged_right, barb200_pecan_stage **out) {
+static int stage_create_impl(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                             const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                             const int64_t *const *anchors, const int64_t *n_anchor,
+                             const uint8_t *ragged_left, const uint8_t *ragged_right, bool shared_scratch, barb200_pecan_stage **out) {
     if (!ctx || !out || n_pairs < 0 || (n_pairs > 0 && (!sx || !sy || !lx || !ly))) { if (ctx) set_error(ctx, "bad argument"); return BARB200_EINVAL; }
     PlanParams P;
     int rc = plan_params(ctx, p, P);
     if (rc) return rc;
     barb200_pecan_stage *st = new barb200_pecan_stage();
-    st->ctx = ctx; st->P = P; st->n_pairs = n_pairs;
+    st->ctx = ctx; st->P = P; st->n_pairs = n_pairs; st->shared_scratch = shared_scratch;
     st->pair_first.assign(n_pairs + 1, 0);
     for (int64_t i = 0; i < n_pairs; ++i) {
         const int64_t na = n_anchor ? n_anchor[i] : 0;
@@ -317,11 +335,19 @@ extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_
         split_pair(P, i, lx[i], ly[i], a, na, ragged_left && ragged_left[i], ragged_right && ragged_right[i], st->subs);
     }
     st->pair_first[n_pairs] = (int64_t)st->subs.size();
-    std::lock_guard<std::mutex> lk(device_mutex(ctx));
     rc = stage_build(st, sx, sy, nullptr, nullptr);
     if (rc) { barb200_pecan_stage_destroy(st); return rc; }
     *out = st;
     return BARB200_OK;
+}
+
+extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                                          const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                                          const int64_t *const *anchors, const int64_t *n_anchor,
+                                          const uint8_t *ragged_left, const uint8_t *ragged_right, barb200_pecan_stage **out) {
+    if (!ctx) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(device_mutex(ctx));
+    return stage_create_impl(ctx, p, n_pairs, sx, lx, sy, ly, anchors, n_anchor, ragged_left, ragged_right, false, out);
 }
 
 static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
@@ -380,28 +406,46 @@ static int stage_collect(barb200_pecan_stage *st, std::vector<std::vector<Pair>>
         dst_off[i + 1] = dst_off[i] + (over ? 0 : out_n[i]);
     }
     const long long total = dst_off[ns];
-    std::vector<Pair> flat((size_t)std::max<long long>(total, 1));
+    std::vector<Pair> flat_own;
+    Pair *flat = st->shared_scratch ? (Pair *)pecan_pinned(ctx, 1, sizeof(Pair) * (size_t)std::max<long long>(total, 1)) : nullptr;
+    if (!flat) { flat_own.resize((size_t)std::max<long long>(total, 1)); flat = flat_own.data(); }
     if (total > 0) {
         long long *d_dst_off = nullptr; Pair *d_flat = nullptr;
-        CUDA_TRY(ctx, cudaMalloc((void **)&d_dst_off, sizeof(long long) * (ns + 1)));
-        cudaError_t e = cudaMalloc((void **)&d_flat, sizeof(Pair) * (size_t)total);
-        if (e != cudaSuccess) { cudaFree(d_dst_off); set_error(ctx, "cudaMalloc (compact output) failed"); return BARB200_ENOMEM; }
+        if (device_alloc(ctx, (void **)&d_dst_off, sizeof(long long) * (ns + 1)) != 0) { set_error(ctx, "device allocation failed (compact offsets)"); return BARB200_ENOMEM; }
+        cudaError_t e = cudaSuccess;
+        if (device_alloc(ctx, (void **)&d_flat, sizeof(Pair) * (size_t)total) != 0) {
+            device_free(ctx, d_dst_off, sizeof(long long) * (ns + 1)); set_error(ctx, "device allocation failed (compact output)"); return BARB200_ENOMEM; }
         cudaMemcpyAsync(d_dst_off, dst_off.data(), sizeof(long long) * (ns + 1), cudaMemcpyHostToDevice, st->stream);
         const int grid = (int)std::min<int64_t>(ns, (int64_t)ctx_sm_count(ctx) * 16);
         pecan_compact_kernel<<<grid, 128, 0, st->stream>>>(st->d_jobs, st->d_out_n, d_dst_off, st->d_out, d_flat, (int)ns);
         ++st->launches;
-        cudaMemcpyAsync(flat.data(), d_flat, sizeof(Pair) * (size_t)total, cudaMemcpyDeviceToHost, st->stream);
+        cudaMemcpyAsync(flat, d_flat, sizeof(Pair) * (size_t)total, cudaMemcpyDeviceToHost, st->stream);
         e = cudaStreamSynchronize(st->stream);
-        cudaFree(d_dst_off); cudaFree(d_flat);
+        device_free(ctx, d_dst_off, sizeof(long long) * (ns + 1)); device_free(ctx, d_flat, sizeof(Pair) * (size_t)total);
         if (e != cudaSuccess) { set_error(ctx, std::string("pecan compaction: ") + cudaGetErrorString(e)); return BARB200_ECUDA; }
     }
     const int nthr = host_threads(ctx);
-#pragma omp parallel for schedule(static) num_threads(nthr)
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthr)
     for (int64_t i = 0; i < ns; ++i) {
-        per_sub[i].assign(flat.begin() + dst_off[i], flat.begin() + dst_off[i + 1]);
+        per_sub[i].assign(flat + dst_off[i], flat + dst_off[i + 1]);
         // the kernel appends the candidates of a diagonal in no particular order: restore the reference's order of emission
+        // (keys computed once per record; the input is nearly sorted, so this is cheap)
         const SubJob &sj = st->subs[i];
-        std::sort(per_sub[i].begin(), per_sub[i].end(), [&](const Pair &a, const Pair &b) { return emission_key(sj, a.x, a.y) < emission_key(sj, b.x, b.y); });
+        std::vector<Pair> &v = per_sub[i];
+        struct Keyed { uint64_t k1; uint32_t k2, idx; };
+        std::vector<Keyed> keys(v.size());
+        bool sorted = true;
+        for (size_t q = 0; q < v.size(); ++q) {
+            const std::pair<uint64_t, uint32_t> k = emission_key(sj, v[q].x, v[q].y);
+            keys[q] = Keyed{k.first, k.second, (uint32_t)q};
+            if (q && (keys[q].k1 < keys[q - 1].k1 || (keys[q].k1 == keys[q - 1].k1 && keys[q].k2 < keys[q - 1].k2))) sorted = false;
+        }
+        if (!sorted) {
+            std::sort(keys.begin(), keys.end(), [](const Keyed &a, const Keyed &b) { return a.k1 != b.k1 ? a.k1 < b.k1 : a.k2 < b.k2; });
+            std::vector<Pair> w(v.size());
+            for (size_t q = 0; q < v.size(); ++q) w[q] = v[keys[q].idx];
+            v.swap(w);
+        }
     }
     if (!retry.empty()) {
         if (st->full_cap) { set_error(ctx, "pecan: output overflow with full capacity (internal error)"); return BARB200_EJOB; }
@@ -484,13 +528,23 @@ extern "C" int barb200_pecan_aligned_pairs_batch(barb200_ctx *ctx, const barb200
         int64_t i1 = i0, rec = 0;
         while (i1 < n_pairs && (i1 == i0 || rec + lx[i1] + ly[i1] + 64 <= kChunkRecords)) { rec += lx[i1] + ly[i1] + 64; ++i1; }
         barb200_pecan_stage *st = nullptr;
-        int rc = barb200_pecan_stage_create(ctx, p, i1 - i0, sx + i0, lx + i0, sy + i0, ly + i0, anchors ? anchors + i0 : nullptr,
-                                            n_anchor ? n_anchor + i0 : nullptr, ragged_left ? ragged_left + i0 : nullptr,
-                                            ragged_right ? ragged_right + i0 : nullptr, &st);
-        if (rc == BARB200_OK) rc = barb200_pecan_stage_run(st, nullptr);
-        if (rc == BARB200_OK) rc = barb200_pecan_stage_fetch(st, triples_out + i0, n_out + i0, posteriors_out ? posteriors_out + i0 : nullptr,
-                                                            cells_out ? cells_out + i0 : nullptr);
+        const double t0 = omp_get_wtime();
+        std::unique_lock<std::mutex> lk(device_mutex(ctx));      // the chunk owns the context's ring scratch from create to collect
+        int rc = stage_create_impl(ctx, p, i1 - i0, sx + i0, lx + i0, sy + i0, ly + i0, anchors ? anchors + i0 : nullptr,
+                                   n_anchor ? n_anchor + i0 : nullptr, ragged_left ? ragged_left + i0 : nullptr,
+                                   ragged_right ? ragged_right + i0 : nullptr, true, &st);
+        const double t1 = omp_get_wtime();
+        if (rc == BARB200_OK) rc = stage_run_locked(st, nullptr);
+        const double t2 = omp_get_wtime();
+        std::vector<std::vector<Pair>> per_sub;
+        if (rc == BARB200_OK) rc = stage_collect(st, per_sub);
+        lk.unlock();
+        if (rc == BARB200_OK) rc = finish_pairs(st, per_sub, triples_out + i0, n_out + i0, posteriors_out ? posteriors_out + i0 : nullptr,
+                                                cells_out ? cells_out + i0 : nullptr);
+        const double t3 = omp_get_wtime();
         barb200_pecan_stage_destroy(st);
+        if (getenv("BARB200_DEBUG")) fprintf(stderr, "[barb200] pecan batch of %lld pairs: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n",
+                                             (long long)(i1 - i0), (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (omp_get_wtime() - t3) * 1e3);
         if (rc) return rc;
         if (n_pairs == 0) break;
         i0 = i1;

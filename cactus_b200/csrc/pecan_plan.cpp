@@ -72,7 +72,7 @@ void split_pair(const PlanParams &P, int64_t pair, int64_t lx, int64_t ly, const
 }
 
 namespace {
-inline int64_t avoid_off_by_one(int64_t xay, int64_t xmy) { return (xay + xmy) % 2 == 0 ? xmy : xmy + 1; }
+inline int64_t avoid_off_by_one(int64_t xay, int64_t xmy) { return xmy + ((xay + xmy) & 1); }   // parity of a two's complement sum
 inline int64_t bound(int64_t z, int64_t l) { return z < 0 ? 0 : (z > l ? l : z); }
 // diagonal_getXCoordinate / YCoordinate use C division (truncation toward zero) on values that are even by construction
 // everywhere except in band_construct's xL..yU, where the reference relies on the same truncation: keep `/ 2`.
@@ -85,12 +85,13 @@ std::string plan_subjob(const PlanParams &P, SubJob &s) {
     int max_w = 0;
     while (xay <= D) {                              // band_construct, pairwiseAligner.c:193-244
         int64_t l = avoid_off_by_one(xay, xL - yL), r = avoid_off_by_one(xay, xU - yU), i;
-        i = (xay + l) / 2; if (i < xL) l += 2 * (xL - i);           // band_setCurrentDiagonal, :114-132
-        i = (xay - l) / 2; if (yL < i) l += 2 * (i - yL);
-        i = (xay + r) / 2; if (xU < i) r -= 2 * (i - xU);
-        i = (xay - r) / 2; if (i < yU) r -= 2 * (yU - i);
-        if (l > r || (xay + l) % 2 != 0 || (xay + r) % 2 != 0) return "invalid band diagonal (the reference throws PAIRWISE_ALIGNMENT_EXCEPTION here)";
-        const int64_t w = (r - l) / 2 + 1;
+        // (xay + l), (xay - l), ... are even here, so the reference's "/ 2" is an exact shift
+        i = (xay + l) >> 1; if (i < xL) l += 2 * (xL - i);           // band_setCurrentDiagonal, :114-132
+        i = (xay - l) >> 1; if (yL < i) l += 2 * (i - yL);
+        i = (xay + r) >> 1; if (xU < i) r -= 2 * (i - xU);
+        i = (xay - r) >> 1; if (i < yU) r -= 2 * (yU - i);
+        if (l > r || ((xay + l) & 1) || ((xay + r) & 1)) return "invalid band diagonal (the reference throws PAIRWISE_ALIGNMENT_EXCEPTION here)";
+        const int64_t w = ((r - l) >> 1) + 1;
         s.bandL[xay] = (int)l; s.coff[xay] = (int)cells;
         cells += w; max_w = std::max<int64_t>(max_w, w);
         if (cells > (int64_t)400 * 1000 * 1000) return "pair-HMM job larger than 4e8 banded cells";
