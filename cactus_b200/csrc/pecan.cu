@@ -3,12 +3,12 @@
 //
 // A *stage* takes n sequence pairs with their anchors, splits each pair at large anchor gaps, builds the anchor band of
 // every sub-matrix and the traceback schedule on host threads (pecan_plan.cpp), packs everything, uploads it once and
-// launches persistent blocks that pull jobs (largest first) from a device counter. Jobs fall into four classes by their
-// widest diagonal: <= 96 cells -> 32-thread blocks (24 per SM), <= 320 -> 128 threads (6 per SM), <= 608 -> 128 threads (4 per SM),
-// <= 800 -> 256 threads (3 per SM), <= 1280 -> 256 threads (2 per SM), all with the diagonal ring in shared memory; wider -> 256
-// threads with the ring in HBM/L2. The classes run
-// concurrently on their own streams. Each resident block owns a slot in HBM for the forward MATCH ring and the ring of
-// complete forward cells. Candidate pairs (x, y, log posterior) are written in the reference's order of emission,
+// launches persistent blocks that pull jobs (largest first) from a device counter. Two block shapes: jobs whose widest
+// diagonal has <= 96 cells run in 32-thread blocks (24 per SM), all others in 128-thread blocks (4 per SM) whose diagonal
+// ring keeps 608 positions in shared memory and spills the flanks of wider diagonals to an HBM/L2 overflow block (a per-job
+// shift centres the band on the shared part, pecan_cta.cuh). The two launches run concurrently on their own streams.
+// Each resident block owns a slot in HBM for the forward MATCH ring, the ring of complete forward cells and the overflow.
+// Candidate pairs (x, y, log posterior) are appended by the kernel, put into the reference's order of emission on the host,
 // compacted on the device, copied back once and finished on the host with libm's exp (the same function the reference
 // calls), threshold and floor. There is no CPU fallback: the DP only exists as the CUDA kernel below.
 #include <cuda_runtime.h>
@@ -41,15 +41,14 @@ struct KernelArgs {
     int *out_n;
     unsigned *counter;
     const double *consts;
-    double *scratch;           // per block: FM ring (maskM + 1), FF ring (maskF + 1) [, ring 10 * RW + tbuf RW when not in smem]
+    double *scratch;           // per block: FM ring (maskM + 1), FF ring (maskF + 1), ring overflow 10 * (RW - RWs), tbuf overflow (RW - RWs)
     size_t slot_doubles;
     unsigned maskM, maskF;
-    int RW;
-    int ring_in_smem;
+    int RW, RWs;
     Params P;
 };
 
-// dynamic shared memory: constants | total | [ring 10 * RW | tbuf RW]
+// dynamic shared memory: constants | total | ring 10 * RWs | tbuf RWs
 extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(const KernelArgs A) {
     extern __shared__ double smem[];
     double *K = smem;
@@ -59,11 +58,11 @@ extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(cons
     CtaMem cm;
     cm.total = smem + K_TOTAL;
     cm.n_out = &n_out;
-    cm.RW = A.RW; cm.T = (int)blockDim.x;
+    cm.RW = A.RW; cm.RWs = A.RWs; cm.T = (int)blockDim.x;
     cm.FM = A.scratch + (size_t)blockIdx.x * A.slot_doubles; cm.maskM = A.maskM;
     cm.FF = cm.FM + (size_t)A.maskM + 1; cm.maskF = A.maskF;
-    if (A.ring_in_smem) { cm.ring = smem + K_TOTAL + 2; cm.tbuf = cm.ring + 10 * (size_t)A.RW; }
-    else { cm.ring = cm.FF + (size_t)A.maskF + 1; cm.tbuf = cm.ring + 10 * (size_t)A.RW; }
+    cm.ring = smem + K_TOTAL + 2; cm.tbuf = cm.ring + 10 * (size_t)A.RWs;
+    cm.ring_o = cm.FF + (size_t)A.maskF + 1; cm.tbuf_o = cm.ring_o + 10 * (size_t)(A.RW - A.RWs);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) next_job = atomicAdd(A.counter, 1u);
@@ -96,8 +95,7 @@ struct PecanGroup {              // one launch: a class of jobs with one block s
     std::vector<int> jobs;       // largest first
     int threads = 32;            // block size
     int ctas = 0;                // resident blocks = slots
-    int RW = 32;                 // ring width (cells)
-    bool ring_in_smem = true;
+    int RW = 32, RWs = 32;       // ring width (the modulus) and its shared-memory part
     unsigned capM = 1024, capF = 1024;   // ring doubles (powers of two)
     size_t slot_doubles = 0, smem_bytes = 0, scratch_off = 0;
     int order_off = 0;           // into d_order
@@ -223,21 +221,21 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     const size_t fixed = (size_t)sym_off + (size_t)band_off * 16 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
     size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
-    // shared memory per block = 8 * (58 + 11 * RW) bytes: 8.9 KB, 28.6 KB, 54 KB, 71 KB, 113 KB; 80 registers per thread
-    // (block shapes from a sweep on the benchmark workload, scripts/pecan_sweep.sh)
-    struct Class { int max_w, threads, ctas_per_sm; bool smem; };
-    std::vector<Class> kClass = {{96, 32, 24, true}, {320, 128, 6, true}, {608, 128, 4, true}, {800, 256, 3, true}, {1280, 256, 2, true}};
-    if (const char *e = getenv("BARB200_PECAN_CLASSES")) {         // tuning aid: "max_w:threads:blocks_per_sm,..." for the shared-memory classes
+    // shared memory per block = 8 * (58 + 11 * RWs) bytes: 8.9 KB for the narrow shape, 54 KB for the general one; 80 registers
+    struct Class { int max_w, threads, ctas_per_sm, rws; };
+    std::vector<Class> kClass = {{96, 32, 24, 96}, {0x7fffffff, 128, 4, 608}};
+    if (const char *e = getenv("BARB200_PECAN_CLASSES")) {         // tuning aid: "max_w:threads:blocks_per_sm:shared_ring,..." (last max_w is ignored)
         kClass.clear();
         for (const char *q = e; *q;) {
-            int a = 0, b = 0, c = 0, n = 0;
-            if (sscanf(q, "%d:%d:%d%n", &a, &b, &c, &n) != 3 || a <= 0 || b < 32 || b > 256 || b % 32 || c <= 0) { set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
-            kClass.push_back(Class{a, b, c, true});
+            int a = 0, b = 0, c = 0, r = 0, n = 0;
+            if (sscanf(q, "%d:%d:%d:%d%n", &a, &b, &c, &r, &n) != 4 || a <= 0 || b < 32 || b > 256 || b % 32 || c <= 0 || r < 32 || 8 * (58 + 11 * (size_t)r) > 200 * 1024) {
+                set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
+            kClass.push_back(Class{a, b, c, r});
             q += n; if (*q == ',') ++q;
         }
-        if (kClass.empty() || 8 * (58 + 11 * (size_t)kClass.back().max_w) > 200 * 1024) { set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
+        if (kClass.empty()) { set_error(ctx, "bad BARB200_PECAN_CLASSES"); return BARB200_EINVAL; }
+        kClass.back().max_w = 0x7fffffff;
     }
-    kClass.push_back(Class{0x7fffffff, kClass.back().threads, 2, false});       // wider: ring in HBM / L2
     st->groups.clear();
     for (int c = 0; c < (int)kClass.size(); ++c) {
         PecanGroup g;
@@ -245,11 +243,12 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         if (g.jobs.empty()) continue;
         int64_t spanM = 1, spanF = 1; int rw = 1;
         for (int j : g.jobs) { spanM = std::max(spanM, st->subs[j].span_cells); spanF = std::max(spanF, st->subs[j].span_full_cells); rw = std::max(rw, st->subs[j].max_w); }
-        g.threads = kClass[c].threads; g.ring_in_smem = kClass[c].smem;
-        g.RW = kClass[c].smem ? kClass[c].max_w : ((rw + 31) & ~31);
+        g.threads = kClass[c].threads;
+        g.RWs = kClass[c].rws; g.RW = std::max(g.RWs, rw);
+        for (int j : g.jobs) st->jobs[j].ring_shift = st->subs[j].ring_center - g.RWs / 2;
         g.capM = pow2ceil((uint64_t)spanM); g.capF = pow2ceil((uint64_t)5 * (uint64_t)spanF);
-        g.slot_doubles = (size_t)g.capM + g.capF + (g.ring_in_smem ? 0 : 11 * (size_t)g.RW);
-        g.smem_bytes = sizeof(double) * (K_TOTAL + 2 + (g.ring_in_smem ? 11 * (size_t)g.RW : 0));
+        g.slot_doubles = (size_t)g.capM + g.capF + 11 * (size_t)(g.RW - g.RWs) + 8;
+        g.smem_bytes = sizeof(double) * (K_TOTAL + 2 + 11 * (size_t)g.RWs);
         g.ctas = (int)std::min<int64_t>((int64_t)ctx_sm_count(ctx) * kClass[c].ctas_per_sm, (int64_t)g.jobs.size());
         std::sort(g.jobs.begin(), g.jobs.end(), [&](int a, int b) { return st->subs[a].cells != st->subs[b].cells ? st->subs[a].cells > st->subs[b].cells : a < b; });
         st->groups.push_back(std::move(g));
@@ -273,14 +272,14 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         // wider classes hold longer jobs: they are launched first and at higher priority so that they are resident from the start
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, g.ring_in_smem && g.RW <= 608 ? prio_lo : prio_hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, g.threads <= 32 ? prio_lo : prio_hi));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     }
     const size_t scratch_bytes = scratch_doubles * 8;
     if (getenv("BARB200_DEBUG"))
         for (const PecanGroup &g : st->groups)
-            fprintf(stderr, "[barb200] pecan class: %zu jobs, %d threads x %d blocks, RW %d (%s), FM ring %u, FF ring %u doubles, smem %zu B\n",
-                    g.jobs.size(), g.threads, g.ctas, g.RW, g.ring_in_smem ? "smem" : "global", g.capM, g.capF, g.smem_bytes);
+            fprintf(stderr, "[barb200] pecan class: %zu jobs, %d threads x %d blocks, ring %d of which %d shared, FM ring %u, FF ring %u doubles, smem %zu B\n",
+                    g.jobs.size(), g.threads, g.ctas, g.RW, g.RWs, g.capM, g.capF, g.smem_bytes);
     // device arrays
     Consts C; fill_constants(C);
     auto dev_alloc = [&](void **p, size_t bytes) -> bool {
@@ -365,7 +364,7 @@ static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
         A.jobs = st->d_jobs; A.order = st->d_order + g.order_off; A.n_jobs = (int)g.jobs.size();
         A.sym = st->d_sym; A.meta = st->d_meta; A.out = st->d_out; A.out_n = st->d_out_n;
         A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch + g.scratch_off; A.slot_doubles = g.slot_doubles;
-        A.maskM = g.capM - 1; A.maskF = g.capF - 1; A.RW = g.RW; A.ring_in_smem = g.ring_in_smem ? 1 : 0; A.P = st->devP;
+        A.maskM = g.capM - 1; A.maskF = g.capF - 1; A.RW = g.RW; A.RWs = g.RWs; A.P = st->devP;
         CUDA_TRY(ctx, cudaStreamWaitEvent(g.stream, st->ev0, 0));
         pecan_posterior_kernel<<<g.ctas, g.threads, g.smem_bytes, g.stream>>>(A);
         CUDA_TRY(ctx, cudaGetLastError());

@@ -15,6 +15,11 @@
 //    IN PLACE over the one two steps back (each thread only overwrites what it alone has read) and the other slot is
 //    read-only during the step; one barrier per diagonal. The same ring holds the backward diagonals during a traceback
 //    -- forward and backward are never live together, the two forward diagonals the sweep resumes from are re-loaded;
+//  * the ring is SPLIT: positions below RWs are in shared memory, the rest in an HBM/L2 overflow block of the same job.
+//    A per-job shift of the absolute coordinate centres the band's cells of mass on the shared part, so that the
+//    narrow diagonals (most of them) never leave shared memory and only the flanks of the widest diagonals spill.
+//    Every job of a launch therefore runs with the same block shape and the same shared-memory footprint, whatever
+//    its widest diagonal, and one work queue balances them;
 //  * of the forward matrix only what a traceback reads goes to HBM: the MATCH plane of every cell (the posterior needs
 //    f_M only) plus all five states of the few diagonals the total probability is recomputed on (every 10th, and its
 //    predecessor) and of the two diagonals a sweep resumes from. Which diagonals those are depends only on the band
@@ -110,6 +115,8 @@ struct Job {
     int lx, ly;
     int ragged;                 // bit 0: ragged left end, bit 1: ragged right end
     int out_cap;                // output records available
+    int ring_shift;             // subtracted from the absolute ring coordinate (centres the band on the shared part)
+    int pad_;
 };
 
 struct Pair { int x, y; double lp; };   // 0-based sequence coordinates, log posterior
@@ -118,11 +125,14 @@ struct DiagMeta { int L, co, fo, pad; };   // per diagonal: xmyL, cells before i
                                             // diagonal d is marked iff fo[d+1] > fo[d])
 
 struct CtaMem {
-    double *ring;         // 2 parity slots x 5 states x RW doubles (shared memory; global scratch for very wide jobs)
-    double *tbuf;         // RW doubles: per-cell terms of a reduction
+    double *ring;         // shared part of the ring: 2 parity slots x 5 states x RWs doubles
+    double *ring_o;       // overflow part in HBM / L2: 2 x 5 x (RW - RWs) doubles
+    double *tbuf;         // RWs doubles: per-cell terms of a reduction (cells >= RWs: tbuf_o)
+    double *tbuf_o;
     double *total;        // 1 double: the running total probability, published by warp 0
     int *n_out;           // candidates appended so far
-    int RW;               // >= widest diagonal of the job
+    int RW;               // ring width (the modulus): >= widest diagonal of every job of the launch
+    int RWs;              // positions [0, RWs) live in shared memory
     double *FM;           // HBM ring of forward MATCH values, maskM + 1 doubles
     unsigned maskM;
     double *FF;           // HBM ring of complete forward cells (marked diagonals only), maskF + 1 doubles
@@ -197,9 +207,13 @@ PC_HD bool chain_inactive(double tot, double t) { return !(tot < t) && (t == log
 
 PC_HD int match_class(int cx, int cy) { return (cx == 4 || cy == 4) ? 3 : (cx == cy ? 0 : (((cx ^ cy) == 2) ? 1 : 2)); }
 
-PC_HD double *slot(const CtaMem &cm, int d) { return cm.ring + (size_t)(d & 1) * (5 * (size_t)cm.RW); }
-// ring index of cell 0 of a diagonal: a = (xmyL + parity) / 2 + ly >= 0, modulo the ring width
-PC_HD int ring_i0(int L, int d, int ly, int RW) { return (((L + (d & 1)) >> 1) + ly) % RW; }
+// state s of ring position i of the slot of parity par
+PC_HD double &ring_at(const CtaMem &cm, int par, int s, int i) {
+    return i < cm.RWs ? cm.ring[(par * 5 + s) * cm.RWs + i] : cm.ring_o[(size_t)(par * 5 + s) * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)];
+}
+PC_HD double &tbuf_at(const CtaMem &cm, int k) { return k < cm.RWs ? cm.tbuf[k] : cm.tbuf_o[k - cm.RWs]; }
+// ring index of cell 0 of a diagonal: a = (xmyL + parity) / 2 + ly - shift, modulo the ring width
+PC_HD int ring_i0(int L, int d, const Job &J, int RW) { const int a = (((L + (d & 1)) >> 1) + J.ly - J.ring_shift) % RW; return a < 0 ? a + RW : a; }
 PC_HD int wrap(int i, int RW) { return i >= RW ? i - RW : (i < 0 ? i + RW : i); }
 PC_HD double &fm_at(const CtaMem &cm, int cell) { return cm.FM[(unsigned)cell & cm.maskM]; }
 PC_HD double &ff_at(const CtaMem &cm, int base, int w, int s, int k) { return cm.FF[(unsigned)(base + s * w + k) & cm.maskF]; }
@@ -217,21 +231,21 @@ struct Cell5 { double m, sx, sy, lx, ly; };
 
 // ---- forward: diagonal d from d-1 (lower: xmy-1, upper: xmy+1) and d-2 (middle: xmy, updated in place) -------------------
 struct FwdDiag {            // per-diagonal uniforms
-    const uint8_t *sx, *sy; const double *K, *o1; double *cur;
+    const uint8_t *sx, *sy; const double *K;
     int d, p, Ld, w, w1, w2, sl, sm, i0, RW;
 };
-PC_HD Cell5 fwd_cell(const FwdDiag &f, int k) {
+PC_HD Cell5 fwd_cell(const CtaMem &cm, const FwdDiag &f, int k) {
     const double LZ = log_zero();
-    const int RW = f.RW;
+    const int RW = f.RW, p = f.p, q = p ^ 1;
     const int xmy = f.Ld + 2 * k, x = (f.d + xmy) >> 1, y = (f.d - xmy) >> 1;
     const int cx = x > 0 ? f.sx[x - 1] : 4, cy = y > 0 ? f.sy[y - 1] : 4;
     const int kl = k + f.sl, ku = kl + 1, km = k + f.sm;
-    const int i = wrap(f.i0 + k, RW), il = wrap(i - f.p, RW), iu = wrap(i + 1 - f.p, RW);
+    const int i = wrap(f.i0 + k, RW), il = wrap(i - p, RW), iu = wrap(i + 1 - p, RW);
     double lM = LZ, lSX = LZ, lLX = LZ, uM = LZ, uSY = LZ, uLY = LZ, mM = LZ, mSX = LZ, mSY = LZ, mLX = LZ, mLY = LZ;
-    if (kl >= 0 && kl < f.w1) { lM = f.o1[S_M * RW + il]; lSX = f.o1[S_SX * RW + il]; lLX = f.o1[S_LX * RW + il]; }
-    if (ku >= 0 && ku < f.w1) { uM = f.o1[S_M * RW + iu]; uSY = f.o1[S_SY * RW + iu]; uLY = f.o1[S_LY * RW + iu]; }
+    if (kl >= 0 && kl < f.w1) { lM = ring_at(cm, q, S_M, il); lSX = ring_at(cm, q, S_SX, il); lLX = ring_at(cm, q, S_LX, il); }
+    if (ku >= 0 && ku < f.w1) { uM = ring_at(cm, q, S_M, iu); uSY = ring_at(cm, q, S_SY, iu); uLY = ring_at(cm, q, S_LY, iu); }
     if (km >= 0 && km < f.w2) {
-        mM = f.cur[S_M * RW + i]; mSX = f.cur[S_SX * RW + i]; mSY = f.cur[S_SY * RW + i]; mLX = f.cur[S_LX * RW + i]; mLY = f.cur[S_LY * RW + i];
+        mM = ring_at(cm, p, S_M, i); mSX = ring_at(cm, p, S_SX, i); mSY = ring_at(cm, p, S_SY, i); mLX = ring_at(cm, p, S_LX, i); mLY = ring_at(cm, p, S_LY, i);
     }
     const double *K = f.K;
     const double *gx = K + K_GAP + 4 * (cx == 4), *gy = K + K_GAP + 4 * (cy == 4), *mt = K + K_MATCH + 3 * match_class(cx, cy);
@@ -246,8 +260,8 @@ PC_HD Cell5 fwd_cell(const FwdDiag &f, int k) {
     v.ly = d_add(uM, gy[2]); v.ly = log_add(v.ly, d_add(uLY, gy[3]), K);
     return v;
 }
-PC_HD void ring_store(double *slotp, int RW, int i, const Cell5 &v) {
-    slotp[S_M * RW + i] = v.m; slotp[S_SX * RW + i] = v.sx; slotp[S_SY * RW + i] = v.sy; slotp[S_LX * RW + i] = v.lx; slotp[S_LY * RW + i] = v.ly;
+PC_HD void ring_store(const CtaMem &cm, int par, int i, const Cell5 &v) {
+    ring_at(cm, par, S_M, i) = v.m; ring_at(cm, par, S_SX, i) = v.sx; ring_at(cm, par, S_SY, i) = v.sy; ring_at(cm, par, S_LX, i) = v.lx; ring_at(cm, par, S_LY, i) = v.ly;
 }
 // md = meta of d, mn = of d+1, m1 = of d-1, m2 = of d-2. (Keeping two cells per thread in flight to interleave their
 // dependent logAdd chains was measured SLOWER, 5.6 vs 8.6 Gcell/s: the duplicated work on narrow diagonals and the
@@ -258,15 +272,13 @@ PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
     f.sx = sx; f.sy = sy; f.K = K; f.RW = cm.RW; f.d = d; f.p = d & 1;
     f.Ld = md.L; f.w = mn.co - md.co; f.w1 = md.co - m1.co; f.w2 = d >= 2 ? m1.co - m2.co : 0;
     f.sl = (f.Ld - m1.L - 1) >> 1; f.sm = (f.Ld - m2.L) >> 1;      // both differences are even
-    f.cur = slot(cm, d);                                           // also the diagonal two back
-    f.o1 = slot(cm, d - 1);
-    f.i0 = ring_i0(f.Ld, d, J.ly, cm.RW);
+    f.i0 = ring_i0(f.Ld, d, J, cm.RW);
     const int w = f.w, cbase = md.co, fbase = 5 * md.fo, RW = cm.RW;
     const bool full = mn.fo > md.fo;
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
-            const Cell5 a = fwd_cell(f, k);
-            ring_store(f.cur, RW, wrap(f.i0 + k, RW), a);
+            const Cell5 a = fwd_cell(cm, f, k);
+            ring_store(cm, f.p, wrap(f.i0 + k, RW), a);                  // in place over the diagonal two back
             fm_at(cm, cbase + k) = a.m;
             if (full) {
                 ff_at(cm, fbase, w, S_M, k) = a.m; ff_at(cm, fbase, w, S_SX, k) = a.sx; ff_at(cm, fbase, w, S_SY, k) = a.sy;
@@ -285,21 +297,21 @@ PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
 // With fuse_emit the posterior candidates of the diagonal (diagonalCalculationPosteriorMatchProbs, :676-699) are produced
 // in the same pass from the total probability already published.
 struct BwdDiag {            // per-diagonal uniforms
-    const uint8_t *sx, *sy; const double *K, *b1; double *cur;
+    const uint8_t *sx, *sy; const double *K;
     int t, p, Lt, w1, w2, s1, s2, i0, RW;
 };
-PC_HD Cell5 bwd_cell(const BwdDiag &g, int k) {
+PC_HD Cell5 bwd_cell(const CtaMem &cm, const BwdDiag &g, int k) {
     const double LZ = log_zero();
-    const int RW = g.RW;
+    const int RW = g.RW, p = g.p, q = p ^ 1;
     const int xmy = g.Lt + 2 * k, x = (g.t + xmy) >> 1, y = (g.t - xmy) >> 1;
     const int ku = k + g.s1, kl = ku + 1, km = k + g.s2;       // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
-    const int i = wrap(g.i0 + k, RW), iu = wrap(i - g.p, RW), il = wrap(i + 1 - g.p, RW);
+    const int i = wrap(g.i0 + k, RW), iu = wrap(i - p, RW), il = wrap(i + 1 - p, RW);
     double mid = LZ, upSY = LZ, upLY = LZ, loSX = LZ, loLX = LZ;
     const double *K = g.K;
     const double *gx = K + K_GAP, *gy = K + K_GAP, *mt = K + K_MATCH;
-    if (km >= 0 && km < g.w2) { mid = g.cur[S_M * RW + i]; mt = K + K_MATCH + 3 * match_class(g.sx[x], g.sy[y]); }                      // cell (x+1, y+1)
-    if (ku >= 0 && ku < g.w1) { upSY = g.b1[S_SY * RW + iu]; upLY = g.b1[S_LY * RW + iu]; gy = K + K_GAP + 4 * (g.sy[y] == 4); }  // cell (x, y+1)
-    if (kl >= 0 && kl < g.w1) { loSX = g.b1[S_SX * RW + il]; loLX = g.b1[S_LX * RW + il]; gx = K + K_GAP + 4 * (g.sx[x] == 4); }  // cell (x+1, y)
+    if (km >= 0 && km < g.w2) { mid = ring_at(cm, p, S_M, i); mt = K + K_MATCH + 3 * match_class(g.sx[x], g.sy[y]); }                            // cell (x+1, y+1)
+    if (ku >= 0 && ku < g.w1) { upSY = ring_at(cm, q, S_SY, iu); upLY = ring_at(cm, q, S_LY, iu); gy = K + K_GAP + 4 * (g.sy[y] == 4); }  // cell (x, y+1)
+    if (kl >= 0 && kl < g.w1) { loSX = ring_at(cm, q, S_SX, il); loLX = ring_at(cm, q, S_LX, il); gx = K + K_GAP + 4 * (g.sx[x] == 4); }  // cell (x+1, y)
     Cell5 v;
     v.m = d_add(mid, mt[0]);
     v.m = log_add(v.m, d_add(upSY, gy[0]), K); v.m = log_add(v.m, d_add(upLY, gy[2]), K);
@@ -316,10 +328,8 @@ PC_HD void bwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
     BwdDiag g;
     g.sx = sx; g.sy = sy; g.K = K; g.RW = cm.RW; g.t = t; g.p = t & 1;
     g.Lt = mt_.L; g.w1 = mt2.co - mt1.co; g.w2 = (t + 2 <= top) ? mt3.co - mt2.co : 0;
-    g.cur = slot(cm, t);                                           // also B[t+2]
-    g.b1 = slot(cm, t + 1);
     g.s1 = (g.Lt - 1 - mt1.L) >> 1; g.s2 = (g.Lt - mt2.L) >> 1;
-    g.i0 = ring_i0(g.Lt, t, J.ly, cm.RW);
+    g.i0 = ring_i0(g.Lt, t, J, cm.RW);
     const int w = mt1.co - mt_.co, cbase = mt_.co, RW = cm.RW, Lt = g.Lt;
     const double total = fuse_emit ? *cm.total : 0.0;
     PC_THREADS(tid, cm.T) {
@@ -327,8 +337,8 @@ PC_HD void bwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
             const int xa = (t + Lt + 2 * k) >> 1, ya = (t - Lt - 2 * k) >> 1;
             const bool cand = fuse_emit && xa > 0 && ya > 0;
             const double fm = cand ? fm_at(cm, cbase + k) : 0.0;   // issued early: the only HBM read of the step
-            const Cell5 a = bwd_cell(g, k);
-            ring_store(g.cur, RW, wrap(g.i0 + k, RW), a);
+            const Cell5 a = bwd_cell(cm, g, k);
+            ring_store(cm, g.p, wrap(g.i0 + k, RW), a);                  // in place over B[t+2]
             if (cand) { const double lp = d_sub(d_add(fm, a.m), total); if (lp >= P.log_thr_lo) emit_one(J, cm, out, xa, ya, lp); }
         }
     }
@@ -344,7 +354,7 @@ PC_HD void chain_warp0(const CtaMem &cm, int w, const double *K, bool accumulate
         const int lane = (int)threadIdx.x;
         double tot = log_zero();
         for (int k0 = 0; k0 < w; k0 += 32) {
-            const double t = (k0 + lane < w) ? cm.tbuf[k0 + lane] : log_zero();
+            const double t = (k0 + lane < w) ? tbuf_at(cm, k0 + lane) : log_zero();
             unsigned rem = 0xffffffffu;
             for (;;) {
                 const unsigned m = __ballot_sync(0xffffffffu, !chain_inactive(tot, t)) & rem;
@@ -364,11 +374,11 @@ PC_HD void chain_warp0(const CtaMem &cm, int w, const double *K, bool accumulate
         for (;;) {
             int j = -1;
             for (int lane = from; lane < 32 && j < 0; ++lane) {
-                const double t = (k0 + lane < w) ? cm.tbuf[k0 + lane] : log_zero();
+                const double t = (k0 + lane < w) ? tbuf_at(cm, k0 + lane) : log_zero();
                 if (!chain_inactive(tot, t)) j = lane;
             }
             if (j < 0) break;
-            tot = log_add(tot, cm.tbuf[k0 + j], K);
+            tot = log_add(tot, tbuf_at(cm, k0 + j), K);
             from = j + 1;
         }
     }
@@ -384,14 +394,13 @@ PC_HD void total_probability(const Job &J, const uint8_t *sx, const uint8_t *sy,
     const DiagMeta mt_ = M[t], mt1 = M[t + 1];
     {
         const int fbase = 5 * mt_.fo, w = mt1.co - mt_.co;
-        const double *bt = slot(cm, t);
-        const int i0 = ring_i0(mt_.L, t, J.ly, RW);
+        const int i0 = ring_i0(mt_.L, t, J, RW), pt = t & 1;
         PC_THREADS(tid, cm.T) {
             for (int k = tid; k < w; k += cm.T) {
                 const int i = wrap(i0 + k, RW);
-                double tt = d_add(ff_at(cm, fbase, w, 0, k), bt[i]);                       // cell_dotProduct, pairwiseAligner.c:412-418
-                for (int s = 1; s < NSTATE; ++s) tt = log_add(tt, d_add(ff_at(cm, fbase, w, s, k), bt[s * RW + i]), K);
-                cm.tbuf[k] = tt;
+                double tt = d_add(ff_at(cm, fbase, w, 0, k), ring_at(cm, pt, 0, i));       // cell_dotProduct, pairwiseAligner.c:412-418
+                for (int s = 1; s < NSTATE; ++s) tt = log_add(tt, d_add(ff_at(cm, fbase, w, s, k), ring_at(cm, pt, s, i)), K);
+                tbuf_at(cm, k) = tt;
             }
         }
         PC_SYNC();
@@ -403,8 +412,7 @@ PC_HD void total_probability(const Job &J, const uint8_t *sx, const uint8_t *sy,
         const int Lq = mt1.L, wq = mt2.co - mt1.co;
         const int fbase = 5 * mf.fo, wf = mt_.co - mf.co;
         const int sm = (Lq - mf.L) >> 1;
-        const double *bq = slot(cm, t + 1);
-        const int i0 = ring_i0(Lq, t + 1, J.ly, RW);
+        const int i0 = ring_i0(Lq, t + 1, J, RW), pq = (t + 1) & 1;
         PC_THREADS(tid, cm.T) {
             for (int k = tid; k < wq; k += cm.T) {
                 const int xmy = Lq + 2 * k, x = (t + 1 + xmy) >> 1, y = (t + 1 - xmy) >> 1, km = k + sm;
@@ -418,7 +426,7 @@ PC_HD void total_probability(const Job &J, const uint8_t *sx, const uint8_t *sy,
                 double vM = d_add(mM, mt[0]);
                 vM = log_add(vM, d_add(mSX, mt[1]), K); vM = log_add(vM, d_add(mSY, mt[1]), K);
                 vM = log_add(vM, d_add(mLX, mt[2]), K); vM = log_add(vM, d_add(mLY, mt[2]), K);
-                cm.tbuf[k] = d_add(vM, bq[wrap(i0 + k, RW)]);   // the other four states of the match-only diagonal are LOG_ZERO
+                tbuf_at(cm, k) = d_add(vM, ring_at(cm, pq, S_M, wrap(i0 + k, RW)));   // the other four states of the match-only diagonal are LOG_ZERO
             }
         }
         PC_SYNC();
@@ -432,14 +440,13 @@ PC_HD void total_probability(const Job &J, const uint8_t *sx, const uint8_t *sy,
 PC_HD void emit_diag(const Job &J, const DiagMeta *M, const CtaMem &cm, const Params &P, int t, Pair *out) {
     const DiagMeta mt_ = M[t], mt1 = M[t + 1];
     const int Lt = mt_.L, cbase = mt_.co, w = mt1.co - mt_.co;
-    const double *bt = slot(cm, t);
     const double total = *cm.total;
-    const int i0 = ring_i0(Lt, t, J.ly, cm.RW);
+    const int i0 = ring_i0(Lt, t, J, cm.RW), pt = t & 1;
     PC_THREADS(tid, cm.T) {
         for (int k = tid; k < w; k += cm.T) {
             const int xmy = Lt + 2 * k, x = (t + xmy) >> 1, y = (t - xmy) >> 1;
             if (x > 0 && y > 0) {
-                const double lp = d_sub(d_add(fm_at(cm, cbase + k), bt[wrap(i0 + k, cm.RW)]), total);
+                const double lp = d_sub(d_add(fm_at(cm, cbase + k), ring_at(cm, pt, S_M, wrap(i0 + k, cm.RW))), total);
                 if (lp >= P.log_thr_lo) emit_one(J, cm, out, x, y, lp);
             }
         }
@@ -460,12 +467,11 @@ PC_HD int run_job(const Job &J, const uint8_t *sym, const DiagMeta *meta, const 
         const double *st = K + ((J.ragged & 1) ? K_RSTART : K_START);
         const int w0 = md.co - m1.co;
         const bool full = md.fo > m1.fo;
-        double *cur = slot(cm, 0);
-        const int i0 = ring_i0(m1.L, 0, J.ly, RW);
+        const int i0 = ring_i0(m1.L, 0, J, RW);
         PC_THREADS(tid, cm.T) {
             if (tid == 0) *cm.n_out = 0;
             for (int k = tid; k < w0; k += cm.T) {
-                for (int s = 0; s < NSTATE; ++s) { cur[s * RW + wrap(i0 + k, RW)] = st[s]; if (full) ff_at(cm, 5 * m1.fo, w0, s, k) = st[s]; }
+                for (int s = 0; s < NSTATE; ++s) { ring_at(cm, 0, s, wrap(i0 + k, RW)) = st[s]; if (full) ff_at(cm, 5 * m1.fo, w0, s, k) = st[s]; }
                 fm_at(cm, m1.co + k) = st[S_M];
             }
         }
@@ -481,9 +487,8 @@ PC_HD int run_job(const Job &J, const uint8_t *sym, const DiagMeta *meta, const 
         if (at_end || tb_point) {
             {   // the diagonal walked back from holds the end state vector (:806-808)
                 const double *en = K + ((at_end && (J.ragged & 2)) ? K_REND : K_END);
-                double *bt = slot(cm, d);
-                const int i0 = ring_i0(md.L, d, J.ly, RW);
-                PC_THREADS(tid, cm.T) { for (int k = tid; k < w; k += cm.T) for (int s = 0; s < NSTATE; ++s) bt[s * RW + wrap(i0 + k, RW)] = en[s]; }
+                const int i0 = ring_i0(md.L, d, J, RW);
+                PC_THREADS(tid, cm.T) { for (int k = tid; k < w; k += cm.T) for (int s = 0; s < NSTATE; ++s) ring_at(cm, d & 1, s, wrap(i0 + k, RW)) = en[s]; }
                 PC_SYNC();
             }
             const int tb_from = d - (at_end ? 0 : P.tb_diags + 1);
@@ -507,9 +512,8 @@ PC_HD int run_job(const Job &J, const uint8_t *sym, const DiagMeta *meta, const 
                 for (int q = 0; q < 2; ++q) {
                     const int dd = d - q;
                     const DiagMeta a = q ? m1 : md, b = q ? md : mn;
-                    const int wd = b.co - a.co, fbase = 5 * a.fo, i0 = ring_i0(a.L, dd, J.ly, RW);
-                    double *sl = slot(cm, dd);
-                    PC_THREADS(tid, cm.T) { for (int k = tid; k < wd; k += cm.T) for (int s = 0; s < NSTATE; ++s) sl[s * RW + wrap(i0 + k, RW)] = ff_at(cm, fbase, wd, s, k); }
+                    const int wd = b.co - a.co, fbase = 5 * a.fo, i0 = ring_i0(a.L, dd, J, RW);
+                    PC_THREADS(tid, cm.T) { for (int k = tid; k < wd; k += cm.T) for (int s = 0; s < NSTATE; ++s) ring_at(cm, dd & 1, s, wrap(i0 + k, RW)) = ff_at(cm, fbase, wd, s, k); }
                 }
                 PC_SYNC();
             }

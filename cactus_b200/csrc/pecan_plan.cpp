@@ -108,6 +108,14 @@ std::string plan_subjob(const PlanParams &P, SubJob &s) {
     }
     s.coff[D + 1] = (int)cells;
     s.cells = cells; s.max_w = max_w;
+    {   // where the band's cells sit on the ring coordinate a = (xmy + parity) / 2 + ly (pecan_cta.cuh): their mean
+        double acc = 0;
+        for (int64_t d = 0; d <= D; ++d) {
+            const int64_t w = s.coff[d + 1] - s.coff[d], a0 = ((s.bandL[d] + (d & 1)) >> 1) + lY;
+            acc += (double)w * (double)a0 + 0.5 * (double)w * (double)(w - 1);
+        }
+        s.ring_center = (int)(acc / (double)std::max<int64_t>(cells, 1));
+    }
     // schedule (pairwiseAligner.c:798-803, 817, 840-848): traceback points only depend on the band geometry
     std::vector<uint8_t> mark((size_t)D + 1, 0);
     s.tb_from.clear();

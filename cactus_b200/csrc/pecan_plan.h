@@ -32,6 +32,7 @@ struct SubJob {
     int64_t span_full_cells = 0;   // most cells of marked diagonals alive at once
     std::vector<int> tb_from;      // the diagonal each traceback starts emitting posteriors from (ascending)
     int max_w = 0;
+    int ring_center = 0;           // cell-weighted mean of the absolute ring coordinate ((xmy + parity) / 2 + ly) over the band
     int out_cap = 0;
 };
 

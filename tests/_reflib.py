@@ -439,11 +439,13 @@ def oracle_pecan_aligned_pairs(sx, sy, anchors=(), ragged_left=False, ragged_rig
 
 
 def hosttest_pecan_aligned_pairs(sx, sy, anchors=(), ragged_left=False, ragged_right=False, p=None, split_bigger=3000 * 3000, threads=32,
-                                 ring_width=0):
-    """the product's block program emulated on the host with `threads` threads per block and a diagonal ring of
-    max(ring_width, widest diagonal) cells (tests/hosttest): (triples, posteriors, banded cells)"""
+                                 ring_width=0, ring_extra=0):
+    """the product's block program emulated on the host with `threads` threads per block; the diagonal ring has
+    (widest diagonal + ring_extra) positions of which the first ring_width (0 = all) are the "shared memory" part and the
+    rest the overflow block (tests/hosttest): (triples, posteriors, banded cells)"""
     _load(build_hosttest()).hosttest_pecan_set_threads(int(threads))
     _load(build_hosttest()).hosttest_pecan_set_ring_width(int(ring_width))
+    _load(build_hosttest()).hosttest_pecan_set_ring_extra(int(ring_extra))
     return _aligned_pairs(_load(build_hosttest()), "hosttest_pecan_aligned_pairs", "hosttest_free", sx, sy, anchors, ragged_left,
                           ragged_right, p or pecan_params(), split_bigger, True)
 

@@ -205,7 +205,8 @@ extern "C" void hosttest_free(void *p) { free(p); }
 
 struct HtPecanParams { double threshold; int64_t minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion; };
 
-static int g_pecan_threads = 32, g_pecan_ring_w = 0;
+static int g_pecan_threads = 32, g_pecan_ring_w = 0, g_pecan_ring_extra = 0;
+extern "C" void hosttest_pecan_set_ring_extra(int e) { g_pecan_ring_extra = e; }
 extern "C" void hosttest_pecan_set_threads(int t) { g_pecan_threads = t; }
 extern "C" void hosttest_pecan_set_ring_width(int w) { g_pecan_ring_w = w; }
 
@@ -232,12 +233,14 @@ extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, con
         for (int k = 0; k < s.ly; ++k) sym[s.lx + k] = (uint8_t)code(csy[s.y1 + k]);
         unsigned capM = 1024; while (capM < (uint64_t)std::max<int64_t>(s.span_cells, 1)) capM <<= 1;
         unsigned capF = 1024; while (capF < 5 * (uint64_t)std::max<int64_t>(s.span_full_cells, 1)) capF <<= 1;
-        const int RW = g_pecan_ring_w > 0 ? std::max(g_pecan_ring_w, s.max_w) : s.max_w;     // any width >= the widest diagonal
-        std::vector<double> fm(capM, NAN), ff(capF, NAN), ring(10 * (size_t)RW, NAN), tbuf((size_t)RW, NAN);
+        // ring: modulus RW >= the widest diagonal, the first RWs positions in "shared memory", the rest in the overflow block
+        const int RW = std::max(s.max_w, 1) + g_pecan_ring_extra, RWs = g_pecan_ring_w > 0 ? std::min(g_pecan_ring_w, RW) : RW;
+        std::vector<double> fm(capM, NAN), ff(capF, NAN), ring(10 * (size_t)RWs, NAN), ring_o(10 * (size_t)(RW - RWs) + 1, NAN), tbuf((size_t)RWs, NAN), tbuf_o((size_t)(RW - RWs) + 1, NAN);
         double total = NAN; int n_out = 0;
-        pc::CtaMem cm; cm.ring = ring.data(); cm.tbuf = tbuf.data(); cm.total = &total; cm.n_out = &n_out; cm.RW = RW; cm.FM = fm.data(); cm.maskM = capM - 1;
-        cm.FF = ff.data(); cm.maskF = capF - 1; cm.T = g_pecan_threads;
-        pc::Job J; J.sx_off = 0; J.sy_off = s.lx; J.band_off = 0; J.out_off = 0; J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged;
+        pc::CtaMem cm; cm.ring = ring.data(); cm.ring_o = ring_o.data(); cm.tbuf = tbuf.data(); cm.tbuf_o = tbuf_o.data(); cm.total = &total; cm.n_out = &n_out;
+        cm.RW = RW; cm.RWs = RWs; cm.FM = fm.data(); cm.maskM = capM - 1; cm.FF = ff.data(); cm.maskF = capF - 1; cm.T = g_pecan_threads;
+        pc::Job J; J.sx_off = 0; J.sy_off = s.lx; J.band_off = 0; J.out_off = 0; J.lx = s.lx; J.ly = s.ly; J.ragged = s.ragged; J.pad_ = 0;
+        J.ring_shift = s.ring_center - RWs / 2;
         J.out_cap = (int)std::min<int64_t>(s.cells, (int64_t)s.lx + s.ly + 64);
         std::vector<pc::DiagMeta> meta((size_t)s.lx + s.ly + 2);
         for (int d = 0; d <= s.lx + s.ly + 1; ++d) meta[d] = pc::DiagMeta{d <= s.lx + s.ly ? s.bandL[d] : 0, s.coff[d], s.foff[d], 0};

@@ -77,7 +77,8 @@ def test_warp_program_vs_oracle_random(oracle_built):
         sx, sy, a, rl, rr, p, sb = _random_case(rng)
         to, po = R.oracle_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb)
         T = int(rng.choice([32, 128, 256]))
-        th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb, threads=T, ring_width=int(rng.choice([0, 96, 640, 1280])))
+        th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, rl, rr, p, sb, threads=T, ring_width=int(rng.choice([0, 8, 40, 96, 608])),
+                                                       ring_extra=int(rng.choice([0, 0, 7, 300])))
         assert np.array_equal(to, th) and np.array_equal(po, ph), (it, T, len(sx), len(sy), len(a))
 
 
