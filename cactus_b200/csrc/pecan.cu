@@ -4,8 +4,8 @@
 // A *stage* takes n sequence pairs with their anchors, splits each pair at large anchor gaps, builds the anchor band of
 // every sub-matrix and the traceback schedule on host threads (pecan_plan.cpp), packs everything, uploads it once and
 // launches persistent blocks that pull jobs (largest first) from a device counter. Two block shapes: jobs whose widest
-// diagonal has <= 96 cells run in 32-thread blocks (24 per SM), all others in 128-thread blocks (4 per SM) whose diagonal
-// ring keeps 608 positions in shared memory and spills the flanks of wider diagonals to an HBM/L2 overflow block (a per-job
+// diagonal has <= 96 cells run in 32-thread blocks (24 per SM), all others in 128-thread blocks (6 per SM) whose diagonal
+// ring keeps 320 positions in shared memory and spills the flanks of wider diagonals to an HBM/L2 overflow block (a per-job
 // shift centres the band on the shared part, pecan_cta.cuh). The two launches run concurrently on their own streams.
 // Each resident block owns a slot in HBM for the forward MATCH ring, the ring of complete forward cells and the overflow.
 // Candidate pairs (x, y, log posterior) are appended by the kernel, put into the reference's order of emission on the host,
@@ -49,7 +49,7 @@ struct KernelArgs {
 };
 
 // dynamic shared memory: constants | total | ring 10 * RWs | tbuf RWs
-extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(const KernelArgs A) {
+template <int kMinBlocks> __device__ __forceinline__ void pecan_posterior_body(const KernelArgs &A) {
     extern __shared__ double smem[];
     double *K = smem;
     for (int i = threadIdx.x; i < K_TOTAL; i += blockDim.x) K[i] = A.consts[i];
@@ -76,6 +76,10 @@ extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(cons
     }
 }
 
+// two register budgets: 80 registers (up to 3 x 256 threads per SM) and 64 registers (up to 4 x 256)
+extern "C" __global__ void __launch_bounds__(256, 3) pecan_posterior_kernel(const KernelArgs A) { pecan_posterior_body<3>(A); }
+extern "C" __global__ void __launch_bounds__(256, 4) pecan_posterior_kernel_r64(const KernelArgs A) { pecan_posterior_body<4>(A); }
+
 // one CTA per job: copy its records to their place in the compact array
 extern "C" __global__ void pecan_compact_kernel(const Job *jobs, const int *out_n, const long long *dst_off, const Pair *out, Pair *dst, int n_jobs) {
     for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
@@ -94,6 +98,7 @@ extern "C" __global__ void pecan_compact_kernel(const Job *jobs, const int *out_
 struct PecanGroup {              // one launch: a class of jobs with one block shape
     std::vector<int> jobs;       // largest first
     int threads = 32;            // block size
+    int per_sm = 1;              // blocks per SM the shape is sized for
     int ctas = 0;                // resident blocks = slots
     int RW = 32, RWs = 32;       // ring width (the modulus) and its shared-memory part
     unsigned capM = 1024, capF = 1024;   // ring doubles (powers of two)
@@ -221,9 +226,11 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
     const size_t fixed = (size_t)sym_off + (size_t)band_off * 16 + (size_t)ns * (sizeof(Job) + 8) + (size_t)out_off * sizeof(Pair) * 2 + (64 << 20);
     if ((double)fixed > ctx_mem_fraction(ctx) * (double)free_b) { set_error(ctx, "pecan stage does not fit in device memory; submit fewer pairs per call"); return BARB200_ENOMEM; }
     size_t budget = (size_t)(ctx_mem_fraction(ctx) * (double)free_b) - fixed;
-    // shared memory per block = 8 * (58 + 11 * RWs) bytes: 8.9 KB for the narrow shape, 54 KB for the general one; 80 registers
+    // shared memory per block = 8 * (58 + 11 * RWs) bytes: 8.9 KB for the narrow shape, 28.6 KB for the general one; 80 registers.
+    // Shapes from a sweep on the benchmark workload (scripts/pecan_sweep.sh; profiles/r01_pecan_sweep.txt): 128 threads x 6 per SM
+    // with 192..320 shared positions are within 1 % of each other; 608 shared x 4 per SM is 25 % slower, 64 threads 17 % slower.
     struct Class { int max_w, threads, ctas_per_sm, rws; };
-    std::vector<Class> kClass = {{96, 32, 24, 96}, {0x7fffffff, 128, 4, 608}};
+    std::vector<Class> kClass = {{96, 32, 24, 96}, {0x7fffffff, 128, 6, 320}};
     if (const char *e = getenv("BARB200_PECAN_CLASSES")) {         // tuning aid: "max_w:threads:blocks_per_sm:shared_ring,..." (last max_w is ignored)
         kClass.clear();
         for (const char *q = e; *q;) {
@@ -243,7 +250,7 @@ static int stage_build(barb200_pecan_stage *st, const char *const *sx, const cha
         if (g.jobs.empty()) continue;
         int64_t spanM = 1, spanF = 1; int rw = 1;
         for (int j : g.jobs) { spanM = std::max(spanM, st->subs[j].span_cells); spanF = std::max(spanF, st->subs[j].span_full_cells); rw = std::max(rw, st->subs[j].max_w); }
-        g.threads = kClass[c].threads;
+        g.threads = kClass[c].threads; g.per_sm = kClass[c].ctas_per_sm;
         g.RWs = kClass[c].rws; g.RW = std::max(g.RWs, rw);
         for (int j : g.jobs) st->jobs[j].ring_shift = st->subs[j].ring_center - g.RWs / 2;
         g.capM = pow2ceil((uint64_t)spanM); g.capF = pow2ceil((uint64_t)5 * (uint64_t)spanF);
@@ -353,7 +360,11 @@ static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
     barb200_ctx *ctx = st->ctx;
     cudaSetDevice(ctx_device(ctx));
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(pecan_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(pecan_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(pecan_posterior_kernel_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned) * (st->groups.size() + 1), st->stream));
     CUDA_TRY(ctx, cudaEventRecord(st->ev0, st->stream));
     st->launches = 0;
@@ -366,7 +377,8 @@ static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
         A.counter = st->d_counter + gi; A.consts = st->d_consts; A.scratch = st->d_scratch + g.scratch_off; A.slot_doubles = g.slot_doubles;
         A.maskM = g.capM - 1; A.maskF = g.capF - 1; A.RW = g.RW; A.RWs = g.RWs; A.P = st->devP;
         CUDA_TRY(ctx, cudaStreamWaitEvent(g.stream, st->ev0, 0));
-        pecan_posterior_kernel<<<g.ctas, g.threads, g.smem_bytes, g.stream>>>(A);
+        if (g.threads * g.per_sm > 768) pecan_posterior_kernel_r64<<<g.ctas, g.threads, g.smem_bytes, g.stream>>>(A);
+        else pecan_posterior_kernel<<<g.ctas, g.threads, g.smem_bytes, g.stream>>>(A);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(g.done, g.stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(st->stream, g.done, 0));
