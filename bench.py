@@ -112,80 +112,83 @@ def cpu_baseline(n_seq, lens, flat, cells, budget_s=20.0):
 PECAN_BYTES_PER_CELL = 120.0   # 5 fp64 states x (forward write + forward read at the traceback + backward write)
 
 
-def pecan_bench(cb, local_rank, world, rank, first_pair, n_pairs, steps, warmup, cpu_budget, want_cpu, barrier, reduce_stats, dev, no_e2e=False):
+def pecan_measure(local_rank, rank, first_pair, n_pairs, steps, warmup, cpu_budget, want_cpu, no_e2e, host_threads):
     """cPecan mode (BASELINE.json configs[3]): banded pair-HMM posteriors of n_pairs synthetic
-    2 kbp pairs per GPU per step with MUM-like anchors (k = 50, Cactus' setting). Returns the "pecan" object of the JSON
-    line (rank 0) or None."""
-    import ctypes as C
-    eng = cb.Engine(cb.PoaParams(device=local_rank))
+    2 kbp pairs per GPU per step with MUM-like anchors (k = 50, Cactus' setting). Runs in a process of its own (see main)
+    and returns this rank's raw measurements."""
+    import cactus_b200 as cb
+    eng = cb.Engine(cb.PoaParams(device=local_rank, host_threads=host_threads))
     pairs = cb.synth_pairs(first_pair, n_pairs, L_BP, k_anchor=50)
     st = eng.pecan_stage(pairs)
     cells = float(st.cells())
     for _ in range(warmup):
         st.run()
-    barrier()
     dev_ms, launches = 0.0, 0
     for _ in range(steps):
-        dev_ms += st.run()
+        dev_ms += st.run()             # CUDA-event time of the launch(es); the call returns after the stream is idle
         launches += st.launches()
-    barrier()
     res = st.fetch(True)
     n_trip = int(sum(len(r[0]) for r in res))
     st.close()
-    # e2e: host strings + anchors in, integer triples out, everything inside the timed region
-    if no_e2e:
-        e2e_ms, same = float("nan"), True
-    else:
+    out = {"dev_ms": dev_ms, "launches": launches, "cells": cells, "n_pairs": n_pairs, "steps": steps, "e2e_ms": float("nan"), "same": True,
+           "h2d": int(sum(len(q[0]) + len(q[1]) + q[2].nbytes for q in pairs)), "d2h": n_trip * 24}
+    if not no_e2e:
         # the timed call is the C ABI itself (host strings + anchors in, malloc'd triples out); building the ctypes argument
         # arrays before and turning the outputs into numpy arrays after are harness work
         table = eng.pecan_table(pairs)
-        eng._take_pairs(*eng.pecan_batch_raw(table), table.n)                  # warm-up (also sizes the context's ring scratch)
-        barrier()
+        eng._take_pairs(*eng.pecan_batch_raw(table), table.n)                  # warm-up (also sizes the context's caches)
         t0 = time.time()
-        raw = eng.pecan_batch_raw(table)
-        barrier()
-        e2e_ms = (time.time() - t0) * 1e3
+        raw = eng.pecan_batch_raw(table)                                       # synchronous: returns with the results on the host
+        out["e2e_ms"] = (time.time() - t0) * 1e3
         res2 = eng._take_pairs(*raw, table.n)
-        same = all(np.array_equal(a[0], b[0]) for a, b in zip(res, res2))
-    h2d = int(sum(len(q[0]) + len(q[1]) + q[2].nbytes for q in pairs)) + 8 * int(sum(len(q[0]) + len(q[1]) + 2 for q in pairs))
-    d2h = n_trip * 16
-    mx, sm = reduce_stats([dev_ms, e2e_ms, cells, float(n_pairs), float(launches)], dev)
-    out = None
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        tot_cells, tot_pairs = float(sm[2]), float(sm[3])
-        launch_ms = dev_ms / max(1, launches)
-        achieved = cells * (steps / max(1, launches)) * PECAN_BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
-        out = {"metric": "cPecan banded pair-HMM forward/backward/posterior Gcell/s (cells = sum of band diagonal widths)",
-               "value": tot_cells * steps / float(mx[0]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs * steps / float(mx[0]) * 1e3,
-               "ms_per_step": float(mx[0]) / steps, "dtype": "f64",
-               "config": {"workload": "synthetic %d pairs x %d bp per GPU per step, 2%% sub / 0.5%% ins / 0.5%% del, anchors = exact co-linear "
-                                      "runs >= 50 bp (MUM-like), diagonalExpansion 20, threshold 0.01" % (n_pairs, L_BP),
-                          "cells_per_pair": cells / n_pairs},
-               "e2e": {"value": tot_cells / float(mx[1]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs / float(mx[1]) * 1e3, "ms_per_step": float(mx[1]),
-                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "barb200_pecan_aligned_pairs_batch (host strings + anchors -> (score, x, y) triples)",
-                       "same_as_staged": bool(same)},
-               "gpu_launches": int(sm[4]),
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "peak_source": peak_src, "kernel": "pecan_posterior_kernel", "bytes_per_cell_algorithmic": PECAN_BYTES_PER_CELL}}
-        if want_cpu:
-            try:
-                import _reflib as R
-                threads = usable_cores()
-                samp = [(q[0], q[1], q[2], False, False) for q in pairs[: max(2, threads)]]
-                s0, kind = R.cpu_pecan_many(samp, threads)
-                n = int(min(n_pairs, max(len(samp), cpu_budget / max(s0 / len(samp), 1e-6))))
-                samp = [(q[0], q[1], q[2], False, False) for q in pairs[:n]]
-                secs, kind = R.cpu_pecan_many(samp, threads)
-                c = float(sum(r[2] for r in res[:n]))
-                # parity on the sample actually timed: the reference's triples must equal the engine's
-                chk = R.ref_pecan_aligned_pairs(*samp[0], R.pecan_params()) if kind == "reference" else R.oracle_pecan_aligned_pairs(*samp[0], R.pecan_params())[0]
-                out["cpu_baseline"] = {"value": c / secs / 1e9, "unit": "Gcell/s", "pairs_per_s": n / secs, "cores": threads, "kind": kind,
-                                       "sample": "first %d of the step's pairs, %.1f s wall, one getAlignedPairsUsingAnchors call per pair on a pool of %d threads" % (n, secs, threads),
-                                       "bit_identical_on_first_pair": bool(np.array_equal(chk, res[0][0]))}
-            except Exception as e:  # noqa: BLE001
-                out["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": usable_cores(), "kind": "unavailable", "sample": str(e)}
+        out["same"] = bool(all(np.array_equal(a[0], b[0]) for a, b in zip(res, res2)))
+    if want_cpu and rank == 0:
+        try:
+            import _reflib as R
+            threads = usable_cores()
+            samp = [(q[0], q[1], q[2], False, False) for q in pairs[: max(2, threads)]]
+            s0, kind = R.cpu_pecan_many(samp, threads)
+            n = int(min(n_pairs, max(len(samp), cpu_budget / max(s0 / len(samp), 1e-6))))
+            samp = [(q[0], q[1], q[2], False, False) for q in pairs[:n]]
+            secs, kind = R.cpu_pecan_many(samp, threads)
+            c = float(sum(r[2] for r in res[:n]))
+            # parity on the sample actually timed: the reference's triples must equal the engine's
+            chk = R.ref_pecan_aligned_pairs(*samp[0], R.pecan_params()) if kind == "reference" else R.oracle_pecan_aligned_pairs(*samp[0], R.pecan_params())[0]
+            out["cpu_baseline"] = {"value": c / secs / 1e9, "unit": "Gcell/s", "pairs_per_s": n / secs, "cores": threads, "kind": kind,
+                                   "sample": "first %d of the step's pairs, %.1f s wall, one getAlignedPairsUsingAnchors call per pair on a pool of %d threads" % (n, secs, threads),
+                                   "bit_identical_on_first_pair": bool(np.array_equal(chk, res[0][0]))}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": usable_cores(), "kind": "unavailable", "sample": str(e)}
     eng.close()
+    return out
+
+
+def pecan_object(mine, mx, sm, n_pairs):
+    """the "pecan" object of the JSON line from rank 0's measurements (mine) and the reductions over ranks"""
+    peak, peak_src = measured_peak()
+    steps = mine["steps"]
+    tot_cells, tot_pairs = float(sm[2]), float(sm[3])
+    launch_ms = mine["dev_ms"] / max(1, mine["launches"])
+    achieved = mine["cells"] * (steps / max(1, mine["launches"])) * PECAN_BYTES_PER_CELL / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["pecan_dram_bytes_per_cell"] * mine["cells"] * (steps / max(1, mine["launches"]))
+    except Exception:  # noqa: BLE001
+        pass
+    out = {"metric": "cPecan banded pair-HMM forward/backward/posterior Gcell/s (cells = sum of band diagonal widths)",
+           "value": tot_cells * steps / float(mx[0]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs * steps / float(mx[0]) * 1e3,
+           "ms_per_step": float(mx[0]) / steps, "dtype": "f64",
+           "config": {"workload": "synthetic %d pairs x %d bp per GPU per step, 2%% sub / 0.5%% ins / 0.5%% del, anchors = exact co-linear "
+                                  "runs >= 50 bp (MUM-like), diagonalExpansion 20, threshold 0.01" % (n_pairs, L_BP),
+                      "cells_per_pair": mine["cells"] / n_pairs},
+           "e2e": {"value": tot_cells / float(mx[1]) / 1e6, "unit": "Gcell/s", "pairs_per_s": tot_pairs / float(mx[1]) * 1e3, "ms_per_step": float(mx[1]),
+                   "h2d_bytes_per_step": mine["h2d"], "d2h_bytes_per_step": mine["d2h"],
+                   "api": "barb200_pecan_aligned_pairs_batch (host strings + anchors -> (score, x, y) triples)", "same_as_staged": bool(mine["same"])},
+           "gpu_launches": int(sm[4]),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "peak_source": peak_src, "kernel": "pecan_posterior_kernel", "bytes_per_cell_algorithmic": PECAN_BYTES_PER_CELL}}
+    if "cpu_baseline" in mine:
+        out["cpu_baseline"] = mine["cpu_baseline"]
     return out
 
 
@@ -201,6 +204,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (for runs under ncu: the streamed e2e path releases jobs "
                     "to a RUNNING kernel from the host, which deadlocks under ncu's kernel serialisation)")
+    ap.add_argument("--pecan-only", action="store_true", help="internal: this process only measures the cPecan section and prints its raw numbers")
     ap.add_argument("--pecan-pairs-per-step", type=int, default=int(os.environ.get("BARB200_PECAN_PAIRS_PER_STEP", "4736")),
                     help="cPecan-mode pairs per GPU per step (default 32 x 148 SMs); 0 skips the cPecan section")
     args = ap.parse_args()
@@ -208,6 +212,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads per rank: the box's usable cores shared by the ranks of this node (torchrun exports OMP_NUM_THREADS=1,
+    # which would make the host side of the end-to-end calls single threaded)
+    host_threads = max(1, usable_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
+    if args.pecan_only:
+        m = pecan_measure(local_rank, rank, rank * args.pecan_pairs_per_step, args.pecan_pairs_per_step, max(1, min(args.steps, 3)),
+                          max(1, min(args.warmup, 2)), min(args.cpu_budget, 12.0), not args.no_cpu_baseline, args.no_e2e, host_threads)
+        print("PECAN_JSON " + json.dumps(m))
+        return 0
     E = args.ends_per_step
     config = {"workload": "synthetic %d ends x %d seqs x %d bp per GPU per step, Cactus default POA parameters "
                           "(convex gap 400/30/1200/1, band 1000+0.1L, progressive order), 2%% sub / 0.5%% ins / 0.5%% del" % (E, K_SEQS, L_BP),
@@ -264,7 +276,16 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        saved = os.dup(1)
+        os.dup2(2, 1)              # NCCL prints its version banner on stdout at the first collective; the JSON line must stand alone
+        try:
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local_rank)
 
     # rank 0 deals the end list out (scatter) -- the only exchange the path needs before the compute
@@ -272,7 +293,7 @@ def main():
     ranges = D.deal_end_ranges(E * world, world) if rank == 0 else None
     first_end, n_ends = D.scatter_end_ranges(ranges, dev) if world > 1 else (0, E)
 
-    eng = cb.Engine(cb.PoaParams(device=local_rank))
+    eng = cb.Engine(cb.PoaParams(device=local_rank, host_threads=host_threads))
     n_seq, lens, flat = cb.synth_ends(first_end, n_ends, K_SEQS, L_BP)
     stage = eng.stage(packed=(n_seq, lens, flat))
 
@@ -345,8 +366,26 @@ def main():
     if args.pecan_pairs_per_step > 0:
         stage.close()
         eng.close()
-        pecan = pecan_bench(cb, local_rank, world, rank, rank * args.pecan_pairs_per_step, args.pecan_pairs_per_step, max(1, min(args.steps, 3)),
-                            max(1, min(args.warmup, 2)), min(args.cpu_budget, 12.0), not args.no_cpu_baseline, barrier, D.reduce_stats, dev, args.no_e2e)
+        # measured in a fresh process per rank (its host-side phases ran several times slower inside this one after the POA
+        # section; a clean process reproduces the stand-alone numbers), all ranks at the same time; reductions happen here
+        cmd = [sys.executable, os.path.abspath(__file__), "--pecan-only", "--pecan-pairs-per-step", str(args.pecan_pairs_per_step),
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--cpu-budget", str(args.cpu_budget)]
+        cmd += ["--no-e2e"] if args.no_e2e else []
+        cmd += ["--no-cpu-baseline"] if args.no_cpu_baseline else []
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(host_threads)
+        barrier()
+        cp = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        mine = None
+        for ln in cp.stdout.splitlines():
+            if ln.startswith("PECAN_JSON "):
+                mine = json.loads(ln[len("PECAN_JSON "):])
+        if mine is None:
+            sys.stderr.write(cp.stderr[-2000:])
+            raise RuntimeError("the cPecan section failed (rank %d)" % rank)
+        mxp, smp = D.reduce_stats([mine["dev_ms"], mine["e2e_ms"], mine["cells"], float(mine["n_pairs"]), float(mine["launches"])], dev)
+        if rank == 0:
+            pecan = pecan_object(mine, mxp, smp, args.pecan_pairs_per_step)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
