@@ -359,12 +359,9 @@ extern "C" int barb200_pecan_stage_create(barb200_ctx *ctx, const barb200_pecan_
 static int stage_run_locked(barb200_pecan_stage *st, float *kernel_ms) {
     barb200_ctx *ctx = st->ctx;
     cudaSetDevice(ctx_device(ctx));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(pecan_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(pecan_posterior_kernel_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    // per device, and cheap: set on every run (a process may hold contexts on several GPUs)
+    cudaFuncSetAttribute(pecan_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pecan_posterior_kernel_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_counter, 0, sizeof(unsigned) * (st->groups.size() + 1), st->stream));
     CUDA_TRY(ctx, cudaEventRecord(st->ev0, st->stream));
     st->launches = 0;
