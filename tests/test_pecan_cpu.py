@@ -105,3 +105,17 @@ def test_cabi_band_and_split_points(oracle_built):
         assert np.array_equal(sp, R.oracle_pecan_split_points(len(sx), len(sy), a, sb, rl, rr)), it
     with pytest.raises(cb.BarB200Error):
         cb.pecan_band(10, 10, [[5, 5], [4, 6]], 20)         # anchors must increase (the reference asserts)
+
+
+def test_block_program_bench_shape(oracle_built):
+    """the benchmark's pair shape (2 kbp, anchors = exact runs >= 50 bp) in the kernel's production configuration:
+    128 threads per block, 320 ring positions in the shared part, the flanks of the wide diagonals in the overflow block"""
+    import cactus_b200 as cb
+    from cactus_b200 import build as b
+    b.build()
+    for sx, sy, a, _, _ in cb.synth_pairs(7, 2, 2000, k_anchor=50):
+        to, po = R.oracle_pecan_aligned_pairs(sx, sy, a, False, False, R.pecan_params())
+        th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, False, False, R.pecan_params(), threads=128, ring_width=320)
+        assert np.array_equal(to, th) and np.array_equal(po, ph)
+        L, Rr = cb.pecan_band(len(sx), len(sy), a, 20)
+        assert cells == int(((Rr - L) // 2 + 1).sum()) and ((Rr - L) // 2 + 1).max() > 320      # wide enough to use the overflow
