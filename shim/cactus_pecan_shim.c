@@ -136,19 +136,28 @@ stList *makeAllPairwiseAlignments(StateMachine *sM, stList *seqFrags, PairwiseAl
     int64_t *lx = st_malloc(8 * pairNo), *ly = st_malloc(8 * pairNo), *na = st_malloc(8 * pairNo), *nOut = st_malloc(8 * pairNo);
     int64_t **anchors = st_malloc(sizeof(int64_t *) * pairNo), **trip = st_malloc(sizeof(int64_t *) * pairNo);
     uint8_t *rl = st_malloc(pairNo), *rr = st_malloc(pairNo);
+    int64_t *first = st_malloc(8 * pairNo), *second = st_malloc(8 * pairNo);
     int64_t k = 0;
     for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {            /* the pairs in the reference's order, multipleAligner.c:675-679 */
         for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
-            SeqFrag *f1 = stList_get(seqFrags, seq1), *f2 = stList_get(seqFrags, seq2);
-            sx[k] = f1->seq; sy[k] = f2->seq; lx[k] = strlen(f1->seq); ly[k] = strlen(f2->seq);
-            /* anchors: the reference's host code (getAlignedPairs, pairwiseAligner.c:1527-1534) */
-            stList *anchorPairs = getAnchorPairsForPairwiseAlignmentParameters(f1->seq, f2->seq, lx[k], ly[k], p);
-            anchors[k] = flatten_anchors(anchorPairs, &na[k]);
-            stList_destruct(anchorPairs);
-            rl[k] = f1->leftEndId != f2->leftEndId;            /* addMultipleAlignedPairs, multipleAligner.c:660-661 */
-            rr[k] = f1->rightEndId != f2->rightEndId;
+            first[k] = seq1; second[k] = seq2;
         }
     }
+    /* anchors: the reference's host code (getAlignedPairs, pairwiseAligner.c:1527-1534), one pair per thread -- the reference
+     * itself runs it concurrently from bar()'s OpenMP loop over ends (bar/impl/bar.c:90-94) */
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t i = 0; i < pairNo; i++) {
+        SeqFrag *f1 = stList_get(seqFrags, first[i]), *f2 = stList_get(seqFrags, second[i]);
+        sx[i] = f1->seq; sy[i] = f2->seq; lx[i] = strlen(f1->seq); ly[i] = strlen(f2->seq);
+        stList *anchorPairs = getAnchorPairsForPairwiseAlignmentParameters(f1->seq, f2->seq, lx[i], ly[i], p);
+        anchors[i] = flatten_anchors(anchorPairs, &na[i]);
+        stList_destruct(anchorPairs);
+        rl[i] = f1->leftEndId != f2->leftEndId;                /* addMultipleAlignedPairs, multipleAligner.c:660-661 */
+        rr[i] = f1->rightEndId != f2->rightEndId;
+    }
+    free(first); free(second);
     if (barb200_pecan_aligned_pairs_batch(ctx, &q, pairNo, sx, lx, sy, ly, (const int64_t *const *) anchors, na, rl, rr, trip, nOut, NULL, NULL) != BARB200_OK) {
         st_errAbort("barb200: pair-HMM batch failed: %s", barb200_last_error(ctx));
     }
