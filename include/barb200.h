@@ -1,6 +1,7 @@
 /*
  * barb200.h -- C ABI of libbarb200.so, the B200-native engine behind Cactus' base-alignment-refinement (BAR)
- * phase in POA mode. Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
+ * phase: POA mode (abPOA's partial-order alignments, below) and cPecan mode (the banded pair-HMM posteriors, further
+ * down: barb200_pecan_*). Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
  *
  * Drop-in boundary (paths relative to the Cactus source tree, commit 2a4a172f):
  *   - barb200_poa_msa_batch ........ replaces the abpoa_init / abpoa_msa / abpoa_free triple the shim issues once per
