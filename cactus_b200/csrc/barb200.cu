@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include "host_api.h"
+#include "batch_merge.h"
 #include "poa_kernel.cuh"
 
 namespace barb200 {
@@ -56,6 +57,8 @@ struct barb200_ctx {
     uint8_t *h_pinned = nullptr; size_t h_pinned_bytes = 0;   // pinned staging buffer for the MSA download
     int *h_ready = nullptr; unsigned ready_slot = 0;          // pinned ring of "jobs released" values (copied to the device by the copy engine)
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
+    GroupCommit<PoaRequest> poa_group;      // concurrent run_jobs callers share device batches (group_commit.h)
+    GroupCommit<PecanRequest> pecan_group;  // likewise for barb200_pecan_aligned_pairs_batch
     void *pecan_scratch = nullptr; size_t pecan_scratch_bytes = 0;   // pecan.cu's batch call (grow-only)
     void *pecan_pinned[2] = {nullptr, nullptr}; size_t pecan_pinned_bytes[2] = {0, 0};   // pinned staging: 0 upload, 1 download
 };
@@ -694,7 +697,22 @@ extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int
 }
 
 namespace barb200 {
+static int run_jobs_now(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results);
+
+// Callers on different host threads (the reference enters the BAR code from OpenMP teams, bar/impl/bar.c:90-94) do not queue up
+// behind the device one by one: whatever is waiting when the device becomes free runs as ONE batch (group_commit.h).
 int run_jobs(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results) {
+    PoaRequest r;
+    r.jobs = &jobs; r.results = &results;
+    ctx->poa_group.submit(&r, [](const PoaRequest &, const PoaRequest &) { return true; },
+                          [ctx](std::vector<PoaRequest *> &batch) {
+                              run_poa_group(batch, [ctx](const std::vector<HostJob> &j, std::vector<JobResult> &res) { return run_jobs_now(ctx, j, res); });
+                          });
+    return r.rc;
+}
+GroupCommit<PecanRequest> &pecan_group(barb200_ctx *ctx) { return ctx->pecan_group; }
+
+static int run_jobs_now(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results) {
     const int64_t n = (int64_t)jobs.size();
     results.assign(n, JobResult());
     if (n == 0) return BARB200_OK;

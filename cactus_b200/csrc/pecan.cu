@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include "host_api.h"
+#include "batch_merge.h"
 #include "pecan_plan.h"
 #include "pecan_cta.cuh"
 
@@ -523,11 +524,41 @@ extern "C" int barb200_pecan_stage_fetch(barb200_pecan_stage *st, int64_t **trip
     return finish_pairs(st, per_sub, triples_out, n_out, posteriors_out, cells_out);
 }
 
+namespace barb200 { GroupCommit<PecanRequest> &pecan_group(barb200_ctx *ctx); }   // barb200.cu
+
+static int pecan_batch_now(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                           const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                           const int64_t *const *anchors, const int64_t *n_anchor,
+                           const uint8_t *ragged_left, const uint8_t *ragged_right,
+                           int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out);
+
+// Concurrent callers (one per OpenMP thread of bar(), bar/impl/bar.c:90-94) share device batches: whatever is waiting when the
+// device becomes free runs as ONE batch (group_commit.h, batch_merge.h); a single caller runs its own request unchanged.
 extern "C" int barb200_pecan_aligned_pairs_batch(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
                                                  const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
                                                  const int64_t *const *anchors, const int64_t *n_anchor,
                                                  const uint8_t *ragged_left, const uint8_t *ragged_right,
                                                  int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out) {
+    if (!ctx || !p || !triples_out || !n_out || n_pairs < 0 || (n_pairs > 0 && (!sx || !sy || !lx || !ly))) { if (ctx) set_error(ctx, "bad argument"); return BARB200_EINVAL; }
+    PecanRequest r;
+    r.p = *p; r.n = n_pairs; r.sx = sx; r.lx = lx; r.sy = sy; r.ly = ly; r.anchors = anchors; r.n_anchor = n_anchor;
+    r.ragged_left = ragged_left; r.ragged_right = ragged_right;
+    r.triples_out = triples_out; r.n_out = n_out; r.posteriors_out = posteriors_out; r.cells_out = cells_out;
+    pecan_group(ctx).submit(&r, pecan_can_merge, [ctx](std::vector<PecanRequest *> &batch) {
+        run_pecan_group(batch, [ctx](const barb200_pecan_params *pp, int64_t n, const char *const *a, const int64_t *la, const char *const *b, const int64_t *lb,
+                                     const int64_t *const *an, const int64_t *na, const uint8_t *rl, const uint8_t *rr, int64_t **trip, int64_t *no,
+                                     double **post, int64_t *cells) {
+            return pecan_batch_now(ctx, pp, n, a, la, b, lb, an, na, rl, rr, trip, no, post, cells);
+        });
+    });
+    return r.rc;
+}
+
+static int pecan_batch_now(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs,
+                           const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                           const int64_t *const *anchors, const int64_t *n_anchor,
+                           const uint8_t *ragged_left, const uint8_t *ragged_right,
+                           int64_t **triples_out, int64_t *n_out, double **posteriors_out, int64_t *cells_out) {
     if (!ctx || !triples_out || !n_out) { if (ctx) set_error(ctx, "bad argument"); return BARB200_EINVAL; }
     // chunks bounded by the output room a stage reserves (16 B per candidate, ~ (lx + ly) candidates per pair)
     const int64_t kChunkRecords = (int64_t)128 << 20;

@@ -270,3 +270,133 @@ extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, con
     if (cells_out) *cells_out = cells;
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// group commit (cactus_b200/csrc/group_commit.h): `threads` callers submit `iters` requests each to a fake device that
+// squares numbers and takes a moment per batch. Returns the number of wrong answers; *merged = batches wider than one request,
+// *batches = batches run, *overlaps = times two batches were inside exec at once (must stay 0).
+// ---------------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include "../../cactus_b200/csrc/group_commit.h"
+
+struct HtReq { bool done = false; int rc = 0; int key = 0; std::vector<long long> in, out; };
+
+extern "C" long long hosttest_group_commit_stress(int threads, int iters, long long *merged, long long *batches, long long *overlaps) {
+    barb200::GroupCommit<HtReq> gc;
+    std::atomic<long long> wrong(0), nmerged(0), nbatches(0), inside(0), noverlap(0);
+    auto worker = [&](int tid) {
+        for (int it = 0; it < iters; ++it) {
+            HtReq r; r.key = (tid + it) % 2;
+            for (int k = 0; k < 1 + (tid * 7 + it) % 5; ++k) r.in.push_back(1000LL * tid + it * 10 + k);
+            gc.submit(&r, [](const HtReq &a, const HtReq &b) { return a.key == b.key; },
+                      [&](std::vector<HtReq *> &batch) {
+                          if (inside.fetch_add(1) != 0) ++noverlap;
+                          ++nbatches; if (batch.size() > 1) ++nmerged;
+                          if (batch.front()->in[0] % 97 == 13) { inside.fetch_sub(1); throw std::bad_alloc(); }     // a failing batch must not wedge the queue
+                          for (HtReq *q : batch) if (q->key != batch.front()->key) ++wrong;       // only mergeable requests share a batch
+                          std::vector<long long> all;                                               // the "device" works on the concatenation
+                          for (HtReq *q : batch) all.insert(all.end(), q->in.begin(), q->in.end());
+                          for (long long &v : all) v = v * v;
+                          std::this_thread::sleep_for(std::chrono::microseconds(200));
+                          size_t o = 0;
+                          for (HtReq *q : batch) { q->out.assign(all.begin() + o, all.begin() + o + q->in.size()); o += q->in.size(); }
+                          inside.fetch_sub(1);
+                      });
+            if (r.rc == -2) { if (!r.out.empty()) ++wrong; continue; }          // its batch "ran out of memory": reported, nothing delivered
+            if (!r.done || r.out.size() != r.in.size()) { ++wrong; continue; }
+            for (size_t k = 0; k < r.in.size(); ++k) if (r.out[k] != r.in[k] * r.in[k]) ++wrong;
+        }
+    };
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; ++t) ts.emplace_back(worker, t);
+    for (auto &t : ts) t.join();
+    *merged = nmerged; *batches = nbatches; *overlaps = noverlap;
+    return wrong;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch_merge.h: the plumbing that turns the requests of concurrent callers into one device batch, driven with stand-in
+// "devices" (POA: the MSA of a job is its first sequence; cPecan: one triple (lx, ly, n_anchor) per pair). Returns the number
+// of callers that got a wrong answer; *merged = batches wider than one request.
+// ---------------------------------------------------------------------------------------------------------
+#include <string>
+#include "../../cactus_b200/csrc/batch_merge.h"
+
+extern "C" long long hosttest_batch_merge_stress(int threads, int iters, long long *merged) {
+    barb200::GroupCommit<barb200::PoaRequest> gpoa;
+    barb200::GroupCommit<barb200::PecanRequest> gpec;
+    std::atomic<long long> wrong(0), nmerged(0);
+    auto poa_impl = [&](const std::vector<barb200::HostJob> &jobs, std::vector<barb200::JobResult> &res) -> int {
+        res.assign(jobs.size(), barb200::JobResult());
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            res[j].msa.assign(jobs[j].seqs, jobs[j].seqs + jobs[j].lens[0]); res[j].msa_len = jobs[j].lens[0]; res[j].cells = jobs[j].n_seq;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+        return 0;
+    };
+    auto pec_impl = [&](const barb200_pecan_params *p, int64_t n, const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
+                        const int64_t *const *an, const int64_t *na, const uint8_t *rl, const uint8_t *rr, int64_t **trip, int64_t *n_out, double **post,
+                        int64_t *cells) -> int {
+        for (int64_t i = 0; i < n; ++i) {
+            trip[i] = (int64_t *)malloc(3 * sizeof(int64_t));
+            trip[i][0] = lx[i] * 1000 + (sx[i] ? sx[i][0] : 0); trip[i][1] = ly[i] + (rl ? rl[i] : 0) * 7 + (rr ? rr[i] : 0) * 11; trip[i][2] = (na ? na[i] : 0) + ((an && an[i]) ? an[i][0] : 0);
+            n_out[i] = 1;
+            if (post) { post[i] = (double *)malloc(sizeof(double)); post[i][0] = p->threshold + (double)lx[i]; }
+            if (cells) cells[i] = lx[i] * ly[i];
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+        return 0;
+    };
+    auto worker = [&](int tid) {
+        for (int it = 0; it < iters; ++it) {
+            {   // POA request: 1..3 jobs
+                const int nj = 1 + (tid + it) % 3;
+                std::vector<std::vector<uint8_t>> seqs(nj); std::vector<std::vector<int>> lens(nj); std::vector<barb200::HostJob> jobs(nj);
+                for (int j = 0; j < nj; ++j) {
+                    const int L = 3 + (tid * 5 + it + j) % 9;
+                    seqs[j].assign((size_t)2 * L, (uint8_t)((tid + j) & 3)); seqs[j][0] = (uint8_t)(tid & 3); lens[j] = {L, L};
+                    jobs[j] = barb200::HostJob{2, lens[j].data(), seqs[j].data(), 1};
+                }
+                std::vector<barb200::JobResult> res;
+                barb200::PoaRequest r; r.jobs = &jobs; r.results = &res;
+                gpoa.submit(&r, [](const barb200::PoaRequest &, const barb200::PoaRequest &) { return true; },
+                            [&](std::vector<barb200::PoaRequest *> &b) { if (b.size() > 1) ++nmerged; barb200::run_poa_group(b, poa_impl); });
+                bool ok = r.rc == 0 && (int)res.size() == nj;
+                for (int j = 0; ok && j < nj; ++j) ok = res[j].msa_len == lens[j][0] && res[j].msa == std::vector<uint8_t>(seqs[j].begin(), seqs[j].begin() + lens[j][0]) && res[j].cells == 2;
+                if (!ok) ++wrong;
+            }
+            {   // cPecan request: 1..4 pairs, two parameter sets, with / without posteriors and optional arrays
+                const int np = 1 + (tid * 3 + it) % 4;
+                std::vector<std::string> xs(np), ys(np); std::vector<const char *> sx(np), sy(np); std::vector<int64_t> lx(np), ly(np), na(np), n_out(np, -1), cells(np, -1);
+                std::vector<std::vector<int64_t>> an(np); std::vector<const int64_t *> anp(np); std::vector<uint8_t> rl(np), rr(np);
+                std::vector<int64_t *> trip(np, nullptr); std::vector<double *> post(np, nullptr);
+                for (int i = 0; i < np; ++i) {
+                    xs[i] = std::string((size_t)(2 + (tid + i) % 5), (char)('A' + (tid + i) % 20)); ys[i] = std::string((size_t)(1 + (it + i) % 7), 'C');
+                    sx[i] = xs[i].c_str(); sy[i] = ys[i].c_str(); lx[i] = (int64_t)xs[i].size(); ly[i] = (int64_t)ys[i].size();
+                    na[i] = (tid + it + i) % 2; an[i] = {(int64_t)(tid + i), 0}; anp[i] = na[i] ? an[i].data() : nullptr; rl[i] = (uint8_t)((tid + i) & 1); rr[i] = (uint8_t)((it + i) & 1);
+                }
+                const bool want_post = (tid + it) % 3 == 0, with_flags = (tid + it) % 5 != 0;
+                barb200::PecanRequest r; memset(&r.p, 0, sizeof(r.p)); r.p.min_diags_between_traceback = 1000; r.p.traceback_diagonals = 40;
+                r.p.diagonal_expansion = 20; r.p.split_matrix_bigger_than_this = 9000000; r.p.threshold = (tid % 2) ? 0.01 : 0.2;
+                r.n = np; r.sx = sx.data(); r.lx = lx.data(); r.sy = sy.data(); r.ly = ly.data(); r.anchors = anp.data(); r.n_anchor = na.data();
+                r.ragged_left = with_flags ? rl.data() : nullptr; r.ragged_right = with_flags ? rr.data() : nullptr;
+                r.triples_out = trip.data(); r.n_out = n_out.data(); r.posteriors_out = want_post ? post.data() : nullptr; r.cells_out = cells.data();
+                gpec.submit(&r, barb200::pecan_can_merge, [&](std::vector<barb200::PecanRequest *> &b) { if (b.size() > 1) ++nmerged; barb200::run_pecan_group(b, pec_impl); });
+                bool ok = r.rc == 0;
+                for (int i = 0; ok && i < np; ++i) {
+                    ok = trip[i] && n_out[i] == 1 && trip[i][0] == lx[i] * 1000 + xs[i][0] && trip[i][1] == ly[i] + (with_flags ? rl[i] * 7 + rr[i] * 11 : 0) &&
+                         trip[i][2] == na[i] + (na[i] ? an[i][0] : 0) && cells[i] == lx[i] * ly[i] && (!want_post || (post[i] && post[i][0] == r.p.threshold + (double)lx[i]));
+                }
+                if (!ok) ++wrong;
+                for (int i = 0; i < np; ++i) { free(trip[i]); free(post[i]); }
+            }
+        }
+    };
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; ++t) ts.emplace_back(worker, t);
+    for (auto &t : ts) t.join();
+    *merged = nmerged;
+    return wrong;
+}

@@ -69,3 +69,21 @@ def test_incremental_topological_order_gives_identical_alignments(oracle_built, 
         for x, y in zip(a["alns"], b["alns"]):
             assert np.array_equal(x["cigar"], y["cigar"]), it
             assert sorted(zip(x["dp_beg"].tolist(), x["dp_end"].tolist())) == sorted(zip(y["dp_beg"].tolist(), y["dp_end"].tolist())), it
+
+
+def test_group_commit_and_batch_merge_under_threads():
+    """cactus_b200/csrc/group_commit.h + batch_merge.h with stand-in devices: concurrent callers get their own answers, batches
+    never overlap, requests pile up into wider batches while one runs, a failing batch does not wedge the queue"""
+    import ctypes as C
+    lib = R._load(R.build_hosttest())
+    f = lib.hosttest_group_commit_stress
+    f.restype = C.c_longlong
+    f.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    m, b, o = C.c_longlong(), C.c_longlong(), C.c_longlong()
+    assert f(1, 40, C.byref(m), C.byref(b), C.byref(o)) == 0 and m.value == 0 and b.value == 40 and o.value == 0     # one caller: its own request, unchanged
+    assert f(8, 200, C.byref(m), C.byref(b), C.byref(o)) == 0 and o.value == 0 and m.value > 0 and b.value < 8 * 200
+    g = lib.hosttest_batch_merge_stress
+    g.restype = C.c_longlong
+    g.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    assert g(1, 20, C.byref(m)) == 0 and m.value == 0
+    assert g(8, 150, C.byref(m)) == 0 and m.value > 0
