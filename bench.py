@@ -157,6 +157,13 @@ def pecan_measure(local_rank, rank, first_pair, n_pairs, steps, warmup, cpu_budg
             out["cpu_baseline"] = {"value": c / secs / 1e9, "unit": "Gcell/s", "pairs_per_s": n / secs, "cores": threads, "kind": kind,
                                    "sample": "first %d of the step's pairs, %.1f s wall, one getAlignedPairsUsingAnchors call per pair on a pool of %d threads" % (n, secs, threads),
                                    "bit_identical_on_first_pair": bool(np.array_equal(chk, res[0][0]))}
+            # max abs difference of the pre-floor posteriors (tolerance 1e-5; the engine is held to 0) on a few pairs,
+            # against the plain-C oracle (itself pinned bit for bit to the compiled reference by tests/test_pecan_cpu.py)
+            md = 0.0
+            for q, r in list(zip(samp, res))[:4]:
+                to, po = R.oracle_pecan_aligned_pairs(q[0], q[1], q[2], False, False, R.pecan_params())
+                md = max(md, float(np.max(np.abs(po - r[1]))) if len(po) == len(r[1]) and len(po) else (0.0 if len(po) == len(r[1]) else float("inf")))
+            out["cpu_baseline"]["max_abs_posterior_diff_4_pairs"] = md
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "Gcell/s", "cores": usable_cores(), "kind": "unavailable", "sample": str(e)}
     eng.close()
