@@ -1,6 +1,6 @@
 """Concurrent callers on one context (-m gpu). The reference enters the BAR code from OpenMP teams (bar/impl/bar.c:90-94), so
 the C ABI is called from several host threads at once; their device batches are merged (cactus_b200/csrc/group_commit.h).
-Whatever the interleaving, every caller must get exactly what it gets when it is alone."""
+Whatever the interleaving, every caller must get exactly what it gets when it is alone. (Named to run after the parity suites.)"""
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -8,7 +8,7 @@ import pytest
 
 from _synth import family, pecan_pair, to_ascii
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.fixture(scope="module")
