@@ -119,3 +119,23 @@ def test_block_program_bench_shape(oracle_built):
         assert np.array_equal(to, th) and np.array_equal(po, ph)
         L, Rr = cb.pecan_band(len(sx), len(sy), a, 20)
         assert cells == int(((Rr - L) // 2 + 1).sum()) and ((Rr - L) // 2 + 1).max() > 320      # wide enough to use the overflow
+
+
+def test_reference_invariants_on_the_block_program():
+    """the reference's own validity checks (submodules/cPecan/tests/pairwiseAlignerTest.c:345-382 checkAlignedPairs, used by
+    test_getAlignedPairsWithBanding :404-450 on random sequences of length 0..100 and their evolved copies): scores in
+    (0, PAIR_ALIGNMENT_PROB_1], coordinates inside the sequences, every (x, y) reported once"""
+    from _synth import evolve, to_ascii
+    rng = np.random.default_rng(404)
+    for it in range(60):
+        L = int(rng.integers(0, 101))
+        x = rng.integers(0, 4, L).astype(np.uint8)
+        sx = to_ascii(x) if L else b""
+        sy = to_ascii(evolve(x, rng, sub=0.1, ins=0.05, dele=0.05)) if L else b""
+        t, po, cells = R.hosttest_pecan_aligned_pairs(sx, sy, [], bool(it & 1), bool(it & 2), R.pecan_params(), threads=int(rng.choice([32, 128])))
+        if len(t) == 0:
+            continue
+        assert t[:, 0].min() > 0 and t[:, 0].max() <= 10000000
+        assert t[:, 1].min() >= 0 and t[:, 1].max() < len(sx) and t[:, 2].min() >= 0 and t[:, 2].max() < len(sy)
+        assert len({(int(a), int(b)) for _, a, b in t}) == len(t)
+        assert cells == (len(sx) + 1) * (len(sy) + 1)          # no anchors: the band is the whole matrix
