@@ -336,7 +336,7 @@ def cpu_poa_msa_many(n_seq, lens, flat, threads=0, p=None, prefer_ref=True):
 
 # ---------------------------------------------------------------------------------------------------
 # cPecan mode checkers: the compiled reference (oracle/_ref/libpecan_ref.so, oracle/pecan_ref_harness.c), the plain-C
-# oracle (oracle/pecan_oracle.c) and the host emulation of the product's warp program (tests/hosttest)
+# oracle (oracle/pecan_oracle.c) and the host emulation of the product's block program (tests/hosttest)
 # ---------------------------------------------------------------------------------------------------
 PECAN_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libpecan_ref.so")
 
