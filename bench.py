@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+import workload  # noqa: E402  (synthetic inputs: a plain host library shared by both arms, not product code)
+
 K_SEQS, L_BP = 8, 2000
 METRIC = "BAR POA DP Gcells/sec and ends/sec at 1/2/4/8 B200 vs reference CPU BAR"
 ALGO_BYTES_PER_CELL = 32.0     # 20 B written + 12 B read per cell (int32 planes)
@@ -118,7 +120,7 @@ def pecan_measure(local_rank, rank, first_pair, n_pairs, steps, warmup, cpu_budg
     and returns this rank's raw measurements."""
     import cactus_b200 as cb
     eng = cb.Engine(cb.PoaParams(device=local_rank, host_threads=host_threads))
-    pairs = cb.synth_pairs(first_pair, n_pairs, L_BP, k_anchor=50)
+    pairs = workload.synth_pairs(first_pair, n_pairs, L_BP, k_anchor=50)
     st = eng.pecan_stage(pairs)
     cells = float(st.cells())
     for _ in range(warmup):
@@ -173,7 +175,7 @@ def pecan_measure(local_rank, rank, first_pair, n_pairs, steps, warmup, cpu_budg
 def reference_pecan(cb, R, args, threads):
     """the reference's own getAlignedPairsUsingAnchors on the host cores, bounded sample of the cPecan workload; cells from the
     checker's band (sum of diagonal widths over the split regions), the same definition the engine reports"""
-    pairs = cb.synth_pairs(0, min(args.pecan_pairs_per_step, 4 * max(2, threads) * (args.steps + args.warmup)), L_BP, k_anchor=50)
+    pairs = workload.synth_pairs(0, min(args.pecan_pairs_per_step, 4 * max(2, threads) * (args.steps + args.warmup)), L_BP, k_anchor=50)
     samp = [(q[0], q[1], q[2], False, False) for q in pairs[: max(2, threads)]]
     s0, kind = R.cpu_pecan_many(samp, threads)
     n = int(min(len(pairs), max(len(samp), min(args.cpu_budget, 12.0) / max(s0 / len(samp), 1e-6) / max(1, args.steps + args.warmup))))
@@ -276,7 +278,7 @@ def main():
         if rank != 0:
             return 0
         import _reflib as R
-        n_seq, lens, flat = cb.synth_ends(0, E, K_SEQS, L_BP)
+        n_seq, lens, flat = workload.synth_ends(0, E, K_SEQS, L_BP)
         threads = usable_cores()
         # cells of the sample from the oracle/reference itself (bounded): per-end count through the trace is slow, so
         # use the port's cell counter on the sample actually timed
@@ -342,7 +344,7 @@ def main():
     first_end, n_ends = D.scatter_end_ranges(ranges, dev) if world > 1 else (0, E)
 
     eng = cb.Engine(cb.PoaParams(device=local_rank, host_threads=host_threads))
-    n_seq, lens, flat = cb.synth_ends(first_end, n_ends, K_SEQS, L_BP)
+    n_seq, lens, flat = workload.synth_ends(first_end, n_ends, K_SEQS, L_BP)
     stage = eng.stage(packed=(n_seq, lens, flat))
 
     def barrier():

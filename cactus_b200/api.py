@@ -89,10 +89,6 @@ def load_library():
     lib.barb200_msa_make_partial_order_alignment.restype = C.POINTER(_CMsa)
     lib.barb200_make_consistent_partial_order_alignments.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, C.c_double]
     lib.barb200_make_consistent_partial_order_alignments.restype = C.POINTER(C.POINTER(_CMsa))
-    lib.barb200_synth_end.argtypes = [C.c_uint64, C.c_uint64, ci, ci, C.c_double, C.c_double, C.c_double, vp, vp]
-    lib.barb200_synth_end.restype = i64
-    lib.barb200_synth_pair.argtypes = [C.c_uint64, C.c_uint64, ci, C.c_double, C.c_double, C.c_double, ci, vp, vp, vp, vp, vp]
-    lib.barb200_synth_pair.restype = i64
     lib.barb200_device_info.argtypes = [vp, C.POINTER(ci), C.POINTER(i64), C.POINTER(i64), C.c_char_p, ci]
     lib.barb200_device_info.restype = ci
     lib.barb200_free.argtypes = [vp]
@@ -481,21 +477,6 @@ class Engine:
         return out
 
 
-def synth_pairs(first_pair, n_pairs, L, k_anchor=50, seed=0xBA5E0000, sub=0.02, ins=0.005, dele=0.005):
-    """Seeded synthetic sequence pairs with MUM-like anchors -> list of (sX, sY, anchors[n, 2], False, False). Host only."""
-    lib = load_library()
-    bx, by = C.create_string_buffer(2 * L + 16), C.create_string_buffer(2 * L + 16)
-    an = np.zeros((2 * L, 2), np.int64)
-    lx, ly = C.c_int64(), C.c_int64()
-    out = []
-    for i in range(n_pairs):
-        na = lib.barb200_synth_pair(seed, first_pair + i, L, sub, ins, dele, k_anchor, bx, C.byref(lx), by, C.byref(ly), an.ctypes.data)
-        if na < 0:
-            raise BarB200Error("barb200_synth_pair failed")
-        out.append((bx.raw[:lx.value], by.raw[:ly.value], an[:na].copy(), False, False))
-    return out
-
-
 def pecan_band(lx, ly, anchors, expansion=20):
     """Host only: (xmyL, xmyR) of the diagonals 0..lx+ly as the engine builds them (band_construct, pairwiseAligner.c:193-244)."""
     lib = load_library()
@@ -518,19 +499,3 @@ def pecan_split_points(lx, ly, anchors, split_matrix_bigger_than_this, ragged_le
     out = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_int64)), shape=(max(4 * n, 1),))[: 4 * n].reshape(n, 4).copy()
     lib.barb200_free(o)
     return out
-
-
-def synth_ends(first_end, n_ends, K, L, seed=0xBA5E0000, sub=0.02, ins=0.005, dele=0.005):
-    """Seeded synthetic ends -> (n_seq[int32 n], lens[int32 n*K], flat uint8). Host only."""
-    lib = load_library()
-    n_seq = np.full(n_ends, K, np.int32)
-    lens = np.zeros(n_ends * K, np.int32)
-    flat = np.zeros(n_ends * K * (2 * L + 16), np.uint8)
-    o = 0
-    for e in range(n_ends):
-        n = lib.barb200_synth_end(seed, first_end + e, K, L, sub, ins, dele, flat.ctypes.data + o,
-                                  lens.ctypes.data + 4 * e * K)
-        if n < 0:
-            raise BarB200Error("barb200_synth_end failed")
-        o += n
-    return n_seq, lens, flat[:o].copy()

@@ -2,6 +2,7 @@
 
     python -m cactus_b200.build
 """
+import glob
 import os
 import subprocess
 import sys
@@ -9,10 +10,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbarb200.so")
-SOURCES = ["poa_kernel.cu", "barb200.cu", "guide_tree.cpp", "host_bar.cpp", "synth.cpp", "pecan.cu", "pecan_plan.cpp"]
-HEADERS = ["poa_types.h", "poa_graph.cuh", "poa_kernel.cuh", "host_api.h", "pecan_cta.cuh", "pecan_plan.h", os.path.join("..", "..", "include", "barb200.h")]
+SOURCES = ["poa_kernel.cu", "barb200.cu", "guide_tree.cpp", "host_bar.cpp", "pecan.cu", "pecan_plan.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 
 
@@ -20,7 +20,8 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    # every file under csrc/ (sources AND headers) plus the public header: an edited .cuh must never leave a stale library behind
+    deps = glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "barb200.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -64,7 +64,15 @@ struct barb200_ctx {
 };
 
 namespace barb200 {
-void set_error(barb200_ctx *ctx, const std::string &msg) { if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = msg; } }
+// the message is kept twice: in the context (for callers whose request ran inside another thread's merged batch) and per
+// thread (concurrent callers do not overwrite each other's text)
+static thread_local std::string tls_err;
+static thread_local const barb200_ctx *tls_err_ctx = nullptr;
+void set_error(barb200_ctx *ctx, const std::string &msg) {
+    if (!ctx) return;
+    tls_err = msg; tls_err_ctx = ctx;
+    std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = msg;
+}
 // threads for host-side work: the OpenMP default capped by the cgroup CPU quota (containers on big hosts often see
 // all logical CPUs but may only use a few; oversubscribing them slows the packing / guide-tree loops down)
 static int usable_host_threads() {
@@ -214,7 +222,14 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
     delete ctx;
 }
 
-extern "C" const char *barb200_last_error(barb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+// The returned pointer stays valid until the calling thread's next engine call (thread-local copy, taken under the lock).
+extern "C" const char *barb200_last_error(barb200_ctx *ctx) {
+    if (!ctx) return "null context";
+    static thread_local std::string out;
+    if (barb200::tls_err_ctx == ctx && !barb200::tls_err.empty()) out = barb200::tls_err;
+    else { std::lock_guard<std::mutex> lk(ctx->err_mu); out = ctx->err; }
+    return out.c_str();
+}
 extern "C" void barb200_free(void *p) { free(p); }
 
 extern "C" int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len) {

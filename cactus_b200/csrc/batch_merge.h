@@ -27,6 +27,12 @@ void run_poa_group(std::vector<PoaRequest *> &batch, Impl impl) {
     for (PoaRequest *q : batch) all.insert(all.end(), q->jobs->begin(), q->jobs->end());
     std::vector<JobResult> res;
     const int rc = impl(all, res);
+    if (rc != 0) {
+        // a merged batch failed (one caller's bad input, or the union was too big): every request runs again on its own, so
+        // that only the offending caller sees an error
+        for (PoaRequest *q : batch) q->rc = impl(*q->jobs, *q->results);
+        return;
+    }
     size_t o = 0;
     for (PoaRequest *q : batch) {
         const size_t n = q->jobs->size();
@@ -85,6 +91,12 @@ void run_pecan_group(std::vector<PecanRequest *> &batch, Impl impl) {
     }
     const int rc = impl(&batch[0]->p, total, sx.data(), lx.data(), sy.data(), ly.data(), an.data(), na.data(), rl.data(), rr.data(), trip.data(),
                         n_out.data(), want_post ? post.data() : nullptr, cells.data());
+    if (rc != 0) {       // as above: isolate the failure to the request that caused it
+        for (PecanRequest *q : batch)
+            q->rc = impl(&q->p, q->n, q->sx, q->lx, q->sy, q->ly, q->anchors, q->n_anchor, q->ragged_left, q->ragged_right, q->triples_out, q->n_out,
+                         q->posteriors_out, q->cells_out);
+        return;
+    }
     o = 0;
     for (PecanRequest *q : batch) {
         q->rc = rc;

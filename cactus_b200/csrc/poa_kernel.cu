@@ -367,7 +367,7 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
             const int j = atomicAdd(A.next_job, 1);
             if (j < A.n_jobs) {                                  // wait until the host has released the job (its read order is uploaded)
                 while (*reinterpret_cast<const volatile int *>(A.ready) <= j) __nanosleep(2000);
-                __threadfence();
+                __threadfence_system();     // the producer is the copy engine (system scope): order the order[] loads below after it
             }
             S.job = j;
         }
@@ -383,7 +383,7 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
         __syncthreads();
         long long cells = 0;
         for (int a = 0; a < K; ++a) {
-            const int read = order[a], L = lens[read];
+            const int read = __ldcg(order + a), L = lens[read];   // L2 load: order[] of neighbouring jobs shares cache lines and is written while the kernel runs
             const uint8_t *q = seqs + soff[read];
             if (a == 0) {
                 if (A.serial_phases) { if (tid == 0) graph_add_first_sequence(S.g, q, L, read); }

@@ -118,13 +118,6 @@ barb200_msa **barb200_make_consistent_partial_order_alignments(barb200_ctx *ctx,
         char ***end_strings, int **end_string_lengths, int64_t **right_end_indexes, int64_t **right_end_row_indexes,
         int64_t **overlaps, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff);
 
-/* Seeded synthetic ends of BASELINE.json's "N ends x K seqs x L bp" shape: per end a uniform random
- * ACGT parent of length L and K descendants with per-base substitution / insertion / deletion events, rows sorted by
- * length descending. codes_out: caller buffer of at least K*(2*L+16) bytes; lens_out[K]. Returns total bases written.
- * Host only; deterministic in (seed, end_index). */
-int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
-                          uint8_t *codes_out, int *lens_out);
-
 /* ------------------------------------------------------------------------------------------------------------
  * cPecan mode (bar/partialOrderAlignment="0"): the banded five-state pair-HMM posteriors.
  *
@@ -183,13 +176,6 @@ int barb200_pecan_band(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n
 int64_t barb200_pecan_split_points(int64_t lx, int64_t ly, const int64_t *anchors, int64_t n_anchor,
                                    int64_t split_matrix_bigger_than_this, int ragged_left, int ragged_right,
                                    int64_t **splits_out);
-
-/* Seeded synthetic sequence pair for the cPecan-mode benchmark: two descendants (ASCII) of a random parent of length L
- * and the anchor pairs MUM anchoring would give on them (every base of every exact co-linear run of >= k_anchor bases of
- * the true alignment). Buffers: sx_out / sy_out >= 2*L+16 bytes, anchors_out >= 2*L int64 pairs. Returns the number of
- * anchor pairs. Host only; deterministic in (seed, pair_index). */
-int64_t barb200_synth_pair(uint64_t seed, uint64_t pair_index, int L, double sub, double ins, double del, int k_anchor,
-                           char *sx_out, int64_t *lx_out, char *sy_out, int64_t *ly_out, int64_t *anchors_out);
 
 /* Device facts for reports. */
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);

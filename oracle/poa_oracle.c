@@ -699,7 +699,7 @@ void oracle_free(void *p) { free(p); }
 /* CPU baseline driver for the port (used only when oracle/_ref is absent): OpenMP over jobs, schedule(dynamic,1) */
 #include <omp.h>
 double oracle_poa_msa_many(const oracle_params_t *p, int64_t n_jobs, const int *n_seq, const int *lens, const uint8_t *flat,
-                           int threads, int *msa_lens, uint64_t *checksum) {
+                           int threads, int *msa_lens, uint64_t *checksum, uint64_t *hashes) {
     int64_t *len_off = (int64_t *)xcalloc(n_jobs + 1, sizeof(int64_t)), *seq_off = (int64_t *)xcalloc(n_jobs + 1, sizeof(int64_t));
     int64_t lo = 0, so = 0;
     for (int64_t j = 0; j < n_jobs; ++j) { len_off[j] = lo; seq_off[j] = so; for (int i = 0; i < n_seq[j]; ++i) so += lens[lo + i]; lo += n_seq[j]; }
@@ -712,6 +712,11 @@ double oracle_poa_msa_many(const oracle_params_t *p, int64_t n_jobs, const int *
         int ml = oracle_poa_msa(p, n_seq[j], lens + len_off[j], flat + seq_off[j], &msa);
         if (msa_lens) msa_lens[j] = ml;
         for (int64_t k = 0; k < (int64_t)n_seq[j] * ml; ++k) sum += msa[k];
+        if (hashes) {          /* FNV-1a over (msa_len, bytes), as oracle/ref_harness.c */
+            uint64_t h = (1469598103934665603ULL ^ (uint64_t)(uint32_t)ml) * 1099511628211ULL;
+            for (int64_t k = 0; k < (int64_t)n_seq[j] * ml; ++k) { h ^= msa[k]; h *= 1099511628211ULL; }
+            hashes[j] = h;
+        }
         free(msa);
     }
     double t1 = omp_get_wtime();

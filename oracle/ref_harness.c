@@ -158,8 +158,24 @@ void ref_free(void *p) { free(p); }
  * Returns the wall time in seconds; msa_lens[n_jobs] (may be NULL) receives msa_len, checksum (may be NULL) a sum of
  * all MSA bytes so the work cannot be optimised away. */
 #include <omp.h>
+#include <malloc.h>
+/* FNV-1a over (msa_len, bytes): the per-end alignment hash bench.py's parity gate compares with the GPU's */
+static uint64_t msa_hash(const uint8_t *m, int64_t n, int msa_len) {
+    uint64_t h = 1469598103934665603ULL ^ (uint64_t)(uint32_t)msa_len;
+    h *= 1099511628211ULL;
+    for (int64_t k = 0; k < n; ++k) { h ^= m[k]; h *= 1099511628211ULL; }
+    return h;
+}
+/* Allocator stand-in. Cactus links jemalloc (include.mk:53-64,119-123) because every window mallocs and frees abPOA's
+ * ~84 MB DP matrix; jemalloc keeps such extents cached, glibc mmap()s and munmap()s them every time (page faults +
+ * mmap_sem contention across threads). jemalloc's autoconf build cannot run in this image, so mode 1 makes glibc retain
+ * and reuse large blocks instead (no mmap for big requests, no trimming): the same effect on this workload. */
+void ref_malloc_mode(int mode) {
+    if (mode) { mallopt(M_MMAP_MAX, 0); mallopt(M_TRIM_THRESHOLD, 0x7fffffff); mallopt(M_TOP_PAD, 512 << 20); }
+    else { mallopt(M_MMAP_MAX, 65536); mallopt(M_TRIM_THRESHOLD, 128 * 1024); mallopt(M_TOP_PAD, 128 * 1024); }
+}
 double ref_poa_msa_many(const ref_params_t *p, int64_t n_jobs, const int *n_seq, const int *lens, const uint8_t *flat,
-                        int threads, int *msa_lens, uint64_t *checksum) {
+                        int threads, int *msa_lens, uint64_t *checksum, uint64_t *hashes) {
     int64_t *len_off = (int64_t *)malloc(sizeof(int64_t) * (n_jobs + 1)), *seq_off = (int64_t *)malloc(sizeof(int64_t) * (n_jobs + 1));
     int64_t lo = 0, so = 0;
     for (int64_t j = 0; j < n_jobs; ++j) { len_off[j] = lo; seq_off[j] = so; for (int i = 0; i < n_seq[j]; ++i) so += lens[lo + i]; lo += n_seq[j]; }
@@ -173,6 +189,7 @@ double ref_poa_msa_many(const ref_params_t *p, int64_t n_jobs, const int *n_seq,
         int ml = ref_poa_msa(p, n_seq[j], lens + len_off[j], flat + seq_off[j], &msa);
         if (msa_lens) msa_lens[j] = ml;
         for (int64_t k = 0; k < (int64_t)n_seq[j] * ml; ++k) sum += msa[k];
+        if (hashes) hashes[j] = msa_hash(msa, (int64_t)n_seq[j] * ml, ml);
         free(msa);
     }
     double t1 = omp_get_wtime();

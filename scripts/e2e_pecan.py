@@ -4,9 +4,10 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cactus_b200 as cb  # noqa: E402
+import workload  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
 eng = cb.Engine()
-pairs = cb.synth_pairs(0, n, 2000, k_anchor=50)
+pairs = workload.synth_pairs(0, n, 2000, k_anchor=50)
 table = eng.pecan_table(pairs)
 for r in range(3):
     t = time.time()

@@ -6,9 +6,10 @@ import ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cactus_b200 as cb
+import workload  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
 eng = cb.Engine()
-n_seq, lens, flat = cb.synth_ends(0, n, 8, 2000)
+n_seq, lens, flat = workload.synth_ends(0, n, 8, 2000)
 def once():
     outs = (C.c_void_p * n)(); ml = np.zeros(n, np.int32); cc = np.zeros(n, np.int64)
     eng._check(eng.lib.barb200_poa_msa_batch(eng.ctx, n, n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, None, outs, ml.ctypes.data, cc.ctypes.data))

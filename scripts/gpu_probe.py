@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cactus_b200 as cb  # noqa: E402
+import workload  # noqa: E402
 import _golden as G  # noqa: E402
 import _reflib as R  # noqa: E402
 
@@ -44,7 +45,7 @@ def main():
             bad.append(c["id"])
     out["golden_bad"] = bad
     # bench shape
-    n_seq, lens, flat = cb.synth_ends(0, n_ends, 8, 2000)
+    n_seq, lens, flat = workload.synth_ends(0, n_ends, 8, 2000)
     t0 = time.time()
     st = eng.stage(packed=(n_seq, lens, flat))
     t1 = time.time()

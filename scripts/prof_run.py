@@ -6,6 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cactus_b200 as cb  # noqa: E402
+import workload  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
@@ -14,7 +15,7 @@ L = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
 T = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 cps = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 eng = cb.Engine(cb.PoaParams(threads_per_block=T, ctas_per_sm=cps))
-st = eng.stage(packed=cb.synth_ends(0, n, K, L))
+st = eng.stage(packed=workload.synth_ends(0, n, K, L))
 for r in range(reps):
     ms = st.run()
     print("run", r, ms, "ms", flush=True)

@@ -25,8 +25,11 @@
 #include "barb200.h"
 
 static pthread_mutex_t shim_mutex = PTHREAD_MUTEX_INITIALIZER;
-static barb200_ctx *shim_ctx = NULL;
-static barb200_params shim_params;
+/* one engine per distinct parameter set, created on first use and kept for the life of the process: another OpenMP thread
+ * may be inside a call on any of them, so a context is never destroyed or replaced in place */
+#define SHIM_MAX_CTX 16
+static struct { barb200_params p; barb200_ctx *ctx; } shim_ctxs[SHIM_MAX_CTX];
+static int shim_ctx_no = 0;
 
 /* abpoa_para_t (as built by abpoaParamaters_constructFromCactusParams, poaBarAligner.c:24-81) -> barb200_params */
 static void params_from_abpoa(const abpoa_para_t *abpt, barb200_params *p) {
@@ -42,24 +45,38 @@ static void params_from_abpoa(const abpoa_para_t *abpt, barb200_params *p) {
     if (dev) p->device = atoi(dev);
 }
 
+/* field-wise comparison (memcmp would read struct padding) */
+static int params_equal(const barb200_params *a, const barb200_params *b) {
+    return memcmp(a->mat, b->mat, sizeof(a->mat)) == 0 && a->gap_open1 == b->gap_open1 && a->gap_ext1 == b->gap_ext1 &&
+           a->gap_open2 == b->gap_open2 && a->gap_ext2 == b->gap_ext2 && a->wb == b->wb && a->wf == b->wf && a->k == b->k &&
+           a->w == b->w && a->min_w == b->min_w && a->progressive_poa == b->progressive_poa &&
+           a->disable_seeding == b->disable_seeding && a->device == b->device;
+}
+
 static barb200_ctx *shim_context(abpoa_para_t *abpt) {
     barb200_params p;
     params_from_abpoa(abpt, &p);
     pthread_mutex_lock(&shim_mutex);
-    if (shim_ctx != NULL && memcmp(&p, &shim_params, sizeof(p)) != 0) {      /* parameters changed between calls */
-        barb200_destroy(shim_ctx);
-        shim_ctx = NULL;
-    }
-    if (shim_ctx == NULL) {
-        char err[256];
-        shim_ctx = barb200_create(&p, err, (int)sizeof(err));
-        if (shim_ctx == NULL) {
+    for (int i = 0; i < shim_ctx_no; i++) {
+        if (params_equal(&p, &shim_ctxs[i].p)) {
+            barb200_ctx *ctx = shim_ctxs[i].ctx;
             pthread_mutex_unlock(&shim_mutex);
-            st_errAbort("barb200: cannot create the GPU BAR engine: %s", err);
+            return ctx;
         }
-        shim_params = p;
     }
-    barb200_ctx *ctx = shim_ctx;
+    if (shim_ctx_no == SHIM_MAX_CTX) {
+        pthread_mutex_unlock(&shim_mutex);
+        st_errAbort("barb200: more than %d distinct POA parameter sets in one process", SHIM_MAX_CTX);
+    }
+    char err[256];
+    barb200_ctx *ctx = barb200_create(&p, err, (int)sizeof(err));
+    if (ctx == NULL) {
+        pthread_mutex_unlock(&shim_mutex);
+        st_errAbort("barb200: cannot create the GPU BAR engine: %s", err);
+    }
+    shim_ctxs[shim_ctx_no].p = p;
+    shim_ctxs[shim_ctx_no].ctx = ctx;
+    shim_ctx_no++;
     pthread_mutex_unlock(&shim_mutex);
     return ctx;
 }

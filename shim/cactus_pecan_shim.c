@@ -65,8 +65,47 @@ static void params_from_pecan(const PairwiseAlignmentParameters *p, barb200_peca
     q->dynamic_anchor_expansion = p->dynamicAnchorExpansion;
 }
 
+/* The engine hard-codes the constants of stateMachine5_construct(fiveState) (stateMachine.c:482-521). StateMachine5's fields
+ * are private to stateMachine.c, so a machine is verified through its public face: every (emission, transition) pair that
+ * cellCalculate hands to its callback, for all 25 symbol pairs, and the start / end vectors must equal those of a freshly
+ * constructed default machine -- a five-state machine loaded from a trained HMM (hmm_getStateMachine) is REJECTED, not
+ * silently mis-evaluated. Verified once per machine. */
+typedef struct { double v[64]; int n; } sm_probe;
+static void probe_transition(double *from, double *to, int64_t f, int64_t t, double eP, double tP, void *extra) {
+    sm_probe *q = extra;
+    (void)from; (void)to;
+    if (q->n + 4 <= 64) { q->v[q->n++] = (double)f; q->v[q->n++] = (double)t; q->v[q->n++] = eP; q->v[q->n++] = tP; }
+}
 static void check_state_machine(StateMachine *sM) {
+    static StateMachine *verified = NULL;
     if (sM->type != fiveState) st_errAbort("barb200: only the five-state pair-HMM (stateMachine5_construct(fiveState)) is supported");
+    pthread_mutex_lock(&shim_mutex);
+    const int known = sM == verified;
+    pthread_mutex_unlock(&shim_mutex);
+    if (known) return;
+    StateMachine *d = stateMachine5_construct(fiveState);
+    int same = sM->stateNumber == d->stateNumber;
+    double cells[20];
+    memset(cells, 0, sizeof(cells));
+    for (int cx = 0; cx < SYMBOL_NUMBER && same; cx++) {
+        for (int cy = 0; cy < SYMBOL_NUMBER && same; cy++) {
+            sm_probe a, b;
+            memset(&a, 0, sizeof(a)); memset(&b, 0, sizeof(b));
+            sM->cellCalculate(sM, cells, cells + 5, cells + 10, cells + 15, (Symbol)cx, (Symbol)cy, probe_transition, &a);
+            d->cellCalculate(d, cells, cells + 5, cells + 10, cells + 15, (Symbol)cx, (Symbol)cy, probe_transition, &b);
+            same = a.n == b.n && memcmp(a.v, b.v, sizeof(double) * (size_t)a.n) == 0;
+        }
+    }
+    for (int64_t st = 0; st < d->stateNumber && same; st++) {
+        same = sM->startStateProb(sM, st) == d->startStateProb(d, st) && sM->endStateProb(sM, st) == d->endStateProb(d, st) &&
+               sM->raggedStartStateProb(sM, st) == d->raggedStartStateProb(d, st) && sM->raggedEndStateProb(sM, st) == d->raggedEndStateProb(d, st);
+    }
+    stateMachine_destruct(d);
+    if (!same) st_errAbort("barb200: the pair-HMM's transition / emission constants differ from stateMachine5_construct(fiveState); "
+                           "trained HMMs are not supported by the GPU engine");
+    pthread_mutex_lock(&shim_mutex);
+    verified = sM;
+    pthread_mutex_unlock(&shim_mutex);
 }
 
 static int64_t *flatten_anchors(stList *anchorPairs, int64_t *n) {

@@ -316,22 +316,40 @@ def hosttest_poa_msa_trace(seqs, p=None):
     return _parse_trace(words, len(seqs))
 
 
-def cpu_poa_msa_many(n_seq, lens, flat, threads=0, p=None, prefer_ref=True):
-    """Time n independent abpoa_msa calls on the host cores (OpenMP over jobs). Returns (seconds, kind, checksum)."""
+def msa_hash(msa):
+    """FNV-1a over (msa_len, bytes) of one K x msa_len matrix -- the per-end hash of bench.py's parity gate
+    (same function as oracle/ref_harness.c:msa_hash)."""
+    m = np.ascontiguousarray(msa, np.uint8)
+    h = ((1469598103934665603 ^ (m.shape[1] & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
+    for b in m.reshape(-1).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xffffffffffffffff
+    return h
+
+
+def cpu_poa_msa_many(n_seq, lens, flat, threads=0, p=None, prefer_ref=True, malloc_mode=None, want_hashes=False):
+    """Time n independent abpoa_msa calls on the host cores (OpenMP over jobs). Returns (seconds, kind, checksum) or, with
+    want_hashes, (seconds, kind, checksum, hashes[uint64 n]). malloc_mode (reference library only): 0 = glibc defaults,
+    1 = large blocks retained and reused (the jemalloc stand-in, see oracle/ref_harness.c:ref_malloc_mode)."""
     p = p or cactus_params()
     n_seq = np.ascontiguousarray(n_seq, np.int32)
     lens = np.ascontiguousarray(lens, np.int32)
     flat = np.ascontiguousarray(flat, np.uint8)
     if prefer_ref and have_ref():
         lib, name, kind = _load(REF_SO), "ref_poa_msa_many", "reference"
+        if malloc_mode is not None:
+            lib.ref_malloc_mode.argtypes = [C.c_int]
+            lib.ref_malloc_mode.restype = None
+            lib.ref_malloc_mode(int(malloc_mode))
     else:
         lib, name, kind = _load(build_oracle()), "oracle_poa_msa_many", "port"
     f = getattr(lib, name)
     f.restype = C.c_double
-    f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    f.argtypes = [C.POINTER(RefParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
     ck = C.c_uint64()
-    secs = f(C.byref(p), len(n_seq), n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, threads, None, C.byref(ck))
-    return secs, kind, ck.value
+    hashes = np.zeros(len(n_seq), np.uint64)
+    secs = f(C.byref(p), len(n_seq), n_seq.ctypes.data, lens.ctypes.data, flat.ctypes.data, threads, None, C.byref(ck),
+             hashes.ctypes.data if want_hashes else None)
+    return (secs, kind, ck.value, hashes) if want_hashes else (secs, kind, ck.value)
 
 
 # ---------------------------------------------------------------------------------------------------

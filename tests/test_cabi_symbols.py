@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import workload  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -41,13 +42,13 @@ def test_defaults_are_cactus_config(lib):
 
 def test_synth_is_deterministic_and_sorted(lib):
     import cactus_b200 as cb
-    a = cb.synth_ends(5, 3, 8, 300)
-    b = cb.synth_ends(5, 3, 8, 300)
+    a = workload.synth_ends(5, 3, 8, 300)
+    b = workload.synth_ends(5, 3, 8, 300)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     lens = a[1].reshape(3, 8)
     assert np.all(lens[:, :-1] >= lens[:, 1:]) and a[2].max() <= 3
-    c = cb.synth_ends(6, 1, 8, 300)
+    c = workload.synth_ends(6, 1, 8, 300)
     assert np.array_equal(c[1], a[1][8:16])        # end index, not call order, defines the data
 
 

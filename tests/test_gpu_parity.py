@@ -7,6 +7,7 @@ import pytest
 import _golden as G
 import _reflib as R
 from _synth import family, to_ascii, two_end_problem
+import workload  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -110,7 +111,7 @@ def test_bench_shape_properties(engine, oracle_built):
     and the first ends equal to the oracle bit for bit."""
     import cactus_b200 as cb
     n = 600
-    n_seq, lens, flat = cb.synth_ends(0, n, 8, 2000)
+    n_seq, lens, flat = workload.synth_ends(0, n, 8, 2000)
     st = engine.stage(packed=(n_seq, lens, flat))
     st.run()
     msas, cells = st.fetch()

@@ -9,6 +9,7 @@ import pytest
 import _golden as G
 import _reflib as R
 from _synth import pecan_pair
+import workload  # noqa: E402
 
 
 def _params(c):
@@ -113,7 +114,7 @@ def test_block_program_bench_shape(oracle_built):
     import cactus_b200 as cb
     from cactus_b200 import build as b
     b.build()
-    for sx, sy, a, _, _ in cb.synth_pairs(7, 2, 2000, k_anchor=50):
+    for sx, sy, a, _, _ in workload.synth_pairs(7, 2, 2000, k_anchor=50):
         to, po = R.oracle_pecan_aligned_pairs(sx, sy, a, False, False, R.pecan_params())
         th, ph, cells = R.hosttest_pecan_aligned_pairs(sx, sy, a, False, False, R.pecan_params(), threads=128, ring_width=320)
         assert np.array_equal(to, th) and np.array_equal(po, ph)

@@ -1,4 +1,5 @@
-// synth.cpp -- seeded synthetic BAR ends of BASELINE.json's "N ends x K seqs x L bp" shape.
+// synth.cpp -- WORKLOAD GENERATOR (not part of the engine: built into workload/libbarsynth.so so that the reference arm of
+// bench.py maps no product library). Seeded synthetic BAR ends of BASELINE.json's "N ends x K seqs x L bp" shape.
 // For end e: xoshiro256** seeded (through splitmix64) with seed + e; parent = L uniform ACGT; K descendants, each base
 // deleted with probability `del`, substituted by a uniformly chosen different base with probability `sub`, and followed by
 // a uniformly random inserted base with probability `ins`; rows sorted by length, longest first (stable), which is the
@@ -7,7 +8,6 @@
 #include <algorithm>
 #include <numeric>
 #include <vector>
-#include "../../include/barb200.h"
 
 namespace {
 struct Xoshiro {
@@ -28,7 +28,7 @@ struct Xoshiro {
 };
 }  // namespace
 
-extern "C" int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
+extern "C" int64_t barsynth_end(uint64_t seed, uint64_t end_index, int K, int L, double sub, double ins, double del,
                                      uint8_t *codes_out, int *lens_out) {
     if (K <= 0 || L <= 0 || !codes_out || !lens_out) return -1;
     Xoshiro rng(seed + end_index);
@@ -62,7 +62,7 @@ extern "C" int64_t barb200_synth_end(uint64_t seed, uint64_t end_index, int K, i
 // position of every run of >= k_anchor identical, co-linear bases of the true alignment (getAlignedMums emits one anchor
 // per base of each maximal unique match of length >= k, submodules/cPecan/impl/pairwiseAligner.c:2032-2059; Cactus
 // configures k = 50, :1389). sx_out / sy_out: at least 2*L+16 bytes each; anchors_out: at least 2*L (x, y) int64 pairs.
-extern "C" int64_t barb200_synth_pair(uint64_t seed, uint64_t pair_index, int L, double sub, double ins, double del, int k_anchor,
+extern "C" int64_t barsynth_pair(uint64_t seed, uint64_t pair_index, int L, double sub, double ins, double del, int k_anchor,
                                       char *sx_out, int64_t *lx_out, char *sy_out, int64_t *ly_out, int64_t *anchors_out) {
     if (L <= 0 || k_anchor <= 0 || !sx_out || !sy_out || !lx_out || !ly_out || !anchors_out) return -1;
     Xoshiro rng(seed * 0x9e3779b97f4a7c15ULL + pair_index + 0x5eed);
