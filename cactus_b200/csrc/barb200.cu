@@ -175,6 +175,8 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     if (p->gap_open1 <= 0 || p->gap_open2 <= 0 || p->gap_ext1 < 0 || p->gap_ext2 < 0 || (p->gap_ext1 == 0 && p->gap_ext2 == 0)) {
         fail(errbuf, errbuf_len, "only the convex gap model (both gap opens > 0) is supported; that is what Cactus configures"); return nullptr; }
     if (p->wb < 0) { fail(errbuf, errbuf_len, "partialOrderAlignmentBandConstant must be >= 0 (adaptive band)"); return nullptr; }
+    if ((int64_t)p->gap_open1 + p->gap_ext1 >= 65535 || (int64_t)p->gap_open2 + p->gap_ext2 >= 65535) {
+        fail(errbuf, errbuf_len, "gap open + extension must be below 65535 (the traceback planes keep E as a 16-bit distance below H)"); return nullptr; }
     if (!p->disable_seeding) { fail(errbuf, errbuf_len, "minimizer seeding (partialOrderAlignmentDisableSeeding=0) is not supported"); return nullptr; }
     if (p->k <= 0 || p->k > 28 || p->w <= 0 || p->w >= 256) { fail(errbuf, errbuf_len, "minimizer k must be in 1..28 and w in 1..255"); return nullptr; }
     int ndev = 0;
@@ -300,7 +302,7 @@ static int plan_stage(barb200_stage *st) {
         max_k = std::max(max_k, K);
         // rows the graph can reach: worst case every base a new node; optimistic: the longest read plus a share of the rest
         int64_t rows = st->worst_case ? sum + 2 : std::min<int64_t>(sum + 2, ml + (sum - ml) / 8 + 256);
-        plane_need = std::max(plane_need, rows * 5 * (align_up(ml + 1, CPT) + CPT));
+        plane_need = std::max(plane_need, rows * (TB / CPT) * (align_up(ml + 1, CPT) + CPT));
     }
     SlotLayout &Y = st->lay;
     memset(&Y, 0, sizeof(Y));
@@ -321,6 +323,7 @@ static int plan_stage(barb200_stage *st) {
     Y.o_row_rec = take(N * 16); Y.o_pre_row = take((int64_t)Y.in_pool * 4);
     Y.o_row_off = take(N * 8); Y.o_row_info = take(N * 16);
     Y.o_cigar = take((int64_t)Y.cigar_cap * 8);
+    Y.fc_cap = (int)(max_len + 2); Y.o_fc = take((int64_t)Y.fc_cap * 8);
     Y.slot_bytes = align_up(o, 256);
 
     // smallest CTA-size class whose 16 columns per thread cover the longest query (+ column 0)

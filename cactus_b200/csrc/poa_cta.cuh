@@ -212,7 +212,7 @@ __device__ void cta_fuse_alignment(Graph &g, const uint8_t *seq, int L, const ui
 __device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const int *smat8, const uint8_t *q, int L) {
     const unsigned FULLM = 0xffffffffu;
     const int lane = threadIdx.x & 31, inf = P.inf_min;
-    if (lane == 0) dp_best_cell(g, rt, d, P, L);
+    if (lane == 0) { dp_best_cell(g, rt, d, P, L); d.fc_row = -1; d.fc_hi = -1; }
     __syncwarp();
     int i = d.best_i, j = d.best_j, cur_op = OP_ALL, nc = 0, last_op = -1;
     uint64_t *cg = d.cigar; const int cap = d.cigar_cap;
@@ -268,7 +268,7 @@ __device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const 
         }
         if (run == 0 && !fail) {
             const int id = g.index_to_node[i], jq = j - 1;
-            const int op = backtrack_step(g, rt, d, P, q, i, j, cur_op);
+            const int op = backtrack_step<true>(g, rt, d, P, q, L, i, j, cur_op);
             if (op < 0) fail = JOB_ERR_BACKTRACK; else push(op, 1, id, jq);
         }
     }

@@ -302,10 +302,84 @@ HD void graph_msa_fill_node(const Graph &g, int v, uint8_t *msa, int64_t stride)
 }
 
 // ---- traceback ------------------------------------------------------------------------------------------------
+// plane 0: H; 1: E1; 2: E2 (the two E values are stored as 16-bit distances below H, poa_types.h)
 HD int plane_cell(const DpState &d, int inf_min, int row, int plane, int j) {
     const int beg = d.info[row].beg, end = d.info[row].end;
     if (j < beg || j > end) return inf_min;                 // out-of-band lanes hold inf_min (abpoa_align_simd.c:1035-1036)
-    return d.planes[d.row_off[row] + plane_index(beg, end, plane, j)];
+    const int *rowp = d.planes + d.row_off[row];
+    const int h = rowp[plane_index(beg, end, 0, j)];
+    if (plane == 0) return h;
+    const unsigned code = (unsigned)rowp[plane_index(beg, end, 1, j)];
+    return e_decode(h, plane == 1 ? (int)(code & 0xffffu) : (int)(code >> 16), inf_min);
+}
+
+// H' = max(M + s, E1, E2) of cell (i, k), k inside row i's band: the value the F recurrences start from
+// (abpoa_align_simd.c:1033-1050), recomputed from the predecessor rows' stored H / E.
+HD int row_h_prime(const RowTables &rt, const DpState &d, const PoaParams &P, const uint8_t *q, int L, int i, int k) {
+    const int inf = P.inf_min;
+    const int p0 = rt.rec[i].pre_off, p1 = p0 + row_npre(rt, i);
+    int m = inf, x1 = inf, x2 = inf;
+    for (int t = p0; t < p1; ++t) {
+        const int pi = rt.pre_row[t];
+        m = imax(m, plane_cell(d, inf, pi, 0, k - 1)); x1 = imax(x1, plane_cell(d, inf, pi, 1, k)); x2 = imax(x2, plane_cell(d, inf, pi, 2, k));
+    }
+    const int s = (k >= 1 && k <= L) ? P.mat[5 * row_base(rt, i) + q[k - 1]] : 0;
+    return imax(imax(m + s, x1), x2);
+}
+
+// F1 / F2 of row i for the columns [beg, j] into the traceback's scratch (d.fc): F[k] = max_{beg <= t < k} H'[t] - oe - (k-1-t) e,
+// in the DP sweep's own "A space" form (poa_kernel.cu: row_pass1 / row_pass2) so that finite values are the ones the sweep
+// would have stored. Row 0 has the closed form of simd_abpoa_cg_first_dp (abpoa_align_simd.c:669-688). WARP: all 32 lanes of
+// a warp call this together (32 columns per step, shuffle prefix maximum); otherwise one thread runs the serial loop.
+template <bool WARP>
+HD void row_f_cache(const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L, int i, int j) {
+    if (d.fc_row == i && d.fc_hi >= j) return;
+    const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, o1 = P.o1, o2 = P.o2;
+    const int beg = d.info[i].beg;
+    int *f1 = d.fc, *f2 = d.fc + d.fc_cap;
+#if defined(__CUDA_ARCH__)
+    if (WARP) {
+        const unsigned FULLM = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        int c1 = inf + beg * e1 + o1, c2 = inf + beg * e2 + o2;           // running prefix maxima (exclusive), the scans' identities
+        for (int k0 = beg; k0 <= j; k0 += 32) {
+            const int k = k0 + lane;
+            int a1 = INT32_MIN, a2 = INT32_MIN;
+            if (i > 0 && k < j) { const int hp = row_h_prime(rt, d, P, q, L, i, k); a1 = hp + k * e1; a2 = hp + k * e2; }
+            int i1 = a1, i2 = a2;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int n1 = __shfl_up_sync(FULLM, i1, off), n2 = __shfl_up_sync(FULLM, i2, off);
+                if (lane >= off) { i1 = imax(i1, n1); i2 = imax(i2, n2); }
+            }
+            int x1 = __shfl_up_sync(FULLM, i1, 1), x2 = __shfl_up_sync(FULLM, i2, 1);
+            if (lane == 0) { x1 = INT32_MIN; x2 = INT32_MIN; }
+            x1 = imax(x1, c1); x2 = imax(x2, c2);                          // exclusive prefix maximum at column k
+            if (k <= j) {
+                if (i == 0) { f1[k] = k == 0 ? inf : -o1 - e1 * k; f2[k] = k == 0 ? inf : -o2 - e2 * k; }
+                else { f1[k] = x1 - o1 - k * e1; f2[k] = x2 - o2 - k * e2; }
+            }
+            c1 = imax(c1, __shfl_sync(FULLM, i1, 31)); c2 = imax(c2, __shfl_sync(FULLM, i2, 31));
+        }
+        __syncwarp();
+        d.fc_row = i; d.fc_hi = j;                                        // (all lanes write the same values)
+        __syncwarp();
+        return;
+    }
+#endif
+    int c1 = inf + beg * e1 + o1, c2 = inf + beg * e2 + o2;
+    for (int k = beg; k <= j; ++k) {
+        if (i == 0) { f1[k] = k == 0 ? inf : -o1 - e1 * k; f2[k] = k == 0 ? inf : -o2 - e2 * k; continue; }
+        f1[k] = c1 - o1 - k * e1; f2[k] = c2 - o2 - k * e2;
+        if (k < j) { const int hp = row_h_prime(rt, d, P, q, L, i, k); c1 = imax(c1, hp + k * e1); c2 = imax(c2, hp + k * e2); }
+    }
+    d.fc_row = i; d.fc_hi = j;
+}
+// F1 (which = 0) / F2 (which = 1) of the cached row at column k (out-of-band -> inf_min, like every plane)
+HD int row_f(const DpState &d, int inf_min, int which, int k) {
+    const int beg = d.info[d.fc_row].beg;
+    if (k < beg || k > d.fc_hi) return inf_min;
+    return d.fc[which * d.fc_cap + k];
 }
 
 HD void push_cigar(DpState &d, Graph &g, int op, int len, int node_id, int query_id) {   // abpoa_push_cigar, abpoa_align.h:58-78
@@ -338,7 +412,8 @@ HD void dp_best_cell(const Graph &g, const RowTables &rt, DpState &d, const PoaP
 // put_gap_at_end = 0: op priority M over predecessors in stored order, then E1/E2 per predecessor, then F1, F2,
 // then M again; cur_op carries which gap state the walk is in. Moves (i, j), returns the cigar op (node `id`,
 // query index j_before - 1) or -1 when no op explains the cell (the reference aborts, :448).
-HD int backtrack_step(const Graph &g, const RowTables &rt, const DpState &d, const PoaParams &P, const uint8_t *q,
+template <bool WARP>
+HD int backtrack_step(const Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L,
                       int &i, int &j, int &cur_op) {
     const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int s = P.mat[5 * row_base(rt, i) + q[j - 1]];
@@ -370,18 +445,19 @@ HD int backtrack_step(const Graph &g, const RowTables &rt, const DpState &d, con
     }
     if (cur_op & OP_F) {
         bool hit = false;
+        row_f_cache<WARP>(rt, d, P, q, L, i, j);            // F1 / F2 of row i up to column j (not stored by the sweep)
         if (cur_op & OP_F1) {
-            const int f = plane_cell(d, inf, i, 3, j);
+            const int f = row_f(d, inf, 0, j);
             if (!(cur_op & OP_M) || hij == f) {
                 if (plane_cell(d, inf, i, 0, j - 1) - oe1 == f) { cur_op = OP_M | OP_E; hit = true; }
-                else if (plane_cell(d, inf, i, 3, j - 1) - e1 == f) { cur_op = OP_F1; hit = true; }
+                else if (row_f(d, inf, 0, j - 1) - e1 == f) { cur_op = OP_F1; hit = true; }
             }
         }
         if (!hit && (cur_op & OP_F2)) {
-            const int f = plane_cell(d, inf, i, 4, j);
+            const int f = row_f(d, inf, 1, j);
             if (!(cur_op & OP_M) || hij == f) {
                 if (plane_cell(d, inf, i, 0, j - 1) - oe2 == f) { cur_op = OP_M | OP_E; hit = true; }
-                else if (plane_cell(d, inf, i, 4, j - 1) - e2 == f) { cur_op = OP_F2; hit = true; }
+                else if (row_f(d, inf, 1, j - 1) - e2 == f) { cur_op = OP_F2; hit = true; }
             }
         }
         if (hit) { --j; return CINS; }
@@ -392,12 +468,12 @@ HD int backtrack_step(const Graph &g, const RowTables &rt, const DpState &d, con
 
 // simd_abpoa_cg_backtrack (abpoa_align_simd.c:309-458), serial form. Emits the graph cigar in forward order.
 HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
-    d.n_cigar = 0;
+    d.n_cigar = 0; d.fc_row = -1; d.fc_hi = -1;
     int i = d.best_i, j = d.best_j, cur_op = OP_ALL;
     if (j < L) push_cigar(d, g, CINS, L - j, -1, L - 1);
     while (i > 0 && j > 0 && !g.err) {
         const int id = g.index_to_node[i], jq = j - 1;
-        const int op = backtrack_step(g, rt, d, P, q, i, j, cur_op);
+        const int op = backtrack_step<false>(g, rt, d, P, q, L, i, j, cur_op);
         if (op < 0) {
 #if defined(__CUDA_ARCH__)
             printf("barb200: backtrack stuck at row %d col %d cur_op %d (band %d..%d, H %d) best %d,%d n_cigar %d\n", i, j, cur_op,

@@ -20,9 +20,10 @@
 //     maximum by the substitution A[k] = H'[k] - oe + (k+1)*e  =>  F[j] = max_{k<j} A[k] - j*e: 16 serial cells per
 //     thread, a warp shuffle scan over the 32 thread aggregates, a redux over the warp aggregates staged in
 //     shared memory;
-//   * all five int32 planes (H, E1, E2, F1, F2) of the row's band are written once for the traceback, in a
-//     thread-blocked layout (poa_types.h: DpState) that makes every 16-byte store of a warp one contiguous 512 B
-//     run: 20 B/cell of HBM write traffic is the kernel's only DRAM stream;
+//   * per cell the sweep writes 8 bytes for the traceback and for later rows -- H (int32) and the two E values as 16-bit
+//     distances below H; F1 / F2 are not stored, the traceback recomputes the few row prefixes it needs
+//     (poa_types.h: DpState) -- in a thread-blocked layout that makes the 256-bit stores of a warp one contiguous run:
+//     8 B/cell of HBM write traffic (the reference streams five int32 planes, 20 B/cell) is the kernel's only DRAM stream;
 //   * two block barriers per row.
 // Integer DP: no tensor cores. int32 everywhere with the reference's own "minus infinity" so that finite cells
 // are bit-identical to abPOA's AVX2 path.
@@ -89,34 +90,31 @@ __device__ __forceinline__ void row_pass2(int (&H)[CPT], int (&E1)[CPT], int (&E
     // (256-bit stores of whole 32-byte sectors: 128-bit halves cost ~20 % of the kernel's throughput in L2 write merging)
 #pragma unroll
     for (int oc = 0; oc < 2; ++oc) {
-        int f1[8], f2[8];
+        int dd[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = oc * 8 + u, u1 = je1 + e * e1, u2 = je2 + e * e2;
-            f1[u] = P1 - o1 - u1; f2[u] = P2 - o2 - u2;                  // F[j] = max_{k<j} A'[k] - o - j*e
+            const int f1 = P1 - o1 - u1, f2 = P2 - o2 - u2;                // F[j] = max_{k<j} A'[k] - o - j*e (used, not stored)
             P1 = __viaddmax_s32(H[e], u1, P1); P2 = __viaddmax_s32(H[e], u2, P2);
-            int h = __vimax3_s32(H[e], f1[u], f2[u]);                    // :1067
-            int x1 = __viaddmax_s32(E1[e], -e1, h - oe1);                // E for the next rows, :1070-1071
+            int h = __vimax3_s32(H[e], f1, f2);                            // :1067
+            int x1 = __viaddmax_s32(E1[e], -e1, h - oe1);                  // E for the next rows, :1070-1071
             int x2 = __viaddmax_s32(E2[e], -e2, h - oe2);
             if (MODE == 1) {
                 const bool inb = (unsigned)(j0 + e - beg) <= (unsigned)(end - beg);
-                h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG; f1[u] = inb ? f1[u] : NEG; f2[u] = inb ? f2[u] : NEG;
+                h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG;
             } else if (MODE == 2) {
                 const bool inb = j0 + e <= end;
                 h = inb ? h : NEG; x1 = inb ? x1 : NEG; x2 = inb ? x2 : NEG;
             }
             H[e] = h; E1[e] = x1; E2[e] = x2;
+            dd[u] = (h - x1) | ((h - x2) << 16);                           // e <= H - E' <= oe < 65535 (0 outside the band)
             tmax = max(tmax, h);
         }
-        st8(tp + 3 * CPT + oc * 8, f1[0], f1[1], f1[2], f1[3], f1[4], f1[5], f1[6], f1[7]);
-        st8(tp + 4 * CPT + oc * 8, f2[0], f2[1], f2[2], f2[3], f2[4], f2[5], f2[6], f2[7]);
+        st8(tp + CPT + oc * 8, dd[0], dd[1], dd[2], dd[3], dd[4], dd[5], dd[6], dd[7]);
     }
 #pragma unroll
-    for (int oc = 0; oc < 2; ++oc) {
+    for (int oc = 0; oc < 2; ++oc)
         st8(tp + oc * 8, H[oc * 8], H[oc * 8 + 1], H[oc * 8 + 2], H[oc * 8 + 3], H[oc * 8 + 4], H[oc * 8 + 5], H[oc * 8 + 6], H[oc * 8 + 7]);
-        st8(tp + CPT + oc * 8, E1[oc * 8], E1[oc * 8 + 1], E1[oc * 8 + 2], E1[oc * 8 + 3], E1[oc * 8 + 4], E1[oc * 8 + 5], E1[oc * 8 + 6], E1[oc * 8 + 7]);
-        st8(tp + 2 * CPT + oc * 8, E2[oc * 8], E2[oc * 8 + 1], E2[oc * 8 + 2], E2[oc * 8 + 3], E2[oc * 8 + 4], E2[oc * 8 + 5], E2[oc * 8 + 6], E2[oc * 8 + 7]);
-    }
 }
 
 // left/right-most column of the thread's cells that attain v (only in-band cells count)
@@ -179,21 +177,18 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
         prev_active = tid < nT;
         if (prev_active) {
             int *tp = planes + tid * TB;
-            int f1[CPT], f2[CPT];
+            int dd[CPT];
 #pragma unroll
             for (int e = 0; e < CPT; ++e) {
                 const int j = j0 + e;
-                if (j == 0) { H[e] = 0; E1[e] = -oe1; E2[e] = -oe2; f1[e] = NEG; f2[e] = NEG; }
-                else if (j <= prev_end) { f1[e] = -P.o1 - e1 * j; f2[e] = -P.o2 - e2 * j; H[e] = max(f1[e], f2[e]); E1[e] = NEG; E2[e] = NEG; }
-                else { H[e] = E1[e] = E2[e] = f1[e] = f2[e] = NEG; }
+                if (j == 0) { H[e] = 0; E1[e] = -oe1; E2[e] = -oe2; dd[e] = oe1 | (oe2 << 16); }
+                else if (j <= prev_end) { H[e] = max(-P.o1 - e1 * j, -P.o2 - e2 * j); E1[e] = NEG; E2[e] = NEG; dd[e] = E_NEG16 | (E_NEG16 << 16); }
+                else { H[e] = E1[e] = E2[e] = NEG; dd[e] = 0; }
             }
 #pragma unroll
             for (int oc = 0; oc < 2; ++oc) {
                 st8(tp + oc * 8, H[oc * 8], H[oc * 8 + 1], H[oc * 8 + 2], H[oc * 8 + 3], H[oc * 8 + 4], H[oc * 8 + 5], H[oc * 8 + 6], H[oc * 8 + 7]);
-                st8(tp + CPT + oc * 8, E1[oc * 8], E1[oc * 8 + 1], E1[oc * 8 + 2], E1[oc * 8 + 3], E1[oc * 8 + 4], E1[oc * 8 + 5], E1[oc * 8 + 6], E1[oc * 8 + 7]);
-                st8(tp + 2 * CPT + oc * 8, E2[oc * 8], E2[oc * 8 + 1], E2[oc * 8 + 2], E2[oc * 8 + 3], E2[oc * 8 + 4], E2[oc * 8 + 5], E2[oc * 8 + 6], E2[oc * 8 + 7]);
-                st8(tp + 3 * CPT + oc * 8, f1[oc * 8], f1[oc * 8 + 1], f1[oc * 8 + 2], f1[oc * 8 + 3], f1[oc * 8 + 4], f1[oc * 8 + 5], f1[oc * 8 + 6], f1[oc * 8 + 7]);
-                st8(tp + 4 * CPT + oc * 8, f2[oc * 8], f2[oc * 8 + 1], f2[oc * 8 + 2], f2[oc * 8 + 3], f2[oc * 8 + 4], f2[oc * 8 + 5], f2[oc * 8 + 6], f2[oc * 8 + 7]);
+                st8(tp + CPT + oc * 8, dd[oc * 8], dd[oc * 8 + 1], dd[oc * 8 + 2], dd[oc * 8 + 3], dd[oc * 8 + 4], dd[oc * 8 + 5], dd[oc * 8 + 6], dd[oc * 8 + 7]);
             }
         } else {
 #pragma unroll
@@ -266,12 +261,13 @@ __device__ long long dp_sweep(KShared &S, const BatchArgs &A, const uint8_t *__r
                 if (ptt >= 0 && ptt < pnT) {
 #pragma unroll
                     for (int oc = 0; oc < 2; ++oc) {
-                        const int8v h = ld8cg(Hp + oc * 8), a = ld8cg(Hp + CPT + oc * 8), c = ld8cg(Hp + 2 * CPT + oc * 8);
+                        const int8v h = ld8cg(Hp + oc * 8), dv = ld8cg(Hp + CPT + oc * 8);
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int e = oc * 8 + u;
+                            const int c1 = dv.v[u] & 0xffff, c2 = (int)((unsigned)dv.v[u] >> 16);
                             if (e + 1 < CPT) H[e + 1] = max(H[e + 1], h.v[u]);
-                            E1[e] = max(E1[e], a.v[u]); E2[e] = max(E2[e], c.v[u]);
+                            E1[e] = max(E1[e], c1 == E_NEG16 ? NEG : h.v[u] - c1); E2[e] = max(E2[e], c2 == E_NEG16 ? NEG : h.v[u] - c2);
                         }
                     }
                 }
@@ -348,6 +344,7 @@ __device__ __forceinline__ void carve(KShared &S, const BatchArgs &A, int slot) 
     d.planes = A.planes + (int64_t)slot * Y.plane_cap; d.plane_cap = Y.plane_cap;
     d.row_off = (int64_t *)(b + Y.o_row_off); d.info = (RowInfo *)(b + Y.o_row_info);
     d.cigar = (uint64_t *)(b + Y.o_cigar); d.cigar_cap = Y.cigar_cap; d.n_cigar = 0;
+    d.fc = (int *)(b + Y.o_fc); d.fc_cap = Y.fc_cap; d.fc_row = -1; d.fc_hi = -1;
 }
 
 #define PHASE_TICK(ph) do { if (A.phase_clk && threadIdx.x == 0) { unsigned long long _n = clock64(); A.phase_clk[(size_t)blockIdx.x * PH_N + (ph)] += _n - t_last; t_last = _n; } } while (0)

@@ -7,13 +7,13 @@ namespace barb200 {
 // Byte offsets of every per-slot array from the slot base (computed once per batch on the host).
 struct SlotLayout {
     int64_t slot_bytes;
-    int node_cap, in_pool, out_pool, W, cigar_cap;
+    int node_cap, in_pool, out_pool, W, cigar_cap, fc_cap;
     int64_t plane_cap;   // ints per slot
     int64_t o_base, o_aln_n, o_aln_id, o_in_off, o_in_n, o_in_cap, o_out_off, o_out_n, o_out_cap;
     int64_t o_in_id, o_in_w, o_out_id, o_out_w, o_out_rid;
     int64_t o_index_to_node, o_node_to_index, o_remain, o_msa_rank, o_tmp0, o_tmp1;
     int64_t o_row_rec, o_pre_row;
-    int64_t o_row_off, o_row_info, o_cigar;
+    int64_t o_row_off, o_row_info, o_cigar, o_fc;
 };
 
 enum { PH_DP = 0, PH_BACKTRACK = 1, PH_FUSE = 2, PH_TOPO = 3, PH_MSA = 4, PH_TOTAL = 5, PH_N = 8 };

@@ -99,26 +99,41 @@ struct alignas(16) RowInfo {
 // Column ownership is fixed: thread t of the CTA owns columns [CPT*t, CPT*t + CPT) of EVERY row, so the values of the
 // previous row stay in that thread's registers. A row with band [beg, end] is stored for the threads
 // t0 = beg/CPT .. t1 = end/CPT only (nT = t1-t0+1), at planes + row_off[r], "thread-major": thread t's block of
-// 5*CPT ints = [H(16) | E1(16) | E2(16) | F1(16) | F2(16)] sits at int offset (t-t0)*5*CPT. A thread therefore writes its
-// 320 bytes of a row with ten 256-bit stores at immediate offsets from one pointer (full 32 B sectors; a warp covers one
-// contiguous 10 KB run), and reads a far predecessor's H/E1/E2 for its own columns with six 256-bit loads.
-// Cells of the stored threads outside [beg, end] hold inf_min.
+// TB = 2*CPT ints = [H(16) | D(16)] sits at int offset (t-t0)*TB; a thread writes its 128 bytes of a row with four
+// 256-bit stores at immediate offsets from one pointer (full 32 B sectors; a warp covers one contiguous 4 KB run).
+//
+// What is stored, and why it is enough for the reference's traceback (abpoa_align_simd.c:309-458) -- 8 bytes per cell
+// instead of the reference's five int32 planes (20 bytes):
+//   H  the cell score, int32.
+//   D  the two E values kept for later rows, as 16-bit DISTANCES below H: D = (H - E1) | (H - E2) << 16. For every row but
+//      the first, E' = max(E_in - e, H - oe) with E_in <= H, so e <= H - E' <= oe: exact in 16 bits for any gap open + extend
+//      below 65535 (barb200_create checks). 0xffff encodes "minus infinity" (row 0, where E does not derive from H);
+//      cells outside the band hold H = inf_min, D = 0.
+//   F1 / F2 are NOT stored: the traceback reads them only at the few cells where an insertion starts or continues, and they
+//      are a pure function of the row's H' = max(M + s, E1, E2), which the predecessor rows' H / D give back; the
+//      traceback recomputes the row prefix it needs (poa_graph.cuh: row_f_cache).
 constexpr int CPT = 16;
+constexpr int E_NEG16 = 0xffff;
 struct DpState {
     int *planes; int64_t plane_cap;     // ints
     int64_t *row_off;                   // [node_cap]
     RowInfo *info;                      // [node_cap]
     uint64_t *cigar; int n_cigar, cigar_cap;
     int best_i, best_j, best_score;
+    int *fc;                            // [2 * fc_cap] F1 / F2 of the cached row prefix (traceback scratch)
+    int fc_cap, fc_row, fc_hi;          // columns per plane; cached row (-1: none) and its highest computed column
 };
 
-// int offset of column j of `plane` inside the row's block (see DpState); j must lie in a stored thread's range
-constexpr int TB = 5 * CPT;   // ints per thread block of a row
+// int offset of column j of `plane` (0: H, 1: D) inside the row's block (see DpState); j must lie in a stored thread's range
+constexpr int TB = 2 * CPT;   // ints per thread block of a row
 HD int64_t plane_index(int beg, int end, int plane, int j) {
     (void)end;
     return (int64_t)(j / CPT - beg / CPT) * TB + plane * CPT + j % CPT;
 }
-HD int64_t row_ints(int beg, int end) { return 5LL * (end / CPT - beg / CPT + 1) * CPT; }
+HD int64_t row_ints(int beg, int end) { return (int64_t)TB * (end / CPT - beg / CPT + 1); }
+// E value from H and its 16-bit distance code
+HD int e_decode(int h, int code, int inf_min) { return code == E_NEG16 ? inf_min : h - code; }
+HD int e_encode(int h, int e) { const int d = h - e; return (d >= 0 && d < E_NEG16) ? d : E_NEG16; }
 
 HD int imax(int a, int b) { return a > b ? a : b; }
 HD int imin(int a, int b) { return a < b ? a : b; }

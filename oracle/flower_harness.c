@@ -1,0 +1,203 @@
+/*
+ * flower_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Drives the reference's FLOWER-level BAR code -- make_flower_alignment_poa (bar/impl/poaBarAligner.c:1115-1237),
+ * stPinchIterator_constructFromAlignedBlocks (:1291-1299) and bar() itself (bar/impl/bar.c:52-176) -- on flowers described
+ * by flat arrays, and returns what they produce as a flat int64 stream, so that tests/ can require the SAME ordered
+ * AlignmentBlock / stPinch streams and the same post-BAR flower from
+ *     oracle/_ref/libflower_ref.so   the unmodified reference objects, and
+ *     oracle/_ref/libflower_shim.so  the same objects with shim/cactus_bar_shim.c (+ pecan shim) linked in place of the
+ *                                    reference's definitions (the CACTUS_BAR_B200 build of INTEGRATION.md).
+ * Both libraries are built by oracle/Makefile from the sources where they lie under /root/reference.
+ *
+ * cactusParams_get_* are supplied here from a key/value table (the reference's cactus_params_parser.c needs libxml2, which this
+ * image lacks): keys are the XML path below <cactusWorkflowConfig>, e.g. "bar/poa/partialOrderAlignmentWindow".
+ *
+ * A flower is described the way bar/tests/flowersShared.h builds one: sequences, stub ends (with a side), and adjacencies --
+ * each a pair of caps on one sequence at coordinates lo < hi, on the side-0 view of end A and the side-1 view of end B, in the
+ * positive-strand (caps at lo / hi, strand 1) or negative-strand (caps at hi / lo, strand 0) representation.
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "cactus.h"
+#include "sonLib.h"
+#include "poaBarAligner.h"
+#include "stCaf.h"
+#include "stPinchIterator.h"
+
+void bar(stList *flowers, CactusParams *params, CactusDisk *cactusDisk, stList *listOfEndAlignmentFiles);
+
+/* ---- parameter table ------------------------------------------------------------------------------------------------ */
+#define MAX_PARAMS 512
+static struct { char *key, *val; } g_tab[MAX_PARAMS];
+static int g_tab_n = 0;
+
+void flower_harness_clear_params(void) {
+    for (int i = 0; i < g_tab_n; ++i) { free(g_tab[i].key); free(g_tab[i].val); }
+    g_tab_n = 0;
+}
+void flower_harness_set_param(const char *path, const char *value) {
+    for (int i = 0; i < g_tab_n; ++i)
+        if (strcmp(g_tab[i].key, path) == 0) { free(g_tab[i].val); g_tab[i].val = strdup(value); return; }
+    if (g_tab_n == MAX_PARAMS) { fprintf(stderr, "flower_harness: parameter table full\n"); exit(1); }
+    g_tab[g_tab_n].key = strdup(path); g_tab[g_tab_n].val = strdup(value); ++g_tab_n;
+}
+static const char *lookup(int num, va_list ap) {
+    char path[512]; path[0] = 0;
+    for (int i = 0; i < num; ++i) { if (i) strcat(path, "/"); strncat(path, va_arg(ap, const char *), 200); }
+    for (int i = 0; i < g_tab_n; ++i) if (strcmp(g_tab[i].key, path) == 0) return g_tab[i].val;
+    fprintf(stderr, "flower_harness: parameter %s not set\n", path);
+    exit(1);
+}
+char *cactusParams_get_string(CactusParams *p, int num, ...) { va_list ap; va_start(ap, num); const char *v = lookup(num, ap); va_end(ap); return stString_copy(v); }
+int64_t cactusParams_get_int(CactusParams *p, int num, ...) { va_list ap; va_start(ap, num); const char *v = lookup(num, ap); va_end(ap); return atoll(v); }
+double cactusParams_get_float(CactusParams *p, int num, ...) { va_list ap; va_start(ap, num); const char *v = lookup(num, ap); va_end(ap); return atof(v); }
+int64_t *cactusParams_get_ints(CactusParams *p, int64_t *length, int num, ...) {
+    va_list ap; va_start(ap, num); const char *v = lookup(num, ap); va_end(ap);
+    char *c = stString_copy(v); int64_t n = 0, cap = 8, *out = st_malloc(sizeof(int64_t) * cap);
+    for (char *t = strtok(c, " "); t; t = strtok(NULL, " ")) { if (n == cap) { cap *= 2; out = realloc(out, sizeof(int64_t) * cap); } out[n++] = atoll(t); }
+    free(c); *length = n; return out;
+}
+void cactusParams_set_root(CactusParams *p, int num, ...) { (void)p; (void)num; }
+CactusParams *cactusParams_load(char *file_name) { (void)file_name; return NULL; }
+void cactusParams_destruct(CactusParams *p) { (void)p; }
+
+/* ---- output stream -------------------------------------------------------------------------------------------------- */
+typedef struct { int64_t *w; size_t n, cap; } wbuf;
+static void push(wbuf *b, int64_t v) {
+    if (b->n == b->cap) { b->cap = b->cap ? 2 * b->cap : 1024; b->w = realloc(b->w, sizeof(int64_t) * b->cap); }
+    b->w[b->n++] = v;
+}
+
+/* ---- the flower ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    CactusDisk *disk; Flower *flower; EventTree *eventTree;
+    int64_t n_seq, n_caps;
+    Sequence **seqs; Name *seq_names;
+    Name *cap_names;            /* [2 * n_adj]: cap A of adjacency i at 2i, cap B at 2i+1 */
+} built;
+
+static End *view(End *end, int side) { return (end_getSide(end) ? 1 : 0) == side ? end : end_getReverse(end); }
+
+static void build(built *B, int64_t n_events, int64_t n_seq, const char **seqs, const int *seq_event, int64_t n_ends, const int *end_side,
+                  int64_t n_adj, const int64_t *adj) {
+    B->disk = cactusDisk_construct();
+    B->eventTree = eventTree_construct2(B->disk);
+    B->flower = flower_construct(B->disk);
+    group_construct2(B->flower);                      /* stCaf_setup expects a leaf group (caf/tests/filteringTest.c:71) */
+    Event *root = eventTree_getRootEvent(B->eventTree);
+    Event *anc = event_construct3("ANC", 0.1, root, B->eventTree);
+    Event **leaves = st_malloc(sizeof(Event *) * (n_events > 0 ? n_events : 1));
+    for (int64_t i = 0; i < n_events; ++i) { char h[32]; sprintf(h, "LEAF%d", (int)i); leaves[i] = event_construct3(h, 0.1, anc, B->eventTree); }
+    B->n_seq = n_seq; B->seqs = st_malloc(sizeof(Sequence *) * n_seq); B->seq_names = st_malloc(sizeof(Name) * n_seq);
+    for (int64_t i = 0; i < n_seq; ++i) {
+        char h[32]; sprintf(h, ">s%d", (int)i);
+        B->seqs[i] = sequence_construct(1, (int64_t)strlen(seqs[i]), seqs[i], h, leaves[seq_event[i]], B->disk);
+        flower_addSequence(B->flower, B->seqs[i]);
+        B->seq_names[i] = sequence_getName(B->seqs[i]);
+    }
+    End **ends = st_malloc(sizeof(End *) * n_ends);
+    for (int64_t i = 0; i < n_ends; ++i) ends[i] = end_construct2(end_side[i] != 0, 1, B->flower);
+    B->n_caps = 2 * n_adj; B->cap_names = st_malloc(sizeof(Name) * (B->n_caps > 0 ? B->n_caps : 1));
+    for (int64_t i = 0; i < n_adj; ++i) {
+        const int64_t *a = adj + 6 * i;           /* seq, lo, hi, positive representation?, end A, end B */
+        Sequence *s = B->seqs[a[0]];
+        Cap *ca, *cb;
+        if (a[3]) { ca = cap_construct2(view(ends[a[4]], 0), a[1], 1, s); cb = cap_construct2(view(ends[a[5]], 1), a[2], 1, s); }
+        else { ca = cap_construct2(view(ends[a[4]], 0), a[2], 0, s); cb = cap_construct2(view(ends[a[5]], 1), a[1], 0, s); }
+        cap_makeAdjacent(ca, cb);
+        B->cap_names[2 * i] = cap_getName(ca); B->cap_names[2 * i + 1] = cap_getName(cb);
+    }
+    free(ends); free(leaves);
+}
+static int64_t cap_index(built *B, Name n) { for (int64_t i = 0; i < B->n_caps; ++i) if (B->cap_names[i] == n) return i; return -1; }
+static int64_t seq_index(built *B, Name n) { for (int64_t i = 0; i < B->n_seq; ++i) if (B->seq_names[i] == n) return i; return -1; }
+
+static void dump_flower(built *B, Flower *f, wbuf *o, int depth) {
+    push(o, -7000 - depth); push(o, flower_getEndNumber(f)); push(o, flower_getBlockNumber(f)); push(o, flower_getGroupNumber(f)); push(o, flower_getChainNumber(f));
+    Flower_EndIterator *eit = flower_getEndIterator(f); End *e;
+    while ((e = flower_getNextEnd(eit)) != NULL) {
+        push(o, end_isBlockEnd(e)); push(o, end_getSide(e)); push(o, end_isAttached(e)); push(o, end_getInstanceNumber(e));
+        End_InstanceIterator *cit = end_getInstanceIterator(e); Cap *c;
+        while ((c = end_getNext(cit)) != NULL) {
+            Sequence *s = cap_getSequence(c);
+            push(o, s ? seq_index(B, sequence_getName(s)) : -1); push(o, s ? cap_getCoordinate(c) : -1); push(o, s ? cap_getStrand(c) : -1); push(o, cap_getSide(c));
+        }
+        end_destructInstanceIterator(cit);
+        if (end_isBlockEnd(e) && end_getSide(e)) {
+            Block *b = end_getBlock(e);
+            push(o, block_getLength(b)); push(o, block_getInstanceNumber(b));
+            Block_InstanceIterator *sit = block_getInstanceIterator(b); Segment *sg;
+            while ((sg = block_getNext(sit)) != NULL) {
+                Sequence *s = segment_getSequence(sg);
+                push(o, s ? seq_index(B, sequence_getName(s)) : -1); push(o, s ? segment_getStart(sg) : -1); push(o, s ? segment_getStrand(sg) : -1); push(o, segment_getLength(sg));
+            }
+            block_destructInstanceIterator(sit);
+        }
+    }
+    flower_destructEndIterator(eit);
+    Flower_GroupIterator *git = flower_getGroupIterator(f); Group *g;
+    while ((g = flower_getNextGroup(git)) != NULL) {
+        push(o, group_isLeaf(g)); push(o, group_getEndNumber(g));
+        if (!group_isLeaf(g)) dump_flower(B, group_getNestedFlower(g), o, depth + 1);
+    }
+    flower_destructGroupIterator(git);
+}
+
+/*
+ * mode 0: make_flower_alignment_poa + stPinchIterator_constructFromAlignedBlocks. Stream:
+ *         n_blocks, then per block: chain length c and c x (cap index, position, strand, length);
+ *         n_pinches, then per pinch: cap index 1, cap index 2, start1, start2, length, strand.
+ *         The POA parameters come from abpoaParamaters_constructFromCactusParams, i.e. the "bar/poa/..." table entries;
+ *         max_seq_length / window / mask_filter / max_prog_rows / max_prog_length_diff from the "bar/..." entries bar() reads.
+ * mode 1: bar() on the one-flower list (bar.c:52-176: alignment, pinch iterator, stCaf_setup / anneal / melt / finish), then a
+ *         recursive dump of the resulting flower hierarchy (ends, caps, blocks and their segments, groups).
+ * Returns a malloc'd stream (*n_words long); release with flower_harness_free.
+ */
+int64_t *flower_harness_run(int mode, int64_t n_events, int64_t n_seq, const char **seqs, const int *seq_event, int64_t n_ends,
+                            const int *end_side, int64_t n_adj, const int64_t *adj, int64_t *n_words) {
+    built B; memset(&B, 0, sizeof(B));
+    build(&B, n_events, n_seq, seqs, seq_event, n_ends, end_side, n_adj, adj);
+    wbuf o = {0, 0, 0};
+    if (mode == 0) {
+        abpoa_para_t *abpt = abpoaParamaters_constructFromCactusParams(NULL);
+        stList *blocks = make_flower_alignment_poa(B.flower, cactusParams_get_int(NULL, 2, "bar", "bandingLimit"),
+                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentWindow"),
+                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentMaskFilter"),
+                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxRows"),
+                cactusParams_get_float(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxLengthDiff"), abpt);
+        push(&o, stList_length(blocks));
+        for (int64_t i = 0; i < stList_length(blocks); ++i) {
+            AlignmentBlock *b = stList_get(blocks, i);
+            int64_t c = 0; for (AlignmentBlock *q = b; q; q = q->next) ++c;
+            push(&o, c);
+            for (AlignmentBlock *q = b; q; q = q->next) { push(&o, cap_index(&B, q->subsequenceIdentifier)); push(&o, q->position); push(&o, q->strand); push(&o, q->length); }
+        }
+        stPinchIterator *it = stPinchIterator_constructFromAlignedBlocks(blocks);
+        stPinchIterator_reset(it);
+        size_t at = o.n; push(&o, 0);
+        stPinch *pinch, fill; int64_t np = 0;
+        while ((pinch = stPinchIterator_getNext(it, &fill)) != NULL) {
+            push(&o, cap_index(&B, pinch->name1)); push(&o, cap_index(&B, pinch->name2)); push(&o, pinch->start1); push(&o, pinch->start2);
+            push(&o, pinch->length); push(&o, pinch->strand); ++np;
+        }
+        o.w[at] = np;
+        stPinchIterator_destruct(it);
+        stList_destruct(blocks);
+        abpoa_free_para(abpt);
+    } else {
+        stList *flowers = stList_construct();
+        stList_append(flowers, B.flower);
+        bar(flowers, NULL, B.disk, NULL);
+        stList_destruct(flowers);
+        dump_flower(&B, B.flower, &o, 0);
+    }
+    cactusDisk_destruct(B.disk);
+    free(B.seqs); free(B.seq_names); free(B.cap_names);
+    *n_words = (int64_t)o.n;
+    return o.w;
+}
+
+void flower_harness_free(void *p) { free(p); }

@@ -58,8 +58,12 @@ static long long emulate_sweep(const Graph &g, const RowTables &rt, DpState &d, 
                     if (h > tmax) { tmax = h; tl = tr = j; } else if (h == tmax) tr = j;
                 }
             }
-            rowp[plane_index(beg, end, 0, j)] = h; rowp[plane_index(beg, end, 1, j)] = x1; rowp[plane_index(beg, end, 2, j)] = x2;
-            rowp[plane_index(beg, end, 3, j)] = f1; rowp[plane_index(beg, end, 4, j)] = f2;
+            // the sweep's plane layout: H and the two E values as 16-bit distances below H (poa_types.h); F is not stored.
+            // In-band cells of rows >= 1 must encode exactly (e <= H - E' <= oe), which this emulation asserts.
+            const int c1 = e_encode(h, x1), c2 = e_encode(h, x2);
+            if (r > 0 && j >= beg && j <= end && (e_decode(h, c1, NEG) != x1 || e_decode(h, c2, NEG) != x2)) return -2;
+            (void)f1; (void)f2;
+            rowp[plane_index(beg, end, 0, j)] = h; rowp[plane_index(beg, end, 1, j)] = c1 | (c2 << 16);
         }
         RowInfo ri; ri.beg = beg; ri.end = end; ri.left = r == 0 ? 0 : tl; ri.right = r == 0 ? 0 : tr;
         d.info[r] = ri; d.row_off[r] = cur_off;
@@ -134,7 +138,8 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
     std::vector<RowRec> rrec(N); std::vector<RowInfo> rinfo(N);
     std::vector<uint64_t> rid((size_t)EP * W), cigar(maxl + N + 16);
     std::vector<int64_t> row_off(N);
-    const int64_t plane_cap = (int64_t)N * 5 * (maxl + 2 * CPT);
+    const int64_t plane_cap = (int64_t)N * (TB / CPT) * (maxl + 2 * CPT);
+    std::vector<int> fcache(2 * (size_t)(maxl + 2));
     std::vector<int> planes((size_t)std::min<int64_t>(plane_cap, (int64_t)1 << 31));
     g.node_cap = N; g.in_pool = EP; g.out_pool = EP;
     g.base = base.data(); g.aln_n = aln_n.data(); g.aln_id = aln_id.data(); g.in_off = in_off.data(); g.in_n = in_n.data(); g.in_cap = in_cap.data();
@@ -144,6 +149,7 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
     rt.rec = rrec.data(); rt.pre_row = pre_row.data();
     d.planes = planes.data(); d.plane_cap = (int64_t)planes.size(); d.row_off = row_off.data(); d.info = rinfo.data();
     d.cigar = cigar.data(); d.cigar_cap = (int)cigar.size(); d.n_cigar = 0;
+    d.fc = fcache.data(); d.fc_cap = maxl + 2; d.fc_row = -1; d.fc_hi = -1;
     graph_reset(g, n_seq);
     std::vector<int64_t> w;
     w.push_back(n_seq); w.push_back(0); w.push_back(0);
@@ -155,7 +161,7 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
         if (a == 0) graph_add_first_sequence(g, q, L, read);
         else {
             long long c = emulate_sweep(g, rt, d, P, q, L);
-            if (c < 0) { g.err = JOB_ERR_PLANE_CAP; break; }
+            if (c < 0) { g.err = c == -2 ? JOB_ERR_BACKTRACK : JOB_ERR_PLANE_CAP; break; }
             cells += c; n_rows = node_n - 1;
             dp_best_cell(g, rt, d, P, L); dp_backtrack(g, rt, d, P, q, L);
         }
