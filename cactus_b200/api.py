@@ -34,7 +34,8 @@ class _CParams(C.Structure):
                 ("gap_ext2", C.c_int), ("wb", C.c_int), ("wf", C.c_float), ("k", C.c_int), ("w", C.c_int),
                 ("min_w", C.c_int), ("progressive_poa", C.c_int), ("disable_seeding", C.c_int), ("device", C.c_int),
                 ("threads_per_block", C.c_int), ("ctas_per_sm", C.c_int), ("mem_fraction", C.c_double),
-                ("host_threads", C.c_int), ("collect_phase_clocks", C.c_int)]
+                ("host_threads", C.c_int), ("collect_phase_clocks", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * 8),
+                ("lanes", C.c_int)]
 
 
 class _CPecanParams(C.Structure):
@@ -89,6 +90,16 @@ def load_library():
     lib.barb200_msa_make_partial_order_alignment.restype = C.POINTER(_CMsa)
     lib.barb200_make_consistent_partial_order_alignments.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, C.c_double]
     lib.barb200_make_consistent_partial_order_alignments.restype = C.POINTER(C.POINTER(_CMsa))
+    lib.barb200_stage_buckets.argtypes = [vp, vp, ci]
+    lib.barb200_stage_buckets.restype = ci
+    lib.barb200_flower_submit.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, C.c_double]
+    lib.barb200_flower_submit.restype = vp
+    lib.barb200_flower_wait.argtypes = [vp, vp]
+    lib.barb200_flower_wait.restype = C.POINTER(C.POINTER(_CMsa))
+    lib.barb200_queue_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.barb200_queue_stats.restype = ci
+    lib.barb200_device_count.argtypes = [vp]
+    lib.barb200_device_count.restype = ci
     lib.barb200_device_info.argtypes = [vp, C.POINTER(ci), C.POINTER(i64), C.POINTER(i64), C.c_char_p, ci]
     lib.barb200_device_info.restype = ci
     lib.barb200_free.argtypes = [vp]
@@ -142,7 +153,7 @@ class PoaParams:
                  partialOrderAlignmentMinimizerK=15, partialOrderAlignmentMinimizerW=5,
                  partialOrderAlignmentMinimizerMinW=500, partialOrderAlignmentProgressiveMode=1,
                  device=0, threads_per_block=0, ctas_per_sm=0, mem_fraction=0.0, host_threads=0,
-                 collect_phase_clocks=0):
+                 collect_phase_clocks=0, devices=None, lanes=0):
         mat = partialOrderAlignmentSubMatrix
         if mat is None:
             mat = CACTUS_SUBMAT
@@ -160,6 +171,13 @@ class PoaParams:
         c.progressive_poa, c.disable_seeding = partialOrderAlignmentProgressiveMode, partialOrderAlignmentDisableSeeding
         c.device, c.threads_per_block, c.ctas_per_sm = device, threads_per_block, ctas_per_sm
         c.mem_fraction, c.host_threads, c.collect_phase_clocks = mem_fraction, host_threads, collect_phase_clocks
+        c.lanes = lanes
+        if devices == "all":
+            c.n_devices = -1
+        elif devices:
+            c.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                c.devices[i] = int(d)
         self.c = c
 
 
@@ -283,6 +301,12 @@ class Stage:
 
     def launches(self):
         return int(self.engine.lib.barb200_stage_launches(self.h))
+
+    def buckets(self):
+        """the stage's CTA-size buckets, largest class first: dicts with threads, jobs, ctas, plane_ints"""
+        out = (C.c_int64 * 32)()
+        n = self.engine.lib.barb200_stage_buckets(self.h, out, 8)
+        return [dict(threads=int(out[4 * i]), jobs=int(out[4 * i + 1]), ctas=int(out[4 * i + 2]), plane_ints=int(out[4 * i + 3])) for i in range(n)]
 
     def phase_clocks(self):
         out = (C.c_uint64 * 6)()
@@ -475,6 +499,46 @@ class Engine:
         out = [self._wrap(ms[i]) for i in range(n)]
         self.lib.barb200_free(C.cast(ms, C.c_void_p))
         return out
+
+    # ---- the end queue, asynchronously (barb200_flower_submit / barb200_flower_wait) ---------------------------------
+    def flower_submit(self, end_strings, right_end_indexes=None, right_end_row_indexes=None, overlaps=None,
+                      window_size=10000, max_prog_rows=5000, max_prog_length_diff=1.0):
+        """Enqueue the ends of one flower; returns a ticket for flower_wait. Without the index lists the ends are independent."""
+        t = _StrTable(end_strings)
+        n = len(end_strings)
+        keep = []
+
+        def table(rows):
+            if rows is None:
+                return None
+            arr = (C.c_void_p * max(n, 1))()
+            for i, r in enumerate(rows):
+                a = (C.c_int64 * max(len(r), 1))(*[int(v) for v in r])
+                keep.append(a)
+                arr[i] = C.cast(a, C.c_void_p)
+            return arr
+        h = self.lib.barb200_flower_submit(self.ctx, n, t.seq_no, t.strs, t.lens, table(right_end_indexes), table(right_end_row_indexes),
+                                           table(overlaps), window_size, max_prog_rows, max_prog_length_diff)
+        if not h:
+            raise BarB200Error("flower_submit: %s" % self.lib.barb200_last_error(self.ctx).decode())
+        return (h, n)
+
+    def flower_wait(self, ticket):
+        h, n = ticket
+        ms = self.lib.barb200_flower_wait(self.ctx, h)
+        if not ms:
+            raise BarB200Error("flower_wait: %s" % self.lib.barb200_last_error(self.ctx).decode())
+        out = [self._wrap(ms[i]) for i in range(n)]
+        self.lib.barb200_free(C.cast(ms, C.c_void_p))
+        return out
+
+    def queue_stats(self):
+        b, j = C.c_int64(), C.c_int64()
+        self._check(self.lib.barb200_queue_stats(self.ctx, C.byref(b), C.byref(j)))
+        return {"batches": b.value, "jobs": j.value}
+
+    def device_count(self):
+        return int(self.lib.barb200_device_count(self.ctx))
 
 
 def pecan_band(lx, ly, anchors, expansion=20):

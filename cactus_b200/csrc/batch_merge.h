@@ -1,5 +1,6 @@
-// batch_merge.h -- the two request types that go through GroupCommit (group_commit.h) and how a group of them becomes ONE
+// batch_merge.h -- the pair-HMM request that goes through GroupCommit (group_commit.h) and how a group of them becomes ONE
 // device batch: inputs concatenated (views, nothing is copied but pointers), outputs handed back to their callers.
+// (POA callers go through the end queue instead, end_queue.h.)
 // The device batch itself is a callable (`impl`), so that tests/hosttest can drive this plumbing with a stand-in on the CPU.
 #pragma once
 #include <stdint.h>
@@ -10,37 +11,6 @@
 #include "host_api.h"
 
 namespace barb200 {
-
-// ---- POA: run_jobs(ctx, jobs, results) of concurrent callers (host_bar.cpp issues one per window round) ----------------------
-struct PoaRequest {
-    bool done = false;
-    const std::vector<HostJob> *jobs = nullptr;
-    std::vector<JobResult> *results = nullptr;
-    int rc = 0;
-};
-
-// impl(const std::vector<HostJob> &, std::vector<JobResult> &) -> int
-template <class Impl>
-void run_poa_group(std::vector<PoaRequest *> &batch, Impl impl) {
-    if (batch.size() == 1) { batch[0]->rc = impl(*batch[0]->jobs, *batch[0]->results); return; }
-    std::vector<HostJob> all;
-    for (PoaRequest *q : batch) all.insert(all.end(), q->jobs->begin(), q->jobs->end());
-    std::vector<JobResult> res;
-    const int rc = impl(all, res);
-    if (rc != 0) {
-        // a merged batch failed (one caller's bad input, or the union was too big): every request runs again on its own, so
-        // that only the offending caller sees an error
-        for (PoaRequest *q : batch) q->rc = impl(*q->jobs, *q->results);
-        return;
-    }
-    size_t o = 0;
-    for (PoaRequest *q : batch) {
-        const size_t n = q->jobs->size();
-        q->rc = rc;
-        if (rc == 0) q->results->assign(std::make_move_iterator(res.begin() + o), std::make_move_iterator(res.begin() + o + n));
-        o += n;
-    }
-}
 
 // ---- cPecan: barb200_pecan_aligned_pairs_batch of concurrent callers ---------------------------------------------------------
 struct PecanRequest {

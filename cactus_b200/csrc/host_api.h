@@ -29,13 +29,19 @@ struct JobResult {
     int64_t cells = 0;
 };
 
-// barb200.cu: run a set of jobs on the device (chunked, retried on capacity misses). Returns BARB200_* code.
-int run_jobs(barb200_ctx *ctx, const std::vector<HostJob> &jobs, std::vector<JobResult> &results);
+// barb200.cu: one device batch of host jobs on device lane `lane` (0 .. total_lanes-1; bucketed by CTA class, capacity misses
+// retried with larger slots). Returns a BARB200_* code; the message is get_error(ctx).
+int run_jobs_on_lane(barb200_ctx *ctx, int lane, const std::vector<HostJob> &jobs, std::vector<JobResult> &results);
+int total_lanes(barb200_ctx *ctx);
+void **dispatcher_slot(barb200_ctx *ctx);         // where host_bar.cpp keeps the context's end queue
+void mark_lanes_shared(barb200_ctx *ctx);
+void dispatcher_destroy(barb200_ctx *ctx);
 void set_error(barb200_ctx *ctx, const std::string &msg);
+std::string get_error(barb200_ctx *ctx);
 int host_threads(barb200_ctx *ctx);
 int default_progressive(barb200_ctx *ctx);
 // context facts for the other translation units (pecan.cu)
-std::mutex &device_mutex(barb200_ctx *ctx);    // serialises device batches on one context
+std::mutex &device_mutex(barb200_ctx *ctx);    // serialises the pair-HMM batches on one context
 int ctx_device(barb200_ctx *ctx);
 int ctx_sm_count(barb200_ctx *ctx);
 double ctx_mem_fraction(barb200_ctx *ctx);

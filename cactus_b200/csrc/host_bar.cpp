@@ -1,253 +1,114 @@
-// host_bar.cpp -- host-side mirror of the MSA-level part of Cactus' POA shim, on top of the batched device engine.
+// host_bar.cpp -- the MSA-level entry points of the C ABI (include/barb200.h) on top of the end queue:
 //
-// What stays on the host (cheap, serial, O(MSA size)) and why:
-//   * slicing every end into sliding windows of `window_size` bases with 50 % overlap, the N stand-in for rows that
-//     ran out of bases, the per-window progressive-mode switch           (bar/impl/poaBarAligner.c:485-571)
-//   * trimming consecutive windows against each other and stitching them (:668-736; trim :376-434)
-//   * trimming the MSAs of two ends that share a string                   (:751-801)
-// What changes: the reference aligns window after window, end after end (one abpoa_msa each, :609). Here the n-th
-// windows of ALL ends of a call form one device batch (window n+1 of an end needs window n's trimmed MSA, so the
-// rounds are sequential, the ends within a round are not).
+//   barb200_flower_submit / barb200_flower_wait      asynchronous: one ticket = the ends of one flower (or any set of ends)
+//   barb200_msa_make_partial_order_alignment[_batch] msa_make_partial_order_alignment, bar/impl/poaBarAligner.c:463-749
+//   barb200_make_consistent_partial_order_alignments make_consistent_partial_order_alignments, :751-801
+//
+// The synchronous calls are submit + wait. The window / trimming / stitching logic lives in bar_windows.h, the queue and its
+// lane workers in end_queue.h (both free of CUDA, so that tests/hosttest runs them on the CPU with a stand-in device); this file
+// binds them to the device lanes of barb200.cu.
 #include <stdlib.h>
 #include <string.h>
 #include <memory>
+#include <mutex>
 #include <vector>
 #include "host_api.h"
+#include "end_queue.h"
 
 namespace barb200 {
-namespace {
 
-constexpr uint8_t GAPB = 5;
-const uint8_t kRc[6] = {3, 2, 1, 0, 4, 5};                  // complement in the POA alphabet (poaBarAligner.c:163)
+static std::mutex g_queue_create_mu;
 
-inline uint8_t ascii_to_code(char c) {                      // nst_nt4_table (poaBarAligner.c:116-133)
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        case '-': return 5;
-        default: return 4;
+static EndQueue *queue_of(barb200_ctx *ctx) {
+    void **slot = dispatcher_slot(ctx);
+    std::lock_guard<std::mutex> lk(g_queue_create_mu);
+    if (!*slot) {
+        mark_lanes_shared(ctx);                 // from now on every lane plans with its share of the device memory
+        int64_t max_jobs = 6144; double max_cost = 8e10;
+        if (getenv("BARB200_QUEUE_MAX_JOBS")) max_jobs = atoll(getenv("BARB200_QUEUE_MAX_JOBS"));
+        if (getenv("BARB200_QUEUE_MAX_COST")) max_cost = atof(getenv("BARB200_QUEUE_MAX_COST"));
+        *slot = new EndQueue(total_lanes(ctx), [ctx](int lane, const std::vector<HostJob> &jobs, std::vector<JobResult> &res, std::string &err) {
+            const int rc = run_jobs_on_lane(ctx, lane, jobs, res);
+            if (rc) err = get_error(ctx);
+            return rc;
+        }, max_jobs, max_cost);
     }
+    return (EndQueue *)*slot;
 }
 
-// A window MSA: rows keep their original stride when trailing empty columns are clipped.
-struct Window {
-    int64_t seq_no = 0, column_no = 0, stride = 0;
-    std::vector<int> seq_lens;
-    std::vector<uint8_t> m;
-    uint8_t &at(int64_t i, int64_t j) { return m[(size_t)(i * stride + j)]; }
-    uint8_t at(int64_t i, int64_t j) const { return m[(size_t)(i * stride + j)]; }
-};
-
-void flip(Window &w) {                                       // flip_msa_seq (:302-317)
-    const int64_t n = w.column_no, mid = n / 2;
-    for (int64_t i = 0; i < w.seq_no; ++i) {
-        for (int64_t j = 0; j < mid; ++j) {
-            const uint8_t a = w.at(i, j);
-            w.at(i, j) = kRc[w.at(i, n - 1 - j)];
-            w.at(i, n - 1 - j) = kRc[a];
-        }
-        if (n & 1) w.at(i, mid) = kRc[w.at(i, mid)];
-    }
-}
-
-std::vector<float> column_scores(const Window &w) {          // make_column_scores (:323-338): max(#bases - 1, 0)
-    std::vector<float> s((size_t)w.column_no, 0.f);
-    for (int64_t c = 0; c < w.column_no; ++c) {
-        for (int64_t r = 0; r < w.seq_no; ++r) if (w.at(r, c) != GAPB) s[c]++;
-        if (s[c] >= 1.0f) s[c]--;
-    }
-    return s;
-}
-
-std::vector<float> cumulative(int64_t row, const Window &w, const std::vector<float> &cs) {   // sum_column_scores (:344-354)
-    std::vector<float> cu; cu.reserve((size_t)w.seq_lens[row] + 1);
-    float acc = 0.f;
-    for (int64_t c = 0; c < w.column_no; ++c) if (w.at(row, c) != GAPB) { acc += cs[c]; cu.push_back(acc); }
-    return cu;
-}
-
-void trim_suffix(Window &w, std::vector<float> &cs, int64_t row, int64_t start) {             // trim_msa_suffix (:360-371)
-    int64_t k = 0;
-    for (int64_t c = 0; c < w.column_no; ++c)
-        if (w.at(row, c) != GAPB && k++ >= start) { w.at(row, c) = GAPB; cs[c] = cs[c] > 1 ? cs[c] - 1 : 0; }
-}
-
-// trim (:376-434): the cut inside the shared overlap that maximises the summed column scores kept on both sides
-bool trim(int64_t r1, Window &m1, std::vector<float> &cs1, int64_t r2, Window &m2, std::vector<float> &cs2, int64_t overlap) {
-    if (overlap == 0) return true;
-    const int64_t l1 = m1.seq_lens[r1], l2 = m2.seq_lens[r2];
-    if (overlap < 0 || overlap > l1 || overlap > l2) return false;
-    const std::vector<float> cu1 = cumulative(r1, m1, cs1), cu2 = cumulative(r2, m2, cs2);
-    if ((int64_t)cu1.size() != l1 || (int64_t)cu2.size() != l2) return false;
-    float best = cu2[l2 - 1];
-    if (overlap < l1) best += cu1[l1 - overlap - 1];
-    int64_t cut = 0;
-    for (int64_t i = 0; i < overlap - 1; ++i) {
-        const float c = cu1[l1 - overlap + i] + cu2[l2 - i - 2];
-        if (c > best) { cut = i + 1; best = c; }
-    }
-    float f = cu1[l1 - 1];
-    if (overlap < l2) f += cu2[l2 - overlap - 1];
-    if (f > best) { best = f; cut = overlap; }
-    trim_suffix(m1, cs1, r1, l1 - overlap + cut);
-    trim_suffix(m2, cs2, r2, l2 - cut);
-    return true;
-}
-
-void fix_trimmed(Window &w) {                                // msa_fix_trimmed (:440-461)
-    for (int64_t r = 0; r < w.seq_no; ++r) {
-        int n = 0;
-        for (int64_t c = 0; c < w.column_no; ++c) if (w.at(r, c) != GAPB) ++n;
-        w.seq_lens[r] = n;
-    }
-    int64_t empty = 0; bool still = true;
-    for (; empty < w.column_no; ++empty) {
-        for (int64_t r = 0; r < w.seq_no && still; ++r) still = w.at(r, w.column_no - 1 - empty) == GAPB;
-        if (!still) break;
-    }
-    w.column_no -= empty;
-}
-
-// the state of one end while its windows are being aligned (locals of msa_make_partial_order_alignment, :485-516)
-struct EndState {
-    int64_t seq_no = 0;
-    std::vector<std::vector<uint8_t>> codes;                // inputs converted once
-    std::vector<int> seq_lens;
-    std::vector<int64_t> offsets, row_overlaps;
-    std::vector<char> empty;
-    int64_t bases_remaining = 0;
-    std::vector<std::unique_ptr<Window>> windows;
-    // the window in flight
-    std::vector<int> cur_lens; std::vector<uint8_t> cur_flat; int cur_progressive = 1;
-    bool done = false;
-};
-
-barb200_msa *to_msa(int64_t seq_no, const std::vector<int> &lens, int64_t cols) {
-    barb200_msa *m = (barb200_msa *)calloc(1, sizeof(barb200_msa));
-    if (!m) return nullptr;
-    m->seq_no = seq_no; m->column_no = cols;
-    m->seq_lens = (int *)malloc(sizeof(int) * (size_t)(seq_no > 0 ? seq_no : 1));
-    m->msa = (uint8_t *)malloc((size_t)(seq_no * cols > 0 ? seq_no * cols : 1));
-    if (!m->seq_lens || !m->msa) { free(m->seq_lens); free(m->msa); free(m); return nullptr; }
-    for (int64_t i = 0; i < seq_no; ++i) m->seq_lens[i] = lens[i];
-    return m;
-}
-
-}  // namespace
-
-// msa_make_partial_order_alignment (:463-749) for many ends; results as Window-free flat matrices
-static int make_alignments(barb200_ctx *ctx, int64_t n_ends, const int64_t *seq_no, char ***seqs, int **seq_lens,
-                           int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff, barb200_msa **out) {
-    if (window_size <= 0) { set_error(ctx, "window_size must be positive"); return BARB200_EINVAL; }
-    int64_t overlap_size = (int64_t)(0.5f * window_size);    // :487-491
-    if (overlap_size > 0) --overlap_size;
-    std::vector<EndState> ends((size_t)n_ends);
-    for (int64_t e = 0; e < n_ends; ++e) {
-        EndState &E = ends[e];
-        E.seq_no = seq_no[e];
-        if (E.seq_no <= 0) { set_error(ctx, "end without sequences"); return BARB200_EINVAL; }
-        E.seq_lens.assign(seq_lens[e], seq_lens[e] + E.seq_no);
-        E.codes.resize(E.seq_no);
-        for (int64_t i = 0; i < E.seq_no; ++i) {
-            if (E.seq_lens[i] < 0) { set_error(ctx, "negative sequence length"); return BARB200_EINVAL; }
-            E.codes[i].resize(E.seq_lens[i]);
-            for (int t = 0; t < E.seq_lens[i]; ++t) E.codes[i][t] = ascii_to_code(seqs[e][i][t]);
-            E.bases_remaining += E.seq_lens[i];
-        }
-        E.offsets.assign(E.seq_no, 0); E.row_overlaps.assign(E.seq_no, 0); E.empty.assign(E.seq_no, 0);
-        // a single string is its own alignment (:471-483); nothing to align when no bases are left
-        E.done = E.seq_no == 1 || E.bases_remaining == 0;
-    }
-    while (true) {
-        // ---- build the next window of every unfinished end (:520-571) ----
-        std::vector<HostJob> jobs; std::vector<int64_t> owner;
-        for (int64_t e = 0; e < n_ends; ++e) {
-            EndState &E = ends[e];
-            if (E.done) continue;
-            if (!E.windows.empty()) {
-                const Window &prev = *E.windows.back();
-                if (prev.column_no <= overlap_size) { set_error(ctx, "window shorter than the window overlap (reference asserts, poaBarAligner.c:522)"); return BARB200_EINVAL; }
-                for (int64_t i = 0; i < E.seq_no; ++i) {
-                    int64_t ov = 0;
-                    for (int64_t c = prev.column_no - overlap_size; c < prev.column_no; ++c) if (prev.at(i, c) != GAPB) ++ov;
-                    E.row_overlaps[i] = ov; E.offsets[i] -= ov; E.bases_remaining += ov;
-                }
-            }
-            E.cur_lens.assign(E.seq_no, 0); E.cur_flat.clear();
-            for (int64_t i = 0; i < E.seq_no; ++i) {
-                int64_t n = std::min<int64_t>(window_size, E.seq_lens[i] - E.offsets[i]);
-                if (n <= 0) { E.empty[i] = 1; E.cur_lens[i] = 1; E.cur_flat.push_back(4); }              // the N stand-in, :551-562
-                else { E.empty[i] = 0; E.cur_lens[i] = (int)n; E.cur_flat.insert(E.cur_flat.end(), E.codes[i].begin() + E.offsets[i], E.codes[i].begin() + E.offsets[i] + n); }
-            }
-            E.cur_progressive = default_progressive(ctx);
-            if (E.seq_no > max_prog_rows || (1. - (double)E.cur_lens[E.seq_no - 1] / (double)E.cur_lens[0] > max_prog_length_diff)) E.cur_progressive = 0;   // :567-571
-            jobs.push_back(HostJob{(int)E.seq_no, E.cur_lens.data(), E.cur_flat.data(), E.cur_progressive});
-            owner.push_back(e);
-        }
-        if (jobs.empty()) break;
-        std::vector<JobResult> res;
-        int rc = run_jobs(ctx, jobs, res);
-        if (rc) return rc;
-        // ---- take the MSAs back, trim against the previous window (:612-700) ----
-        bool ok = true;
-#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads(ctx))
-        for (int64_t k = 0; k < (int64_t)jobs.size(); ++k) {
-            EndState &E = ends[owner[k]];
-            std::unique_ptr<Window> w(new Window());
-            w->seq_no = E.seq_no; w->column_no = w->stride = res[k].msa_len; w->seq_lens = E.cur_lens; w->m.swap(res[k].msa);
-            for (int64_t i = 0; i < E.seq_no; ++i) if (E.empty[i])
-                for (int64_t c = 0; c < w->column_no; ++c) if (w->at(i, c) != GAPB) { w->at(i, c) = GAPB; --w->seq_lens[i]; break; }   // :631-644
-            for (int64_t i = 0; i < E.seq_no; ++i) { E.bases_remaining -= w->seq_lens[i]; E.offsets[i] += w->seq_lens[i]; }
-            if (!E.windows.empty()) {
-                Window &prev = *E.windows.back();
-                flip(*w);
-                std::vector<float> pcs = column_scores(prev), cs = column_scores(*w);
-                for (int64_t i = 0; i < E.seq_no; ++i) {
-                    const int64_t ov = std::min<int64_t>(w->seq_lens[i], E.row_overlaps[i]);
-                    if (ov > 0 && !trim(i, *w, cs, i, prev, pcs, ov)) {
-#pragma omp atomic write
-                        ok = false;
-                    }
-                }
-                fix_trimmed(*w); fix_trimmed(prev);
-                flip(*w);
-            }
-            E.windows.push_back(std::move(w));
-            if (E.bases_remaining <= 0) E.done = true;
-        }
-        if (!ok) { set_error(ctx, "inconsistent overlap while trimming windows"); return BARB200_EINVAL; }
-    }
-    // ---- stitch (:703-736) ----
-    for (int64_t e = 0; e < n_ends; ++e) {
-        EndState &E = ends[e];
-        int64_t cols = 0;
-        if (E.seq_no == 1) cols = E.seq_lens[0]; else for (auto &w : E.windows) cols += w->column_no;
-        barb200_msa *m = to_msa(E.seq_no, E.seq_lens, cols);
-        if (!m) { for (int64_t x = 0; x < e; ++x) { barb200_msa_destruct(out[x]); out[x] = nullptr; } set_error(ctx, "host allocation failed"); return BARB200_ENOMEM; }
-        if (E.seq_no == 1) memcpy(m->msa, E.codes[0].data(), (size_t)cols);
-        else for (int64_t i = 0; i < E.seq_no; ++i) {
-            int64_t o = 0;
-            for (auto &w : E.windows) { memcpy(m->msa + (size_t)(i * cols + o), &w->m[(size_t)(i * w->stride)], (size_t)w->column_no); o += w->column_no; }
-        }
-        out[e] = m;
-    }
-    return BARB200_OK;
+void dispatcher_destroy(barb200_ctx *ctx) {
+    void **slot = dispatcher_slot(ctx);
+    std::lock_guard<std::mutex> lk(g_queue_create_mu);
+    if (*slot) { delete (EndQueue *)*slot; *slot = nullptr; }
 }
 
 }  // namespace barb200
 
 using namespace barb200;
 
+struct barb200_ticket { Ticket t; };
+
 extern "C" void barb200_msa_destruct(barb200_msa *m) { if (m) { free(m->seq_lens); free(m->msa); free(m); } }
+
+extern "C" barb200_ticket *barb200_flower_submit(barb200_ctx *ctx, int64_t end_no, const int64_t *end_lengths, char ***end_strings,
+        int **end_string_lengths, int64_t **right_end_indexes, int64_t **right_end_row_indexes, int64_t **overlaps,
+        int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff) {
+    if (!ctx) return nullptr;
+    if (end_no < 0 || (end_no > 0 && (!end_lengths || !end_strings || !end_string_lengths))) { set_error(ctx, "bad arguments"); return nullptr; }
+    if (window_size <= 0) { set_error(ctx, "window_size must be positive"); return nullptr; }
+    std::unique_ptr<barb200_ticket> bt(new barb200_ticket());
+    Ticket &t = bt->t;
+    t.n_ends = end_no; t.window_size = window_size; t.max_prog_rows = max_prog_rows; t.max_prog_length_diff = max_prog_length_diff;
+    t.default_progressive = default_progressive(ctx);
+    t.ends.resize((size_t)end_no);
+    for (int64_t e = 0; e < end_no; ++e) {
+        const std::string err = barwin::end_init(t.ends[e], end_lengths[e], end_strings[e], end_string_lengths[e]);
+        if (!err.empty()) { set_error(ctx, err); return nullptr; }
+    }
+    t.consistent = right_end_indexes != nullptr;
+    if (t.consistent) {
+        if (!right_end_row_indexes || !overlaps) { set_error(ctx, "bad arguments"); return nullptr; }
+        t.right_end_indexes.resize(end_no); t.right_end_row_indexes.resize(end_no); t.overlaps.resize(end_no);
+        for (int64_t e = 0; e < end_no; ++e) {
+            t.right_end_indexes[e].assign(right_end_indexes[e], right_end_indexes[e] + end_lengths[e]);
+            t.right_end_row_indexes[e].assign(right_end_row_indexes[e], right_end_row_indexes[e] + end_lengths[e]);
+            t.overlaps[e].assign(overlaps[e], overlaps[e] + end_lengths[e]);
+        }
+    }
+    queue_of(ctx)->submit(&t);
+    return bt.release();
+}
+
+extern "C" barb200_msa **barb200_flower_wait(barb200_ctx *ctx, barb200_ticket *bt) {
+    if (!ctx || !bt) return nullptr;
+    std::unique_ptr<barb200_ticket> own(bt);
+    Ticket &t = bt->t;
+    queue_of(ctx)->wait(&t);
+    if (t.rc) { set_error(ctx, t.err.empty() ? "device batch failed" : t.err); return nullptr; }
+    barb200_msa **msas = (barb200_msa **)calloc((size_t)(t.n_ends > 0 ? t.n_ends : 1), sizeof(barb200_msa *));
+    if (!msas) { set_error(ctx, "host allocation failed"); return nullptr; }
+    bool ok = true;
+    for (int64_t e = 0; e < t.n_ends && ok; ++e) { msas[e] = barwin::end_stitch(t.ends[e]); ok = msas[e] != nullptr; }
+    if (!ok) set_error(ctx, "host allocation failed");
+    if (ok && t.consistent && !barwin::consistency_trim(t.n_ends, msas, t.right_end_indexes, t.right_end_row_indexes, t.overlaps)) {
+        set_error(ctx, "inconsistent end / row indexes or overlaps"); ok = false;
+    }
+    if (!ok) { for (int64_t e = 0; e < t.n_ends; ++e) barb200_msa_destruct(msas[e]); free(msas); return nullptr; }
+    return msas;
+}
 
 extern "C" int barb200_msa_make_partial_order_alignment_batch(barb200_ctx *ctx, int64_t n_ends, const int64_t *seq_no,
         char ***seqs, int **seq_lens, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff,
         barb200_msa **out) {
     if (!ctx || n_ends < 0 || (n_ends > 0 && (!seq_no || !seqs || !seq_lens || !out))) return BARB200_EINVAL;
     for (int64_t e = 0; e < n_ends; ++e) out[e] = nullptr;
-    return make_alignments(ctx, n_ends, seq_no, seqs, seq_lens, window_size, max_prog_rows, max_prog_length_diff, out);
+    barb200_ticket *t = barb200_flower_submit(ctx, n_ends, seq_no, seqs, seq_lens, nullptr, nullptr, nullptr, window_size, max_prog_rows, max_prog_length_diff);
+    if (!t) return BARB200_EINVAL;
+    barb200_msa **ms = barb200_flower_wait(ctx, t);
+    if (!ms) return BARB200_EJOB;
+    for (int64_t e = 0; e < n_ends; ++e) out[e] = ms[e];
+    free(ms);
+    return BARB200_OK;
 }
 
 extern "C" barb200_msa *barb200_msa_make_partial_order_alignment(barb200_ctx *ctx, char **seqs, int *seq_lens, int64_t seq_no,
@@ -262,33 +123,15 @@ extern "C" barb200_msa **barb200_make_consistent_partial_order_alignments(barb20
         char ***end_strings, int **end_string_lengths, int64_t **right_end_indexes, int64_t **right_end_row_indexes,
         int64_t **overlaps, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff) {
     if (!ctx || end_no < 0) return nullptr;
-    barb200_msa **msas = (barb200_msa **)calloc((size_t)(end_no > 0 ? end_no : 1), sizeof(barb200_msa *));
-    if (!msas) return nullptr;
-    if (barb200_msa_make_partial_order_alignment_batch(ctx, end_no, end_lengths, end_strings, end_string_lengths, window_size,
-                                                       max_prog_rows, max_prog_length_diff, msas)) { free(msas); return nullptr; }
-    // cross-end consistency (:781-793), serial exactly as in the reference: the order of trims matters
-    std::vector<Window> ws((size_t)end_no); std::vector<std::vector<float>> cs((size_t)end_no);
-    for (int64_t i = 0; i < end_no; ++i) {
-        Window &w = ws[i];
-        w.seq_no = msas[i]->seq_no; w.column_no = w.stride = msas[i]->column_no;
-        w.seq_lens.assign(msas[i]->seq_lens, msas[i]->seq_lens + w.seq_no);
-        w.m.assign(msas[i]->msa, msas[i]->msa + (size_t)(w.seq_no * w.column_no));
-        cs[i] = column_scores(w);
-    }
-    bool ok = true;
-    for (int64_t i = 0; i < end_no && ok; ++i)
-        for (int64_t j = 0; j < ws[i].seq_no && ok; ++j) {
-            const int64_t re = right_end_indexes[i][j], rr = right_end_row_indexes[i][j];
-            if (re > i || (re == i && rr > j)) {
-                if (re < 0 || re >= end_no || rr < 0 || rr >= ws[re].seq_no) { ok = false; break; }
-                ok = trim(j, ws[i], cs[i], rr, ws[re], cs[re], overlaps[i][j]);
-            }
-        }
-    if (!ok) {
-        set_error(ctx, "inconsistent end / row indexes or overlaps");
-        for (int64_t i = 0; i < end_no; ++i) barb200_msa_destruct(msas[i]);
-        free(msas); return nullptr;
-    }
-    for (int64_t i = 0; i < end_no; ++i) memcpy(msas[i]->msa, ws[i].m.data(), ws[i].m.size());
-    return msas;
+    if (end_no > 0 && (!right_end_indexes || !right_end_row_indexes || !overlaps)) { set_error(ctx, "bad arguments"); return nullptr; }
+    barb200_ticket *t = barb200_flower_submit(ctx, end_no, end_lengths, end_strings, end_string_lengths, right_end_indexes, right_end_row_indexes,
+                                              overlaps, window_size, max_prog_rows, max_prog_length_diff);
+    if (!t) return nullptr;
+    return barb200_flower_wait(ctx, t);
+}
+
+extern "C" int barb200_queue_stats(barb200_ctx *ctx, int64_t *batches, int64_t *jobs) {
+    if (!ctx) return BARB200_EINVAL;
+    queue_of(ctx)->stats(batches, jobs);
+    return BARB200_OK;
 }

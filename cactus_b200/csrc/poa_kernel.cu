@@ -361,8 +361,10 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
 
     while (true) {
         if (tid == 0) {
-            const int j = atomicAdd(A.next_job, 1);
-            if (j < A.n_jobs) {                                  // wait until the host has released the job (its read order is uploaded)
+            const int k = atomicAdd(A.next_job, 1);
+            int j = -1;
+            if (k < A.n_jobs) {                                  // wait until the host has released the job (its read order is uploaded)
+                j = A.job_base + k;
                 while (*reinterpret_cast<const volatile int *>(A.ready) <= j) __nanosleep(2000);
                 __threadfence_system();     // the producer is the copy engine (system scope): order the order[] loads below after it
             }
@@ -370,7 +372,7 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
         }
         __syncthreads();
         const int job = S.job;
-        if (job >= A.n_jobs) break;
+        if (job < 0) break;
         const JobDesc jd = A.jobs[job];
         const int K = jd.n_seq;
         const int *lens = A.lens + jd.len_off, *order = A.order + jd.len_off;

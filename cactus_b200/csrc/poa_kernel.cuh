@@ -19,15 +19,16 @@ struct SlotLayout {
 enum { PH_DP = 0, PH_BACKTRACK = 1, PH_FUSE = 2, PH_TOPO = 3, PH_MSA = 4, PH_TOTAL = 5, PH_N = 8 };
 
 struct BatchArgs {
-    const JobDesc *jobs; int n_jobs;
+    const JobDesc *jobs;        // all jobs of the stage (internal order)
+    int job_base, n_jobs;       // this launch's class: jobs [job_base, job_base + n_jobs)
     const uint8_t *seqs;        // packed 0..4 codes of all jobs
     const int *lens;            // per sequence
     const int64_t *soff;        // per sequence: offset from the job's seq_off
     const int *order;           // per sequence slot a: which read is aligned a-th (guide tree, host computed)
     uint8_t *msa; int *msa_len; int *status; long long *cells;
     uint8_t *slots; int *planes;
-    int *next_job;              // work queue head
-    const int *ready;           // jobs [0, *ready) may start (the host streams guide-tree orders in behind the launch)
+    int *next_job;              // the class's work counter
+    const int *ready;           // jobs [0, *ready) of the STAGE may start (the host streams guide-tree orders in behind the launches)
     unsigned long long *phase_clk;   // [gridDim.x * PH_N] clock64 per phase, or nullptr
     int serial_phases;          // debugging aid: 1 = run the graph phases in their serial reference form
     int bfs_order;              // debugging aid: 1 = recompute abPOA's BFS order after every fusion instead of splicing

@@ -24,8 +24,10 @@
  * err_fatal; the shim in INTEGRATION.md converts a non-zero return into st_errAbort to keep that behaviour.)
  * There is NO CPU fallback: without a CUDA device barb200_create fails.
  *
- * Thread safety: a context may be shared by threads; batch calls on one context are serialised internally
- * (the reference calls msa_make_partial_order_alignment concurrently from OpenMP teams, bar/impl/bar.c:90-94).
+ * Thread safety: a context may be shared by threads (the reference calls msa_make_partial_order_alignment concurrently from
+ * OpenMP teams, bar/impl/bar.c:90-94). The MSA-level calls below go through one queue of ends per context: whatever several
+ * threads have submitted when a device lane becomes free runs as ONE device batch; barb200_flower_submit / _wait expose the
+ * queue directly so that a caller can submit every end of every leaf flower before waiting for the first.
  */
 #ifndef BARB200_H
 #define BARB200_H
@@ -56,11 +58,17 @@ typedef struct {
     int disable_seeding;         /* partialOrderAlignmentDisableSeeding; must be 1 (Cactus' default) */
     /* engine */
     int device;                  /* CUDA device ordinal */
-    int threads_per_block;       /* 0 = auto (128..512 by longest query) */
+    int threads_per_block;       /* 0 = auto: every job runs in the smallest CTA class (32..1024 threads) its longest sequence fits; > 0: minimum class */
     int ctas_per_sm;             /* 0 = auto (occupancy / memory limited) */
     double mem_fraction;         /* fraction of free device memory the slots may take; 0 = 0.85 */
     int host_threads;            /* threads for host-side packing / guide trees; 0 = all */
     int collect_phase_clocks;    /* 1: accumulate per-phase SM clock counters (profiling aid) */
+    /* several GPUs behind ONE context (cactus_consolidated is one process): n_devices > 0 -> devices[0 .. n_devices),
+     * n_devices < 0 -> every visible device, 0 -> the single `device` above. Ends are dealt to the devices by estimated cost
+     * (batch call) or pulled by whichever device lane is free (end queue); results land in the caller's buffers. */
+    int n_devices;
+    int devices[8];
+    int lanes;                   /* batches in flight per device, 1 or 2; 0 = 2 */
 } barb200_params;
 
 /* Cactus' defaults (src/cactus/cactus_progressive_config.xml:307-325) */
@@ -89,6 +97,9 @@ int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *msa_len, int6
 int64_t barb200_stage_launches(barb200_stage *st);   /* kernels launched by the last barb200_stage_run */
 /* per-phase SM clock totals of the last run (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total */
 int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[6]);
+/* the stage's CTA-size buckets (largest first): out[4b .. 4b+3] = threads per CTA, jobs, resident CTAs, plane ints per slot;
+ * returns the number of buckets */
+int barb200_stage_buckets(barb200_stage *st, int64_t *out, int max_buckets);
 void barb200_stage_destroy(barb200_stage *st);
 
 /* The reference's Msa (bar/inc/poaBarAligner.h:37-43) with one flat matrix instead of row pointers. */
@@ -177,7 +188,24 @@ int64_t barb200_pecan_split_points(int64_t lx, int64_t ly, const int64_t *anchor
                                    int64_t split_matrix_bigger_than_this, int ragged_left, int ragged_right,
                                    int64_t **splits_out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The end queue, asynchronously. barb200_flower_submit takes the arguments of make_consistent_partial_order_alignments
+ * (bar/inc/poaBarAligner.h:108; right_end_indexes == NULL: independent ends, no cross-end trimming -- the single-end case of
+ * make_flower_alignment_poa, poaBarAligner.c:1119-1143), copies what it needs and returns at once; the strings may be released
+ * after the call. barb200_flower_wait blocks until every end of the ticket is aligned, does the stitching and the cross-end
+ * trimming in the calling thread and returns what barb200_make_consistent_partial_order_alignments returns (NULL + last_error on
+ * failure; a failure of one ticket does not affect the others). The ticket is consumed by the wait.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct barb200_ticket barb200_ticket;
+barb200_ticket *barb200_flower_submit(barb200_ctx *ctx, int64_t end_no, const int64_t *end_lengths, char ***end_strings,
+        int **end_string_lengths, int64_t **right_end_indexes, int64_t **right_end_row_indexes, int64_t **overlaps,
+        int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff);
+barb200_msa **barb200_flower_wait(barb200_ctx *ctx, barb200_ticket *ticket);
+/* device batches the queue has run so far and the jobs in them (reports, tests) */
+int barb200_queue_stats(barb200_ctx *ctx, int64_t *batches, int64_t *jobs);
+
 /* Device facts for reports. */
+int barb200_device_count(barb200_ctx *ctx);
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);
 
 void barb200_free(void *p);

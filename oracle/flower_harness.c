@@ -26,6 +26,7 @@
 #include "poaBarAligner.h"
 #include "stCaf.h"
 #include "stPinchIterator.h"
+#include <omp.h>
 
 void bar(stList *flowers, CactusParams *params, CactusDisk *cactusDisk, stList *listOfEndAlignmentFiles);
 
@@ -71,133 +72,188 @@ static void push(wbuf *b, int64_t v) {
     b->w[b->n++] = v;
 }
 
-/* ---- the flower ------------------------------------------------------------------------------------------------------- */
+/* ---- flowers ------------------------------------------------------------------------------------------------------- */
 typedef struct {
-    CactusDisk *disk; Flower *flower; EventTree *eventTree;
+    Flower *flower;
     int64_t n_seq, n_caps;
-    Sequence **seqs; Name *seq_names;
+    Name *seq_names;
     Name *cap_names;            /* [2 * n_adj]: cap A of adjacency i at 2i, cap B at 2i+1 */
 } built;
 
+typedef struct {
+    CactusDisk *disk; EventTree *eventTree; Event **leaves; int64_t n_events;
+    built *f; int64_t n_flowers, cap_flowers;
+} session;
+
 static End *view(End *end, int side) { return (end_getSide(end) ? 1 : 0) == side ? end : end_getReverse(end); }
 
-static void build(built *B, int64_t n_events, int64_t n_seq, const char **seqs, const int *seq_event, int64_t n_ends, const int *end_side,
-                  int64_t n_adj, const int64_t *adj) {
-    B->disk = cactusDisk_construct();
-    B->eventTree = eventTree_construct2(B->disk);
-    B->flower = flower_construct(B->disk);
+void *flower_harness_begin(int64_t n_events) {
+    session *S = st_calloc(1, sizeof(session));
+    S->disk = cactusDisk_construct();
+    S->eventTree = eventTree_construct2(S->disk);
+    Event *root = eventTree_getRootEvent(S->eventTree);
+    Event *anc = event_construct3("ANC", 0.1, root, S->eventTree);
+    S->n_events = n_events;
+    S->leaves = st_malloc(sizeof(Event *) * (n_events > 0 ? n_events : 1));
+    for (int64_t i = 0; i < n_events; ++i) { char h[32]; sprintf(h, "LEAF%d", (int)i); S->leaves[i] = event_construct3(h, 0.1, anc, S->eventTree); }
+    return S;
+}
+
+/* adds one flower to the session's disk; returns its index */
+int64_t flower_harness_add_flower(void *session_, int64_t n_seq, const char **seqs, const int *seq_event, int64_t n_ends, const int *end_side,
+                                  int64_t n_adj, const int64_t *adj) {
+    session *S = session_;
+    if (S->n_flowers == S->cap_flowers) { S->cap_flowers = S->cap_flowers ? 2 * S->cap_flowers : 16; S->f = realloc(S->f, sizeof(built) * S->cap_flowers); }
+    built *B = &S->f[S->n_flowers];
+    memset(B, 0, sizeof(*B));
+    B->flower = flower_construct(S->disk);
     group_construct2(B->flower);                      /* stCaf_setup expects a leaf group (caf/tests/filteringTest.c:71) */
-    Event *root = eventTree_getRootEvent(B->eventTree);
-    Event *anc = event_construct3("ANC", 0.1, root, B->eventTree);
-    Event **leaves = st_malloc(sizeof(Event *) * (n_events > 0 ? n_events : 1));
-    for (int64_t i = 0; i < n_events; ++i) { char h[32]; sprintf(h, "LEAF%d", (int)i); leaves[i] = event_construct3(h, 0.1, anc, B->eventTree); }
-    B->n_seq = n_seq; B->seqs = st_malloc(sizeof(Sequence *) * n_seq); B->seq_names = st_malloc(sizeof(Name) * n_seq);
+    B->n_seq = n_seq; B->seq_names = st_malloc(sizeof(Name) * (n_seq > 0 ? n_seq : 1));
+    Sequence **sq = st_malloc(sizeof(Sequence *) * (n_seq > 0 ? n_seq : 1));
     for (int64_t i = 0; i < n_seq; ++i) {
-        char h[32]; sprintf(h, ">s%d", (int)i);
-        B->seqs[i] = sequence_construct(1, (int64_t)strlen(seqs[i]), seqs[i], h, leaves[seq_event[i]], B->disk);
-        flower_addSequence(B->flower, B->seqs[i]);
-        B->seq_names[i] = sequence_getName(B->seqs[i]);
+        char h[48]; sprintf(h, ">f%ds%d", (int)S->n_flowers, (int)i);
+        sq[i] = sequence_construct(1, (int64_t)strlen(seqs[i]), seqs[i], h, S->leaves[seq_event[i]], S->disk);
+        flower_addSequence(B->flower, sq[i]);
+        B->seq_names[i] = sequence_getName(sq[i]);
     }
-    End **ends = st_malloc(sizeof(End *) * n_ends);
+    End **ends = st_malloc(sizeof(End *) * (n_ends > 0 ? n_ends : 1));
     for (int64_t i = 0; i < n_ends; ++i) ends[i] = end_construct2(end_side[i] != 0, 1, B->flower);
     B->n_caps = 2 * n_adj; B->cap_names = st_malloc(sizeof(Name) * (B->n_caps > 0 ? B->n_caps : 1));
     for (int64_t i = 0; i < n_adj; ++i) {
         const int64_t *a = adj + 6 * i;           /* seq, lo, hi, positive representation?, end A, end B */
-        Sequence *s = B->seqs[a[0]];
+        Sequence *s = sq[a[0]];
         Cap *ca, *cb;
         if (a[3]) { ca = cap_construct2(view(ends[a[4]], 0), a[1], 1, s); cb = cap_construct2(view(ends[a[5]], 1), a[2], 1, s); }
         else { ca = cap_construct2(view(ends[a[4]], 0), a[2], 0, s); cb = cap_construct2(view(ends[a[5]], 1), a[1], 0, s); }
         cap_makeAdjacent(ca, cb);
         B->cap_names[2 * i] = cap_getName(ca); B->cap_names[2 * i + 1] = cap_getName(cb);
     }
-    free(ends); free(leaves);
+    free(ends); free(sq);
+    return S->n_flowers++;
 }
 static int64_t cap_index(built *B, Name n) { for (int64_t i = 0; i < B->n_caps; ++i) if (B->cap_names[i] == n) return i; return -1; }
 static int64_t seq_index(built *B, Name n) { for (int64_t i = 0; i < B->n_seq; ++i) if (B->seq_names[i] == n) return i; return -1; }
 
-static void dump_flower(built *B, Flower *f, wbuf *o, int depth) {
-    push(o, -7000 - depth); push(o, flower_getEndNumber(f)); push(o, flower_getBlockNumber(f)); push(o, flower_getGroupNumber(f)); push(o, flower_getChainNumber(f));
+/* Canonical dump of what BAR produced: every block of the flower hierarchy as the sorted list of its segments
+ * (sequence index, lowest forward-strand coordinate, length, orientation within the block), with the block's arbitrary
+ * orientation normalised (the first segment in sorted order is forward), and the blocks themselves sorted. Object names,
+ * iteration order and block orientation depend on hash iteration / the order in which concurrently processed flowers drew
+ * ids from the disk -- they differ between two runs of the UNMODIFIED reference -- so they are not part of the comparison. */
+typedef struct { int64_t *w; size_t n; } rec;
+static int rec_cmp(const void *a, const void *b) {
+    const rec *x = a, *y = b;
+    const size_t n = x->n < y->n ? x->n : y->n;
+    for (size_t i = 0; i < n; ++i) if (x->w[i] != y->w[i]) return x->w[i] < y->w[i] ? -1 : 1;
+    return x->n < y->n ? -1 : (x->n > y->n ? 1 : 0);
+}
+typedef struct { rec *r; size_t n, cap; } recs;
+static void recs_add(recs *R, int64_t *w, size_t n) {
+    if (R->n == R->cap) { R->cap = R->cap ? 2 * R->cap : 64; R->r = realloc(R->r, sizeof(rec) * R->cap); }
+    R->r[R->n].w = w; R->r[R->n].n = n; ++R->n;
+}
+static void collect_blocks(built *B, Flower *f, recs *out) {
     Flower_EndIterator *eit = flower_getEndIterator(f); End *e;
     while ((e = flower_getNextEnd(eit)) != NULL) {
-        push(o, end_isBlockEnd(e)); push(o, end_getSide(e)); push(o, end_isAttached(e)); push(o, end_getInstanceNumber(e));
-        End_InstanceIterator *cit = end_getInstanceIterator(e); Cap *c;
-        while ((c = end_getNext(cit)) != NULL) {
-            Sequence *s = cap_getSequence(c);
-            push(o, s ? seq_index(B, sequence_getName(s)) : -1); push(o, s ? cap_getCoordinate(c) : -1); push(o, s ? cap_getStrand(c) : -1); push(o, cap_getSide(c));
+        if (!(end_isBlockEnd(e) && end_getSide(e))) continue;
+        Block *b = end_getBlock(e);
+        recs segs = {0, 0, 0};
+        Block_InstanceIterator *sit = block_getInstanceIterator(b); Segment *sg;
+        while ((sg = block_getNext(sit)) != NULL) {
+            Sequence *sq = segment_getSequence(sg);
+            if (sq == NULL) continue;
+            Segment *fw = segment_getStrand(sg) ? sg : segment_getReverse(sg);
+            int64_t *w = malloc(sizeof(int64_t) * 4);
+            w[0] = seq_index(B, sequence_getName(sq)); w[1] = segment_getStart(fw); w[2] = segment_getLength(sg); w[3] = segment_getStrand(sg) ? 1 : 0;
+            recs_add(&segs, w, 4);
         }
-        end_destructInstanceIterator(cit);
-        if (end_isBlockEnd(e) && end_getSide(e)) {
-            Block *b = end_getBlock(e);
-            push(o, block_getLength(b)); push(o, block_getInstanceNumber(b));
-            Block_InstanceIterator *sit = block_getInstanceIterator(b); Segment *sg;
-            while ((sg = block_getNext(sit)) != NULL) {
-                Sequence *s = segment_getSequence(sg);
-                push(o, s ? seq_index(B, sequence_getName(s)) : -1); push(o, s ? segment_getStart(sg) : -1); push(o, s ? segment_getStrand(sg) : -1); push(o, segment_getLength(sg));
-            }
-            block_destructInstanceIterator(sit);
-        }
+        block_destructInstanceIterator(sit);
+        if (segs.n == 0) { free(segs.r); continue; }
+        qsort(segs.r, segs.n, sizeof(rec), rec_cmp);
+        const int64_t flip = segs.r[0].w[3] ? 0 : 1;
+        int64_t *w = malloc(sizeof(int64_t) * (1 + 4 * segs.n));
+        w[0] = block_getLength(b);
+        for (size_t i = 0; i < segs.n; ++i) { memcpy(w + 1 + 4 * i, segs.r[i].w, sizeof(int64_t) * 4); w[1 + 4 * i + 3] ^= flip; free(segs.r[i].w); }
+        recs_add(out, w, 1 + 4 * segs.n);
+        free(segs.r);
     }
     flower_destructEndIterator(eit);
     Flower_GroupIterator *git = flower_getGroupIterator(f); Group *g;
-    while ((g = flower_getNextGroup(git)) != NULL) {
-        push(o, group_isLeaf(g)); push(o, group_getEndNumber(g));
-        if (!group_isLeaf(g)) dump_flower(B, group_getNestedFlower(g), o, depth + 1);
-    }
+    while ((g = flower_getNextGroup(git)) != NULL) if (!group_isLeaf(g)) collect_blocks(B, group_getNestedFlower(g), out);
     flower_destructGroupIterator(git);
 }
+static void dump_flower(built *B, Flower *f, wbuf *o, int depth) {
+    (void)depth;
+    recs all = {0, 0, 0};
+    collect_blocks(B, f, &all);
+    qsort(all.r, all.n, sizeof(rec), rec_cmp);
+    push(o, (int64_t)all.n);
+    for (size_t i = 0; i < all.n; ++i) { push(o, (int64_t)all.r[i].n); for (size_t k = 0; k < all.r[i].n; ++k) push(o, all.r[i].w[k]); free(all.r[i].w); }
+    free(all.r);
+}
 
-/*
- * mode 0: make_flower_alignment_poa + stPinchIterator_constructFromAlignedBlocks. Stream:
- *         n_blocks, then per block: chain length c and c x (cap index, position, strand, length);
- *         n_pinches, then per pinch: cap index 1, cap index 2, start1, start2, length, strand.
- *         The POA parameters come from abpoaParamaters_constructFromCactusParams, i.e. the "bar/poa/..." table entries;
- *         max_seq_length / window / mask_filter / max_prog_rows / max_prog_length_diff from the "bar/..." entries bar() reads.
- * mode 1: bar() on the one-flower list (bar.c:52-176: alignment, pinch iterator, stCaf_setup / anneal / melt / finish), then a
- *         recursive dump of the resulting flower hierarchy (ends, caps, blocks and their segments, groups).
- * Returns a malloc'd stream (*n_words long); release with flower_harness_free.
- */
-int64_t *flower_harness_run(int mode, int64_t n_events, int64_t n_seq, const char **seqs, const int *seq_event, int64_t n_ends,
-                            const int *end_side, int64_t n_adj, const int64_t *adj, int64_t *n_words) {
-    built B; memset(&B, 0, sizeof(B));
-    build(&B, n_events, n_seq, seqs, seq_event, n_ends, end_side, n_adj, adj);
+/* make_flower_alignment_poa + stPinchIterator_constructFromAlignedBlocks on flower `index`. Stream:
+ *   n_blocks, then per block: chain length c and c x (cap index, position, strand, length);
+ *   n_pinches, then per pinch: cap index 1, cap index 2, start1, start2, length, strand.
+ * The POA parameters come from abpoaParamaters_constructFromCactusParams, i.e. the "bar/poa/..." table entries;
+ * max_seq_length / window / mask_filter / max_prog_rows / max_prog_length_diff from the "bar/..." entries bar() reads. */
+int64_t *flower_harness_blocks(void *session_, int64_t index, int64_t *n_words) {
+    session *S = session_;
+    built *B = &S->f[index];
     wbuf o = {0, 0, 0};
-    if (mode == 0) {
-        abpoa_para_t *abpt = abpoaParamaters_constructFromCactusParams(NULL);
-        stList *blocks = make_flower_alignment_poa(B.flower, cactusParams_get_int(NULL, 2, "bar", "bandingLimit"),
-                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentWindow"),
-                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentMaskFilter"),
-                cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxRows"),
-                cactusParams_get_float(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxLengthDiff"), abpt);
-        push(&o, stList_length(blocks));
-        for (int64_t i = 0; i < stList_length(blocks); ++i) {
-            AlignmentBlock *b = stList_get(blocks, i);
-            int64_t c = 0; for (AlignmentBlock *q = b; q; q = q->next) ++c;
-            push(&o, c);
-            for (AlignmentBlock *q = b; q; q = q->next) { push(&o, cap_index(&B, q->subsequenceIdentifier)); push(&o, q->position); push(&o, q->strand); push(&o, q->length); }
-        }
-        stPinchIterator *it = stPinchIterator_constructFromAlignedBlocks(blocks);
-        stPinchIterator_reset(it);
-        size_t at = o.n; push(&o, 0);
-        stPinch *pinch, fill; int64_t np = 0;
-        while ((pinch = stPinchIterator_getNext(it, &fill)) != NULL) {
-            push(&o, cap_index(&B, pinch->name1)); push(&o, cap_index(&B, pinch->name2)); push(&o, pinch->start1); push(&o, pinch->start2);
-            push(&o, pinch->length); push(&o, pinch->strand); ++np;
-        }
-        o.w[at] = np;
-        stPinchIterator_destruct(it);
-        stList_destruct(blocks);
-        abpoa_free_para(abpt);
-    } else {
-        stList *flowers = stList_construct();
-        stList_append(flowers, B.flower);
-        bar(flowers, NULL, B.disk, NULL);
-        stList_destruct(flowers);
-        dump_flower(&B, B.flower, &o, 0);
+    abpoa_para_t *abpt = abpoaParamaters_constructFromCactusParams(NULL);
+    stList *blocks = make_flower_alignment_poa(B->flower, cactusParams_get_int(NULL, 2, "bar", "bandingLimit"),
+            cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentWindow"),
+            cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentMaskFilter"),
+            cactusParams_get_int(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxRows"),
+            cactusParams_get_float(NULL, 3, "bar", "poa", "partialOrderAlignmentProgressiveMaxLengthDiff"), abpt);
+    push(&o, stList_length(blocks));
+    for (int64_t i = 0; i < stList_length(blocks); ++i) {
+        AlignmentBlock *b = stList_get(blocks, i);
+        int64_t c = 0; for (AlignmentBlock *q = b; q; q = q->next) ++c;
+        push(&o, c);
+        for (AlignmentBlock *q = b; q; q = q->next) { push(&o, cap_index(B, q->subsequenceIdentifier)); push(&o, q->position); push(&o, q->strand); push(&o, q->length); }
     }
-    cactusDisk_destruct(B.disk);
-    free(B.seqs); free(B.seq_names); free(B.cap_names);
+    stPinchIterator *it = stPinchIterator_constructFromAlignedBlocks(blocks);
+    stPinchIterator_reset(it);
+    size_t at = o.n; push(&o, 0);
+    stPinch *pinch, fill; int64_t np = 0;
+    while ((pinch = stPinchIterator_getNext(it, &fill)) != NULL) {
+        push(&o, cap_index(B, pinch->name1)); push(&o, cap_index(B, pinch->name2)); push(&o, pinch->start1); push(&o, pinch->start2);
+        push(&o, pinch->length); push(&o, pinch->strand); ++np;
+    }
+    o.w[at] = np;
+    stPinchIterator_destruct(it);
+    stList_destruct(blocks);
+    abpoa_free_para(abpt);
     *n_words = (int64_t)o.n;
     return o.w;
+}
+
+/* bar() on ALL flowers of the session (bar.c:52-176: alignment, pinch iterator, stCaf_setup / anneal / melt / finish); threads > 0
+ * sets the OpenMP team size of bar()'s loop over flowers */
+void flower_harness_bar(void *session_, int threads) {
+    session *S = session_;
+    stList *flowers = stList_construct();
+    for (int64_t i = 0; i < S->n_flowers; ++i) stList_append(flowers, S->f[i].flower);
+    if (threads > 0) omp_set_num_threads(threads);
+    bar(flowers, NULL, S->disk, NULL);
+    stList_destruct(flowers);
+}
+
+/* recursive dump of flower `index`'s hierarchy (ends, caps, blocks and their segments, groups), e.g. after flower_harness_bar */
+int64_t *flower_harness_dump(void *session_, int64_t index, int64_t *n_words) {
+    session *S = session_;
+    wbuf o = {0, 0, 0};
+    dump_flower(&S->f[index], S->f[index].flower, &o, 0);
+    *n_words = (int64_t)o.n;
+    return o.w;
+}
+
+void flower_harness_end(void *session_) {
+    session *S = session_;
+    cactusDisk_destruct(S->disk);
+    for (int64_t i = 0; i < S->n_flowers; ++i) { free(S->f[i].seq_names); free(S->f[i].cap_names); }
+    free(S->f); free(S->leaves); free(S);
 }
 
 void flower_harness_free(void *p) { free(p); }

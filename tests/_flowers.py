@@ -44,9 +44,18 @@ def _lib(which):
         lib.flower_harness_set_param.argtypes = [C.c_char_p, C.c_char_p]
         lib.flower_harness_set_param.restype = None
         lib.flower_harness_clear_params.restype = None
-        lib.flower_harness_run.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                           C.POINTER(C.c_int64)]
-        lib.flower_harness_run.restype = C.c_void_p
+        lib.flower_harness_begin.argtypes = [C.c_int64]
+        lib.flower_harness_begin.restype = C.c_void_p
+        lib.flower_harness_add_flower.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        lib.flower_harness_add_flower.restype = C.c_int64
+        lib.flower_harness_blocks.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        lib.flower_harness_blocks.restype = C.c_void_p
+        lib.flower_harness_bar.argtypes = [C.c_void_p, C.c_int]
+        lib.flower_harness_bar.restype = None
+        lib.flower_harness_dump.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        lib.flower_harness_dump.restype = C.c_void_p
+        lib.flower_harness_end.argtypes = [C.c_void_p]
+        lib.flower_harness_end.restype = None
         lib.flower_harness_free.argtypes = [C.c_void_p]
         lib.flower_harness_free.restype = None
         _LIBS[which] = lib
@@ -145,30 +154,59 @@ def random_flower(seed, n_threads=6, n_blocks=4, seg_len=60, n_events=3, sub=0.0
     return {"n_events": n_events, "seqs": seqs, "seq_event": seq_event, "end_side": end_side, "adj": adj}
 
 
-def run(which, flower, mode=0, params=None):
-    """mode 0 -> {"blocks": [[(cap, position, strand, length), ...], ...], "pinches": int64 [n, 6]};
-    mode 1 -> {"flower": int64 stream of the post-bar() flower hierarchy}. params override CACTUS_BAR_CONFIG."""
-    lib = _lib(which)
+def _set_params(lib, params):
     lib.flower_harness_clear_params()
     cfg = dict(CACTUS_BAR_CONFIG)
     cfg.update(params or {})
     for k, v in cfg.items():
         lib.flower_harness_set_param(k.encode(), str(v).encode())
+
+
+def _add(lib, h, flower):
     seqs = flower["seqs"]
     arr = (C.c_char_p * len(seqs))(*seqs)
     ev = np.ascontiguousarray(flower["seq_event"], np.int32)
     es = np.ascontiguousarray(flower["end_side"], np.int32)
     adj = np.ascontiguousarray(np.asarray(flower["adj"], np.int64).reshape(-1, 6))
-    n = C.c_int64()
-    p = lib.flower_harness_run(mode, flower["n_events"], len(seqs), arr, ev.ctypes.data, len(es), es.ctypes.data, len(adj), adj.ctypes.data, C.byref(n))
+    return lib.flower_harness_add_flower(h, len(seqs), arr, ev.ctypes.data, len(es), es.ctypes.data, len(adj), adj.ctypes.data)
+
+
+def _words(lib, p, n):
     w = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(max(n.value, 1),))[: n.value].copy()
     lib.flower_harness_free(p)
-    if mode == 1:
-        return {"flower": w}
-    o, blocks = 1, []
+    return w
+
+
+def blocks(which, flower, params=None):
+    """make_flower_alignment_poa + stPinchIterator_constructFromAlignedBlocks on one flower ->
+    {"blocks": [[(cap, position, strand, length), ...], ...], "pinches": int64 [n, 6], "raw": the whole stream}"""
+    lib = _lib(which)
+    _set_params(lib, params)
+    h = lib.flower_harness_begin(max(flower["seq_event"]) + 1)
+    i = _add(lib, h, flower)
+    n = C.c_int64()
+    w = _words(lib, lib.flower_harness_blocks(h, i, C.byref(n)), n)
+    lib.flower_harness_end(h)
+    o, out = 1, []
     for _ in range(int(w[0])):
         c = int(w[o]); o += 1
-        blocks.append([tuple(int(x) for x in w[o + 4 * k: o + 4 * k + 4]) for k in range(c)])
+        out.append([tuple(int(x) for x in w[o + 4 * k: o + 4 * k + 4]) for k in range(c)])
         o += 4 * c
     npinch = int(w[o]); o += 1
-    return {"blocks": blocks, "pinches": w[o: o + 6 * npinch].reshape(npinch, 6), "raw": w}
+    return {"blocks": out, "pinches": w[o: o + 6 * npinch].reshape(npinch, 6), "raw": w}
+
+
+def bar(which, flowers, params=None, threads=0):
+    """bar() over a list of flowers in ONE cactus disk -> list of int64 streams, the post-BAR hierarchy of every flower"""
+    lib = _lib(which)
+    _set_params(lib, params)
+    h = lib.flower_harness_begin(max(max(f["seq_event"]) for f in flowers) + 1)
+    for f in flowers:
+        _add(lib, h, f)
+    lib.flower_harness_bar(h, threads)
+    out = []
+    for i in range(len(flowers)):
+        n = C.c_int64()
+        out.append(_words(lib, lib.flower_harness_dump(h, i, C.byref(n)), n))
+    lib.flower_harness_end(h)
+    return out

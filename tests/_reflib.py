@@ -291,7 +291,7 @@ def oracle_make_consistent_partial_order_alignments(ends, ri, rr, ov, window_siz
 # ---------------------------------------------------------------------------------------------------
 # host build of the product's __host__ __device__ graph code (tests/hosttest), CPU only
 # ---------------------------------------------------------------------------------------------------
-HOSTTEST_SO = os.path.join(ROOT, "tests", "hosttest", "_build", "libhosttest.so")
+HOSTTEST_SO = os.environ.get("HOSTTEST_SO") or os.path.join(ROOT, "tests", "hosttest", "_build", "libhosttest.so")
 
 
 def build_hosttest():
@@ -314,6 +314,54 @@ def hosttest_poa_msa_trace(seqs, p=None):
     lib.hosttest_free(ptr)
     assert status.value == 0, "hosttest job status %d" % status.value
     return _parse_trace(words, len(seqs))
+
+
+def hosttest_flowers(flowers, p=None, n_lanes=2, n_threads=3, max_jobs=6144, fail_every=0, window_size=10000, max_prog_rows=5000,
+                     max_prog_length_diff=1.0, consistent=True):
+    """The product's end queue + window logic (end_queue.h, bar_windows.h) on the CPU with a stand-in device (hosttest.cpp).
+    flowers: list of (ends, right_end_indexes, right_end_row_indexes, overlaps) with ends = list of lists of ASCII strings.
+    Returns (per flower: list of uint8 [K, cols] or None if the ticket failed, per-flower rc, batches)."""
+    lib = _load(build_hosttest())
+    p = p or cactus_params()
+    hp = p            # RefParams has HtParams' layout (tests/hosttest/hosttest.cpp)
+    end_no = np.array([len(f[0]) for f in flowers], np.int64)
+    end_lengths = np.array([len(e) for f in flowers for e in f[0]], np.int64)
+    strs = [s if isinstance(s, (bytes, bytearray)) else s.encode() for f in flowers for e in f[0] for s in e]
+    string_lens = np.array([len(s) for s in strs] or [0], np.int64)
+    blob = b"".join(strs) + b"\0"
+    flat = lambda k: np.array([int(v) for f in flowers for r in f[k] for v in r] or [0], np.int64)   # noqa: E731
+    rei, reri, ov = (flat(1), flat(2), flat(3)) if consistent else (None, None, None)
+    n_ends = int(end_no.sum())
+    cols = np.zeros(max(n_ends, 1), np.int64)
+    outs = (C.c_void_p * max(n_ends, 1))()
+    batches = C.c_int64()
+    rcs = np.zeros(max(len(flowers), 1), np.int32)
+    lib.hosttest_flowers.restype = C.c_int
+    lib.hosttest_free.argtypes = [C.c_void_p]
+    lib.hosttest_free.restype = None
+    lib.hosttest_flowers.argtypes = [C.POINTER(RefParams), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    rc = lib.hosttest_flowers(C.byref(hp), n_lanes, n_threads, max_jobs, fail_every, len(flowers), end_no.ctypes.data, end_lengths.ctypes.data, blob,
+                              string_lens.ctypes.data, rei.ctypes.data if consistent else None, reri.ctypes.data if consistent else None,
+                              ov.ctypes.data if consistent else None, window_size, max_prog_rows, max_prog_length_diff, cols.ctypes.data, outs,
+                              C.byref(batches), rcs.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("hosttest_flowers failed: %d" % rc)
+    res, e = [], 0
+    for fi, f in enumerate(flowers):
+        ms = []
+        for end in f[0]:
+            if cols[e] < 0:
+                ms = None
+            elif ms is not None:
+                k, c = len(end), int(cols[e])
+                a = np.ctypeslib.as_array(C.cast(outs[e], C.POINTER(C.c_uint8)), shape=(max(k * c, 1),))[: k * c].reshape(k, c).copy()
+                ms.append(a)
+            if outs[e]:
+                lib.hosttest_free(outs[e])
+            e += 1
+        res.append(ms)
+    return res, rcs[: len(flowers)].copy(), batches.value
 
 
 def msa_hash(msa):

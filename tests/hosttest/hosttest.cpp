@@ -324,24 +324,15 @@ extern "C" long long hosttest_group_commit_stress(int threads, int iters, long l
 
 // ---------------------------------------------------------------------------------------------------------
 // batch_merge.h: the plumbing that turns the requests of concurrent callers into one device batch, driven with stand-in
-// "devices" (POA: the MSA of a job is its first sequence; cPecan: one triple (lx, ly, n_anchor) per pair). Returns the number
+// "device" (cPecan: one triple (lx, ly, n_anchor) per pair). Returns the number
 // of callers that got a wrong answer; *merged = batches wider than one request.
 // ---------------------------------------------------------------------------------------------------------
 #include <string>
 #include "../../cactus_b200/csrc/batch_merge.h"
 
 extern "C" long long hosttest_batch_merge_stress(int threads, int iters, long long *merged) {
-    barb200::GroupCommit<barb200::PoaRequest> gpoa;
     barb200::GroupCommit<barb200::PecanRequest> gpec;
     std::atomic<long long> wrong(0), nmerged(0);
-    auto poa_impl = [&](const std::vector<barb200::HostJob> &jobs, std::vector<barb200::JobResult> &res) -> int {
-        res.assign(jobs.size(), barb200::JobResult());
-        for (size_t j = 0; j < jobs.size(); ++j) {
-            res[j].msa.assign(jobs[j].seqs, jobs[j].seqs + jobs[j].lens[0]); res[j].msa_len = jobs[j].lens[0]; res[j].cells = jobs[j].n_seq;
-        }
-        std::this_thread::sleep_for(std::chrono::microseconds(100));
-        return 0;
-    };
     auto pec_impl = [&](const barb200_pecan_params *p, int64_t n, const char *const *sx, const int64_t *lx, const char *const *sy, const int64_t *ly,
                         const int64_t *const *an, const int64_t *na, const uint8_t *rl, const uint8_t *rr, int64_t **trip, int64_t *n_out, double **post,
                         int64_t *cells) -> int {
@@ -357,22 +348,6 @@ extern "C" long long hosttest_batch_merge_stress(int threads, int iters, long lo
     };
     auto worker = [&](int tid) {
         for (int it = 0; it < iters; ++it) {
-            {   // POA request: 1..3 jobs
-                const int nj = 1 + (tid + it) % 3;
-                std::vector<std::vector<uint8_t>> seqs(nj); std::vector<std::vector<int>> lens(nj); std::vector<barb200::HostJob> jobs(nj);
-                for (int j = 0; j < nj; ++j) {
-                    const int L = 3 + (tid * 5 + it + j) % 9;
-                    seqs[j].assign((size_t)2 * L, (uint8_t)((tid + j) & 3)); seqs[j][0] = (uint8_t)(tid & 3); lens[j] = {L, L};
-                    jobs[j] = barb200::HostJob{2, lens[j].data(), seqs[j].data(), 1};
-                }
-                std::vector<barb200::JobResult> res;
-                barb200::PoaRequest r; r.jobs = &jobs; r.results = &res;
-                gpoa.submit(&r, [](const barb200::PoaRequest &, const barb200::PoaRequest &) { return true; },
-                            [&](std::vector<barb200::PoaRequest *> &b) { if (b.size() > 1) ++nmerged; barb200::run_poa_group(b, poa_impl); });
-                bool ok = r.rc == 0 && (int)res.size() == nj;
-                for (int j = 0; ok && j < nj; ++j) ok = res[j].msa_len == lens[j][0] && res[j].msa == std::vector<uint8_t>(seqs[j].begin(), seqs[j].begin() + lens[j][0]) && res[j].cells == 2;
-                if (!ok) ++wrong;
-            }
             {   // cPecan request: 1..4 pairs, two parameter sets, with / without posteriors and optional arrays
                 const int np = 1 + (tid * 3 + it) % 4;
                 std::vector<std::string> xs(np), ys(np); std::vector<const char *> sx(np), sy(np); std::vector<int64_t> lx(np), ly(np), na(np), n_out(np, -1), cells(np, -1);
@@ -405,4 +380,93 @@ extern "C" long long hosttest_batch_merge_stress(int threads, int iters, long lo
     for (auto &t : ts) t.join();
     *merged = nmerged;
     return wrong;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// end_queue.h + bar_windows.h: the product's end queue (tickets, lane workers, window rounds, trimming, stitching, cross-end
+// consistency) driven by application threads, with a stand-in device: every job's MSA comes from the host build of the
+// product's graph code above (hosttest_poa_msa_trace). flowers: n_flowers tickets; flat description as in the arguments.
+// Returns 0, or a negative code; col_out[e] / msa_out[e] (malloc'd, seq_no x column_no) per end, in submission order.
+// ---------------------------------------------------------------------------------------------------------
+#include "../../cactus_b200/csrc/end_queue.h"
+
+extern "C" int hosttest_flowers(const HtParams *hp, int n_lanes, int n_threads, int64_t max_jobs, int fail_every, int64_t n_flowers, const int64_t *end_no,
+                                const int64_t *end_lengths, const char *strings, const int64_t *string_lens, const int64_t *rei, const int64_t *reri,
+                                const int64_t *ov, int64_t window_size, int64_t max_prog_rows, double max_prog_length_diff,
+                                int64_t *col_out, uint8_t **msa_out, int64_t *batches_out, int *ticket_rc) {
+    std::atomic<long long> calls(0);
+    barb200::EndQueue::Exec exec = [&](int lane, const std::vector<barb200::HostJob> &jobs, std::vector<barb200::JobResult> &res, std::string &err) -> int {
+        (void)lane;
+        const long long c = ++calls;
+        if (fail_every > 0 && jobs.size() > 2 && c % fail_every == 0) { err = "stand-in device: injected batch failure"; return -2; }
+        res.assign(jobs.size(), barb200::JobResult());
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            HtParams q = *hp; q.progressive = jobs[j].progressive;
+            int64_t nw = 0; int status = 0, sum = 0;
+            for (int i = 0; i < jobs[j].n_seq; ++i) sum += jobs[j].lens[i];
+            for (int b = 0; b < sum; ++b) if (jobs[j].seqs[b] > 4) { err = "sequence code > 4"; return -3; }      // what the device rejects too
+            int64_t *w = hosttest_poa_msa_trace(&q, jobs[j].n_seq, jobs[j].lens, jobs[j].seqs, &nw, &status);
+            if (status) { free(w); err = "stand-in device: job failed"; return -5; }
+            const int ml = (int)w[1];
+            const size_t nb = (size_t)jobs[j].n_seq * ml, nwm = (nb + 7) / 8;
+            res[j].msa.assign((const uint8_t *)(w + (nw - (int64_t)nwm)), (const uint8_t *)(w + (nw - (int64_t)nwm)) + nb);
+            res[j].msa_len = ml; res[j].cells = w[2];
+            free(w);
+        }
+        return 0;
+    };
+    barb200::EndQueue q(n_lanes, exec, max_jobs, 1e18);
+    // flat -> per-flower pointer tables
+    std::vector<int64_t> f_end0(n_flowers + 1, 0);
+    for (int64_t f = 0; f < n_flowers; ++f) f_end0[f + 1] = f_end0[f] + end_no[f];
+    const int64_t n_ends = f_end0[n_flowers];
+    std::vector<int64_t> e_str0(n_ends + 1, 0);
+    for (int64_t e = 0; e < n_ends; ++e) e_str0[e + 1] = e_str0[e] + end_lengths[e];
+    const int64_t n_str = e_str0[n_ends];
+    std::vector<int64_t> s_off(n_str + 1, 0);
+    for (int64_t k = 0; k < n_str; ++k) s_off[k + 1] = s_off[k] + string_lens[k];
+    std::vector<std::unique_ptr<barb200::Ticket>> tickets(n_flowers);
+    std::atomic<int> bad(0);
+    auto worker = [&](int tid) {
+        // submit every flower of this thread first, then collect them in order (as the shim's bar() does)
+        for (int64_t f = tid; f < n_flowers; f += n_threads) {
+            std::unique_ptr<barb200::Ticket> t(new barb200::Ticket());
+            t->n_ends = end_no[f]; t->window_size = window_size; t->max_prog_rows = max_prog_rows; t->max_prog_length_diff = max_prog_length_diff;
+            t->default_progressive = hp->progressive; t->consistent = rei != nullptr;
+            t->ends.resize((size_t)end_no[f]);
+            for (int64_t e = 0; e < end_no[f]; ++e) {
+                const int64_t ge = f_end0[f] + e, K = end_lengths[ge];
+                std::vector<char *> sp(K); std::vector<int> sl(K);
+                for (int64_t i = 0; i < K; ++i) { sp[i] = (char *)strings + s_off[e_str0[ge] + i]; sl[i] = (int)string_lens[e_str0[ge] + i]; }
+                if (!barb200::barwin::end_init(t->ends[e], K, sp.data(), sl.data()).empty()) ++bad;
+                if (rei) {
+                    t->right_end_indexes.emplace_back(rei + e_str0[ge], rei + e_str0[ge] + K);
+                    t->right_end_row_indexes.emplace_back(reri + e_str0[ge], reri + e_str0[ge] + K);
+                    t->overlaps.emplace_back(ov + e_str0[ge], ov + e_str0[ge] + K);
+                }
+            }
+            q.submit(t.get());
+            tickets[f] = std::move(t);
+        }
+        for (int64_t f = tid; f < n_flowers; f += n_threads) {
+            barb200::Ticket &t = *tickets[f];
+            q.wait(&t);
+            if (ticket_rc) ticket_rc[f] = t.rc;
+            if (t.rc) { for (int64_t e = 0; e < t.n_ends; ++e) { col_out[f_end0[f] + e] = -1; msa_out[f_end0[f] + e] = nullptr; } continue; }
+            std::vector<barb200_msa *> ms((size_t)t.n_ends);
+            for (int64_t e = 0; e < t.n_ends; ++e) ms[e] = barb200::barwin::end_stitch(t.ends[e]);
+            if (t.consistent && !barb200::barwin::consistency_trim(t.n_ends, ms.data(), t.right_end_indexes, t.right_end_row_indexes, t.overlaps)) ++bad;
+            for (int64_t e = 0; e < t.n_ends; ++e) {
+                col_out[f_end0[f] + e] = ms[e]->column_no; msa_out[f_end0[f] + e] = ms[e]->msa;
+                free(ms[e]->seq_lens); free(ms[e]);
+            }
+        }
+    };
+    std::vector<std::thread> ts;
+    for (int t = 0; t < n_threads; ++t) ts.emplace_back(worker, t);
+    for (auto &t : ts) t.join();
+    int64_t nb = 0, nj = 0; q.stats(&nb, &nj);
+    if (batches_out) *batches_out = nb;
+    return bad ? -1 : 0;
 }

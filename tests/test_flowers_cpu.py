@@ -1,0 +1,30 @@
+"""Flower level, no GPU: the golden fixture is what the UNMODIFIED reference library produces here (when oracle/_ref holds
+it), the harness's canonical post-bar() dump does not depend on the OpenMP team size, and the generators are deterministic."""
+import numpy as np
+import pytest
+
+import _flowers as F
+import _flower_golden as G
+
+
+def test_fixture_has_the_references_own_flower():
+    names = [c[0] for c in G.cases()]
+    assert "shared_maxlen2" in names and "shared_iterator" in names and len(names) >= 10
+    for name, fl, params, stream, bar in G.cases():
+        assert stream[0] > 0 and bar[0] > 0, name
+
+
+def test_random_flower_is_deterministic():
+    a, b = F.random_flower(3), F.random_flower(3)
+    assert a["seqs"] == b["seqs"] and a["adj"] == b["adj"]
+
+
+@pytest.mark.skipif(not F.have("ref"), reason="oracle/_ref/libflower_ref.so not built (needs /root/reference)")
+def test_reference_library_reproduces_the_fixture():
+    for name, fl, params, stream, bar in G.cases():
+        r = F.blocks("ref", fl, params)
+        assert np.array_equal(r["raw"], stream), name
+    some = [c for c in G.cases() if c[0].startswith("random_")]
+    out = F.bar("ref", [c[1] for c in some], threads=3)          # several flowers in ONE bar() call, three threads
+    for c, o in zip(some, out):
+        assert np.array_equal(o, c[4]), c[0]

@@ -203,3 +203,84 @@ def test_pipelined_batch_equals_single_stage(engine, oracle_built):
     for j in range(0, len(jobs), 173):
         tr = R.oracle_poa_msa_trace(jobs[j])
         assert np.array_equal(msas[j], tr["msa"]) and int(cells[j]) == tr["cells"], j
+
+
+def test_mixed_shapes_are_bucketed(engine, oracle_built):
+    """ends bucketed by the CTA class their longest sequence needs (north star: "bucketed by (seq-count x max-length)"): a
+    batch of short adjacencies, 2 kbp windows and a long window runs as several class launches with per-class slot sizes and
+    returns, job by job in the caller's order, what the oracle computes"""
+    rng = np.random.default_rng(47)
+    shapes = [(4, 150)] * 12 + [(3, 700)] * 6 + [(5, 1500)] * 3 + [(3, 2500)] * 2 + [(2, 5200)] + [(6, 40)] * 9
+    order = rng.permutation(len(shapes))
+    jobs = [family(rng, shapes[i][0], shapes[i][1], sub=0.03, ins=0.01, dele=0.01) for i in order]
+    msas, cells = engine.poa_msa_batch(jobs, return_cells=True)
+    for j, job in enumerate(jobs):
+        tr = R.oracle_poa_msa_trace(job)
+        assert msas[j].shape == tr["msa"].shape and np.array_equal(msas[j], tr["msa"]) and int(cells[j]) == tr["cells"], (j, shapes[order[j]])
+    st = engine.stage(jobs)
+    b = st.buckets()
+    st.close()
+    assert len(b) >= 4 and [x["threads"] for x in b] == sorted([x["threads"] for x in b], reverse=True)
+    assert sum(x["jobs"] for x in b) == len(jobs)
+    assert b[0]["plane_ints"] > 20 * b[-1]["plane_ints"]          # slots are sized per class, not from the largest job
+
+
+def test_capacity_misses_grow_geometrically(oracle_built):
+    """unrelated sequences outgrow the optimistic plane / MSA sizing: the flagged jobs are re-run with x4 slots, then at worst
+    case, and still equal the oracle"""
+    rng = np.random.default_rng(48)
+    jobs = [[rng.integers(0, 4, size=int(rng.integers(150, 400))).astype(np.uint8) for _ in range(int(rng.integers(6, 12)))] for _ in range(10)]
+    jobs += [family(rng, 4, 300) for _ in range(6)]
+    import cactus_b200 as cb
+    e = cb.Engine()
+    msas = e.poa_msa_batch(jobs)
+    e.close()
+    for j, job in enumerate(jobs):
+        o = R.oracle_poa_msa(job)
+        assert msas[j].shape == o.shape and np.array_equal(msas[j], o), j
+
+
+def test_flower_submit_wait_equals_the_synchronous_call(engine, oracle_built):
+    """barb200_flower_submit / barb200_flower_wait: 30 tickets submitted before the first wait share a few device batches and
+    deliver what the synchronous call (and the oracle) delivers"""
+    rng = np.random.default_rng(49)
+    probs = [two_end_problem(rng, int(rng.integers(1, 7)), int(rng.choice([20, 90, 300])), sub=0.04, ins=0.02, dele=0.02) for _ in range(30)]
+    before = engine.queue_stats()
+    tickets = [engine.flower_submit(*p) for p in probs]
+    res = [engine.flower_wait(t) for t in tickets]
+    after = engine.queue_stats()
+    assert after["batches"] - before["batches"] < len(probs) // 2
+    for k, (p, ms) in enumerate(zip(probs, res)):
+        if k % 5 == 0:
+            o = R.oracle_make_consistent_partial_order_alignments(*p)
+            for a, b in zip(ms, o):
+                assert a.msa_seq.shape == b.shape and np.array_equal(a.msa_seq, b), k
+        else:
+            s = engine.make_consistent_partial_order_alignments(*p)
+            for a, b in zip(ms, s):
+                assert np.array_equal(a.msa_seq, b.msa_seq), k
+    # independent ends (no consistency information), several windows
+    ends = [[to_ascii(s) for s in family(rng, 4, 260)] for _ in range(5)]
+    t = engine.flower_submit(ends, window_size=100)
+    ms = engine.flower_wait(t)
+    for e, m in zip(ends, ms):
+        o = R.oracle_msa_make_partial_order_alignment(e, window_size=100)
+        assert m.msa_seq.shape == o.shape and np.array_equal(m.msa_seq, o)
+
+
+def test_a_bad_ticket_fails_alone(engine):
+    """one caller's invalid input ('-' is code 5, which the device rejects) must not fail the tickets that shared its batch"""
+    import cactus_b200 as cb
+    rng = np.random.default_rng(50)
+    probs = [two_end_problem(rng, 3, 40) for _ in range(8)]
+    ends, ri, rr, ov = probs[3]
+    ends = [list(e) for e in ends]
+    ends[0][0] = ends[0][0][:2] + b"-" + ends[0][0][3:]
+    probs[3] = (ends, ri, rr, ov)
+    tickets = [engine.flower_submit(*p) for p in probs]
+    for k, t in enumerate(tickets):
+        if k == 3:
+            with pytest.raises(cb.BarB200Error):
+                engine.flower_wait(t)
+        else:
+            assert len(engine.flower_wait(t)) == 2

@@ -1,5 +1,5 @@
 """Concurrent callers on one context (-m gpu). The reference enters the BAR code from OpenMP teams (bar/impl/bar.c:90-94), so
-the C ABI is called from several host threads at once; their device batches are merged (cactus_b200/csrc/group_commit.h).
+the C ABI is called from several host threads at once; their requests meet in the engine's queues (POA: end_queue.h, pair-HMM: group_commit.h) and share device batches.
 Whatever the interleaving, every caller must get exactly what it gets when it is alone. (Named to run after the parity suites.)"""
 from concurrent.futures import ThreadPoolExecutor
 
