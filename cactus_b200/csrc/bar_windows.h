@@ -132,7 +132,7 @@ struct EndState {
 // :471-483, 494-516. Returns an error text or "".
 inline std::string end_init(EndState &E, int64_t seq_no, char **seqs, const int *seq_lens) {
     E.seq_no = seq_no;
-    if (E.seq_no <= 0) return "end without sequences";
+    if (E.seq_no <= 0) return "end without sequences";         // the reference asserts seq_no > 0 (poaBarAligner.c:466)
     E.seq_lens.assign(seq_lens, seq_lens + E.seq_no);
     E.codes.resize(E.seq_no);
     for (int64_t i = 0; i < E.seq_no; ++i) {

@@ -10,6 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FLOWER_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_ref.so")
 FLOWER_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_shim.so")
+FLOWER_STANDIN_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_standin.so")   # shims + real host code over a CPU stand-in device
+_PATHS = {"ref": FLOWER_REF_SO, "shim": FLOWER_SHIM_SO, "standin": FLOWER_STANDIN_SO}
 
 # the <bar> element of src/cactus/cactus_progressive_config.xml:246-325 (values only; the keys are the XML path)
 CACTUS_BAR_CONFIG = {
@@ -35,12 +37,12 @@ _LIBS = {}
 
 
 def have(which):
-    return os.path.exists(FLOWER_REF_SO if which == "ref" else FLOWER_SHIM_SO)
+    return os.path.exists(_PATHS[which])
 
 
 def _lib(which):
     if which not in _LIBS:
-        lib = C.CDLL(FLOWER_REF_SO if which == "ref" else FLOWER_SHIM_SO)
+        lib = C.CDLL(_PATHS[which])
         lib.flower_harness_set_param.argtypes = [C.c_char_p, C.c_char_p]
         lib.flower_harness_set_param.restype = None
         lib.flower_harness_clear_params.restype = None
@@ -151,6 +153,12 @@ def random_flower(seed, n_threads=6, n_blocks=4, seg_len=60, n_events=3, sub=0.0
                 adj.append((idx, n + 1 - hi, n + 1 - lo, 0, ea, eb))
             else:
                 adj.append((idx, lo, hi, 1, ea, eb))
+    # ends no thread passes through are dropped (an End without caps is not a valid input: the reference asserts seq_no > 0,
+    # poaBarAligner.c:466)
+    used = sorted({a[4] for a in adj} | {a[5] for a in adj})
+    remap = {e: i for i, e in enumerate(used)}
+    adj = [(a[0], a[1], a[2], a[3], remap[a[4]], remap[a[5]]) for a in adj]
+    end_side = [end_side[e] for e in used]
     return {"n_events": n_events, "seqs": seqs, "seq_event": seq_event, "end_side": end_side, "adj": adj}
 
 

@@ -28,3 +28,20 @@ def test_reference_library_reproduces_the_fixture():
     out = F.bar("ref", [c[1] for c in some], threads=3)          # several flowers in ONE bar() call, three threads
     for c, o in zip(some, out):
         assert np.array_equal(o, c[4]), c[0]
+
+
+@pytest.mark.skipif(not F.have("standin"), reason="oracle/_ref/libflower_standin.so not built (needs /root/reference)")
+def test_shims_and_host_code_over_a_standin_device_reproduce_the_fixture():
+    """no GPU: the REAL shims (shim/cactus_bar_shim.c incl. its bar()) and the REAL host code of the product (host_bar.cpp,
+    end_queue.h, bar_windows.h) under the reference's own flower-level objects, with a TEST-ONLY CPU stand-in for the device
+    layer (tests/hosttest/standin_device.cpp: every job computed by the host build of the product's graph code). The GPU
+    suite runs the same checks against the real libbarb200 (tests/test_gpu_flowers.py)."""
+    for name, fl, params, stream, bar in G.cases():
+        r = F.blocks("standin", fl, params)
+        assert np.array_equal(r["raw"], stream), name
+        assert np.array_equal(F.bar("standin", [fl], params)[0], bar), name
+    flowers = [F.random_flower(100 + s, n_threads=int(4 + s % 5), n_blocks=int(2 + s % 4), seg_len=40 + 7 * (s % 9)) for s in range(24)]
+    got = F.bar("standin", flowers, threads=4)                    # 24 flowers in one bar() call: submit all, then collect
+    want = F.bar("ref", flowers, threads=2)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), i
