@@ -98,6 +98,8 @@ def load_library():
     lib.barb200_flower_wait.restype = C.POINTER(C.POINTER(_CMsa))
     lib.barb200_queue_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.barb200_queue_stats.restype = ci
+    lib.barb200_last_batch_timing.argtypes = [vp, vp]
+    lib.barb200_last_batch_timing.restype = ci
     lib.barb200_device_count.argtypes = [vp]
     lib.barb200_device_count.restype = ci
     lib.barb200_device_info.argtypes = [vp, C.POINTER(ci), C.POINTER(i64), C.POINTER(i64), C.c_char_p, ci]
@@ -536,6 +538,11 @@ class Engine:
         b, j = C.c_int64(), C.c_int64()
         self._check(self.lib.barb200_queue_stats(self.ctx, C.byref(b), C.byref(j)))
         return {"batches": b.value, "jobs": j.value}
+
+    def last_batch_timing(self):
+        out = (C.c_double * 6)()
+        self._check(self.lib.barb200_last_batch_timing(self.ctx, out))
+        return dict(zip(["build_ms", "run_ms", "device_ms", "fetch_ms", "total_ms", "jobs"], [float(v) for v in out]))
 
     def device_count(self):
         return int(self.lib.barb200_device_count(self.ctx))

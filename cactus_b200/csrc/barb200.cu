@@ -87,6 +87,7 @@ struct barb200_ctx {
     void *pecan_scratch = nullptr; size_t pecan_scratch_bytes = 0;   // pecan.cu's batch call (grow-only)
     void *pecan_pinned[2] = {nullptr, nullptr}; size_t pecan_pinned_bytes[2] = {0, 0};   // pinned staging: 0 upload, 1 download
     void *dispatcher = nullptr;         // host_bar.cpp's end queue (created on first use, destroyed with the context)
+    double last_timing[6] = {0, 0, 0, 0, 0, 0};   // of the most recent device batch (barb200_last_batch_timing), under err_mu
 };
 
 namespace barb200 {
@@ -872,6 +873,11 @@ static int batch_on_lane(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *
     const double t3 = now_ms();
     barb200_stage_destroy(st);
     if (device_ms) *device_ms = kms;
+    {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        ctx->last_timing[0] = t1 - t0; ctx->last_timing[1] = t2 - t1; ctx->last_timing[2] = kms; ctx->last_timing[3] = t3 - t2;
+        ctx->last_timing[4] = now_ms() - t0; ctx->last_timing[5] = (double)n_jobs;
+    }
     if (timing_on()) fprintf(stderr, "barb200 timing: lane %d, %lld jobs: build %.1f ms, run %.1f ms (%.1f on the device), fetch %.1f ms, destroy %.1f ms\n",
                              lane, (long long)n_jobs, t1 - t0, t2 - t1, kms, t3 - t2, now_ms() - t3);
     return rc;
@@ -958,6 +964,15 @@ extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int
         if (msa_out) for (int64_t j = 0; j < n_jobs; ++j) { free(msa_out[j]); msa_out[j] = nullptr; }
         set_error(ctx, errs[d]); return rcs[d];
     }
+    return BARB200_OK;
+}
+
+// host-side phases of the most recent device batch, milliseconds: out[0] build (pack, validation, planning, H2D), out[1] launch +
+// streamed guide trees + wait, out[2] device time of the kernels, out[3] fetch (D2H + unpack), out[4] total, out[5] jobs
+extern "C" int barb200_last_batch_timing(barb200_ctx *ctx, double out[6]) {
+    if (!ctx || !out) return BARB200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    for (int k = 0; k < 6; ++k) out[k] = ctx->last_timing[k];
     return BARB200_OK;
 }
 

@@ -51,20 +51,62 @@ def gather_checksums(value, device):
     return [float(x[0]) for x in out] if out is not None else None
 
 
+_PINNED = {}
+
+
+def _pinned(n, key):
+    """grow-only pinned host buffer (plain memory when CUDA is absent, i.e. in the gloo tests)"""
+    t = _PINNED.get(key)
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1) + max(n, 1) // 4, dtype=torch.uint8)
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        _PINNED[key] = t
+    return t[:n]
+
+
 def gather_bytes(host_bytes, device):
-    """gather a variable-length uint8 tensor per rank on rank 0 (device buffers over the backend's transport; returns
-    the list of host tensors on rank 0, None elsewhere). Lengths travel first, payloads are padded to the longest."""
+    """gather a variable-length uint8 tensor per rank on rank 0: lengths first (all_gather of one int64), then every rank SENDS its
+    un-padded payload and rank 0 RECEIVES them into consecutive slices of ONE device buffer (batched isend / irecv: an
+    ncclSend / ncclRecv group on the GPU box), followed by one copy into pinned host memory. Returns the list of host tensors
+    (views of that buffer) on rank 0, None elsewhere."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [host_bytes]
     world, rank = dist.get_world_size(), dist.get_rank()
     n = torch.tensor([host_bytes.numel()], dtype=torch.int64, device=device)
     lens = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(lens, n)
-    mx = max(int(x.item()) for x in lens)
-    pad = torch.zeros(mx, dtype=torch.uint8, device=device)
-    pad[: host_bytes.numel()].copy_(host_bytes, non_blocking=True)
-    out = [torch.empty(mx, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
-    dist.gather(pad, out, dst=0)
+    lens = [int(x.item()) for x in lens]
+    mine = host_bytes.to(device, non_blocking=True)
     if rank != 0:
+        if lens[rank]:
+            dist.send(mine, dst=0)
         return None
-    return [out[r][: int(lens[r].item())].cpu() for r in range(world)]
+    offs = [0]
+    for v in lens:
+        offs.append(offs[-1] + v)
+    buf = torch.empty(max(offs[-1], 1), dtype=torch.uint8, device=device)
+    buf[: lens[0]].copy_(mine)
+    ops = [dist.P2POp(dist.irecv, buf[offs[r]: offs[r + 1]], r) for r in range(1, world) if lens[r]]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    host = _pinned(offs[-1], "gather")
+    host.copy_(buf[: offs[-1]])
+    return [host[offs[r]: offs[r + 1]] for r in range(world)]
+
+
+def gather_msa_bytes(outs, msa_len, K, device):
+    """the MSA rows of this rank's ends (malloc'd K x msa_len blocks, `outs[i]`) -> one pinned host buffer -> rank 0 (gather_bytes)"""
+    import ctypes as C
+    import numpy as np
+    sizes = msa_len.astype(np.int64) * K
+    total = int(sizes.sum())
+    buf = _pinned(total, "msa")
+    base = buf.data_ptr()
+    o = 0
+    for i in range(len(sizes)):
+        nb = int(sizes[i])
+        C.memmove(base + o, outs[i], nb)
+        o += nb
+    return gather_bytes(buf, device)

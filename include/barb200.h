@@ -204,6 +204,11 @@ barb200_msa **barb200_flower_wait(barb200_ctx *ctx, barb200_ticket *ticket);
 /* device batches the queue has run so far and the jobs in them (reports, tests) */
 int barb200_queue_stats(barb200_ctx *ctx, int64_t *batches, int64_t *jobs);
 
+/* Host-side phases of the context's most recent device batch, in milliseconds: out[0] build (pack, validation, planning, H2D),
+ * out[1] launch + streamed guide trees + wait, out[2] device time of the kernels, out[3] fetch (D2H + unpack), out[4] total,
+ * out[5] = number of jobs. For reports (bench.py's per-phase breakdown). */
+int barb200_last_batch_timing(barb200_ctx *ctx, double out[6]);
+
 /* Device facts for reports. */
 int barb200_device_count(barb200_ctx *ctx);
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);

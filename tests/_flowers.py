@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FLOWER_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_ref.so")
 FLOWER_SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_shim.so")
 FLOWER_STANDIN_SO = os.path.join(ROOT, "oracle", "_ref", "libflower_standin.so")   # shims + real host code over a CPU stand-in device
-_PATHS = {"ref": FLOWER_REF_SO, "shim": FLOWER_SHIM_SO, "standin": FLOWER_STANDIN_SO}
+_PATHS = {"ref": FLOWER_REF_SO, "shim": FLOWER_SHIM_SO, "standin": FLOWER_STANDIN_SO,
+          "harvest": os.path.join(ROOT, "oracle", "_ref", "libflower_harvest.so")}    # reference + input recorder (shim/cactus_bar_harvest.c)
 
 # the <bar> element of src/cactus/cactus_progressive_config.xml:246-325 (values only; the keys are the XML path)
 CACTUS_BAR_CONFIG = {

@@ -28,5 +28,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+    assert d.get("product_library_loaded") is False            # the reference arm maps no product code
+    assert d["cpu_baseline"]["allocator"]["glibc_default_gcells"] > 0 and d["cpu_baseline"]["allocator"]["retained_blocks_gcells"] > 0
     p = d["pecan"]
     assert p["impl"] == "reference" and p["value"] > 0 and p["cpu_baseline"]["kind"] == "reference"

@@ -45,3 +45,33 @@ def test_shims_and_host_code_over_a_standin_device_reproduce_the_fixture():
     want = F.bar("ref", flowers, threads=2)
     for i, (a, b) in enumerate(zip(got, want)):
         assert np.array_equal(a, b), i
+
+
+@pytest.mark.skipif(not (F.have("harvest") and F.have("standin")), reason="oracle/_ref/libflower_harvest.so not built (needs /root/reference)")
+def test_harvested_inputs_replay_to_the_same_alignments(tmp_path, oracle_built):
+    """shim/cactus_bar_harvest.c records the inputs of every top-level alignment call of a REFERENCE bar() run (the way real
+    datasets are to be captured for bench.py --workload); replaying the record through the product's host code (stand-in
+    device) and through the oracle gives the same MSAs"""
+    import os
+    import workload
+    import _reflib as R
+    dump = str(tmp_path / "bar.harvest")
+    flowers = [F.random_flower(300 + s, n_threads=5, n_blocks=3, seg_len=50) for s in range(5)]
+    os.environ["BARB200_HARVEST"] = dump
+    try:
+        got = F.bar("harvest", flowers, threads=2)
+    finally:
+        del os.environ["BARB200_HARVEST"]
+    want = F.bar("ref", flowers, threads=2)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)                     # recording does not change the run
+    recs = workload.read_harvest(dump)
+    assert len(recs) == len(flowers)
+    assert sorted(sum(len(e) for e in r["ends"]) for r in recs) == sorted(2 * len(f["adj"]) for f in flowers)
+    multi = [r for r in recs if r["right_end_indexes"] is not None]
+    res, rcs, _ = R.hosttest_flowers([(r["ends"], r["right_end_indexes"], r["right_end_row_indexes"], r["overlaps"]) for r in multi])
+    assert not rcs.any()
+    for r, ms in zip(multi, res):
+        o = R.oracle_make_consistent_partial_order_alignments(r["ends"], r["right_end_indexes"], r["right_end_row_indexes"], r["overlaps"])
+        for a, b in zip(ms, o):
+            assert a.shape == b.shape and np.array_equal(a, b)

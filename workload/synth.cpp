@@ -99,3 +99,12 @@ extern "C" int64_t barsynth_pair(uint64_t seed, uint64_t pair_index, int L, doub
     }
     return na;
 }
+
+// FNV-1a over (msa_len, bytes) of a K x msa_len alignment matrix: the per-end hash bench.py's parity gate compares between the
+// GPU arm and the CPU arm (same function as oracle/ref_harness.c: msa_hash)
+extern "C" uint64_t barsynth_msa_hash(const uint8_t *m, int64_t n, int msa_len) {
+    uint64_t h = 1469598103934665603ULL ^ (uint64_t)(uint32_t)msa_len;
+    h *= 1099511628211ULL;
+    for (int64_t k = 0; k < n; ++k) { h ^= m[k]; h *= 1099511628211ULL; }
+    return h;
+}
