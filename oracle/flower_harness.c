@@ -89,6 +89,7 @@ static End *view(End *end, int side) { return (end_getSide(end) ? 1 : 0) == side
 
 void *flower_harness_begin(int64_t n_events) {
     session *S = st_calloc(1, sizeof(session));
+    st_randomSeed(20260923);            /* the cPecan configuration draws st_random() numbers (tie breaks, multipleAligner.c:853) */
     S->disk = cactusDisk_construct();
     S->eventTree = eventTree_construct2(S->disk);
     Event *root = eventTree_getRootEvent(S->eventTree);

@@ -160,28 +160,22 @@ static int64_t alignment_score(int64_t *trip, int64_t n, int64_t seqLength1, int
     return d * PAIR_ALIGNMENT_PROB_1;
 }
 
-stList *makeAllPairwiseAlignments(StateMachine *sM, stList *seqFrags, PairwiseAlignmentParameters *p, stList **seqPairSimilarityScores) {
+/* addMultipleAlignedPairs (multipleAligner.c:651-666, static there) for a LIST of sequence pairs in one device batch: pair i is
+ * (first[i], second[i]); the pairs' 5-tuples are appended to multipleAlignedPairs and (similarity, first, second) to scores, pair
+ * after pair in list order -- exactly what the reference's one-pair-at-a-time loop leaves behind. */
+static void align_pair_list(StateMachine *sM, stList *seqFrags, const int64_t *first, const int64_t *second, int64_t pairNo,
+                            PairwiseAlignmentParameters *p, stList *multipleAlignedPairs, stList *scores) {
+    if (pairNo <= 0) {
+        return;
+    }
     check_state_machine(sM);
     barb200_ctx *ctx = shim_context();
     barb200_pecan_params q;
     params_from_pecan(p, &q);
-    *seqPairSimilarityScores = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    stList *multipleAlignedPairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
-    const int64_t seqNo = stList_length(seqFrags), pairNo = seqNo * (seqNo - 1) / 2;
-    if (pairNo <= 0) {
-        return multipleAlignedPairs;
-    }
     const char **sx = st_malloc(sizeof(char *) * pairNo), **sy = st_malloc(sizeof(char *) * pairNo);
     int64_t *lx = st_malloc(8 * pairNo), *ly = st_malloc(8 * pairNo), *na = st_malloc(8 * pairNo), *nOut = st_malloc(8 * pairNo);
     int64_t **anchors = st_malloc(sizeof(int64_t *) * pairNo), **trip = st_malloc(sizeof(int64_t *) * pairNo);
     uint8_t *rl = st_malloc(pairNo), *rr = st_malloc(pairNo);
-    int64_t *first = st_malloc(8 * pairNo), *second = st_malloc(8 * pairNo);
-    int64_t k = 0;
-    for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {            /* the pairs in the reference's order, multipleAligner.c:675-679 */
-        for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
-            first[k] = seq1; second[k] = seq2;
-        }
-    }
     /* anchors: the reference's host code (getAlignedPairs, pairwiseAligner.c:1527-1534), one pair per thread -- the reference
      * itself runs it concurrently from bar()'s OpenMP loop over ends (bar/impl/bar.c:90-94) */
 #if defined(_OPENMP)
@@ -196,36 +190,111 @@ stList *makeAllPairwiseAlignments(StateMachine *sM, stList *seqFrags, PairwiseAl
         rl[i] = f1->leftEndId != f2->leftEndId;                /* addMultipleAlignedPairs, multipleAligner.c:660-661 */
         rr[i] = f1->rightEndId != f2->rightEndId;
     }
-    free(first); free(second);
     if (barb200_pecan_aligned_pairs_batch(ctx, &q, pairNo, sx, lx, sy, ly, (const int64_t *const *) anchors, na, rl, rr, trip, nOut, NULL, NULL) != BARB200_OK) {
         st_errAbort("barb200: pair-HMM batch failed: %s", barb200_last_error(ctx));
     }
-    k = 0;
-    for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {
-        for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
-            SeqFrag *f1 = stList_get(seqFrags, seq1), *f2 = stList_get(seqFrags, seq2);
-            stList *alignedPairs = reweightAlignedPairs2(triples_to_list(trip[k], nOut[k]), f1->length, f2->length, p->gapGamma);
-            int64_t distance;
-            if (p->gapGamma <= 0.0) {
-                distance = alignment_score(trip[k], nOut[k], f1->length, f2->length);
-            } else {                                           /* scores were reweighted: sum them from the list */
-                int64_t n = stList_length(alignedPairs), *t2 = st_malloc(24 * (n > 0 ? n : 1));
-                for (int64_t i = 0; i < n; i++) { t2[3 * i] = stIntTuple_get(stList_get(alignedPairs, i), 0); }
-                distance = alignment_score(t2, n, f1->length, f2->length);
-                free(t2);
-            }
-            /* convertAlignedPairsToMultipleAlignedPairs, multipleAligner.c:619-633 (static there): pops, i.e. reverses */
-            while (stList_length(alignedPairs) > 0) {
-                stIntTuple *aP = stList_pop(alignedPairs);
-                stList_append(multipleAlignedPairs, stIntTuple_construct5(stIntTuple_get(aP, 0), seq1, stIntTuple_get(aP, 1), seq2, stIntTuple_get(aP, 2)));
-                stIntTuple_destruct(aP);
-            }
-            stList_destruct(alignedPairs);
-            stList_append(*seqPairSimilarityScores, stIntTuple_construct3(distance, seq1, seq2));
-            barb200_free(trip[k]);
-            free(anchors[k]);
+    for (int64_t k = 0; k < pairNo; k++) {
+        SeqFrag *f1 = stList_get(seqFrags, first[k]), *f2 = stList_get(seqFrags, second[k]);
+        stList *alignedPairs = reweightAlignedPairs2(triples_to_list(trip[k], nOut[k]), f1->length, f2->length, p->gapGamma);
+        int64_t distance;
+        if (p->gapGamma <= 0.0) {
+            distance = alignment_score(trip[k], nOut[k], f1->length, f2->length);
+        } else {                                           /* scores were reweighted: sum them from the list */
+            int64_t n = stList_length(alignedPairs), *t2 = st_malloc(24 * (n > 0 ? n : 1));
+            for (int64_t i = 0; i < n; i++) { t2[3 * i] = stIntTuple_get(stList_get(alignedPairs, i), 0); }
+            distance = alignment_score(t2, n, f1->length, f2->length);
+            free(t2);
         }
+        /* convertAlignedPairsToMultipleAlignedPairs, multipleAligner.c:619-633 (static there): pops, i.e. reverses */
+        while (stList_length(alignedPairs) > 0) {
+            stIntTuple *aP = stList_pop(alignedPairs);
+            stList_append(multipleAlignedPairs, stIntTuple_construct5(stIntTuple_get(aP, 0), first[k], stIntTuple_get(aP, 1), second[k], stIntTuple_get(aP, 2)));
+            stIntTuple_destruct(aP);
+        }
+        stList_destruct(alignedPairs);
+        stList_append(scores, stIntTuple_construct3(distance, first[k], second[k]));
+        barb200_free(trip[k]);
+        free(anchors[k]);
     }
     free(sx); free(sy); free(lx); free(ly); free(na); free(nOut); free(anchors); free(trip); free(rl); free(rr);
+}
+
+stList *makeAllPairwiseAlignments(StateMachine *sM, stList *seqFrags, PairwiseAlignmentParameters *p, stList **seqPairSimilarityScores) {
+    *seqPairSimilarityScores = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    stList *multipleAlignedPairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    const int64_t seqNo = stList_length(seqFrags), pairNo = seqNo * (seqNo - 1) / 2;
+    if (pairNo <= 0) {
+        return multipleAlignedPairs;
+    }
+    int64_t *first = st_malloc(8 * pairNo), *second = st_malloc(8 * pairNo);
+    int64_t k = 0;
+    for (int64_t seq1 = 0; seq1 < seqNo; seq1++) {            /* the pairs in the reference's order, multipleAligner.c:675-679 */
+        for (int64_t seq2 = seq1 + 1; seq2 < seqNo; seq2++, k++) {
+            first[k] = seq1; second[k] = seq2;
+        }
+    }
+    align_pair_list(sM, seqFrags, first, second, pairNo, p, multipleAlignedPairs, *seqPairSimilarityScores);
+    free(first); free(second);
     return multipleAlignedPairs;
+}
+
+/* defined (not static) in multipleAligner.c but missing from multipleAligner.h */
+stSortedSet *getReferencePairwiseAlignments2(stList *seqFrags);
+int64_t *getDistanceMatrix(stSet *columns, stList *seqFrags, int64_t maxPairsToConsider);
+int64_t getNextBestPair(int64_t seq1, int64_t *distanceCounts, int64_t seqNo, stSortedSet *chosenPairsOfSequencesToAlign);
+stSet *getMultipleSequenceAlignment(stList *seqFrags, stList *multipleAlignedPairs, double gapGamma);
+stSet *getMultipleSequenceAlignmentProgressive(stList *seqFrags, stList *multipleAlignedPairs, double gapGamma, stList *seqPairSimilarityScores);
+stList *filterMultipleAlignedPairs(stSet *columns, stList *multipleAlignedPairs);
+
+/* makeAlignment (inc/multipleAligner.h, impl/multipleAligner.c:887-939) -- the entry point of endAligner.c:87 (makeEndAlignment) and with
+ * it of flowerAligner.c / bar() in the cPecan configuration. With fewer than all pairs affordable (spanningTrees * (n-1) < n(n-1)/2) the
+ * reference aligns n-1 "reference" pairs and then, spanningTrees-1 times, one more pair per sequence chosen from the current MSA. WHICH
+ * pairs are chosen in a round depends on the MSA of the previous round and on the pairs chosen so far -- not on the alignments of the
+ * round itself -- so every round is selected first (same calls, same order, same st_random() draws as the reference's loop) and then
+ * aligned as ONE device batch; the tuples are appended in the order the reference's one-by-one loop appends them. */
+MultipleAlignment *makeAlignment(StateMachine *sM, stList *seqFrags, int64_t spanningTrees, int64_t maxPairsToConsider, bool useProgressiveMerging,
+                                 float matchGamma, PairwiseAlignmentParameters *p) {
+    int64_t seqNo = stList_length(seqFrags);
+    if (spanningTrees * (seqNo - 1) >= (seqNo * (seqNo - 1)) / 2) {          /* all pairs: the reference's code, batched by makeAllPairwiseAlignments above */
+        return makeAlignmentUsingAllPairs(sM, seqFrags, useProgressiveMerging, matchGamma, p);
+    }
+    MultipleAlignment *mA = st_calloc(1, sizeof(MultipleAlignment));
+    mA->alignedPairs = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    mA->chosenPairwiseAlignments = stList_construct3(0, (void (*)(void *)) stIntTuple_destruct);
+    stSortedSet *chosen = getReferencePairwiseAlignments2(seqFrags);
+    int64_t cap = stSortedSet_size(chosen) + seqNo + 1, n = 0;
+    int64_t *first = st_malloc(8 * cap), *second = st_malloc(8 * cap);
+    stSortedSetIterator *pairIt = stSortedSet_getIterator(chosen);
+    stIntTuple *pairToAlign;
+    while ((pairToAlign = stSortedSet_getNext(pairIt)) != NULL) {           /* :898-906 */
+        first[n] = stIntTuple_get(pairToAlign, 0); second[n] = stIntTuple_get(pairToAlign, 1); n++;
+    }
+    stSortedSet_destructIterator(pairIt);
+    align_pair_list(sM, seqFrags, first, second, n, p, mA->alignedPairs, mA->chosenPairwiseAlignments);
+    int64_t iteration = 0;
+    while (1) {                                                              /* :910-937 */
+        mA->columns = (stList_length(seqFrags) == 2 || useProgressiveMerging)
+                ? getMultipleSequenceAlignmentProgressive(seqFrags, mA->alignedPairs, matchGamma, mA->chosenPairwiseAlignments)
+                : getMultipleSequenceAlignment(seqFrags, mA->alignedPairs, matchGamma);
+        if (++iteration >= spanningTrees) {
+            stSortedSet_destruct(chosen);
+            mA->alignedPairs = filterMultipleAlignedPairs(mA->columns, mA->alignedPairs);
+            free(first); free(second);
+            return mA;
+        }
+        int64_t *distanceCounts = getDistanceMatrix(mA->columns, seqFrags, maxPairsToConsider);
+        stSet_destruct(mA->columns);
+        n = 0;
+        for (int64_t seq = 0; seq < seqNo; seq++) {                          /* selection: as the reference, the chosen set grows pair by pair */
+            int64_t otherSeq = getNextBestPair(seq, distanceCounts, seqNo, chosen);
+            if (otherSeq != INT64_MAX) {
+                assert(seq != otherSeq);
+                first[n] = seq; second[n] = otherSeq; n++;
+                stSortedSet_insert(chosen, seq < otherSeq ? stIntTuple_construct2(seq, otherSeq) : stIntTuple_construct2(otherSeq, seq));
+            }
+        }
+        free(distanceCounts);
+        align_pair_list(sM, seqFrags, first, second, n, p, mA->alignedPairs, mA->chosenPairwiseAlignments);
+    }
+    return NULL;
 }

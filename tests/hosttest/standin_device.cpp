@@ -14,6 +14,11 @@
 struct HtParams { int wb; float wf; int o1, e1, o2, e2; int mat[25]; int k, w, min_w; int progressive, disable_seeding; };
 extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const int *lens, const uint8_t *flat, int64_t *n_words, int *status);
 
+struct HtPecanParams { double threshold; int64_t minDiagsBetweenTraceBack, traceBackDiagonals, diagonalExpansion; };
+extern "C" int64_t hosttest_pecan_aligned_pairs(const char *csx, int64_t lX, const char *csy, int64_t lY, const int64_t *anchors, int64_t n_anchor,
+                                                int ragged_left, int ragged_right, const HtPecanParams *pp, int64_t split_bigger,
+                                                int64_t **trip, double **post, int64_t *cells_out);
+
 struct barb200_ctx {
     barb200_params p;
     std::mutex err_mu; std::string err;
@@ -62,3 +67,25 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *, int) { b
 extern "C" void barb200_destroy(barb200_ctx *ctx) { if (ctx) { barb200::dispatcher_destroy(ctx); delete ctx; } }
 extern "C" const char *barb200_last_error(barb200_ctx *ctx) { static thread_local std::string out; out = ctx ? barb200::get_error(ctx) : "null context"; return out.c_str(); }
 extern "C" void barb200_free(void *p) { free(p); }
+
+// cPecan mode: every pair through the host emulation of the product's block program (hosttest_pecan_aligned_pairs)
+extern "C" void barb200_pecan_params_default(barb200_pecan_params *p) {
+    p->threshold = 0.01; p->min_diags_between_traceback = 1000; p->traceback_diagonals = 40; p->diagonal_expansion = 20;
+    p->split_matrix_bigger_than_this = (int64_t)3000 * 3000; p->dynamic_anchor_expansion = 0;
+}
+extern "C" int barb200_pecan_aligned_pairs_batch(barb200_ctx *ctx, const barb200_pecan_params *p, int64_t n_pairs, const char *const *sx, const int64_t *lx,
+                                                 const char *const *sy, const int64_t *ly, const int64_t *const *anchors, const int64_t *n_anchor,
+                                                 const uint8_t *ragged_left, const uint8_t *ragged_right, int64_t **triples_out, int64_t *n_out,
+                                                 double **posteriors_out, int64_t *cells_out) {
+    HtPecanParams q{p->threshold, p->min_diags_between_traceback, p->traceback_diagonals, p->diagonal_expansion};
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        int64_t *t = nullptr; double *po = nullptr; int64_t cells = 0;
+        const int64_t n = hosttest_pecan_aligned_pairs(sx[i], lx[i], sy[i], ly[i], (anchors && n_anchor && n_anchor[i]) ? anchors[i] : nullptr, n_anchor ? n_anchor[i] : 0,
+                                                       ragged_left ? ragged_left[i] : 0, ragged_right ? ragged_right[i] : 0, &q, p->split_matrix_bigger_than_this, &t, &po, &cells);
+        if (n < 0) { barb200::set_error(ctx, "stand-in device: pair-HMM job failed"); return BARB200_EJOB; }
+        triples_out[i] = t; n_out[i] = n;
+        if (posteriors_out) posteriors_out[i] = po; else free(po);
+        if (cells_out) cells_out[i] = cells;
+    }
+    return BARB200_OK;
+}

@@ -75,3 +75,26 @@ def test_harvested_inputs_replay_to_the_same_alignments(tmp_path, oracle_built):
         o = R.oracle_make_consistent_partial_order_alignments(r["ends"], r["right_end_indexes"], r["right_end_row_indexes"], r["overlaps"])
         for a, b in zip(ms, o):
             assert a.shape == b.shape and np.array_equal(a, b)
+
+
+PECAN = {"bar/partialOrderAlignment": "0"}
+
+
+def pecan_flowers():
+    """ends with up to 8 strings (all-pairs path of makeAlignment) and with 14+ strings (the incremental pair selection,
+    multipleAligner.c:887-939: spanningTrees * (n - 1) < n (n - 1) / 2)"""
+    return [F.random_flower(400 + s, n_threads=int(5 + s % 4), n_blocks=3, seg_len=60) for s in range(3)] + \
+           [F.random_flower(500 + s, n_threads=14 + s, n_blocks=2, seg_len=70, p_skip=0.0, p_loop=0.0) for s in range(2)]
+
+
+@pytest.mark.skipif(not F.have("standin"), reason="oracle/_ref/libflower_standin.so not built (needs /root/reference)")
+def test_cpecan_configuration_through_the_pecan_shim_on_the_standin_device():
+    """bar() with partialOrderAlignment="0": the reference's makeFlowerAlignment3 / makeEndAlignment / poset code over
+    shim/cactus_pecan_shim.c (makeAlignment with every selection round as one device batch, makeAllPairwiseAlignments,
+    getAlignedPairsUsingAnchors). One OpenMP thread: the reference's tie breaks draw from ONE st_random() stream, so its own
+    output depends on the thread interleaving."""
+    fls = pecan_flowers()
+    want = F.bar("ref", fls, PECAN, threads=1)
+    got = F.bar("standin", fls, PECAN, threads=1)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), i

@@ -51,3 +51,18 @@ def test_streams_equal_the_reference_library_on_fresh_seeds():
         params = {"bar/poa/partialOrderAlignmentWindow": "60"} if seed % 4 == 0 else {}
         a, b = F.blocks("shim", fl, params), F.blocks("ref", fl, params)
         assert np.array_equal(a["raw"], b["raw"]), seed
+
+
+def test_cpecan_configuration_bar_equals_the_reference():
+    """bar() with partialOrderAlignment="0" (SURVEY rows a13 / a14): the reference's flowerAligner.c / endAligner.c / multipleAligner.c
+    over shim/cactus_pecan_shim.c -- makeAlignment's selection rounds, makeAllPairwiseAlignments and getAlignedPairsUsingAnchors
+    served by the pair-HMM kernel -- leaves every flower exactly as the unmodified reference does (one thread: the reference's
+    st_random() tie breaks make its own output depend on the interleaving of concurrent flowers)"""
+    _need_shim()
+    assert F.have("ref"), "oracle/_ref/libflower_ref.so is missing"
+    from test_flowers_cpu import PECAN, pecan_flowers
+    fls = pecan_flowers()
+    want = F.bar("ref", fls, PECAN, threads=1)
+    got = F.bar("shim", fls, PECAN, threads=1)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), i
