@@ -311,9 +311,9 @@ class Stage:
         return [dict(threads=int(out[4 * i]), jobs=int(out[4 * i + 1]), ctas=int(out[4 * i + 2]), plane_ints=int(out[4 * i + 3])) for i in range(n)]
 
     def phase_clocks(self):
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 7)()
         self.engine._check(self.engine.lib.barb200_stage_phase_clocks(self.h, out))
-        return dict(zip(["dp", "backtrack", "fuse", "topo", "msa", "total"], [int(v) for v in out]))
+        return dict(zip(["dp", "backtrack", "fuse", "topo", "msa", "total", "guide_tree"], [int(v) for v in out]))
 
     def fetch(self):
         n = len(self.n_seq)

@@ -6,8 +6,8 @@
 //     job, its own persistent launch on its own stream (largest class first; the launches run concurrently, the block
 //     scheduler fills whatever a class leaves free) and its own work counter -- a batch of thousands of short adjacencies
 //     and a few 10 kbp windows no longer runs everything in the CTA shape and the slot size of the largest job;
-//   * the jobs' guide-tree orders are computed on host threads BEHIND the running kernels and released to them in launch
-//     order through a copy-engine counter ("ready");
+//   * the host does no per-job work besides packing: the guide-tree read orders are computed by the CTA that owns the job
+//     (guide_tree.cuh);
 //   * jobs that outgrow the optimistic plane / MSA sizing come back flagged and are re-run with geometrically larger
 //     slots (x4, then worst case).
 // A context drives one or more devices; every device has two *lanes* (slot arena + streams + pinned staging) so that one
@@ -59,7 +59,6 @@ struct Lane {
     int *d_planes = nullptr; size_t planes_bytes = 0;
     cudaStream_t main = nullptr, copy = nullptr, cls[kNumKernels] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t cls_done[kNumKernels] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int *h_ready = nullptr; unsigned ready_slot = 0;           // pinned ring of "jobs released" values (copied by the copy engine)
     uint8_t *h_down = nullptr; size_t h_down_bytes = 0;        // pinned staging of the MSA download
     uint8_t *h_up = nullptr; size_t h_up_bytes = 0;            // pinned staging of packed inputs (dispatcher batches)
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
@@ -215,7 +214,7 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
     if ((int64_t)p->gap_open1 + p->gap_ext1 >= 65535 || (int64_t)p->gap_open2 + p->gap_ext2 >= 65535) {
         fail(errbuf, errbuf_len, "gap open + extension must be below 65535 (the traceback planes keep E as a 16-bit distance below H)"); return nullptr; }
     if (!p->disable_seeding) { fail(errbuf, errbuf_len, "minimizer seeding (partialOrderAlignmentDisableSeeding=0) is not supported"); return nullptr; }
-    if (p->k <= 0 || p->k > 28 || p->w <= 0 || p->w >= 256) { fail(errbuf, errbuf_len, "minimizer k must be in 1..28 and w in 1..255"); return nullptr; }
+    if (p->k <= 0 || p->k > 20 || p->w <= 0 || p->w >= 256) { fail(errbuf, errbuf_len, "minimizer k must be in 1..20 and w in 1..255 (guide-tree keys are hash << 24 | span << 16 | read)"); return nullptr; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { fail(errbuf, errbuf_len, std::string("no CUDA device: ") + cudaGetErrorString(e)); return nullptr; }
@@ -253,8 +252,7 @@ extern "C" barb200_ctx *barb200_create(const barb200_params *p, char *errbuf, in
         for (int l = 0; l < ctx->lanes_per_device && ok; ++l) {
             std::unique_ptr<Lane> L(new Lane());
             L->index = lane_index++;
-            ok = cudaStreamCreateWithFlags(&L->main, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&L->copy, cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaMallocHost((void **)&L->h_ready, 1024 * sizeof(int)) == cudaSuccess;
+            ok = cudaStreamCreateWithFlags(&L->main, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&L->copy, cudaStreamNonBlocking) == cudaSuccess;
             for (int c = 0; c < kNumKernels && ok; ++c)
                 ok = cudaStreamCreateWithFlags(&L->cls[c], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&L->cls_done[c], cudaEventDisableTiming) == cudaSuccess;
             D->lanes.push_back(std::move(L));
@@ -280,7 +278,6 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
             for (int c = 0; c < kNumKernels; ++c) { if (L->cls[c]) cudaStreamDestroy(L->cls[c]); if (L->cls_done[c]) cudaEventDestroy(L->cls_done[c]); }
             if (L->main) cudaStreamDestroy(L->main);
             if (L->copy) cudaStreamDestroy(L->copy);
-            if (L->h_ready) cudaFreeHost(L->h_ready);
             if (L->h_down) cudaFreeHost(L->h_down);
             if (L->h_up) cudaFreeHost(L->h_up);
         }
@@ -333,7 +330,7 @@ struct barb200_stage {
     // everything below is in the stage's INTERNAL job order: class-major (largest class first), cost-descending inside a
     // class; perm[internal] = the caller's job index
     std::vector<int64_t> perm;
-    std::vector<int> n_seq, lens, order, progressive;
+    std::vector<int> n_seq, lens, progressive;
     std::vector<int64_t> soff, job_len_off, job_seq_off, job_sum_len;
     std::vector<int> job_max_len;
     std::vector<JobDesc> desc;
@@ -342,21 +339,21 @@ struct barb200_stage {
     double grow = 1.0; bool worst_case = false;
     // device: one block from the device's cache holds all per-stage arrays
     void *d_block = nullptr; size_t d_block_bytes = 0;
-    uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr, *d_order = nullptr; int64_t *d_soff = nullptr;
+    uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr; int64_t *d_soff = nullptr;
     JobDesc *d_desc = nullptr; int *d_msa_len = nullptr, *d_status = nullptr, *d_next = nullptr; long long *d_cells = nullptr;
     // results of the last run
     std::vector<int> status, msa_len; std::vector<long long> cells;
     barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;     // internal ids
     int64_t launches = 0; bool ran = false;
     cudaEvent_t e0 = nullptr, e1 = nullptr; bool launched = false;
-    int *d_ready = nullptr; const uint8_t *host_seqs = nullptr; int64_t orders_done = 0;   // streamed guide trees (see stage_stream_orders)
-    uint64_t clk[6] = {0, 0, 0, 0, 0, 0};
+    const uint8_t *host_seqs = nullptr;      // the caller's buffer while it is valid (capacity-miss retries re-upload from it)
+    uint64_t clk[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 static void stage_free_device(barb200_stage *st) {
     dev_free(dev_of_lane(st->ctx, st->lane), st->d_block, st->d_block_bytes);
     st->d_block = nullptr;
-    st->d_seqs = st->d_msa = nullptr; st->d_lens = st->d_order = nullptr; st->d_soff = nullptr; st->d_desc = nullptr;
+    st->d_seqs = st->d_msa = nullptr; st->d_lens = nullptr; st->d_soff = nullptr; st->d_desc = nullptr;
     st->d_msa_len = st->d_status = st->d_next = nullptr; st->d_cells = nullptr;
 }
 
@@ -387,7 +384,7 @@ static int plan_stage(barb200_stage *st) {
     Device &D = dev_of_lane(ctx, st->lane);
     Lane &LN = lane_of(ctx, st->lane);
     for (Bucket &B : st->buckets) {
-        int64_t max_nodes = 4, max_edges = 4, max_len = 1, max_k = 1, plane_need = 0;
+        int64_t max_nodes = 4, max_edges = 4, max_len = 1, max_k = 1, plane_need = 0, key_need = 64;
         for (int64_t j = B.job_base; j < B.job_base + B.n_jobs; ++j) {
             const int64_t sum = st->job_sum_len[j], ml = st->job_max_len[j], K = st->n_seq[j];
             max_nodes = std::max(max_nodes, sum + 2); max_edges = std::max(max_edges, sum + K); max_len = std::max(max_len, ml);
@@ -396,6 +393,11 @@ static int plan_stage(barb200_stage *st) {
             int64_t rows = sum + 2;
             if (!st->worst_case) rows = std::min<int64_t>(rows, (int64_t)(st->grow * (double)(ml + (sum - ml) / 8 + 256)));
             plane_need = std::max(plane_need, rows * (TB / CPT) * (align_up(ml + 1, CPT) + CPT));
+            // minimizer keys of the guide tree: ~2 / (w + 1) per base; ties (repeats) can push up to 2 w per base
+            if (st->progressive[j] && K > 2) {
+                const int64_t worst = 2 * (int64_t)ctx->p.w * sum + K;
+                key_need = std::max(key_need, st->worst_case ? worst : std::min<int64_t>(worst, (int64_t)(st->grow * (double)(sum / 2 + 64))));
+            }
         }
         SlotLayout &Y = B.lay;
         memset(&Y, 0, sizeof(Y));
@@ -417,6 +419,10 @@ static int plan_stage(barb200_stage *st) {
         Y.o_row_off = take(N * 8); Y.o_row_info = take(N * 16);
         Y.o_cigar = take((int64_t)Y.cigar_cap * 8);
         Y.fc_cap = (int)(max_len + 2); Y.o_fc = take((int64_t)Y.fc_cap * 8);
+        int64_t kc = 64; while (kc < key_need) kc <<= 1;            // the sort pads to a power of two
+        Y.gt_key_cap = (int)kc; Y.max_k = (int)max_k;
+        Y.o_order = take(max_k * 4); Y.o_gt_keys = take(kc * 8); Y.o_gt_hit = take(max_k * (max_k + 1) / 2 * 4);
+        Y.o_gt_jac = take(max_k * (max_k - 1) / 2 * 8 + 8); Y.o_gt_score = take(max_k * 8);
         Y.slot_bytes = align_up(o, 256);
         B.T = kKernels[B.cls].T; B.dyn_smem = kKernels[B.cls].scratch;
         if (getenv("BARB200_SCRATCH_KB")) B.dyn_smem = (size_t)atoi(getenv("BARB200_SCRATCH_KB")) * 1024;   // tuning aid
@@ -472,34 +478,10 @@ static int ensure_arena(barb200_ctx *ctx, Lane &LN, size_t slots_bytes, size_t p
     return BARB200_OK;
 }
 
-// tell the device that jobs [0, n) may start: a 4-byte copy from a pinned ring by the COPY ENGINE (a kernel could not
-// be used for this: the persistent POA kernels own every SM while their CTAs wait for the value)
-static cudaError_t post_ready(barb200_stage *st, int64_t n) {
-    Lane &LN = lane_of(st->ctx, st->lane);
-    if (LN.ready_slot && (LN.ready_slot & 1023) == 0) { cudaError_t e = cudaStreamSynchronize(LN.copy); if (e != cudaSuccess) return e; }
-    int *slot = LN.h_ready + (LN.ready_slot++ & 1023);
-    *slot = (int)n;
-    return cudaMemcpyAsync(st->d_ready, slot, 4, cudaMemcpyHostToDevice, LN.copy);
-}
-
-// guide-tree orders (abpoa_seed.c:85-156, 232-325 via guide_tree.cpp) of the internal jobs [j0, j1) into st->order
-static void host_orders(barb200_stage *st, int64_t j0, int64_t j1) {
-    barb200_ctx *ctx = st->ctx;
-    const int nthreads = host_threads(ctx);
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
-    for (int64_t j = j0; j < j1; ++j) {
-        const int K = st->n_seq[j];
-        std::vector<const uint8_t *> ptr(K);
-        const uint8_t *base = st->host_seqs + st->job_seq_off[j];
-        for (int i = 0; i < K; ++i) ptr[i] = base + st->soff[st->job_len_off[j] + i];
-        guide_tree_order(ctx->hp, st->progressive[j], K, ptr.data(), st->lens.data() + st->job_len_off[j], st->order.data() + st->job_len_off[j]);
-    }
-}
-
 // n_seq / seq_lens / seqs / progressive are in the CALLER's job order; seq_off[j] (may be null = consecutive) is the offset of
 // job j's first base in `seqs`, n_bases_total the size of `seqs`. grow / worst_case size the slots (capacity-miss retries).
 static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs, const int64_t *seq_off,
-                       int64_t n_bases_total, const int *progressive, double grow, bool worst_case, bool defer_orders, barb200_stage **out) {
+                       int64_t n_bases_total, const int *progressive, double grow, bool worst_case, barb200_stage **out) {
     if (!ctx || n_jobs < 0 || (n_jobs > 0 && (!n_seq || !seq_lens || !seqs))) { set_error(ctx, "bad arguments"); return BARB200_EINVAL; }
     if (n_jobs > 0x7ffffff0) { set_error(ctx, "too many jobs in one stage"); return BARB200_EINVAL; }
     Device &D = dev_of_lane(ctx, lane);
@@ -550,7 +532,7 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     });
     st->n_seq.resize(n_jobs); st->progressive.resize(n_jobs);
     st->job_len_off.resize(n_jobs + 1); st->job_seq_off.resize(n_jobs + 1); st->job_sum_len.resize(n_jobs); st->job_max_len.resize(n_jobs);
-    st->lens.resize(ns); st->soff.resize(ns); st->order.resize(ns); st->desc.resize(n_jobs);
+    st->lens.resize(ns); st->soff.resize(ns); st->desc.resize(n_jobs);
     int64_t lo = 0, msa_off = 0;
     for (int64_t j = 0; j < n_jobs; ++j) {
         const int64_t c = st->perm[j];
@@ -564,7 +546,8 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
         if (!worst_case) stride = std::min<int64_t>(sum, (int64_t)(grow * (double)(ml + ml / 2 + 64)));
         stride = align_up(stride, 16);
         JobDesc &d = st->desc[j];
-        d.n_seq = K; d.seq_off = c_seq_off[c]; d.len_off = lo; d.msa_off = msa_off; d.msa_stride = (int)stride;
+        d.n_seq = K; d.seq_off = c_seq_off[c]; d.len_off = lo; d.msa_off = msa_off; d.msa_stride = (int)stride; d.progressive = st->progressive[j];
+        if (d.progressive && K > 65535) { set_error(ctx, "progressive mode with more than 65535 sequences in one window is not supported"); return BARB200_EINVAL; }
         msa_off += stride * K;
         lo += K;
         if (st->buckets.empty() || st->buckets.back().cls != c_cls[c]) { Bucket B; B.cls = c_cls[c]; B.job_base = j; st->buckets.push_back(B); }
@@ -573,13 +556,12 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     st->job_len_off[n_jobs] = lo; st->job_seq_off[n_jobs] = n_bases_total;
     st->msa_bytes = msa_off;
     st->host_seqs = seqs;
-    if (!defer_orders) { host_orders(st.get(), 0, n_jobs); st->orders_done = n_jobs; }
     if (n_jobs == 0) { *out = st.release(); return BARB200_OK; }
     // device buffers (one cached block) + upload on the lane's copy stream, so that it overlaps a running kernel
     size_t off = 0;
     auto sub = [&](size_t bytes) { size_t r = off; off = (off + std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return r; };
-    const size_t o_seqs = sub(n_bases_total), o_lens = sub(ns * 4), o_order = sub(ns * 4), o_soff = sub(ns * 8), o_desc = sub(n_jobs * sizeof(JobDesc)),
-                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4 * kNumKernels), o_ready = sub(4);
+    const size_t o_seqs = sub(n_bases_total), o_lens = sub(ns * 4), o_soff = sub(ns * 8), o_desc = sub(n_jobs * sizeof(JobDesc)),
+                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4 * kNumKernels);
     st->d_block_bytes = off;
     int rc = plan_stage(st.get());
     if (rc) return rc;
@@ -589,14 +571,12 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
         st->d_block = nullptr; return BARB200_ENOMEM;
     }
     uint8_t *blk = (uint8_t *)st->d_block;
-    st->d_seqs = blk + o_seqs; st->d_lens = (int *)(blk + o_lens); st->d_order = (int *)(blk + o_order); st->d_soff = (int64_t *)(blk + o_soff);
+    st->d_seqs = blk + o_seqs; st->d_lens = (int *)(blk + o_lens); st->d_soff = (int64_t *)(blk + o_soff);
     st->d_desc = (JobDesc *)(blk + o_desc); st->d_msa = blk + o_msa; st->d_msa_len = (int *)(blk + o_msa_len); st->d_status = (int *)(blk + o_status);
-    st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next); st->d_ready = (int *)(blk + o_ready);
+    st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next);
     cudaStream_t s = LN.copy;
     if ((e = cudaMemcpyAsync(st->d_seqs, seqs, n_bases_total, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
-        (st->orders_done && (e = cudaMemcpyAsync(st->d_order, st->order.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) ||
-        (e = post_ready(st.get(), st->orders_done)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_soff, st->soff.data(), ns * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_desc, st->desc.data(), n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaStreamSynchronize(s)) != cudaSuccess) {
@@ -610,37 +590,12 @@ extern "C" int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int 
                                     const uint8_t *seqs, const int *progressive, barb200_stage **out) {
     if (!ctx || !out) return BARB200_EINVAL;
     std::lock_guard<std::mutex> lk(lane_of(ctx, 0).busy);
-    int rc = stage_build(ctx, 0, n_jobs, n_seq, seq_lens, seqs, nullptr, 0, progressive, 1.0, false, false, out);
+    int rc = stage_build(ctx, 0, n_jobs, n_seq, seq_lens, seqs, nullptr, 0, progressive, 1.0, false, out);
     if (!rc) (*out)->host_seqs = nullptr;       // the caller's buffer is only guaranteed during this call
     return rc;
 }
 
 static int stage_run_locked(barb200_stage *st, float *kernel_ms);
-
-// Guide trees behind the running kernels: the stage was built with defer_orders, its kernels are already queued and their
-// CTAs wait for `ready`. Jobs are released chunk by chunk (in the internal order, which is the order the classes were
-// launched in) as soon as their read orders have been computed and uploaded.
-static int stage_stream_orders(barb200_stage *st) {
-    barb200_ctx *ctx = st->ctx;
-    Lane &LN = lane_of(ctx, st->lane);
-    int total_slots = 0;
-    for (const Bucket &B : st->buckets) total_slots += B.slots;
-    const int64_t chunk = std::max<int64_t>(256, total_slots);
-    while (st->orders_done < st->n_jobs) {
-        const int64_t j0 = st->orders_done, j1 = std::min<int64_t>(st->n_jobs, j0 + chunk);
-        host_orders(st, j0, j1);
-        const int64_t a = st->job_len_off[j0], b = st->job_len_off[j1];
-        cudaError_t e = cudaMemcpyAsync(st->d_order + a, st->order.data() + a, (b - a) * 4, cudaMemcpyHostToDevice, LN.copy);
-        if (e == cudaSuccess) e = post_ready(st, j1);
-        if (e != cudaSuccess) {
-            // release everything so that the kernels can drain, then report
-            post_ready(st, st->n_jobs); cudaStreamSynchronize(LN.copy); cudaStreamSynchronize(LN.main);
-            set_error(ctx, std::string("streaming guide trees: ") + cudaGetErrorString(e)); return BARB200_ECUDA;
-        }
-        st->orders_done = j1;
-    }
-    return BARB200_OK;
-}
 
 // queue the stage's kernels on its lane's streams; returns without waiting
 static int stage_launch(barb200_stage *st) {
@@ -665,13 +620,13 @@ static int stage_launch(barb200_stage *st) {
     for (size_t b = 0; b < st->buckets.size(); ++b) {          // largest class first
         const Bucket &B = st->buckets[b];
         BatchArgs A;
-        A.jobs = st->d_desc; A.job_base = (int)B.job_base; A.n_jobs = (int)B.n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff; A.order = st->d_order;
+        A.jobs = st->d_desc; A.job_base = (int)B.job_base; A.n_jobs = (int)B.n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff;
         A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
-        A.slots = LN.d_slots + B.slot_off; A.planes = LN.d_planes + B.plane_off; A.next_job = st->d_next + b; A.ready = st->d_ready;
+        A.slots = LN.d_slots + B.slot_off; A.planes = LN.d_planes + B.plane_off; A.next_job = st->d_next + b;
         A.phase_clk = clk_n ? LN.d_clk + B.clk_off : nullptr;
         A.serial_phases = getenv("BARB200_DEBUG_SERIAL") ? 1 : 0;
         A.bfs_order = getenv("BARB200_DEBUG_BFS") ? 1 : 0;
-        A.scratch_bytes = (int)B.dyn_smem; A.lay = B.lay; A.P = ctx->P;
+        A.scratch_bytes = (int)B.dyn_smem; A.lay = B.lay; A.P = ctx->P; A.gt_k = ctx->p.k; A.gt_w = ctx->p.w;
         cudaStream_t cs = single ? s : LN.cls[B.cls];
         if (!single) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, st->e0, 0));
         kKernels[B.cls].fn<<<B.slots, B.T, B.dyn_smem, cs>>>(A);
@@ -704,20 +659,20 @@ static int stage_finish(barb200_stage *st, float *kernel_ms) {
     st->status.resize(st->n_jobs);
     CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    for (int k = 0; k < 6; ++k) st->clk[k] = 0;
+    for (int k = 0; k < 7; ++k) st->clk[k] = 0;
     if (ctx->p.collect_phase_clocks) {
         size_t clk_n = 0;
         for (const Bucket &B : st->buckets) clk_n += (size_t)B.slots * PH_N;
         std::vector<unsigned long long> h(clk_n);
         CUDA_TRY(ctx, cudaMemcpy(h.data(), LN.d_clk, clk_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (size_t b = 0; b < clk_n / PH_N; ++b) for (int k = 0; k < 6; ++k) st->clk[k] += h[b * PH_N + k];
+        for (size_t b = 0; b < clk_n / PH_N; ++b) for (int k = 0; k < 7; ++k) st->clk[k] += h[b * PH_N + k];
     }
     // capacity misses -> retry launch for just those jobs with larger slots (x4 first, then worst case)
     std::vector<int64_t> redo;
     for (int64_t j = 0; j < st->n_jobs; ++j) {
         const int sc = st->status[j];
         if (sc == JOB_OK) continue;
-        if (!st->worst_case && (sc == JOB_ERR_PLANE_CAP || sc == JOB_ERR_MSA_CAP)) redo.push_back(j);
+        if (!st->worst_case && (sc == JOB_ERR_PLANE_CAP || sc == JOB_ERR_MSA_CAP || sc == JOB_ERR_GT_CAP)) redo.push_back(j);
         else {
             char buf[160]; snprintf(buf, sizeof(buf), "job %lld failed on the device with status %d", (long long)st->perm[j], sc);
             set_error(ctx, buf); return BARB200_EJOB;
@@ -740,14 +695,14 @@ static int stage_finish(barb200_stage *st, float *kernel_ms) {
         barb200_stage *rs = nullptr;
         const bool go_worst = st->grow >= 4.0;
         int rc = stage_build(ctx, st->lane, (int64_t)redo.size(), r_nseq.data(), r_lens.data(), src, r_off.data(), st->n_bases, r_prog.data(),
-                             go_worst ? 1.0 : st->grow * 4.0, go_worst, false, &rs);
+                             go_worst ? 1.0 : st->grow * 4.0, go_worst, &rs);
         if (rc) return rc;
         float rms = 0.f;
         rc = stage_run_locked(rs, &rms);
         rs->host_seqs = nullptr;
         if (rc) { barb200_stage_destroy(rs); return rc; }
         st->retry = rs; st->retry_jobs = redo; st->launches += rs->launches; ms += rms;
-        for (int k = 0; k < 6; ++k) st->clk[k] += rs->clk[k];
+        for (int k = 0; k < 7; ++k) st->clk[k] += rs->clk[k];
     }
     if (kernel_ms) *kernel_ms = ms;
     st->ran = true;
@@ -768,9 +723,9 @@ extern "C" int barb200_stage_run(barb200_stage *st, float *kernel_ms) {
 
 extern "C" int64_t barb200_stage_launches(barb200_stage *st) { return st ? st->launches : 0; }
 
-extern "C" int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[6]) {
+extern "C" int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[7]) {
     if (!st || !out) return BARB200_EINVAL;
-    for (int k = 0; k < 6; ++k) out[k] = st->clk[k];
+    for (int k = 0; k < 7; ++k) out[k] = st->clk[k];
     return BARB200_OK;
 }
 
@@ -860,13 +815,10 @@ static int batch_on_lane(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *
                          int64_t n_bases, const int *progressive, const MsaDest &dest, int *msa_len, int64_t *cells, float *device_ms) {
     barb200_stage *st = nullptr;
     const double t0 = now_ms();
-    // the guide trees are computed behind the launch and jobs are released to the kernels as their orders arrive
-    const bool stream = n_jobs >= 512 && !getenv("BARB200_NO_PIPELINE");
-    int rc = stage_build(ctx, lane, n_jobs, n_seq, seq_lens, seqs, seq_off, n_bases, progressive, 1.0, false, stream, &st);
+    int rc = stage_build(ctx, lane, n_jobs, n_seq, seq_lens, seqs, seq_off, n_bases, progressive, 1.0, false, &st);
     if (rc) return rc;
     const double t1 = now_ms(); float kms = 0.f;
     rc = stage_launch(st);
-    if (!rc && stream) rc = stage_stream_orders(st);
     if (!rc) rc = stage_finish(st, &kms);
     const double t2 = now_ms();
     if (!rc) rc = stage_fetch_locked(st, dest, msa_len, cells);

@@ -14,6 +14,7 @@
 // so only the offending caller sees the error. Stitching and the cross-end trimming run in the waiting thread.
 // No CUDA in this file.
 #pragma once
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -57,6 +58,8 @@ public:
         std::lock_guard<std::mutex> lk(mu_);
         if (t->active == 0 || t->rc) { t->done = true; return; }
         pending_.push_back(t);
+        pending_jobs_ += t->active;
+        last_submit_ = std::chrono::steady_clock::now();
         work_cv_.notify_one();
     }
     void wait(Ticket *t) {
@@ -80,11 +83,17 @@ private:
                 std::unique_lock<std::mutex> lk(mu_);
                 work_cv_.wait(lk, [this] { return stop_ || !pending_.empty(); });
                 if (pending_.empty()) return;               // stop requested and nothing left
+                // a burst of submissions is still arriving (the shim's bar() submits thousands of flowers in a row): give it a
+                // moment to pile up instead of launching a batch of the first few -- bounded, and only while tickets keep coming
+                for (int spins = 0; spins < 8 && !stop_ && pending_jobs_ < linger_jobs_ &&
+                     std::chrono::steady_clock::now() - last_submit_ < std::chrono::microseconds(600); ++spins)
+                    work_cv_.wait_for(lk, std::chrono::microseconds(700));
+                if (pending_.empty()) { if (stop_) return; continue; }
                 int64_t jobs = 0; double cost = 0;
                 while (!pending_.empty()) {
                     Ticket *t = pending_.front();
                     if (!batch.empty() && (jobs + t->active > max_jobs_ || cost + t->cost > max_cost_)) break;
-                    pending_.pop_front(); batch.push_back(t); jobs += t->active; cost += t->cost;
+                    pending_.pop_front(); batch.push_back(t); jobs += t->active; cost += t->cost; pending_jobs_ -= t->active;
                 }
                 if (!pending_.empty()) work_cv_.notify_one();   // more work than one batch: wake another lane
             }
@@ -93,7 +102,7 @@ private:
                 std::lock_guard<std::mutex> lk(mu_);
                 for (auto it = batch.rbegin(); it != batch.rend(); ++it) {
                     Ticket *t = *it;
-                    if (t->rc || t->active == 0) t->done = true; else pending_.push_front(t);
+                    if (t->rc || t->active == 0) t->done = true; else { pending_.push_front(t); pending_jobs_ += t->active; }
                 }
                 if (!pending_.empty()) work_cv_.notify_one();
             }
@@ -172,7 +181,8 @@ private:
     }
 
     Exec exec_;
-    int64_t max_jobs_, max_chunk_ = 1 << 15; double max_cost_;
+    int64_t max_jobs_, max_chunk_ = 1 << 15, linger_jobs_ = 1024, pending_jobs_ = 0; double max_cost_;
+    std::chrono::steady_clock::time_point last_submit_ = std::chrono::steady_clock::now();
     std::mutex mu_;
     std::condition_variable work_cv_, done_cv_;
     std::deque<Ticket *> pending_;

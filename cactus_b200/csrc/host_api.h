@@ -12,9 +12,6 @@ struct HostParams {
     int k, w, min_w, progressive_poa;
 };
 
-// guide_tree.cpp
-void guide_tree_order(const HostParams &hp, int progressive, int n, const uint8_t *const *seqs, const int *lens, int *order);
-
 // One POA job on the host side: views into caller memory (codes 0..4).
 struct HostJob {
     int n_seq;

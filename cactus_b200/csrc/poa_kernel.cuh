@@ -14,9 +14,11 @@ struct SlotLayout {
     int64_t o_index_to_node, o_node_to_index, o_remain, o_msa_rank, o_tmp0, o_tmp1;
     int64_t o_row_rec, o_pre_row;
     int64_t o_row_off, o_row_info, o_cigar, o_fc;
+    int64_t o_order, o_gt_keys, o_gt_hit, o_gt_jac, o_gt_score;   // guide tree (guide_tree.cuh)
+    int gt_key_cap, max_k;
 };
 
-enum { PH_DP = 0, PH_BACKTRACK = 1, PH_FUSE = 2, PH_TOPO = 3, PH_MSA = 4, PH_TOTAL = 5, PH_N = 8 };
+enum { PH_DP = 0, PH_BACKTRACK = 1, PH_FUSE = 2, PH_TOPO = 3, PH_MSA = 4, PH_TOTAL = 5, PH_GUIDE = 6, PH_N = 8 };
 
 struct BatchArgs {
     const JobDesc *jobs;        // all jobs of the stage (internal order)
@@ -24,15 +26,14 @@ struct BatchArgs {
     const uint8_t *seqs;        // packed 0..4 codes of all jobs
     const int *lens;            // per sequence
     const int64_t *soff;        // per sequence: offset from the job's seq_off
-    const int *order;           // per sequence slot a: which read is aligned a-th (guide tree, host computed)
     uint8_t *msa; int *msa_len; int *status; long long *cells;
     uint8_t *slots; int *planes;
     int *next_job;              // the class's work counter
-    const int *ready;           // jobs [0, *ready) of the STAGE may start (the host streams guide-tree orders in behind the launches)
     unsigned long long *phase_clk;   // [gridDim.x * PH_N] clock64 per phase, or nullptr
     int serial_phases;          // debugging aid: 1 = run the graph phases in their serial reference form
     int bfs_order;              // debugging aid: 1 = recompute abPOA's BFS order after every fusion instead of splicing
     int scratch_bytes;          // dynamic shared memory per CTA (topological sort scratch)
+    int gt_k, gt_w;             // minimizer k / w of the guide tree
     SlotLayout lay;
     PoaParams P;
 };

@@ -32,7 +32,8 @@ enum JobStatus : int {
     JOB_ERR_TOPO = 6,        // "Failed to set node index" in the reference (abpoa_graph.c:265)
     JOB_ERR_BACKTRACK = 7,   // "Error in cg_backtrack" in the reference (abpoa_align_simd.c:448)
     JOB_ERR_ALIGNED_CAP = 8,
-    JOB_ERR_QUERY_LEN = 9    // query longer than 16 x threads per CTA (host sizing bug)
+    JOB_ERR_QUERY_LEN = 9,   // query longer than 16 x threads per CTA (host sizing bug)
+    JOB_ERR_GT_CAP = 10      // minimizer keys of the guide tree outgrew the slot (host retries with a larger slot)
 };
 
 // Scoring / banding parameters: what abpoaParamaters_constructFromCactusParams builds
@@ -52,6 +53,7 @@ struct JobDesc {
     int64_t len_off;      // offset into the lens / order arrays
     int64_t msa_off;      // offset of the job's output block in the msa buffer
     int msa_stride;       // column capacity of the output block (rows are msa_stride apart)
+    int progressive;      // abpt->progressive_poa of this job (poaBarAligner.c:567-571): read order from the guide tree
 };
 
 // The partial-order graph of one job (abPOA include/abpoa.h:96-116), SoA in the slot workspace.

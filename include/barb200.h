@@ -95,8 +95,8 @@ int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, con
 int barb200_stage_run(barb200_stage *st, float *kernel_ms /* may be NULL: device time of the launch(es) */);
 int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *msa_len, int64_t *cells);
 int64_t barb200_stage_launches(barb200_stage *st);   /* kernels launched by the last barb200_stage_run */
-/* per-phase SM clock totals of the last run (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total */
-int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[6]);
+/* per-phase SM clock totals of the last run (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total, guide tree */
+int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[7]);
 /* the stage's CTA-size buckets (largest first): out[4b .. 4b+3] = threads per CTA, jobs, resident CTAs, plane ints per slot;
  * returns the number of buckets */
 int barb200_stage_buckets(barb200_stage *st, int64_t *out, int max_buckets);
@@ -205,7 +205,7 @@ barb200_msa **barb200_flower_wait(barb200_ctx *ctx, barb200_ticket *ticket);
 int barb200_queue_stats(barb200_ctx *ctx, int64_t *batches, int64_t *jobs);
 
 /* Host-side phases of the context's most recent device batch, in milliseconds: out[0] build (pack, validation, planning, H2D),
- * out[1] launch + streamed guide trees + wait, out[2] device time of the kernels, out[3] fetch (D2H + unpack), out[4] total,
+ * out[1] launch + wait, out[2] device time of the kernels, out[3] fetch (D2H + unpack), out[4] total,
  * out[5] = number of jobs. For reports (bench.py's per-phase breakdown). */
 int barb200_last_batch_timing(barb200_ctx *ctx, double out[6]);
 

@@ -1,6 +1,7 @@
 // hosttest.cpp -- TEST-ONLY build (never shipped, never loaded by cactus_b200): compiles the product's
-// __host__ __device__ graph / traceback code (cactus_b200/csrc/poa_graph.cuh) and its host guide tree
-// (guide_tree.cpp) with g++ so that the CPU suite can check them against the oracle in a container without a GPU.
+// __host__ __device__ graph / traceback code (cactus_b200/csrc/poa_graph.cuh) and its guide tree (guide_tree.cuh, the
+// CTA program with its threads run one after the other) with g++ so that the CPU suite can check them against the oracle
+// in a container without a GPU.
 // The DP sweep itself is CUDA-only; here it is stood in for by a scalar emulation of the kernel's per-row
 // formulation (gathered band, prefix-maximum form of F) writing the same plane layout, which also pins that
 // formulation's arithmetic. The real kernel is checked on the GPU by tests/test_gpu_*.py.
@@ -9,7 +10,9 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <math.h>
 #include "../../cactus_b200/csrc/poa_graph.cuh"
+#include "../../cactus_b200/csrc/guide_tree.cuh"
 #include "../../cactus_b200/csrc/host_api.h"
 
 using namespace barb200;
@@ -128,8 +131,16 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
     std::vector<const uint8_t *> seqs(n_seq); int64_t sum = 0; int maxl = 0;
     for (int i = 0; i < n_seq; ++i) { seqs[i] = flat + sum; sum += lens[i]; maxl = std::max(maxl, lens[i]); }
     std::vector<int> order(n_seq);
-    HostParams hpp{hp->k, hp->w, hp->min_w, hp->progressive};
-    guide_tree_order(hpp, hp->progressive, n_seq, seqs.data(), lens, order.data());
+    {   // the product's guide tree (guide_tree.cuh), a block of 64 emulated threads
+        int64_t kc = 64; while (kc < 2 * (int64_t)hp->w * sum + n_seq) kc <<= 1;
+        std::vector<uint64_t> keys((size_t)kc);
+        std::vector<int> hit((size_t)n_seq * (n_seq + 1) / 2 + 1);
+        std::vector<double> jac((size_t)n_seq * (n_seq - 1) / 2 + 1), score(n_seq);
+        int n_keys = 0; double wsv[33]; long long wsi[33];
+        GtScratch G; G.keys = keys.data(); G.key_cap = (int)kc; G.hit = hit.data(); G.jac = jac.data(); G.score = score.data(); G.n_keys = &n_keys; G.red_i = nullptr; G.red_v = nullptr;
+        const GuideTreeParams GP{hp->k, hp->w};
+        if (cta_guide_tree(GP, hp->progressive, n_seq, [&](int i) { return seqs[i]; }, lens, order.data(), G, wsv, wsi, 64) != 0) { *status = JOB_ERR_GT_CAP; *n_words = 0; return nullptr; }
+    }
     const int N = (int)sum + 2, EP = (int)(4 * (sum + n_seq) + 64), W = 1 + ((n_seq - 1) >> 6);
     Graph g; RowTables rt; DpState d;
     std::vector<uint8_t> base(N), aln_n(N);
