@@ -360,7 +360,7 @@ def shapes_leg(eng):
     return out
 
 
-def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end):
+def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end, flowers=None):
     """N synthetic flowers (4 ends x 8 x 2 kbp each, ends pairwise reverse complements: cross-end trimming does real work) through the
     end queue from `threads` host threads: (a) synchronous barb200_make_consistent_partial_order_alignments calls, (b) every thread
     submits its flowers (barb200_flower_submit) before it collects them (barb200_flower_wait) -- what the shim's bar() does.
@@ -368,15 +368,19 @@ def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end):
     import ctypes as C
     from concurrent.futures import ThreadPoolExecutor
     from cactus_b200.api import _StrTable
-    flowers = workload.synth_flowers(first_flower, n_flowers, 4, K_SEQS, L_BP)
+    if flowers is None:
+        flowers = workload.synth_flowers(first_flower, n_flowers, 4, K_SEQS, L_BP)
+    n_flowers = len(flowers)
     lib, ctx = eng.lib, eng.ctx
 
     def tables(fl):
-        ends, ri, rr, ov = fl
+        ends, ri, rr, ov = fl[:4]
         t = _StrTable(ends)
         keep = []
 
         def tab(rows):
+            if rows is None:
+                return None
             arr = (C.c_void_p * len(rows))()
             for i, r in enumerate(rows):
                 a = (C.c_int64 * len(r))(*[int(v) for v in r])
@@ -394,7 +398,11 @@ def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end):
     def sync_worker(tid):
         for f in range(tid, n_flowers, threads):
             t, ri, rr, ov, _, n = tabs[f]
-            ms = lib.barb200_make_consistent_partial_order_alignments(ctx, n, t.seq_no, t.strs, t.lens, ri, rr, ov, 10000, 5000, 1.0)
+            if ri is not None:
+                ms = lib.barb200_make_consistent_partial_order_alignments(ctx, n, t.seq_no, t.strs, t.lens, ri, rr, ov, 10000, 5000, 1.0)
+            else:                                       # a single-end record: the synchronous call is submit + wait
+                h = lib.barb200_flower_submit(ctx, n, t.seq_no, t.strs, t.lens, None, None, None, 10000, 5000, 1.0)
+                ms = lib.barb200_flower_wait(ctx, h) if h else None
             if not ms:
                 raise RuntimeError(lib.barb200_last_error(ctx).decode())
             free_msas(ms, n)
@@ -414,7 +422,8 @@ def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end):
                 raise RuntimeError(lib.barb200_last_error(ctx).decode())
             free_msas(ms, tabs[f][5])
     res = {}
-    cells = cells_per_end * 4 * n_flowers
+    n_ends_total = sum(len(f[0]) for f in flowers)
+    cells = cells_per_end * n_ends_total
     for name, worker in (("sync_calls", sync_worker), ("submit_all_then_collect", async_worker)):
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(worker, range(threads)))          # warm-up (sizes the lanes' arenas)
@@ -424,11 +433,49 @@ def flowers_leg(eng, first_flower, n_flowers, threads, cells_per_end):
             list(ex.map(worker, range(threads)))
         dt = time.time() - t0
         q1 = eng.queue_stats()
-        res[name] = {"gcells_per_s": cells / dt / 1e9, "ends_per_s": 4 * n_flowers / dt, "ms": dt * 1e3, "device_batches": q1["batches"] - q0["batches"]}
+        res[name] = {"gcells_per_s": cells / dt / 1e9, "ends_per_s": n_ends_total / dt, "ms": dt * 1e3, "device_batches": q1["batches"] - q0["batches"]}
     res["flowers"] = n_flowers
-    res["ends_per_flower"] = 4
+    res["ends"] = n_ends_total
     res["host_threads"] = threads
     return res, flowers
+
+
+def replay_arm(args):
+    """`--workload <file>`: the BAR inputs of a real run recorded by shim/cactus_bar_harvest.c (workload.read_harvest), replayed through
+    the end queue from 16 host threads (synchronous calls and submit-all / collect), next to the reference library on a bounded
+    sample of the same flowers, with the MSAs of that sample compared byte for byte. ends/s and bases/s (no cell count: the
+    flower-level API does not return one)."""
+    import cactus_b200 as cb
+    import _reflib as R
+    recs = workload.read_harvest(args.workload)
+    flowers = [(r["ends"], r["right_end_indexes"], r["right_end_row_indexes"], r["overlaps"]) for r in recs]
+    windows = sorted({(r["window_size"], r["max_prog_rows"], r["max_prog_length_diff"]) for r in recs})
+    if len(windows) != 1 or windows[0] != (10000, 5000, 1.0):
+        sys.stderr.write("[bench] note: the record uses window / progressive parameters %s; the replay uses Cactus' defaults\n" % (windows,))
+    bases = sum(len(s) for f in flowers for e in f[0] for s in e)
+    eng = cb.Engine(cb.PoaParams(host_threads=usable_cores()))
+    res, _ = flowers_leg(eng, 0, len(flowers), 16, 0.0, flowers=flowers)
+    for k in ("sync_calls", "submit_all_then_collect"):
+        res[k]["bases_per_s"] = bases / (res[k]["ms"] * 1e-3)
+        del res[k]["gcells_per_s"]
+    # reference library on a bounded sample + parity of that sample
+    sample = [f for f in flowers if f[1] is not None][: max(1, min(len(flowers), 4 * usable_cores()))]
+    t0 = time.time()
+    same = True
+    for f in sample:
+        want = R.ref_make_consistent_partial_order_alignments(f[0], f[1], f[2], f[3])
+        got = eng.make_consistent_partial_order_alignments(f[0], f[1], f[2], f[3])
+        same = same and all(a.msa_seq.shape == b.shape and np.array_equal(a.msa_seq, b) for a, b in zip(got, want))
+    line = {"metric": "BAR POA ends/s on harvested inputs (replay of %s)" % os.path.basename(args.workload), "unit": "ends/s",
+            "value": res["submit_all_then_collect"]["ends_per_s"], "n_gpus": 1, "data": "harvested", "higher_is_better": True,
+            "config": {"workload": "replay of %d recorded flowers, %d ends, %d bases" % (len(flowers), res["ends"], bases)},
+            "replay": res, "parity": {"flowers_checked": len(sample), "identical": bool(same), "seconds_incl_reference": time.time() - t0}}
+    eng.close()
+    if not same:
+        sys.stderr.write("[bench] PARITY GATE FAILED on the replayed sample\n")
+        return 3
+    print(json.dumps(line))
+    return 0
 
 
 def gpu_arm(args):
@@ -692,6 +739,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the shapes / e2e_flowers / in-process multi-GPU legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (for runs under ncu: the streamed e2e path releases jobs "
                     "to a RUNNING kernel from the host, which deadlocks under ncu's kernel serialisation)")
+    ap.add_argument("--workload", default=None, help="replay a record made by shim/cactus_bar_harvest.c (BARB200_HARVEST=<file> during a reference "
+                    "bar() run) instead of the synthetic workload")
     ap.add_argument("--pecan-only", action="store_true", help="internal: this process only measures the cPecan section and prints its raw numbers")
     ap.add_argument("--pecan-pairs-per-step", type=int, default=int(os.environ.get("BARB200_PECAN_PAIRS_PER_STEP", "4736")),
                     help="cPecan-mode pairs per GPU per step (default 32 x 148 SMs); 0 skips the cPecan section")
@@ -707,6 +756,8 @@ def main():
         return 0
     if args.impl == "reference":
         return reference_arm(args) if rank == 0 else 0     # the reference's CPU implementation; rank 0 only
+    if args.workload:
+        return replay_arm(args) if rank == 0 else 0
     return gpu_arm(args)
 
 

@@ -341,6 +341,8 @@ struct barb200_stage {
     void *d_block = nullptr; size_t d_block_bytes = 0;
     uint8_t *d_seqs = nullptr, *d_msa = nullptr; int *d_lens = nullptr; int64_t *d_soff = nullptr;
     JobDesc *d_desc = nullptr; int *d_msa_len = nullptr, *d_status = nullptr, *d_next = nullptr; long long *d_cells = nullptr;
+    int *d_order = nullptr, *d_gt_status = nullptr; uint8_t *d_gt_scratch = nullptr;
+    GuideTreeArgs gt; int gt_ctas = 0; float gt_ms = 0.f; cudaEvent_t e_gt = nullptr;   // K0: the guide trees of the stage (guide_tree.cu)
     // results of the last run
     std::vector<int> status, msa_len; std::vector<long long> cells;
     barb200_stage *retry = nullptr; std::vector<int64_t> retry_jobs;     // internal ids
@@ -354,7 +356,7 @@ static void stage_free_device(barb200_stage *st) {
     dev_free(dev_of_lane(st->ctx, st->lane), st->d_block, st->d_block_bytes);
     st->d_block = nullptr;
     st->d_seqs = st->d_msa = nullptr; st->d_lens = nullptr; st->d_soff = nullptr; st->d_desc = nullptr;
-    st->d_msa_len = st->d_status = st->d_next = nullptr; st->d_cells = nullptr;
+    st->d_msa_len = st->d_status = st->d_next = nullptr; st->d_cells = nullptr; st->d_order = st->d_gt_status = nullptr; st->d_gt_scratch = nullptr;
 }
 
 extern "C" void barb200_stage_destroy(barb200_stage *st) {
@@ -362,6 +364,7 @@ extern "C" void barb200_stage_destroy(barb200_stage *st) {
     cudaSetDevice(dev_of_lane(st->ctx, st->lane).ordinal);
     if (st->retry) barb200_stage_destroy(st->retry);
     if (st->e0) { cudaEventDestroy(st->e0); cudaEventDestroy(st->e1); }
+    if (st->e_gt) cudaEventDestroy(st->e_gt);
     stage_free_device(st);
     delete st;
 }
@@ -384,7 +387,7 @@ static int plan_stage(barb200_stage *st) {
     Device &D = dev_of_lane(ctx, st->lane);
     Lane &LN = lane_of(ctx, st->lane);
     for (Bucket &B : st->buckets) {
-        int64_t max_nodes = 4, max_edges = 4, max_len = 1, max_k = 1, plane_need = 0, key_need = 64;
+        int64_t max_nodes = 4, max_edges = 4, max_len = 1, max_k = 1, plane_need = 0;
         for (int64_t j = B.job_base; j < B.job_base + B.n_jobs; ++j) {
             const int64_t sum = st->job_sum_len[j], ml = st->job_max_len[j], K = st->n_seq[j];
             max_nodes = std::max(max_nodes, sum + 2); max_edges = std::max(max_edges, sum + K); max_len = std::max(max_len, ml);
@@ -393,11 +396,6 @@ static int plan_stage(barb200_stage *st) {
             int64_t rows = sum + 2;
             if (!st->worst_case) rows = std::min<int64_t>(rows, (int64_t)(st->grow * (double)(ml + (sum - ml) / 8 + 256)));
             plane_need = std::max(plane_need, rows * (TB / CPT) * (align_up(ml + 1, CPT) + CPT));
-            // minimizer keys of the guide tree: ~2 / (w + 1) per base; ties (repeats) can push up to 2 w per base
-            if (st->progressive[j] && K > 2) {
-                const int64_t worst = 2 * (int64_t)ctx->p.w * sum + K;
-                key_need = std::max(key_need, st->worst_case ? worst : std::min<int64_t>(worst, (int64_t)(st->grow * (double)(sum / 2 + 64))));
-            }
         }
         SlotLayout &Y = B.lay;
         memset(&Y, 0, sizeof(Y));
@@ -419,10 +417,6 @@ static int plan_stage(barb200_stage *st) {
         Y.o_row_off = take(N * 8); Y.o_row_info = take(N * 16);
         Y.o_cigar = take((int64_t)Y.cigar_cap * 8);
         Y.fc_cap = (int)(max_len + 2); Y.o_fc = take((int64_t)Y.fc_cap * 8);
-        int64_t kc = 64; while (kc < key_need) kc <<= 1;            // the sort pads to a power of two
-        Y.gt_key_cap = (int)kc; Y.max_k = (int)max_k;
-        Y.o_order = take(max_k * 4); Y.o_gt_keys = take(kc * 8); Y.o_gt_hit = take(max_k * (max_k + 1) / 2 * 4);
-        Y.o_gt_jac = take(max_k * (max_k - 1) / 2 * 8 + 8); Y.o_gt_score = take(max_k * 8);
         Y.slot_bytes = align_up(o, 256);
         B.T = kKernels[B.cls].T; B.dyn_smem = kKernels[B.cls].scratch;
         if (getenv("BARB200_SCRATCH_KB")) B.dyn_smem = (size_t)atoi(getenv("BARB200_SCRATCH_KB")) * 1024;   // tuning aid
@@ -560,8 +554,29 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     // device buffers (one cached block) + upload on the lane's copy stream, so that it overlaps a running kernel
     size_t off = 0;
     auto sub = [&](size_t bytes) { size_t r = off; off = (off + std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return r; };
+    // K0's scratch: one slot per resident guide-tree CTA, sized from the stage's largest job (keys: ~2 / (w + 1) per base; ties in
+    // repeats can push up to 2 w per base -- capacity misses are retried like the planes')
+    GuideTreeArgs &GA = st->gt;
+    memset(&GA, 0, sizeof(GA));
+    {
+        int64_t key_need = 64, gx_need = 8, mk = 1;
+        for (int64_t j = 0; j < n_jobs; ++j) {
+            if (!(st->progressive[j] && st->n_seq[j] > 2)) continue;
+            const int64_t sum = st->job_sum_len[j], worst = 2 * (int64_t)ctx->p.w * sum + st->n_seq[j];
+            key_need = std::max(key_need, worst_case ? worst : std::min<int64_t>(worst, (int64_t)(grow * (double)(sum / 2 + 64))));
+            gx_need = std::max(gx_need, sum); mk = std::max<int64_t>(mk, st->n_seq[j]);
+        }
+        int64_t kc = 64; while (kc < key_need) kc <<= 1;            // the sort pads to a power of two
+        int64_t o = 0;
+        auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 16); return r; };
+        GA.key_cap = (int)kc;
+        GA.o_keys = take(kc * 8); GA.o_gx = take(gx_need * 8); GA.o_hit = take(mk * (mk + 1) / 2 * 4); GA.o_jac = take(mk * (mk - 1) / 2 * 8 + 8); GA.o_score = take(mk * 8);
+        GA.slot_bytes = align_up(o, 256);
+        st->gt_ctas = (int)std::min<int64_t>(std::min<int64_t>(n_jobs, (int64_t)4 * D.sm_count), std::max<int64_t>(1, ((int64_t)2 << 30) / GA.slot_bytes));
+    }
     const size_t o_seqs = sub(n_bases_total), o_lens = sub(ns * 4), o_soff = sub(ns * 8), o_desc = sub(n_jobs * sizeof(JobDesc)),
-                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4 * kNumKernels);
+                 o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4 * (kNumKernels + 1)),
+                 o_order = sub(ns * 4), o_gts = sub(n_jobs * 4), o_gtscr = sub((size_t)GA.slot_bytes * st->gt_ctas);
     st->d_block_bytes = off;
     int rc = plan_stage(st.get());
     if (rc) return rc;
@@ -574,6 +589,9 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     st->d_seqs = blk + o_seqs; st->d_lens = (int *)(blk + o_lens); st->d_soff = (int64_t *)(blk + o_soff);
     st->d_desc = (JobDesc *)(blk + o_desc); st->d_msa = blk + o_msa; st->d_msa_len = (int *)(blk + o_msa_len); st->d_status = (int *)(blk + o_status);
     st->d_cells = (long long *)(blk + o_cells); st->d_next = (int *)(blk + o_next);
+    st->d_order = (int *)(blk + o_order); st->d_gt_status = (int *)(blk + o_gts); st->d_gt_scratch = blk + o_gtscr;
+    GA.jobs = st->d_desc; GA.n_jobs = (int)n_jobs; GA.seqs = st->d_seqs; GA.lens = st->d_lens; GA.soff = st->d_soff; GA.order = st->d_order; GA.gt_status = st->d_gt_status;
+    GA.next_job = st->d_next + kNumKernels; GA.scratch = st->d_gt_scratch; GA.k = ctx->p.k; GA.w = ctx->p.w;
     cudaStream_t s = LN.copy;
     if ((e = cudaMemcpyAsync(st->d_seqs, seqs, n_bases_total, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
@@ -612,23 +630,30 @@ static int stage_launch(barb200_stage *st) {
     int rc = ensure_arena(ctx, LN, slots_bytes, plane_ints * 4, clk_n);
     if (rc) return rc;
     cudaStream_t s = LN.main;
-    CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4 * kNumKernels, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4 * (kNumKernels + 1), s));
     if (clk_n) CUDA_TRY(ctx, cudaMemsetAsync(LN.d_clk, 0, clk_n * sizeof(unsigned long long), s));
     if (!st->e0) { CUDA_TRY(ctx, cudaEventCreate(&st->e0)); CUDA_TRY(ctx, cudaEventCreate(&st->e1)); }
+    if (!st->e_gt) CUDA_TRY(ctx, cudaEventCreate(&st->e_gt));
     CUDA_TRY(ctx, cudaEventRecord(st->e0, s));
+    // K0: the guide trees of every job (guide_tree.cu); the POA launches below wait for it through the stream / e_gt
+    launch_guide_tree(st->gt, st->gt_ctas, (void *)s);
+    { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) { set_error(ctx, std::string("guide tree launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; } }
+    CUDA_TRY(ctx, cudaEventRecord(st->e_gt, s));
+    st->launches++;
     const bool single = st->buckets.size() == 1;
     for (size_t b = 0; b < st->buckets.size(); ++b) {          // largest class first
         const Bucket &B = st->buckets[b];
         BatchArgs A;
         A.jobs = st->d_desc; A.job_base = (int)B.job_base; A.n_jobs = (int)B.n_jobs; A.seqs = st->d_seqs; A.lens = st->d_lens; A.soff = st->d_soff;
+        A.order = st->d_order; A.gt_status = st->d_gt_status;
         A.msa = st->d_msa; A.msa_len = st->d_msa_len; A.status = st->d_status; A.cells = st->d_cells;
         A.slots = LN.d_slots + B.slot_off; A.planes = LN.d_planes + B.plane_off; A.next_job = st->d_next + b;
         A.phase_clk = clk_n ? LN.d_clk + B.clk_off : nullptr;
         A.serial_phases = getenv("BARB200_DEBUG_SERIAL") ? 1 : 0;
         A.bfs_order = getenv("BARB200_DEBUG_BFS") ? 1 : 0;
-        A.scratch_bytes = (int)B.dyn_smem; A.lay = B.lay; A.P = ctx->P; A.gt_k = ctx->p.k; A.gt_w = ctx->p.w;
+        A.scratch_bytes = (int)B.dyn_smem; A.lay = B.lay; A.P = ctx->P;
         cudaStream_t cs = single ? s : LN.cls[B.cls];
-        if (!single) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, st->e0, 0));
+        if (!single) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, st->e_gt, 0));
         kKernels[B.cls].fn<<<B.slots, B.T, B.dyn_smem, cs>>>(A);
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { set_error(ctx, std::string("kernel launch: ") + cudaGetErrorString(le)); return BARB200_ECUDA; }
@@ -655,17 +680,19 @@ static int stage_finish(barb200_stage *st, float *kernel_ms) {
     cudaError_t se = cudaStreamSynchronize(s);
     if (se != cudaSuccess) { set_error(ctx, std::string("kernel execution: ") + cudaGetErrorString(se)); return BARB200_ECUDA; }
     float ms = 0.f; cudaEventElapsedTime(&ms, st->e0, st->e1);
+    st->gt_ms = 0.f; cudaEventElapsedTime(&st->gt_ms, st->e0, st->e_gt);
     st->launched = false;
     st->status.resize(st->n_jobs);
     CUDA_TRY(ctx, cudaMemcpyAsync(st->status.data(), st->d_status, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     for (int k = 0; k < 7; ++k) st->clk[k] = 0;
+    st->clk[6] = (uint64_t)(st->gt_ms * 1e6f);          // K0 is a kernel of its own: its device time, in nanoseconds
     if (ctx->p.collect_phase_clocks) {
         size_t clk_n = 0;
         for (const Bucket &B : st->buckets) clk_n += (size_t)B.slots * PH_N;
         std::vector<unsigned long long> h(clk_n);
         CUDA_TRY(ctx, cudaMemcpy(h.data(), LN.d_clk, clk_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (size_t b = 0; b < clk_n / PH_N; ++b) for (int k = 0; k < 7; ++k) st->clk[k] += h[b * PH_N + k];
+        for (size_t b = 0; b < clk_n / PH_N; ++b) for (int k = 0; k < 6; ++k) st->clk[k] += h[b * PH_N + k];
     }
     // capacity misses -> retry launch for just those jobs with larger slots (x4 first, then worst case)
     std::vector<int64_t> redo;

@@ -6,8 +6,9 @@
 // multisets and a greedy order (abpoa_build_guide_tree, :232-325). Round 1 computed this on host threads and streamed the
 // orders in behind the running kernel; here it is the first phase of the job on the device, so the host does
 // no per-job work at all and K in the hundreds costs no host time:
-//   1. sketch: one THREAD per sequence runs the reference's serial window scan (ties and duplicates exactly as mm_sketch
-//      reports them -- the multiset matters) and appends keys (hash << 8 | span) << 16 | read to one array;
+//   1. sketch: the reference's serial window scan (ties and duplicates exactly as mm_sketch reports them -- the multiset
+//      matters), cut into 64-position chunks that all threads work on (see gt_scan_chunk for why that is exact); keys
+//      (hash << 8 | span) << 16 | read are appended to one array;
 //   2. the keys are sorted by the CTA (bitonic network in global memory; only the grouping by hash matters);
 //   3. every group of equal hashes adds min(count_a, count_b) to the pair counters (integer atomics: order free);
 //   4. Jaccard = shared / total in double (one IEEE division of two integers, the same value as the reference's), first
@@ -33,11 +34,13 @@ struct GuideTreeParams { int k, w; };        // partialOrderAlignmentMinimizerK 
 // per-slot scratch of the guide tree (carved from the slot by the kernel)
 struct GtScratch {
     uint64_t *keys; int key_cap;             // minimizer keys, capacity a power of two
+    uint64_t *gx;                            // [bases of the job] per-position k-mer values (phase A of the sketch)
     int *hit;                                // [K (K + 1) / 2] pair counters, tri(i, j) = i (i + 1) / 2 + j, i >= j
     double *jac;                             // [K (K - 1) / 2] similarities, jidx(i, j) = i (i - 1) / 2 + j, i > j
     double *score;                           // [K] running greedy scores (-1 once placed)
     int *n_keys;                             // 1 int: keys appended (shared or global)
     int *red_i; double *red_v;               // [T / 32 + 1] block reductions
+    uint64_t *tile; int tile_cap;            // shared-memory tile of the sort (a power of two, >= 64 keys)
 };
 
 HD uint64_t gt_hash64(uint64_t key, uint64_t mask) {   // minimap2's hash64, abpoa_seed.c:36-46
@@ -60,44 +63,65 @@ HD void gt_push(const GtScratch &G, uint64_t x, uint32_t rid) {
     if (pos < G.key_cap) G.keys[pos] = x << 16 | (uint64_t)rid;
 }
 
-// Windowed minimizer sampling of ONE sequence with the reference's treatment of ties (abpoa_seed.c:85-156): when several k-mers of
-// a window share the minimal hash all of them are reported. Serial; x = hash << 8 | span, y = position << 1 (only compared).
-HD void gt_sketch(const GtScratch &G, const uint8_t *s, int len, int w, int k, uint32_t rid) {
-    const uint64_t mask = (1ULL << 2 * k) - 1, NONE = ~0ULL;
-    uint64_t rx[256], ry[256];               // the window (w < 256, checked at create)
-    for (int j = 0; j < w; ++j) { rx[j] = NONE; ry[j] = NONE; }
-    uint64_t bx = NONE, by = NONE, kmer = 0;
-    int run = 0, pos = 0, best_pos = 0;      // run: bases since the last ambiguous one
-    for (int i = 0; i < len; ++i) {
-        const int c = s[i];
-        uint64_t cx = NONE, cy = NONE;
+// ---- minimizer sketch (mm_sketch, abpoa_seed.c:85-156; forward strand only, no homopolymer compression) ------------------------
+// The reference scans a sequence serially with a ring of the last w k-mers and a running minimum. Two facts make the scan
+// parallel WITHOUT changing a single emission (ties, duplicates and the first-window quirk included):
+//   * the ring always equals the last w entries of the per-position array X[i] = (hash << 8 | span) of the k-mer ending at i
+//     (NONE where fewer than k unambiguous bases end at i), and "bases since the last ambiguous one" (run) is a function of the
+//     position alone -- so X can be computed for all positions independently (phase A);
+//   * the scan's state before step i -- the running minimum `best` and its slot -- is always the RIGHTMOST minimum of
+//     X[i-w .. i-1] (NONE included as the largest value; checked case by case against the update rule below) -- so any chunk of
+//     positions can start from that state and replay the reference's step rule, emitting exactly what the serial scan emits in
+//     that chunk (phase B). The emission order differs, which is irrelevant: the keys are sorted next.
+constexpr uint64_t GT_NONE = ~0ULL;
+
+// phase A for positions [s, e) of one sequence: X[i] into gx[i]
+HD void gt_hash_chunk(const uint8_t *q, int s, int e, int k, uint64_t *gx) {
+    const uint64_t mask = (1ULL << 2 * k) - 1;
+    int run = 0;                                   // unambiguous bases ending at s-1, capped at k (all that matters here)
+    uint64_t kmer = 0;
+    for (int i = s - 1; i >= 0 && run < k && q[i] < 4; --i) ++run;
+    for (int i = s - run; i < s; ++i) kmer = (kmer << 2 | (uint64_t)q[i]) & mask;
+    for (int i = s; i < e; ++i) {
+        const int c = q[i];
+        uint64_t x = GT_NONE;
         if (c < 4) {
-            const int span = run + 1 < k ? run + 1 : k;
             kmer = (kmer << 2 | (uint64_t)c) & mask;
-            ++run;
-            if (run >= k) { cx = gt_hash64(kmer, mask) << 8 | (uint64_t)span; cy = (uint64_t)(uint32_t)i << 1; }
-        } else run = 0;
-        rx[pos] = cx; ry[pos] = cy;
-        if (run == w + k - 1 && bx != NONE) {
-            for (int j = pos + 1; j < w; ++j) if (bx == rx[j] && by != ry[j]) gt_push(G, rx[j], rid);
-            for (int j = 0; j < pos; ++j) if (bx == rx[j] && by != ry[j]) gt_push(G, rx[j], rid);
+            if (run < k) ++run;
+            if (run >= k) x = gt_hash64(kmer, mask) << 8 | (uint64_t)k;        // span = k once k bases are there (abpoa_seed.c:117)
+        } else { run = 0; kmer = 0; }
+        gx[i] = x;
+    }
+}
+
+// phase B for positions [s, e) of one sequence of length len (read id rid): the reference's step rule on X = gx
+HD void gt_scan_chunk(const GtScratch &G, const uint8_t *q, const uint64_t *gx, int len, int s, int e, int w, int k, uint32_t rid) {
+    auto X = [&](int i) { return i >= 0 ? gx[i] : GT_NONE; };
+    // run before the chunk, capped at w + k (the rule only compares it with w + k - 1 and w + k)
+    int run = 0;
+    for (int i = s - 1; i >= 0 && run < w + k && q[i] < 4; --i) ++run;
+    // state before step s: rightmost minimum of X[s-w .. s-1]
+    uint64_t bx = GT_NONE; int bi = s - w;         // (bi only matters through bi % w == slot; any slot is fine while bx is NONE ... see below)
+    for (int j = s - w; j < s; ++j) { const uint64_t v = X(j); if (bx >= v) { bx = v; bi = j; } }
+    for (int i = s; i < e; ++i) {
+        const uint64_t cx = gx[i];
+        if (q[i] < 4) { if (run < w + k) ++run; } else run = 0;
+        if (run == w + k - 1 && bx != GT_NONE) {                              // the first full window: ties of the minimum so far
+            for (int j = i - w + 1; j < i; ++j) if (bx == X(j) && j != bi) gt_push(G, bx, rid);
         }
         if (cx <= bx) {
-            if (run >= w + k && bx != NONE) gt_push(G, bx, rid);
-            bx = cx; by = cy; best_pos = pos;
-        } else if (pos == best_pos) {
-            if (run >= w + k - 1 && bx != NONE) gt_push(G, bx, rid);
-            bx = NONE;
-            for (int j = pos + 1; j < w; ++j) if (bx >= rx[j]) { bx = rx[j]; by = ry[j]; best_pos = j; }
-            for (int j = 0; j <= pos; ++j) if (bx >= rx[j]) { bx = rx[j]; by = ry[j]; best_pos = j; }
-            if (run >= w + k - 1 && bx != NONE) {
-                for (int j = pos + 1; j < w; ++j) if (bx == rx[j] && by != ry[j]) gt_push(G, rx[j], rid);
-                for (int j = 0; j < pos + 1; ++j) if (bx == rx[j] && by != ry[j]) gt_push(G, rx[j], rid);
+            if (run >= w + k && bx != GT_NONE) gt_push(G, bx, rid);
+            bx = cx; bi = i;
+        } else if (bi == i - w) {                                             // the minimum slides out of the window
+            if (run >= w + k - 1 && bx != GT_NONE) gt_push(G, bx, rid);
+            bx = GT_NONE;
+            for (int j = i - w + 1; j <= i; ++j) { const uint64_t v = X(j); if (bx >= v) { bx = v; bi = j; } }
+            if (run >= w + k - 1 && bx != GT_NONE) {
+                for (int j = i - w + 1; j <= i; ++j) if (bx == X(j) && j != bi) gt_push(G, bx, rid);
             }
         }
-        if (++pos == w) pos = 0;
     }
-    if (bx != NONE) gt_push(G, bx, rid);
+    if (e == len && bx != GT_NONE) gt_push(G, bx, rid);                        // the last minimum of the sequence
 }
 
 HD int64_t gt_tri(int64_t i, int64_t j) { return i * (i + 1) / 2 + j; }     // i >= j
@@ -139,27 +163,96 @@ HD int cta_guide_tree(const GuideTreeParams &P, int progressive, int n, SeqFn se
     GT_THREADS(tid, T) { for (int i = tid; i < n; i += T) order[i] = i; if (tid == 0) *G.n_keys = 0; }
     GT_SYNC();
     if (!(progressive && n > 2)) return 0;
-    // ---- 1. sketches: one thread per sequence ----
-    GT_THREADS(tid, T) { for (int i = tid; i < n; i += T) gt_sketch(G, seq(i), lens[i], P.w, P.k, (uint32_t)i); }
-    GT_SYNC();
+    // ---- 1. sketches: every thread takes chunks of GT_CHUNK positions (offsets of the sequences in gx = prefix sums of lens) ----
+    constexpr int GT_CHUNK = 64;
+    int64_t total_chunks = 0;
+    for (int i = 0; i < n; ++i) total_chunks += (lens[i] + GT_CHUNK - 1) / GT_CHUNK;
+    for (int phase = 0; phase < 2; ++phase) {
+        GT_THREADS(tid, T) {
+            int64_t c0 = 0, off = 0;                  // chunks / bases of the sequences before sequence i
+            int i = 0;
+            for (int64_t c = tid; c < total_chunks; c += T) {
+                while (c >= c0 + (lens[i] + GT_CHUNK - 1) / GT_CHUNK) { c0 += (lens[i] + GT_CHUNK - 1) / GT_CHUNK; off += lens[i]; ++i; }
+                const int s0 = (int)(c - c0) * GT_CHUNK, e0 = s0 + GT_CHUNK < lens[i] ? s0 + GT_CHUNK : lens[i];
+                if (phase == 0) gt_hash_chunk(seq(i), s0, e0, P.k, G.gx + off);
+                else gt_scan_chunk(G, seq(i), G.gx + off, lens[i], s0, e0, P.w, P.k, (uint32_t)i);
+            }
+        }
+        GT_SYNC();
+    }
     const int nk = *G.n_keys;
     if (nk > G.key_cap) return -1;
     if (nk == 0) return 0;
-    // ---- 2. sort (bitonic, padded to a power of two with the maximal key) ----
+    // ---- 2. sort (bitonic network, padded to a power of two with the maximal key). Exchanges whose partners lie within one
+    // tile run in shared memory (load the tile once, all strides below the tile size, store it back); only the few passes with a
+    // stride >= the tile size touch global memory, and there every thread loads a batch of pairs before it stores any ----
     int n2 = 1;
     while (n2 < nk) n2 <<= 1;
     GT_THREADS(tid, T) { for (int i = nk + tid; i < n2; i += T) G.keys[i] = ~0ULL; }
     GT_SYNC();
-    for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    int tile = 64;
+    while (tile * 2 <= G.tile_cap && tile < n2) tile <<= 1;
+    if (tile > n2) tile = n2;
+    // stage 1: every merge size up to the tile size, tile by tile, entirely in shared memory
+    for (int base = 0; base < n2; base += tile) {
+        GT_THREADS(tid, T) { for (int i = tid; i < tile; i += T) G.tile[i] = G.keys[base + i]; }
+        GT_SYNC();
+        for (int size = 2; size <= tile; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                GT_THREADS(tid, T) {
+                    for (int t = tid; t < (tile >> 1); t += T) {
+                        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+                        const bool up = ((base + lo) & size) == 0;
+                        const uint64_t a = G.tile[lo], b = G.tile[hi];
+                        if ((a > b) == up) { G.tile[lo] = b; G.tile[hi] = a; }
+                    }
+                }
+                GT_SYNC();
+            }
+        }
+        GT_THREADS(tid, T) { for (int i = tid; i < tile; i += T) G.keys[base + i] = G.tile[i]; }
+        GT_SYNC();
+    }
+    // stage 2: the larger merge sizes: strides >= tile in global memory, the rest of the step tile by tile in shared memory
+    for (int size = tile << 1; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride >= tile; stride >>= 1) {
             GT_THREADS(tid, T) {
-                for (int t = tid; t < (n2 >> 1); t += T) {
-                    const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    const uint64_t a = G.keys[lo], b = G.keys[hi];
-                    if ((a > b) == up) { G.keys[lo] = b; G.keys[hi] = a; }
+                for (int t0 = tid; t0 < (n2 >> 1); t0 += 4 * T) {
+                    uint64_t a[4], b[4]; int lo[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u * T;
+                        lo[u] = t < (n2 >> 1) ? ((t / stride) * (stride << 1)) + (t % stride) : -1;
+                        if (lo[u] >= 0) { a[u] = G.keys[lo[u]]; b[u] = G.keys[lo[u] + stride]; }
+                    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                    for (int u = 0; u < 4; ++u) if (lo[u] >= 0) {
+                        const bool up = (lo[u] & size) == 0;
+                        if ((a[u] > b[u]) == up) { G.keys[lo[u]] = b[u]; G.keys[lo[u] + stride] = a[u]; }
+                    }
                 }
             }
+            GT_SYNC();
+        }
+        for (int base = 0; base < n2; base += tile) {
+            GT_THREADS(tid, T) { for (int i = tid; i < tile; i += T) G.tile[i] = G.keys[base + i]; }
+            GT_SYNC();
+            for (int stride = tile >> 1; stride > 0; stride >>= 1) {
+                GT_THREADS(tid, T) {
+                    for (int t = tid; t < (tile >> 1); t += T) {
+                        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+                        const bool up = ((base + lo) & size) == 0;
+                        const uint64_t a = G.tile[lo], b = G.tile[hi];
+                        if ((a > b) == up) { G.tile[lo] = b; G.tile[hi] = a; }
+                    }
+                }
+                GT_SYNC();
+            }
+            GT_THREADS(tid, T) { for (int i = tid; i < tile; i += T) G.keys[base + i] = G.tile[i]; }
             GT_SYNC();
         }
     }

@@ -31,7 +31,6 @@
 #include <stdint.h>
 #include "poa_graph.cuh"
 #include "poa_cta.cuh"
-#include "guide_tree.cuh"
 #include "poa_kernel.cuh"
 
 namespace barb200 {
@@ -44,7 +43,6 @@ struct KShared {
     int smat[5 * 8];       // [graph base][query code 0..4, 5 = "no base": column 0 / beyond the query -> 0]
     int wF[2][2][32];      // [row parity][plane F1/F2][warp] block scan staging
     int wM[2][4][32];      // [row parity][max, leftmost, rightmost, H of the warp's last column][warp]
-    int gt_n_keys; double gt_v[33]; long long gt_i[33];   // guide tree: key counter, block reductions
 };
 
 __device__ __forceinline__ int4 ld4cg(const int *p) { return __ldcg(reinterpret_cast<const int4 *>(p)); }
@@ -378,20 +376,10 @@ __device__ __forceinline__ void poa_msa_body(const BatchArgs &A) {
         const uint8_t *seqs = A.seqs + jd.seq_off;
         if (tid == 0) { graph_reset(S.g, K); S.abort_s = 0; }
         __syncthreads();
-        // ---- read order: the guide tree of the job (abpoa_seed.c:705-722), computed here (guide_tree.cuh) ----
-        int *const order = reinterpret_cast<int *>(A.slots + (int64_t)blockIdx.x * A.lay.slot_bytes + A.lay.o_order);
-        {
-            uint8_t *const sb = A.slots + (int64_t)blockIdx.x * A.lay.slot_bytes;
-            GtScratch G;
-            G.keys = reinterpret_cast<uint64_t *>(sb + A.lay.o_gt_keys); G.key_cap = A.lay.gt_key_cap;
-            G.hit = reinterpret_cast<int *>(sb + A.lay.o_gt_hit); G.jac = reinterpret_cast<double *>(sb + A.lay.o_gt_jac);
-            G.score = reinterpret_cast<double *>(sb + A.lay.o_gt_score); G.n_keys = &S.gt_n_keys; G.red_i = nullptr; G.red_v = nullptr;
-            const GuideTreeParams GP{A.gt_k, A.gt_w};
-            const int rc = cta_guide_tree(GP, jd.progressive, K, [&](int i) { return seqs + soff[i]; }, lens, order, G, S.gt_v, S.gt_i, (int)blockDim.x);
-            if (rc < 0 && tid == 0) S.g.err = JOB_ERR_GT_CAP;
-            __syncthreads();
-        }
-        PHASE_TICK(PH_GUIDE);
+        // read order: the job's guide tree (abpoa_seed.c:705-722), computed by guide_tree_kernel before this launch (guide_tree.cu)
+        const int *const order = A.order + jd.len_off;
+        if (tid == 0 && A.gt_status[job]) S.g.err = JOB_ERR_GT_CAP;
+        __syncthreads();
         long long cells = 0;
         for (int a = 0; a < K && !S.g.err; ++a) {
             const int read = order[a], L = lens[read];

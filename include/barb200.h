@@ -95,7 +95,8 @@ int barb200_stage_create(barb200_ctx *ctx, int64_t n_jobs, const int *n_seq, con
 int barb200_stage_run(barb200_stage *st, float *kernel_ms /* may be NULL: device time of the launch(es) */);
 int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *msa_len, int64_t *cells);
 int64_t barb200_stage_launches(barb200_stage *st);   /* kernels launched by the last barb200_stage_run */
-/* per-phase SM clock totals of the last run (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total, guide tree */
+/* per-phase SM clock totals of the last run over all POA CTAs (needs collect_phase_clocks): dp, backtrack, fuse, topo, msa, total;
+ * out[6] = device time of the guide-tree kernel (K0) in nanoseconds (always filled) */
 int barb200_stage_phase_clocks(barb200_stage *st, uint64_t out[7]);
 /* the stage's CTA-size buckets (largest first): out[4b .. 4b+3] = threads per CTA, jobs, resident CTAs, plane ints per slot;
  * returns the number of buckets */

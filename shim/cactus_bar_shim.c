@@ -41,8 +41,21 @@ static void params_from_abpoa(const abpoa_para_t *abpt, barb200_params *p) {
     p->k = abpt->k; p->w = abpt->w; p->min_w = abpt->min_w;
     p->progressive_poa = abpt->progressive_poa;
     p->disable_seeding = abpt->disable_seeding;
-    const char *dev = getenv("BARB200_DEVICE");          /* one cactus_consolidated process per GPU */
+    const char *dev = getenv("BARB200_DEVICE");          /* one GPU for this process ... */
     if (dev) p->device = atoi(dev);
+    const char *devs = getenv("BARB200_DEVICES");        /* ... or several behind ONE context: "all" or "0,1,2,3" */
+    if (devs) {
+        if (strcmp(devs, "all") == 0) {
+            p->n_devices = -1;
+        } else {
+            p->n_devices = 0;
+            for (const char *c = devs; *c && p->n_devices < 8; ) {
+                p->devices[p->n_devices++] = atoi(c);
+                while (*c && *c != ',') c++;
+                if (*c == ',') c++;
+            }
+        }
+    }
 }
 
 /* field-wise comparison (memcmp would read struct padding) */
@@ -50,7 +63,8 @@ static int params_equal(const barb200_params *a, const barb200_params *b) {
     return memcmp(a->mat, b->mat, sizeof(a->mat)) == 0 && a->gap_open1 == b->gap_open1 && a->gap_ext1 == b->gap_ext1 &&
            a->gap_open2 == b->gap_open2 && a->gap_ext2 == b->gap_ext2 && a->wb == b->wb && a->wf == b->wf && a->k == b->k &&
            a->w == b->w && a->min_w == b->min_w && a->progressive_poa == b->progressive_poa &&
-           a->disable_seeding == b->disable_seeding && a->device == b->device;
+           a->disable_seeding == b->disable_seeding && a->device == b->device && a->n_devices == b->n_devices &&
+           memcmp(a->devices, b->devices, sizeof(a->devices)) == 0;
 }
 
 static barb200_ctx *shim_context(abpoa_para_t *abpt) {

@@ -133,11 +133,11 @@ extern "C" int64_t *hosttest_poa_msa_trace(const HtParams *hp, int n_seq, const 
     std::vector<int> order(n_seq);
     {   // the product's guide tree (guide_tree.cuh), a block of 64 emulated threads
         int64_t kc = 64; while (kc < 2 * (int64_t)hp->w * sum + n_seq) kc <<= 1;
-        std::vector<uint64_t> keys((size_t)kc);
+        std::vector<uint64_t> keys((size_t)kc), gx((size_t)sum + 8), tile(256);       // a small tile: the global-stride passes run too
         std::vector<int> hit((size_t)n_seq * (n_seq + 1) / 2 + 1);
         std::vector<double> jac((size_t)n_seq * (n_seq - 1) / 2 + 1), score(n_seq);
         int n_keys = 0; double wsv[33]; long long wsi[33];
-        GtScratch G; G.keys = keys.data(); G.key_cap = (int)kc; G.hit = hit.data(); G.jac = jac.data(); G.score = score.data(); G.n_keys = &n_keys; G.red_i = nullptr; G.red_v = nullptr;
+        GtScratch G; G.keys = keys.data(); G.key_cap = (int)kc; G.gx = gx.data(); G.hit = hit.data(); G.jac = jac.data(); G.score = score.data(); G.n_keys = &n_keys; G.red_i = nullptr; G.red_v = nullptr; G.tile = tile.data(); G.tile_cap = (int)tile.size();
         const GuideTreeParams GP{hp->k, hp->w};
         if (cta_guide_tree(GP, hp->progressive, n_seq, [&](int i) { return seqs[i]; }, lens, order.data(), G, wsv, wsi, 64) != 0) { *status = JOB_ERR_GT_CAP; *n_words = 0; return nullptr; }
     }
