@@ -231,14 +231,17 @@ int64_t *flower_harness_blocks(void *session_, int64_t index, int64_t *n_words) 
 }
 
 /* bar() on ALL flowers of the session (bar.c:52-176: alignment, pinch iterator, stCaf_setup / anneal / melt / finish); threads > 0
- * sets the OpenMP team size of bar()'s loop over flowers */
-void flower_harness_bar(void *session_, int threads) {
+ * sets the OpenMP team size of bar()'s loop over flowers. Returns the wall time of the bar() call in seconds. */
+double flower_harness_bar(void *session_, int threads) {
     session *S = session_;
     stList *flowers = stList_construct();
     for (int64_t i = 0; i < S->n_flowers; ++i) stList_append(flowers, S->f[i].flower);
     if (threads > 0) omp_set_num_threads(threads);
+    const double t0 = omp_get_wtime();
     bar(flowers, NULL, S->disk, NULL);
+    const double dt = omp_get_wtime() - t0;         /* wall time of bar() itself: alignment + CAF of every flower */
     stList_destruct(flowers);
+    return dt;
 }
 
 /* recursive dump of flower `index`'s hierarchy (ends, caps, blocks and their segments, groups), e.g. after flower_harness_bar */

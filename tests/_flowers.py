@@ -54,7 +54,7 @@ def _lib(which):
         lib.flower_harness_blocks.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         lib.flower_harness_blocks.restype = C.c_void_p
         lib.flower_harness_bar.argtypes = [C.c_void_p, C.c_int]
-        lib.flower_harness_bar.restype = None
+        lib.flower_harness_bar.restype = C.c_double
         lib.flower_harness_dump.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         lib.flower_harness_dump.restype = C.c_void_p
         lib.flower_harness_end.argtypes = [C.c_void_p]
@@ -205,17 +205,18 @@ def blocks(which, flower, params=None):
     return {"blocks": out, "pinches": w[o: o + 6 * npinch].reshape(npinch, 6), "raw": w}
 
 
-def bar(which, flowers, params=None, threads=0):
-    """bar() over a list of flowers in ONE cactus disk -> list of int64 streams, the post-BAR hierarchy of every flower"""
+def bar(which, flowers, params=None, threads=0, want_seconds=False):
+    """bar() over a list of flowers in ONE cactus disk -> list of int64 streams, the canonical block list of every flower after
+    BAR (with want_seconds: (streams, wall seconds of the bar() call))"""
     lib = _lib(which)
     _set_params(lib, params)
     h = lib.flower_harness_begin(max(max(f["seq_event"]) for f in flowers) + 1)
     for f in flowers:
         _add(lib, h, f)
-    lib.flower_harness_bar(h, threads)
+    secs = lib.flower_harness_bar(h, threads)
     out = []
     for i in range(len(flowers)):
         n = C.c_int64()
         out.append(_words(lib, lib.flower_harness_dump(h, i, C.byref(n)), n))
     lib.flower_harness_end(h)
-    return out
+    return (out, secs) if want_seconds else out

@@ -284,3 +284,26 @@ def test_a_bad_ticket_fails_alone(engine):
                 engine.flower_wait(t)
         else:
             assert len(engine.flower_wait(t)) == 2
+
+
+def test_one_context_over_every_visible_device(engine, oracle_built):
+    """barb200_params.devices[]: ONE context drives every GPU of the box (the batch call deals jobs by estimated cost, the end queue's
+    lane workers of every device pull ends); results are those of the single-device context, in the caller's order. On a one-GPU
+    box this is the same code path with one device."""
+    import cactus_b200 as cb
+    rng = np.random.default_rng(51)
+    jobs = [family(rng, int(rng.integers(2, 9)), int(rng.choice([60, 300, 900, 1800])), sub=0.03, ins=0.01, dele=0.01) for _ in range(300)]
+    one = engine.poa_msa_batch(jobs)
+    e = cb.Engine(cb.PoaParams(devices="all"))
+    assert e.device_count() >= 1
+    many, cells = e.poa_msa_batch(jobs, return_cells=True)
+    for a, b in zip(one, many):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    probs = [two_end_problem(rng, int(rng.integers(2, 6)), int(rng.choice([50, 400]))) for _ in range(40)]
+    tickets = [e.flower_submit(*p) for p in probs]
+    for p, t in zip(probs, tickets):
+        got = e.flower_wait(t)
+        want = engine.make_consistent_partial_order_alignments(*p)
+        for a, b in zip(got, want):
+            assert np.array_equal(a.msa_seq, b.msa_seq)
+    e.close()
