@@ -623,6 +623,9 @@ def gpu_arm(args):
     # estimated cost, results land in the caller's buffers, no gather); rank 0 drives, the other ranks idle at the barrier ----
     if world > 1 and not args.no_e2e and not args.no_extras:
         barrier()
+        # (the other ranks must wait on the HOST: a rank parked in an NCCL barrier keeps a spinning kernel on its GPU, and a second process's
+        # context on that GPU would be time-sliced against it)
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             try:
                 eng_all = cb.Engine(cb.PoaParams(devices=list(range(world)), host_threads=cores))
@@ -651,6 +654,9 @@ def gpu_arm(args):
                 eng_all.close()
             except Exception as e:  # noqa: BLE001
                 extra["e2e_in_process"] = {"error": str(e)}
+            store.set("barb200_inproc_done", "1")
+        else:
+            store.wait(["barb200_inproc_done"])
         barrier()
     # ---- cPecan mode (its own context: the POA arenas are released first) ----
     pecan = None

@@ -25,16 +25,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=None, out_path=None):
+    """extra_flags / out_path: development aid (A/B builds of differently tuned kernels into another file; see scripts/)"""
+    if out_path is None and not force and not needs_build():
         return LIB
     objs = []
-    bdir = os.path.join(HERE, "_build")
+    bdir = os.path.join(HERE, "_build" if out_path is None else "_build_" + os.path.basename(out_path))
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for s in SOURCES:
         o = os.path.join(bdir, os.path.splitext(s)[0] + ".o")
-        cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC] + FLAGS + list(extra_flags or []) + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
@@ -44,9 +45,10 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % s)
         if verbose:
             sys.stderr.write(out)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
+    target = LIB if out_path is None else out_path
+    cmd = [NVCC, "-shared", "-o", target] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
     subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -44,7 +44,7 @@ typedef void (*poa_kernel_fn)(const barb200::BatchArgs);
 // CTA-size classes: a CTA of T threads sweeps rows of up to 16*T columns (query length + 1)
 // scratch = dynamic shared memory per CTA for the topological sort, sized so that the class's CTAs per SM still fit
 static const struct { int T; poa_kernel_fn fn; int scratch; } kKernels[] = {
-    {32, barb200::poa_msa_kernel_t32, 10 * 1024}, {64, barb200::poa_msa_kernel_t64, 24 * 1024}, {128, barb200::poa_msa_kernel_t128, 48 * 1024},
+    {32, barb200::poa_msa_kernel_t32, 10 * 1024}, {64, barb200::poa_msa_kernel_t64, 24 * 1024}, {128, barb200::poa_msa_kernel_t128, 40 * 1024},
     {256, barb200::poa_msa_kernel_t256, 96 * 1024}, {640, barb200::poa_msa_kernel_t640, 200 * 1024}, {1024, barb200::poa_msa_kernel_t1024, 200 * 1024}};
 static const int kNumKernels = 6;
 static const int kMaxDevices = 8;

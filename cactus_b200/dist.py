@@ -80,7 +80,8 @@ def gather_bytes(host_bytes, device):
     mine = host_bytes.to(device, non_blocking=True)
     if rank != 0:
         if lens[rank]:
-            dist.send(mine, dst=0)
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, 0)]):     # batched like the receiver's side (one ncclGroup)
+                w.wait()
         return None
     offs = [0]
     for v in lens:
