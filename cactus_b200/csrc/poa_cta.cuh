@@ -202,13 +202,104 @@ __device__ void cta_fuse_alignment(Graph &g, const uint8_t *seq, int L, const ui
 
 
 // ---- traceback (simd_abpoa_cg_backtrack, abpoa_align_simd.c:309-458) by ONE WARP -------------------------------
-// The walk is a chain of dependent lookups in planes that live in HBM (~1 us per step for a single thread). Most of
-// it is runs of MATCH ops along first predecessors, and in the ALL state the M test has priority over everything else
-// (:319-336), so a run can be verified for 31 cells at once: lane k takes the cell (c_k, j-k) on the first-predecessor
-// chain c_0 = i, c_{k+1} = first pred of c_k, all lanes load their H in parallel, lane k tests
-// H[c_{k+1}][j-k-1] + s == H[c_k][j-k], and the leading run of hits is emitted as MATCH ops in one go. Wherever the run
-// stops (gap, mismatching first predecessor, band edge) one step of the general serial rule (backtrack_step) is
-// taken by all lanes uniformly. The result is the serial walk's cigar, entry for entry.
+// The walk is a chain of dependent lookups in planes that live in HBM (~1 us per lookup while the other CTAs sweep).
+//  * Most of it is runs of MATCH ops along first predecessors, and in the ALL state the M test has priority over everything
+//    else (:319-336), so a run can be verified for 31 cells at once: lane k takes the cell (c_k, j-k) on the
+//    first-predecessor chain c_0 = i, c_{k+1} = first pred of c_k, all lanes load their H in parallel, lane k tests
+//    H[c_{k+1}][j-k-1] + s == H[c_k][j-k], and the leading run of hits is emitted as MATCH ops in one go. The rows 32 further
+//    down the chain guess are prefetched into L2 meanwhile.
+//  * Wherever the run stops (gap, other predecessor, band edge) warp_backtrack_step applies the general rule once, the lanes
+//    probing the predecessors side by side.
+// The result is the serial walk's cigar (dp_backtrack, poa_graph.cuh), entry for entry.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One iteration of the reference's loop (:319-450; serial form: backtrack_step) by the 32 lanes of a warp, uniformly.
+// Insertions are taken whole. The sweep does not store F1 / F2, and the walk does not need them: with
+// F[j] = max_t H[i][j-t] - oe - (t-1) e (:1060-1075) and H[i][j] >= F[j],
+//   H[i][j] == F1[j]  <=>  some t >= 1 has H[i][j-t] == H[i][j] + oe1 + (t-1) e1,
+// the smallest such t is where the reference's walk leaves the F1 state (it tests "open" before "extend" at every column,
+// :401-415), i.e. the length of the insertion, and because H[i][j] >= F2[j] bounds H[i][j-t] <= H[i][j] + oe2 + (t-1) e2 the F1
+// equation has no solution beyond t1_max = (oe2 - oe1) / (e1 - e2) + 1 columns (27 with Cactus' 400/30, 1200/1). F2 is
+// scanned leftwards until it is found (its insertion length) or the band ends (no op explains the cell: -1, as :448).
+// States with F always carry M here (ALL, or M|F after a deletion), since an insertion is never left half walked.
+__device__ int warp_backtrack_step(const RowTables &rt, const DpState &d, const PoaParams &P, const int *smat8, const uint8_t *q,
+                                   int &i, int &j, int &cur_op, int &len) {
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31, inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    len = 1;
+    const RowRec rc = rt.rec[i];
+    const RowInfo ri = d.info[i];
+    const int *rowi = d.planes + d.row_off[i];
+    const int npre = rc.base_npre >> 8;
+    const int s = smat8[8 * (rc.base_npre & 0xff) + q[j - 1]];
+    int hij = inf; unsigned cij = (unsigned)E_NEG16 | (unsigned)E_NEG16 << 16;
+    if (j >= ri.beg && j <= ri.end) { const int64_t o = plane_index(ri.beg, ri.end, 0, j); hij = __ldcg(rowi + o); cij = (unsigned)__ldcg(rowi + o + CPT); }
+    // the first 32 columns left of j in row i (for the F tests), in flight together with the predecessor probes
+    int hk0 = inf;
+    if ((cur_op & OP_F) && j - 1 - lane >= ri.beg && j - 1 - lane <= ri.end) hk0 = __ldcg(rowi + plane_index(ri.beg, ri.end, 0, j - 1 - lane));
+    // the lane's predecessor of a chunk of 32: row, H[j-1], H[j], E1[j], E2[j]
+    int pi = -1, pm = inf, ph = inf, pe1 = inf, pe2 = inf; bool m_in = false, e_in = false;
+    auto probe = [&](int kb) {
+        const int k = kb + lane;
+        pi = -1; m_in = false; e_in = false;
+        if (k >= npre) return;
+        pi = k == 0 ? rc.pre0 : rt.pre_row[rc.pre_off + k];
+        const RowInfo pin = d.info[pi];
+        const int *prow = d.planes + d.row_off[pi];
+        m_in = (cur_op & OP_M) && j - 1 >= pin.beg && j - 1 <= pin.end;
+        e_in = (cur_op & OP_E) && j >= pin.beg && j <= pin.end;
+        if (m_in) pm = __ldcg(prow + plane_index(pin.beg, pin.end, 0, j - 1));
+        if (e_in) {
+            const int64_t o = plane_index(pin.beg, pin.end, 0, j);
+            ph = __ldcg(prow + o);
+            const unsigned code = (unsigned)__ldcg(prow + o + CPT);
+            pe1 = e_decode(ph, (int)(code & 0xffffu), inf); pe2 = e_decode(ph, (int)(code >> 16), inf);
+        }
+    };
+    if (cur_op & OP_M) {                                                       // :319-336
+        for (int kb = 0; kb < npre; kb += 32) {
+            probe(kb);
+            const unsigned hit = __ballot_sync(FULLM, m_in && pm + s == hij);
+            if (hit) { i = __shfl_sync(FULLM, pi, __ffs(hit) - 1); --j; cur_op = OP_ALL; return CMATCH; }
+        }
+    }
+    if (cur_op & OP_E) {                                                       // :337-392, per predecessor E1 then E2
+        const int own_e1 = e_decode(hij, (int)(cij & 0xffffu), inf), own_e2 = e_decode(hij, (int)(cij >> 16), inf);
+        for (int kb = 0; kb < npre; kb += 32) {
+            if (npre > 32 || !(cur_op & OP_M)) probe(kb);                      // (else the M loop's single probe is still in the registers)
+            const bool ok1 = e_in && (cur_op & OP_E1) && ((cur_op & OP_M) ? hij == pe1 : own_e1 == pe1 - e1);
+            const bool ok2 = e_in && (cur_op & OP_E2) && ((cur_op & OP_M) ? hij == pe2 : own_e2 == pe2 - e2);
+            const unsigned hit = __ballot_sync(FULLM, ok1 || ok2);
+            if (hit) {
+                const int f = __ffs(hit) - 1;
+                const int nop = ok1 ? ((ph - oe1 == pe1) ? (OP_M | OP_F) : OP_E1) : ((ph - oe2 == pe2) ? (OP_M | OP_F) : OP_E2);
+                cur_op = __shfl_sync(FULLM, nop, f); i = __shfl_sync(FULLM, pi, f);
+                return CDEL;
+            }
+        }
+    }
+    if (cur_op & OP_F) {                                                       // :393-428
+        if (!(cur_op & OP_M)) return -1;                                       // (never the case, see above)
+        const int avail = j - ri.beg;                                          // columns of the row left of j
+        int t1_max;
+        if (e1 > e2) t1_max = oe2 >= oe1 ? (oe2 - oe1) / (e1 - e2) + 1 : 0;
+        else t1_max = (e1 < e2 || oe1 <= oe2) ? avail : 0;
+        if (t1_max > avail) t1_max = avail;
+        for (int which = 0; which < 2; ++which) {
+            if (!(cur_op & (which ? OP_F2 : OP_F1))) continue;
+            const int oe = which ? oe2 : oe1, e = which ? e2 : e1, tmax = which ? avail : t1_max;
+            for (int t0 = 0; t0 < tmax; t0 += 32) {
+                const int t = t0 + lane + 1;
+                int hk = hk0;
+                if (t0 > 0) { hk = inf; if (t <= avail) hk = __ldcg(rowi + plane_index(ri.beg, ri.end, 0, j - t)); }
+                const unsigned hit = __ballot_sync(FULLM, t <= tmax && hk == hij + oe + (t - 1) * e);
+                if (hit) { len = __ffs(hit); len += t0; j -= len; cur_op = OP_M | OP_E; return CINS; }
+            }
+        }
+    }
+    return -1;
+}
+
 __device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const int *smat8, const uint8_t *q, int L) {
     const unsigned FULLM = 0xffffffffu;
     const int lane = threadIdx.x & 31, inf = P.inf_min;
@@ -229,30 +320,49 @@ __device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const 
         last_op = op;
     };
     if (j < L) push(CINS, L - j, -1, L - 1);
+#ifdef BT_PROFILE
+    long long pf_t0 = clock64(), pf_run_t = 0, pf_step_t = 0; int pf_iters = 0, pf_runs = 0, pf_cells = 0, pf_steps = 0, pf_ins = 0;
+#endif
     while (i > 0 && j > 0 && !fail) {
         int run = 0;
+#ifdef BT_PROFILE
+        long long pf_a = clock64();
+#endif
         if (cur_op == OP_ALL) {
-            // rows of the first-predecessor chain: start from the linear guess i-k and re-base after each jump
-            int c = i - lane, pre = -1, base = 0, n_ok = 0;
+            // rows of the first-predecessor chain: start from the linear guess i-k and re-base after each jump; every table entry
+            // of a row is fetched in the same round trip
+            int c = i - lane, pre = -1, base = 0, n_ok = 0, node = 0;
+            RowInfo ric; ric.beg = 0; ric.end = -1; ric.left = 0; ric.right = 0;
+            int64_t ro = 0;
+            bool fresh = true;
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
-                pre = -1;
-                if (c > 0) { const RowRec rc = rt.rec[c]; base = rc.base_npre & 0xff; pre = (rc.base_npre >> 8) ? rc.pre0 : -1; }
+                if (fresh) {
+                    pre = -1;
+                    if (c > 0) { const RowRec rc = rt.rec[c]; base = rc.base_npre & 0xff; pre = (rc.base_npre >> 8) ? rc.pre0 : -1; node = g.index_to_node[c]; }
+                    if (c >= 0) { ric = d.info[c]; ro = d.row_off[c]; }
+                }
                 const int nxt = __shfl_down_sync(FULLM, c, 1);
                 const bool ok = lane < 31 && pre >= 0 && pre == nxt;
                 n_ok = __ffs(~__ballot_sync(FULLM, ok)) - 1;               // lanes 0..n_ok hold true chain rows
                 if (n_ok >= 31 || it == 3) break;
                 const int pre_b = __shfl_sync(FULLM, pre, n_ok);
                 if (pre_b < 0) break;                                        // the chain ends at lane n_ok
-                if (lane > n_ok) c = pre_b - (lane - n_ok - 1);
+                fresh = lane > n_ok;
+                if (fresh) c = pre_b - (lane - n_ok - 1);
             }
             const int jj = j - lane;
             int hv = inf, inb = 0;
             if (lane <= n_ok && c >= 0 && jj >= 0) {
-                const RowInfo ri = d.info[c];
-                inb = jj >= ri.beg && jj <= ri.end;
-                if (inb) hv = __ldcg(d.planes + d.row_off[c] + plane_index(ri.beg, ri.end, 0, jj));
+                inb = jj >= ric.beg && jj <= ric.end;
+                if (inb) hv = __ldcg(d.planes + ro + plane_index(ric.beg, ric.end, 0, jj));
             }
+            // the same diagonal 32 rows on: table entries now (they are back long before the end of the iteration), the plane line
+            // from there
+            const int cl = c - 32, jl = jj - 32;
+            RowInfo ril; ril.beg = 0; ril.end = -1; ril.left = 0; ril.right = 0;
+            int64_t rol = 0;
+            if (cl >= 0 && jl >= 0) { ril = d.info[cl]; rol = d.row_off[cl]; prefetch_l2(rt.rec + cl); prefetch_l2(g.index_to_node + cl); }
             const int h_next = __shfl_down_sync(FULLM, hv, 1), inb_next = __shfl_down_sync(FULLM, inb, 1);
             bool hit = false;
             if (lane < n_ok && c > 0 && jj >= 1 && inb_next) hit = h_next + smat8[8 * base + q[jj - 1]] == hv;
@@ -260,18 +370,29 @@ __device__ void warp_backtrack(Graph &g, const RowTables &rt, DpState &d, const 
             if (run > 0) {
                 if (nc + run > cap) fail = JOB_ERR_CIGAR_CAP;
                 else {
-                    if (lane < run) cg[nc + lane] = (uint64_t)g.index_to_node[c] << 34 | (uint64_t)(jj - 1) << 4 | (uint64_t)CMATCH;
+                    if (lane < run) cg[nc + lane] = (uint64_t)node << 34 | (uint64_t)(jj - 1) << 4 | (uint64_t)CMATCH;
                     nc += run; last_op = CMATCH;
                     i = __shfl_sync(FULLM, c, run); j -= run;               // cur_op stays ALL
                 }
             }
+            if (cl >= 0 && jl >= 0 && jl <= ril.end) prefetch_l2(d.planes + rol + plane_index(ril.beg, ril.end, 0, jl < ril.beg ? ril.beg : jl));
         }
+#ifdef BT_PROFILE
+        long long pf_b = clock64(); if (cur_op == OP_ALL) { pf_run_t += pf_b - pf_a; ++pf_iters; if (run) { ++pf_runs; pf_cells += run; } }
+#endif
         if (run == 0 && !fail) {
             const int id = g.index_to_node[i], jq = j - 1;
-            const int op = backtrack_step<true>(g, rt, d, P, q, L, i, j, cur_op);
-            if (op < 0) fail = JOB_ERR_BACKTRACK; else push(op, 1, id, jq);
+            int len = 1;
+            const int op = warp_backtrack_step(rt, d, P, smat8, q, i, j, cur_op, len);
+            if (op < 0) fail = JOB_ERR_BACKTRACK; else push(op, len, id, jq);
+#ifdef BT_PROFILE
+            pf_step_t += clock64() - pf_b; ++pf_steps; if (op == CINS) ++pf_ins;
+#endif
         }
     }
+#ifdef BT_PROFILE
+    if (lane == 0 && blockIdx.x == 0) printf("bt L=%d total=%lld run_t=%lld step_t=%lld iters=%d runs=%d cells=%d steps=%d ins=%d\n", L, clock64() - pf_t0, pf_run_t, pf_step_t, pf_iters, pf_runs, pf_cells, pf_steps, pf_ins);
+#endif
     if (!fail && j > 0) push(CINS, j, -1, j - 1);
     if (fail) { if (lane == 0) g.err = fail; return; }
     if (lane == 0) d.n_cigar = nc;

@@ -329,44 +329,13 @@ HD int row_h_prime(const RowTables &rt, const DpState &d, const PoaParams &P, co
 
 // F1 / F2 of row i for the columns [beg, j] into the traceback's scratch (d.fc): F[k] = max_{beg <= t < k} H'[t] - oe - (k-1-t) e,
 // in the DP sweep's own "A space" form (poa_kernel.cu: row_pass1 / row_pass2) so that finite values are the ones the sweep
-// would have stored. Row 0 has the closed form of simd_abpoa_cg_first_dp (abpoa_align_simd.c:669-688). WARP: all 32 lanes of
-// a warp call this together (32 columns per step, shuffle prefix maximum); otherwise one thread runs the serial loop.
-template <bool WARP>
+// would have stored. Row 0 has the closed form of simd_abpoa_cg_first_dp (abpoa_align_simd.c:669-688). Serial form (one thread): the host build and
+// the serial_phases debug mode; the kernel's warp traceback (poa_cta.cuh: warp_backtrack_step) never builds F rows.
 HD void row_f_cache(const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L, int i, int j) {
     if (d.fc_row == i && d.fc_hi >= j) return;
     const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, o1 = P.o1, o2 = P.o2;
     const int beg = d.info[i].beg;
     int *f1 = d.fc, *f2 = d.fc + d.fc_cap;
-#if defined(__CUDA_ARCH__)
-    if (WARP) {
-        const unsigned FULLM = 0xffffffffu;
-        const int lane = threadIdx.x & 31;
-        int c1 = inf + beg * e1 + o1, c2 = inf + beg * e2 + o2;           // running prefix maxima (exclusive), the scans' identities
-        for (int k0 = beg; k0 <= j; k0 += 32) {
-            const int k = k0 + lane;
-            int a1 = INT32_MIN, a2 = INT32_MIN;
-            if (i > 0 && k < j) { const int hp = row_h_prime(rt, d, P, q, L, i, k); a1 = hp + k * e1; a2 = hp + k * e2; }
-            int i1 = a1, i2 = a2;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int n1 = __shfl_up_sync(FULLM, i1, off), n2 = __shfl_up_sync(FULLM, i2, off);
-                if (lane >= off) { i1 = imax(i1, n1); i2 = imax(i2, n2); }
-            }
-            int x1 = __shfl_up_sync(FULLM, i1, 1), x2 = __shfl_up_sync(FULLM, i2, 1);
-            if (lane == 0) { x1 = INT32_MIN; x2 = INT32_MIN; }
-            x1 = imax(x1, c1); x2 = imax(x2, c2);                          // exclusive prefix maximum at column k
-            if (k <= j) {
-                if (i == 0) { f1[k] = k == 0 ? inf : -o1 - e1 * k; f2[k] = k == 0 ? inf : -o2 - e2 * k; }
-                else { f1[k] = x1 - o1 - k * e1; f2[k] = x2 - o2 - k * e2; }
-            }
-            c1 = imax(c1, __shfl_sync(FULLM, i1, 31)); c2 = imax(c2, __shfl_sync(FULLM, i2, 31));
-        }
-        __syncwarp();
-        d.fc_row = i; d.fc_hi = j;                                        // (all lanes write the same values)
-        __syncwarp();
-        return;
-    }
-#endif
     int c1 = inf + beg * e1 + o1, c2 = inf + beg * e2 + o2;
     for (int k = beg; k <= j; ++k) {
         if (i == 0) { f1[k] = k == 0 ? inf : -o1 - e1 * k; f2[k] = k == 0 ? inf : -o2 - e2 * k; continue; }
@@ -412,7 +381,6 @@ HD void dp_best_cell(const Graph &g, const RowTables &rt, DpState &d, const PoaP
 // put_gap_at_end = 0: op priority M over predecessors in stored order, then E1/E2 per predecessor, then F1, F2,
 // then M again; cur_op carries which gap state the walk is in. Moves (i, j), returns the cigar op (node `id`,
 // query index j_before - 1) or -1 when no op explains the cell (the reference aborts, :448).
-template <bool WARP>
 HD int backtrack_step(const Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L,
                       int &i, int &j, int &cur_op) {
     const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
@@ -445,7 +413,7 @@ HD int backtrack_step(const Graph &g, const RowTables &rt, DpState &d, const Poa
     }
     if (cur_op & OP_F) {
         bool hit = false;
-        row_f_cache<WARP>(rt, d, P, q, L, i, j);            // F1 / F2 of row i up to column j (not stored by the sweep)
+        row_f_cache(rt, d, P, q, L, i, j);            // F1 / F2 of row i up to column j (not stored by the sweep)
         if (cur_op & OP_F1) {
             const int f = row_f(d, inf, 0, j);
             if (!(cur_op & OP_M) || hij == f) {
@@ -473,7 +441,7 @@ HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams 
     if (j < L) push_cigar(d, g, CINS, L - j, -1, L - 1);
     while (i > 0 && j > 0 && !g.err) {
         const int id = g.index_to_node[i], jq = j - 1;
-        const int op = backtrack_step<false>(g, rt, d, P, q, L, i, j, cur_op);
+        const int op = backtrack_step(g, rt, d, P, q, L, i, j, cur_op);
         if (op < 0) {
 #if defined(__CUDA_ARCH__)
             printf("barb200: backtrack stuck at row %d col %d cur_op %d (band %d..%d, H %d) best %d,%d n_cigar %d\n", i, j, cur_op,
