@@ -56,28 +56,52 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    """SM clock / throttle reasons sampled during the timed region. In-process NVML (nvidia_ml_py): spawning nvidia-smi five times a
+    second takes the driver's global lock at every start and stalls the timed host-side CUDA calls (it cost the e2e leg ~20 ms of a
+    260 ms step); the nvidia-smi query is the fallback when the module is missing."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:  # noqa: BLE001
+            self.nv, self.h, self.source = None, None, "nvidia-smi"
+
+    def _nvml_row(self):
+        nv, h = self.nv, self.h
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:  # noqa: BLE001
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bit = lambda name: "Active" if r & getattr(nv, name, 0) else "Not Active"   # noqa: E731
+        return [str(sm), str(mx), "", hex(r), bit("nvmlClocksThrottleReasonHwSlowdown"), bit("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                bit("nvmlClocksThrottleReasonSwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nv is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nv is not None else 1.0)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "source": self.source}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         reasons = set()
         for r in self.rows:
@@ -85,7 +109,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "samples": len(self.rows), "reasons": sorted(reasons)}
+                "samples": len(self.rows), "reasons": sorted(reasons), "source": self.source}
 
 
 def usable_cores():

@@ -59,8 +59,6 @@ struct Lane {
     int *d_planes = nullptr; size_t planes_bytes = 0;
     cudaStream_t main = nullptr, copy = nullptr, cls[kNumKernels] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t cls_done[kNumKernels] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    uint8_t *h_down = nullptr; size_t h_down_bytes = 0;        // pinned staging of the MSA download
-    uint8_t *h_up = nullptr; size_t h_up_bytes = 0;            // pinned staging of packed inputs (dispatcher batches)
     unsigned long long *d_clk = nullptr; size_t clk_entries = 0;
 };
 struct Device {
@@ -69,6 +67,9 @@ struct Device {
     // grow-only cache of device blocks for the per-stage buffers (cudaMalloc / cudaFree per call cost milliseconds
     // and cudaFree synchronises the device, which would stall the upload / kernel overlap)
     std::mutex cache_mu; std::vector<std::pair<void *, size_t>> free_blocks; size_t cached_bytes = 0;
+    // pinned staging blocks (packed inputs up, MSA bytes down), shared by the device's lanes: cudaMallocHost of a 60 MB block takes
+    // ~25 ms, so a lane that meets its first large batch borrows the block the other lane has grown already
+    std::mutex pin_mu; std::vector<std::pair<void *, size_t>> free_pinned;
 };
 }  // namespace barb200
 
@@ -156,6 +157,38 @@ static cudaError_t dev_alloc(Device &D, void **p, size_t bytes) {
     }
     return e;
 }
+static void *pinned_take(Device &D, size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> lk(D.pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < D.free_pinned.size(); ++i)
+            if (D.free_pinned[i].second >= bytes && (best < 0 || D.free_pinned[i].second < D.free_pinned[best].second)) best = (int)i;
+        if (best >= 0) { void *p = D.free_pinned[best].first; *got = D.free_pinned[best].second; D.free_pinned.erase(D.free_pinned.begin() + best); return p; }
+        // nothing fits: retire the smallest block (the pool stays at a handful of blocks, each grown to the largest batch seen)
+        if (D.free_pinned.size() >= 4) {
+            size_t m = 0;
+            for (size_t i = 1; i < D.free_pinned.size(); ++i) if (D.free_pinned[i].second < D.free_pinned[m].second) m = i;
+            cudaFreeHost(D.free_pinned[m].first); D.free_pinned.erase(D.free_pinned.begin() + m);
+        }
+    }
+    void *p = nullptr;
+    const size_t want = bytes + (bytes >> 2) + 4096;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = want;
+    return p;
+}
+static void pinned_give(Device &D, void *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(D.pin_mu);
+    D.free_pinned.emplace_back(p, bytes);
+}
+struct PinnedBlock {       // scope guard
+    Device &D; void *p = nullptr; size_t bytes = 0;
+    PinnedBlock(Device &d, size_t want) : D(d) { p = pinned_take(D, want, &bytes); }
+    ~PinnedBlock() { pinned_give(D, p, bytes); }
+    PinnedBlock(const PinnedBlock &) = delete; PinnedBlock &operator=(const PinnedBlock &) = delete;
+};
+
 static void dev_free(Device &D, void *p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(D.cache_mu);
@@ -278,10 +311,9 @@ extern "C" void barb200_destroy(barb200_ctx *ctx) {
             for (int c = 0; c < kNumKernels; ++c) { if (L->cls[c]) cudaStreamDestroy(L->cls[c]); if (L->cls_done[c]) cudaEventDestroy(L->cls_done[c]); }
             if (L->main) cudaStreamDestroy(L->main);
             if (L->copy) cudaStreamDestroy(L->copy);
-            if (L->h_down) cudaFreeHost(L->h_down);
-            if (L->h_up) cudaFreeHost(L->h_up);
         }
         for (auto &b : D->free_blocks) cudaFree(b.first);
+        for (auto &b : D->free_pinned) cudaFreeHost(b.first);
     }
     if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0]->ordinal);
     if (ctx->pecan_scratch) cudaFree(ctx->pecan_scratch);
@@ -450,19 +482,28 @@ static int plan_stage(barb200_stage *st) {
     return BARB200_OK;
 }
 
-static int ensure_arena(barb200_ctx *ctx, Lane &LN, size_t slots_bytes, size_t planes_bytes, size_t clk_entries) {
-    if (slots_bytes > LN.slots_bytes) {
-        if (LN.d_slots) cudaFree(LN.d_slots);
-        LN.d_slots = nullptr; LN.slots_bytes = 0;
-        if (cudaMalloc(&LN.d_slots, slots_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(slots) failed"); return BARB200_ENOMEM; }
-        LN.slots_bytes = slots_bytes;
-    }
-    if (planes_bytes > LN.planes_bytes) {
-        if (LN.d_planes) cudaFree(LN.d_planes);
-        LN.d_planes = nullptr; LN.planes_bytes = 0;
-        if (cudaMalloc(&LN.d_planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMalloc(planes) failed"); return BARB200_ENOMEM; }
-        LN.planes_bytes = planes_bytes;
-    }
+static int ensure_arena(barb200_ctx *ctx, Device &D, Lane &LN, size_t slots_bytes, size_t planes_bytes, size_t clk_entries) {
+    // a lane that has to grow goes straight to what its sibling already needed (same workload, same budget: plan_stage): which lane
+    // meets the first large batch is a matter of timing, and a re-allocation costs tens of milliseconds plus a device synchronisation.
+    // If that much is not free (the sibling was sized while it had the device to itself) the lane takes what the stage needs.
+    auto grow = [&](void **p, size_t *have, size_t need, size_t sibling_max, const char *what) {
+        if (need <= *have) return BARB200_OK;
+        if (*p) cudaFree(*p);
+        *p = nullptr; *have = 0;
+        size_t want = std::max(need, sibling_max);
+        if (cudaMalloc(p, want) != cudaSuccess) {
+            cudaGetLastError(); *p = nullptr;
+            if (want == need || cudaMalloc(p, need) != cudaSuccess) { cudaGetLastError(); *p = nullptr; set_error(ctx, std::string("cudaMalloc(") + what + ") failed"); return BARB200_ENOMEM; }
+            want = need;
+        }
+        *have = want;
+        return BARB200_OK;
+    };
+    size_t sib_slots = 0, sib_planes = 0;
+    for (auto &other : D.lanes) if (other.get() != &LN) { sib_slots = std::max(sib_slots, other->slots_bytes); sib_planes = std::max(sib_planes, other->planes_bytes); }
+    int rc = grow((void **)&LN.d_slots, &LN.slots_bytes, slots_bytes, sib_slots, "slots");
+    if (!rc) rc = grow((void **)&LN.d_planes, &LN.planes_bytes, planes_bytes, sib_planes, "planes");
+    if (rc) return rc;
     if (clk_entries > LN.clk_entries) {
         if (LN.d_clk) cudaFree(LN.d_clk);
         LN.d_clk = nullptr; LN.clk_entries = 0;
@@ -474,6 +515,9 @@ static int ensure_arena(barb200_ctx *ctx, Lane &LN, size_t slots_bytes, size_t p
 
 // n_seq / seq_lens / seqs / progressive are in the CALLER's job order; seq_off[j] (may be null = consecutive) is the offset of
 // job j's first base in `seqs`, n_bases_total the size of `seqs`. grow / worst_case size the slots (capacity-miss retries).
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool timing_on() { static const bool on = getenv("BARB200_TIMING") != nullptr; return on; }
+
 static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs, const int64_t *seq_off,
                        int64_t n_bases_total, const int *progressive, double grow, bool worst_case, barb200_stage **out) {
     if (!ctx || n_jobs < 0 || (n_jobs > 0 && (!n_seq || !seq_lens || !seqs))) { set_error(ctx, "bad arguments"); return BARB200_EINVAL; }
@@ -483,6 +527,7 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     cudaSetDevice(D.ordinal);
     std::unique_ptr<barb200_stage> st(new barb200_stage());
     st->ctx = ctx; st->lane = lane; st->n_jobs = n_jobs; st->grow = grow; st->worst_case = worst_case;
+    const double tb0 = now_ms();
     // ---- caller-order facts ----
     std::vector<int64_t> c_len_off(n_jobs + 1), c_seq_off(n_jobs + 1), c_sum(n_jobs);
     std::vector<int> c_ml(n_jobs), c_cls(n_jobs);
@@ -517,6 +562,7 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
         }
         if (bad) { set_error(ctx, "sequence code > 4"); return BARB200_EINVAL; }
     }
+    const double tb1 = now_ms();
     // ---- internal order: largest class first, inside a class by estimated cost, largest first (stable) ----
     st->perm.resize(n_jobs);
     std::iota(st->perm.begin(), st->perm.end(), (int64_t)0);
@@ -578,8 +624,10 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
                  o_msa = sub(st->msa_bytes), o_msa_len = sub(n_jobs * 4), o_status = sub(n_jobs * 4), o_cells = sub(n_jobs * 8), o_next = sub(4 * (kNumKernels + 1)),
                  o_order = sub(ns * 4), o_gts = sub(n_jobs * 4), o_gtscr = sub((size_t)GA.slot_bytes * st->gt_ctas);
     st->d_block_bytes = off;
+    const double tb2 = now_ms();
     int rc = plan_stage(st.get());
     if (rc) return rc;
+    const double tb3 = now_ms();
     cudaError_t e = dev_alloc(D, &st->d_block, off);
     if (e != cudaSuccess) {
         cudaGetLastError(); set_error(ctx, std::string("cudaMalloc(stage) failed: ") + cudaGetErrorString(e));
@@ -593,6 +641,7 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
     GA.jobs = st->d_desc; GA.n_jobs = (int)n_jobs; GA.seqs = st->d_seqs; GA.lens = st->d_lens; GA.soff = st->d_soff; GA.order = st->d_order; GA.gt_status = st->d_gt_status;
     GA.next_job = st->d_next + kNumKernels; GA.scratch = st->d_gt_scratch; GA.k = ctx->p.k; GA.w = ctx->p.w;
     cudaStream_t s = LN.copy;
+    const double tb4 = now_ms();
     if ((e = cudaMemcpyAsync(st->d_seqs, seqs, n_bases_total, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_lens, st->lens.data(), ns * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaMemcpyAsync(st->d_soff, st->soff.data(), ns * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
@@ -600,6 +649,8 @@ static int stage_build(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_
         (e = cudaStreamSynchronize(s)) != cudaSuccess) {
         set_error(ctx, std::string("H2D failed: ") + cudaGetErrorString(e)); stage_free_device(st.get()); return BARB200_ECUDA;
     }
+    if (timing_on()) fprintf(stderr, "barb200 timing: stage_build: scan + validate %.2f ms, order + descriptors %.2f, plan %.2f, alloc %.2f, upload %.2f\n",
+                             tb1 - tb0, tb2 - tb1, tb3 - tb2, tb4 - tb3, now_ms() - tb4);
     *out = st.release();
     return BARB200_OK;
 }
@@ -627,7 +678,7 @@ static int stage_launch(barb200_stage *st) {
     size_t slots_bytes = 0, plane_ints = 0, clk_n = 0;
     for (const Bucket &B : st->buckets) { slots_bytes += (size_t)B.lay.slot_bytes * B.slots; plane_ints += (size_t)B.lay.plane_cap * B.slots; clk_n += (size_t)B.slots * PH_N; }
     if (!ctx->p.collect_phase_clocks) clk_n = 0;
-    int rc = ensure_arena(ctx, LN, slots_bytes, plane_ints * 4, clk_n);
+    int rc = ensure_arena(ctx, dev_of_lane(ctx, st->lane), LN, slots_bytes, plane_ints * 4, clk_n);
     if (rc) return rc;
     cudaStream_t s = LN.main;
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4 * (kNumKernels + 1), s));
@@ -788,14 +839,9 @@ static int stage_fetch_locked(barb200_stage *st, const MsaDest &dest, int *msa_l
         if (rc) return rc;
     }
     st->msa_len.resize(st->n_jobs); st->cells.resize(st->n_jobs);
-    if ((size_t)st->msa_bytes > LN.h_down_bytes) {
-        if (LN.h_down) cudaFreeHost(LN.h_down);
-        LN.h_down = nullptr; LN.h_down_bytes = 0;
-        const size_t want = (size_t)st->msa_bytes + ((size_t)st->msa_bytes >> 2);
-        if (cudaMallocHost((void **)&LN.h_down, want) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMallocHost failed"); return BARB200_ENOMEM; }
-        LN.h_down_bytes = want;
-    }
-    uint8_t *h_msa = LN.h_down;
+    PinnedBlock down(D, (size_t)st->msa_bytes);
+    if (!down.p) { set_error(ctx, "cudaMallocHost failed"); return BARB200_ENOMEM; }
+    uint8_t *h_msa = (uint8_t *)down.p;
     cudaStream_t s = LN.main;
     CUDA_TRY(ctx, cudaMemcpyAsync(st->msa_len.data(), st->d_msa_len, st->n_jobs * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(st->cells.data(), st->d_cells, st->n_jobs * 8, cudaMemcpyDeviceToHost, s));
@@ -834,8 +880,6 @@ extern "C" int barb200_stage_fetch(barb200_stage *st, uint8_t **msa_out, int *ms
     return stage_fetch_locked(st, malloc_dest(msa_out), msa_len, cells);
 }
 
-static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-static bool timing_on() { static const bool on = getenv("BARB200_TIMING") != nullptr; return on; }
 
 // one device batch on one lane (the caller holds the lane): build + launch + streamed guide trees + finish + fetch
 static int batch_on_lane(barb200_ctx *ctx, int lane, int64_t n_jobs, const int *n_seq, const int *seq_lens, const uint8_t *seqs, const int64_t *seq_off,
@@ -972,21 +1016,17 @@ int run_jobs_on_lane(barb200_ctx *ctx, int lane, const std::vector<HostJob> &job
         for (int i = 0; i < jobs[j].n_seq; ++i) { lens.push_back(jobs[j].lens[i]); nb += jobs[j].lens[i]; }
     }
     off[n] = nb;
-    if ((size_t)nb > LN.h_up_bytes) {
-        if (LN.h_up) cudaFreeHost(LN.h_up);
-        LN.h_up = nullptr; LN.h_up_bytes = 0;
-        const size_t want = (size_t)nb + ((size_t)nb >> 2) + 4096;
-        if (cudaMallocHost((void **)&LN.h_up, want) != cudaSuccess) { cudaGetLastError(); set_error(ctx, "cudaMallocHost failed"); return BARB200_ENOMEM; }
-        LN.h_up_bytes = want;
-    }
+    PinnedBlock up(dev_of_lane(ctx, lane), (size_t)nb);
+    if (!up.p) { set_error(ctx, "cudaMallocHost failed"); return BARB200_ENOMEM; }
+    uint8_t *const h_up = (uint8_t *)up.p;
     const int nthreads = host_threads(ctx);
 #pragma omp parallel for schedule(static) num_threads(nthreads)
-    for (int64_t j = 0; j < n; ++j) memcpy(LN.h_up + off[j], jobs[j].seqs, (size_t)(off[j + 1] - off[j]));
+    for (int64_t j = 0; j < n; ++j) memcpy(h_up + off[j], jobs[j].seqs, (size_t)(off[j + 1] - off[j]));
     std::vector<int> ml(n, 0); std::vector<int64_t> cells(n, 0);
     JobResult *res = results.data();
     static uint8_t empty_sink[1];
     MsaDest dest = [res](int64_t c, int K, int m) { res[c].msa.resize((size_t)K * m); return res[c].msa.empty() ? empty_sink : res[c].msa.data(); };
-    const int rc = batch_on_lane(ctx, lane, n, n_seq.data(), lens.data(), LN.h_up, nullptr, nb, prog.data(), dest, ml.data(), cells.data(), nullptr);
+    const int rc = batch_on_lane(ctx, lane, n, n_seq.data(), lens.data(), h_up, nullptr, nb, prog.data(), dest, ml.data(), cells.data(), nullptr);
     if (rc) return rc;
     for (int64_t j = 0; j < n; ++j) { results[j].msa_len = ml[j]; results[j].cells = cells[j]; }
     return BARB200_OK;

@@ -14,6 +14,9 @@
 // so only the offending caller sees the error. Stitching and the cross-end trimming run in the waiting thread.
 // No CUDA in this file.
 #pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -83,11 +86,17 @@ private:
                 std::unique_lock<std::mutex> lk(mu_);
                 work_cv_.wait(lk, [this] { return stop_ || !pending_.empty(); });
                 if (pending_.empty()) return;               // stop requested and nothing left
-                // a burst of submissions is still arriving (the shim's bar() submits thousands of flowers in a row): give it a
-                // moment to pile up instead of launching a batch of the first few -- bounded, and only while tickets keep coming
-                for (int spins = 0; spins < 8 && !stop_ && pending_jobs_ < linger_jobs_ &&
-                     std::chrono::steady_clock::now() - last_submit_ < std::chrono::microseconds(600); ++spins)
-                    work_cv_.wait_for(lk, std::chrono::microseconds(700));
+                // a burst of submissions is still arriving (the shim's bar() submits thousands of flowers in a row): let it pile up
+                // instead of launching a batch of the first few -- only while tickets keep coming (the last one less than 600 us ago),
+                // until a full batch is waiting, and for 20 ms at most
+                {
+                    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(20);
+                    while (!stop_ && pending_jobs_ < max_jobs_) {
+                        const auto now = std::chrono::steady_clock::now();
+                        if (now >= t_end || now - last_submit_ >= std::chrono::microseconds(600)) break;
+                        work_cv_.wait_for(lk, std::chrono::microseconds(300));
+                    }
+                }
                 if (pending_.empty()) { if (stop_) return; continue; }
                 int64_t jobs = 0; double cost = 0;
                 while (!pending_.empty()) {
@@ -125,6 +134,9 @@ private:
         }
         // (jobs of tickets that just failed are still in the list; they are run and dropped -- simpler than compacting, and rare)
         if (jobs.empty()) return;
+        static const bool trace = getenv("BARB200_TIMING") != nullptr;
+        auto ms_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double tq0 = trace ? ms_now() : 0;
         std::vector<JobResult> res; std::string err;
         int rc = 0;
         for (size_t at = 0; at < jobs.size() && !rc; at += (size_t)max_chunk_) {           // a single huge ticket is cut into chunks
@@ -158,8 +170,11 @@ private:
             finish_counts(batch);
             return;
         }
+        const double tq1 = trace ? ms_now() : 0;
         consume(owner, 0, owner.size(), res);
         finish_counts(batch);
+        if (trace) fprintf(stderr, "barb200 timing: queue lane %d: %zu tickets, %zu jobs, start %.1f ms, device batch %.1f ms, trim %.1f ms\n", lane, batch.size(),
+                           jobs.size(), fmod(tq0, 100000.0), tq1 - tq0, ms_now() - tq1);
     }
 
     void consume(std::vector<std::pair<Ticket *, barwin::EndState *>> &owner, size_t at, size_t n, std::vector<JobResult> &res) {
@@ -181,7 +196,7 @@ private:
     }
 
     Exec exec_;
-    int64_t max_jobs_, max_chunk_ = 1 << 15, linger_jobs_ = 1024, pending_jobs_ = 0; double max_cost_;
+    int64_t max_jobs_, max_chunk_ = 1 << 15, pending_jobs_ = 0; double max_cost_;
     std::chrono::steady_clock::time_point last_submit_ = std::chrono::steady_clock::now();
     std::mutex mu_;
     std::condition_variable work_cv_, done_cv_;
