@@ -682,6 +682,7 @@ static int stage_launch(barb200_stage *st) {
     if (rc) return rc;
     cudaStream_t s = LN.main;
     CUDA_TRY(ctx, cudaMemsetAsync(st->d_next, 0, 4 * (kNumKernels + 1), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(st->d_msa, 0, st->msa_bytes, s));     // the rows' padding travels back with the MSAs (one D2H copy): defined bytes
     if (clk_n) CUDA_TRY(ctx, cudaMemsetAsync(LN.d_clk, 0, clk_n * sizeof(unsigned long long), s));
     if (!st->e0) { CUDA_TRY(ctx, cudaEventCreate(&st->e0)); CUDA_TRY(ctx, cudaEventCreate(&st->e1)); }
     if (!st->e_gt) CUDA_TRY(ctx, cudaEventCreate(&st->e_gt));

@@ -146,8 +146,8 @@ __device__ void cta_fuse_alignment(Graph &g, const uint8_t *seq, int L, const ui
     }
     __syncthreads();
     // (2) ids of the new nodes in query order. is_new becomes the exclusive prefix count; keep the flag in node_of's sign
+    const int first_new = g.node_n;            // (read before the scan's barriers: thread 0 moves node_n below)
     const int n_new = cta_excl_scan(is_new, L, ws);
-    const int first_new = g.node_n;
     if (first_new + n_new > g.node_cap) { if (tid == 0) g.err = JOB_ERR_NODE_CAP; __syncthreads(); return; }
     // (3) create the new nodes (+ aligned-group links for mismatch columns)
     for (int q = tid; q < L; q += T) {

@@ -107,3 +107,23 @@ def pecan_pair(rng, L, k_anchor=12, keep=1.0, **kw):
         run = [c]
     a = np.array(anchors, dtype=np.int64).reshape(-1, 2)
     return to_ascii(x), to_ascii(y), a
+
+
+def gapped_family(rng, K, L, gap_lens):
+    """K copies of one parent, each with a point-mutation background and a few block insertions / deletions of the given lengths:
+    the traceback's insertion scan (whole insertions, F1 within its crossover distance, F2 beyond) and deletion chains"""
+    parent = rng.integers(0, 4, L).astype(np.uint8)
+    seqs = []
+    for _ in range(K):
+        s = parent.copy()
+        flip = rng.random(len(s)) < 0.02
+        s[flip] = (s[flip] + rng.integers(1, 4, int(flip.sum()))) % 4
+        for g in rng.permutation(gap_lens)[: int(rng.integers(0, 4))]:
+            at = int(rng.integers(0, max(1, len(s) - g)))
+            if rng.random() < 0.5:
+                s = np.concatenate([s[:at], rng.integers(0, 4, int(g)).astype(np.uint8), s[at:]])
+            elif len(s) > g + 8:
+                s = np.concatenate([s[:at], s[at + int(g):]])
+        seqs.append(s.astype(np.uint8))
+    seqs.sort(key=lambda x: -len(x))
+    return seqs

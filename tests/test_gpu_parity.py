@@ -6,7 +6,7 @@ import pytest
 
 import _golden as G
 import _reflib as R
-from _synth import family, to_ascii, two_end_problem
+from _synth import family, gapped_family, to_ascii, two_end_problem
 import workload  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -94,6 +94,23 @@ def test_narrow_band_params(oracle_built):
             o = R.oracle_poa_msa(job, p)
             assert m.shape == o.shape and np.array_equal(m, o), (wb, wf, j)
         e.close()
+
+
+@pytest.mark.parametrize("gaps", [(400, 30, 1200, 1), (4, 2, 24, 1), (400, 30, 1200, 30), (1200, 1, 400, 30), (400, 30, 300, 1), (6, 2, 6, 2)])
+def test_long_gaps_and_gap_models(oracle_built, gaps):
+    """block indels of 1..300 bases under Cactus' penalties, abPOA's defaults, equal extensions, swapped gap pairs, a second gap
+    that is cheaper everywhere, and two identical gaps: the insertion scan's crossover bound in every regime"""
+    o1, e1, o2, e2 = gaps
+    rng = np.random.default_rng(4242 + o1 + 7 * e2)
+    p = R.cactus_params(o1=o1, e1=e1, o2=o2, e2=e2, wb=300, wf=0.05)
+    e = engine_for(R.params_dict(p))
+    jobs = [gapped_family(rng, int(rng.integers(3, 9)), int(rng.choice([120, 500, 1100])), [1, 2, 3, 8, 27, 28, 29, 33, 64, 65, 150, 300]) for _ in range(14)]
+    msas, cells = e.poa_msa_batch(jobs, return_cells=True)
+    for j, (m, job) in enumerate(zip(msas, jobs)):
+        tr = R.oracle_poa_msa_trace(job, p)
+        assert m.shape == tr["msa"].shape and np.array_equal(m, tr["msa"]), (gaps, j)
+        assert int(cells[j]) == tr["cells"], (gaps, j)
+    e.close()
 
 
 def test_long_window_10k(engine, oracle_built):

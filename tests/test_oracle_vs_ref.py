@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import _reflib as R
-from _synth import family, to_ascii, two_end_problem
+from _synth import family, gapped_family, to_ascii, two_end_problem
 
 pytestmark = pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 
@@ -35,6 +35,21 @@ def test_poa_msa_trace_random_families(oracle_built, seed):
         p = R.cactus_params() if rng.random() < 0.6 else R.cactus_params(
             wb=int(rng.choice([10, 30, 100])), wf=float(rng.choice([0.01, 0.02, 0.1])), progressive=int(rng.integers(0, 2)))
         assert_same_trace(R.ref_poa_msa_trace(seqs, p), R.oracle_poa_msa_trace(seqs, p), (seed, it, K, L, kw))
+
+
+@pytest.mark.parametrize("gaps", [(400, 30, 1200, 1), (4, 2, 24, 1), (400, 30, 1200, 30), (1200, 1, 400, 30), (400, 30, 300, 1), (6, 2, 6, 2)])
+def test_poa_msa_long_gaps_and_gap_models(oracle_built, gaps):
+    """the inputs of test_gpu_parity.py::test_long_gaps_and_gap_models: the oracle (and the serial traceback the host build runs)
+    against the compiled reference, so that the GPU test's checker is pinned in these regimes too"""
+    o1, e1, o2, e2 = gaps
+    rng = np.random.default_rng(4242 + o1 + 7 * e2)
+    p = R.cactus_params(o1=o1, e1=e1, o2=o2, e2=e2, wb=300, wf=0.05)
+    for it in range(14):
+        seqs = gapped_family(rng, int(rng.integers(3, 9)), int(rng.choice([120, 500, 1100])), [1, 2, 3, 8, 27, 28, 29, 33, 64, 65, 150, 300])
+        ref = R.ref_poa_msa_trace(seqs, p)
+        assert_same_trace(ref, R.oracle_poa_msa_trace(seqs, p), (gaps, it))
+        if it < 4:
+            assert_same_trace(ref, R.hosttest_poa_msa_trace(seqs, p), (gaps, it, "hosttest"))
 
 
 def test_poa_msa_unrelated_ragged(oracle_built):
