@@ -18,16 +18,22 @@ from _synth import pecan_pair  # noqa: E402
 big = len(sys.argv) > 1 and sys.argv[1] == "big"
 eng = cb.Engine()
 jobs = []
-shapes = [(5, 120), (8, 300), (4, 700), (3, 1500), (3, 3000)] + ([(3, 6000)] if big else [])
+shapes = [(5, 120), (8, 300), (4, 700), (3, 1500), (3, 3000)] + ([(3, 6000), (2, 11000)] if big else [])
 for K, L in shapes:
     n_seq, lens, flat = workload.synth_ends(len(jobs), 2, K, L)
     offs = np.concatenate([[0], np.cumsum(lens)])
     for e in range(2):
         jobs.append([flat[offs[e * K + i]:offs[e * K + i + 1]] for i in range(K)])
+# divergent families (bubbles, N bases, unsorted reads), ragged unrelated rows with K > 64 (two read-id words)
+from _synth import family  # noqa: E402
+rng0 = np.random.default_rng(11)
+for K, L, sub in [(9, 150, 0.2), (13, 300, 0.08), (6, 60, 0.0), (2, 1, 0.0)]:
+    jobs.append(family(rng0, K, L, sort=False, sub=sub, ins=0.03, dele=0.03, nfrac=0.01))
+jobs.append([rng0.integers(0, 5, int(rng0.integers(1, 200))).astype(np.uint8) for _ in range(70)])
 msas, cells = eng.poa_msa_batch(jobs, return_cells=True)
 bad = 0
 for e, job in enumerate(jobs):
-    if sum(len(s) for s in job) > 6000:
+    if sum(len(s) for s in job) > 9000:
         continue                     # (oracle time)
     tr = R.oracle_poa_msa_trace(job)
     ok = msas[e].shape == tr["msa"].shape and np.array_equal(msas[e], tr["msa"]) and int(cells[e]) == tr["cells"]
