@@ -125,8 +125,8 @@ struct DiagMeta { int L, co, fo, pad; };   // per diagonal: xmyL, cells before i
                                             // diagonal d is marked iff fo[d+1] > fo[d])
 
 struct CtaMem {
-    double *ring;         // shared part of the ring: 2 parity slots x 5 states x RWs doubles
-    double *ring_o;       // overflow part in HBM / L2: 2 x 5 x (RW - RWs) doubles
+    double *ring;         // shared part of the ring: 2 parity slots x RWs positions x 5 states (doubles)
+    double *ring_o;       // overflow part in HBM / L2: 2 x (RW - RWs) x 5 doubles
     double *tbuf;         // RWs doubles: per-cell terms of a reduction (cells >= RWs: tbuf_o)
     double *tbuf_o;
     double *total;        // 1 double: the running total probability, published by warp 0
@@ -207,9 +207,20 @@ PC_HD bool chain_inactive(double tot, double t) { return !(tot < t) && (t == log
 
 PC_HD int match_class(int cx, int cy) { return (cx == 4 || cy == 4) ? 3 : (cx == cy ? 0 : (((cx ^ cy) == 2) ? 1 : 2)); }
 
-// state s of ring position i of the slot of parity par
+// The ring holds complete cells: the five states of ring position i of the slot of parity par are consecutive doubles
+// (a thread fetches a neighbour with one address and immediate offsets; 40-byte strides are conflict-free for 64-bit
+// shared-memory accesses). Positions [0, RWs) are in shared memory, the rest in the job's overflow block.
 PC_HD double &ring_at(const CtaMem &cm, int par, int s, int i) {
-    return i < cm.RWs ? cm.ring[(par * 5 + s) * cm.RWs + i] : cm.ring_o[(size_t)(par * 5 + s) * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)];
+    return i < cm.RWs ? cm.ring[(par * cm.RWs + i) * 5 + s] : cm.ring_o[((size_t)par * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)) * 5 + (size_t)s];
+}
+// hot-path forms: one shared / overflow decision per cell (two plain branches instead of a generic pointer per state)
+PC_HD void ring_load3(const CtaMem &cm, int par, int i, int s0, int s1, int s2, double &a, double &b, double &c) {
+    if (i < cm.RWs) { const double *q = cm.ring + (par * cm.RWs + i) * 5; a = q[s0]; b = q[s1]; c = q[s2]; }
+    else { const double *q = cm.ring_o + ((size_t)par * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)) * 5; a = q[s0]; b = q[s1]; c = q[s2]; }
+}
+PC_HD void ring_load2(const CtaMem &cm, int par, int i, int s0, int s1, double &a, double &b) {
+    if (i < cm.RWs) { const double *q = cm.ring + (par * cm.RWs + i) * 5; a = q[s0]; b = q[s1]; }
+    else { const double *q = cm.ring_o + ((size_t)par * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)) * 5; a = q[s0]; b = q[s1]; }
 }
 PC_HD double &tbuf_at(const CtaMem &cm, int k) { return k < cm.RWs ? cm.tbuf[k] : cm.tbuf_o[k - cm.RWs]; }
 // ring index of cell 0 of a diagonal: a = (xmyL + parity) / 2 + ly - shift, modulo the ring width
@@ -232,21 +243,19 @@ struct Cell5 { double m, sx, sy, lx, ly; };
 // ---- forward: diagonal d from d-1 (lower: xmy-1, upper: xmy+1) and d-2 (middle: xmy, updated in place) -------------------
 struct FwdDiag {            // per-diagonal uniforms
     const uint8_t *sx, *sy; const double *K;
-    int d, p, Ld, w, w1, w2, sl, sm, i0, RW;
+    int d, p, Ld, w, w1, w2, sl, sm, i0, RW, x0, y0;
 };
 PC_HD Cell5 fwd_cell(const CtaMem &cm, const FwdDiag &f, int k) {
     const double LZ = log_zero();
     const int RW = f.RW, p = f.p, q = p ^ 1;
-    const int xmy = f.Ld + 2 * k, x = (f.d + xmy) >> 1, y = (f.d - xmy) >> 1;
+    const int x = f.x0 + k, y = f.y0 - k;                                // x = (d + xmy) / 2, y = (d - xmy) / 2 with xmy = Ld + 2k
     const int cx = x > 0 ? f.sx[x - 1] : 4, cy = y > 0 ? f.sy[y - 1] : 4;
-    const int kl = k + f.sl, ku = kl + 1, km = k + f.sm;
+    const int kl = k + f.sl, km = k + f.sm;
     const int i = wrap(f.i0 + k, RW), il = wrap(i - p, RW), iu = wrap(i + 1 - p, RW);
     double lM = LZ, lSX = LZ, lLX = LZ, uM = LZ, uSY = LZ, uLY = LZ, mM = LZ, mSX = LZ, mSY = LZ, mLX = LZ, mLY = LZ;
-    if (kl >= 0 && kl < f.w1) { lM = ring_at(cm, q, S_M, il); lSX = ring_at(cm, q, S_SX, il); lLX = ring_at(cm, q, S_LX, il); }
-    if (ku >= 0 && ku < f.w1) { uM = ring_at(cm, q, S_M, iu); uSY = ring_at(cm, q, S_SY, iu); uLY = ring_at(cm, q, S_LY, iu); }
-    if (km >= 0 && km < f.w2) {
-        mM = ring_at(cm, p, S_M, i); mSX = ring_at(cm, p, S_SX, i); mSY = ring_at(cm, p, S_SY, i); mLX = ring_at(cm, p, S_LX, i); mLY = ring_at(cm, p, S_LY, i);
-    }
+    if ((unsigned)kl < (unsigned)f.w1) ring_load3(cm, q, il, S_M, S_SX, S_LX, lM, lSX, lLX);
+    if ((unsigned)(kl + 1) < (unsigned)f.w1) ring_load3(cm, q, iu, S_M, S_SY, S_LY, uM, uSY, uLY);
+    if ((unsigned)km < (unsigned)f.w2) { ring_load3(cm, p, i, S_M, S_SX, S_SY, mM, mSX, mSY); ring_load2(cm, p, i, S_LX, S_LY, mLX, mLY); }
     const double *K = f.K;
     const double *gx = K + K_GAP + 4 * (cx == 4), *gy = K + K_GAP + 4 * (cy == 4), *mt = K + K_MATCH + 3 * match_class(cx, cy);
     // stateMachine.c:450-480 in its order of transitions; the first transition into a state is an assignment
@@ -261,7 +270,9 @@ PC_HD Cell5 fwd_cell(const CtaMem &cm, const FwdDiag &f, int k) {
     return v;
 }
 PC_HD void ring_store(const CtaMem &cm, int par, int i, const Cell5 &v) {
-    ring_at(cm, par, S_M, i) = v.m; ring_at(cm, par, S_SX, i) = v.sx; ring_at(cm, par, S_SY, i) = v.sy; ring_at(cm, par, S_LX, i) = v.lx; ring_at(cm, par, S_LY, i) = v.ly;
+    double *q = i < cm.RWs ? nullptr : cm.ring_o + ((size_t)par * (size_t)(cm.RW - cm.RWs) + (size_t)(i - cm.RWs)) * 5;
+    if (i < cm.RWs) { double *r = cm.ring + (par * cm.RWs + i) * 5; r[S_M] = v.m; r[S_SX] = v.sx; r[S_SY] = v.sy; r[S_LX] = v.lx; r[S_LY] = v.ly; }
+    else { q[S_M] = v.m; q[S_SX] = v.sx; q[S_SY] = v.sy; q[S_LX] = v.lx; q[S_LY] = v.ly; }
 }
 // md = meta of d, mn = of d+1, m1 = of d-1, m2 = of d-2. (Keeping two cells per thread in flight to interleave their
 // dependent logAdd chains was measured SLOWER, 5.6 vs 8.6 Gcell/s: the duplicated work on narrow diagonals and the
@@ -273,6 +284,7 @@ PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
     f.Ld = md.L; f.w = mn.co - md.co; f.w1 = md.co - m1.co; f.w2 = d >= 2 ? m1.co - m2.co : 0;
     f.sl = (f.Ld - m1.L - 1) >> 1; f.sm = (f.Ld - m2.L) >> 1;      // both differences are even
     f.i0 = ring_i0(f.Ld, d, J, cm.RW);
+    f.x0 = (d + f.Ld) >> 1; f.y0 = (d - f.Ld) >> 1;
     const int w = f.w, cbase = md.co, fbase = 5 * md.fo, RW = cm.RW;
     const bool full = mn.fo > md.fo;
     PC_THREADS(tid, cm.T) {
@@ -298,20 +310,20 @@ PC_HD void fwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
 // in the same pass from the total probability already published.
 struct BwdDiag {            // per-diagonal uniforms
     const uint8_t *sx, *sy; const double *K;
-    int t, p, Lt, w1, w2, s1, s2, i0, RW;
+    int t, p, Lt, w1, w2, s1, s2, i0, RW, x0, y0;
 };
 PC_HD Cell5 bwd_cell(const CtaMem &cm, const BwdDiag &g, int k) {
     const double LZ = log_zero();
     const int RW = g.RW, p = g.p, q = p ^ 1;
-    const int xmy = g.Lt + 2 * k, x = (g.t + xmy) >> 1, y = (g.t - xmy) >> 1;
-    const int ku = k + g.s1, kl = ku + 1, km = k + g.s2;       // ku: cell (t+1, xmy-1) whose upper is c; kl: cell (t+1, xmy+1) whose lower is c
+    const int x = g.x0 + k, y = g.y0 - k;
+    const int ku = k + g.s1, km = k + g.s2;                    // ku: cell (t+1, xmy-1) whose upper is c; ku+1: cell (t+1, xmy+1) whose lower is c
     const int i = wrap(g.i0 + k, RW), iu = wrap(i - p, RW), il = wrap(i + 1 - p, RW);
     double mid = LZ, upSY = LZ, upLY = LZ, loSX = LZ, loLX = LZ;
     const double *K = g.K;
     const double *gx = K + K_GAP, *gy = K + K_GAP, *mt = K + K_MATCH;
-    if (km >= 0 && km < g.w2) { mid = ring_at(cm, p, S_M, i); mt = K + K_MATCH + 3 * match_class(g.sx[x], g.sy[y]); }                            // cell (x+1, y+1)
-    if (ku >= 0 && ku < g.w1) { upSY = ring_at(cm, q, S_SY, iu); upLY = ring_at(cm, q, S_LY, iu); gy = K + K_GAP + 4 * (g.sy[y] == 4); }  // cell (x, y+1)
-    if (kl >= 0 && kl < g.w1) { loSX = ring_at(cm, q, S_SX, il); loLX = ring_at(cm, q, S_LX, il); gx = K + K_GAP + 4 * (g.sx[x] == 4); }  // cell (x+1, y)
+    if ((unsigned)km < (unsigned)g.w2) { mid = ring_at(cm, p, S_M, i); mt = K + K_MATCH + 3 * match_class(g.sx[x], g.sy[y]); }                 // cell (x+1, y+1)
+    if ((unsigned)ku < (unsigned)g.w1) { ring_load2(cm, q, iu, S_SY, S_LY, upSY, upLY); gy = K + K_GAP + 4 * (g.sy[y] == 4); }               // cell (x, y+1)
+    if ((unsigned)(ku + 1) < (unsigned)g.w1) { ring_load2(cm, q, il, S_SX, S_LX, loSX, loLX); gx = K + K_GAP + 4 * (g.sx[x] == 4); }         // cell (x+1, y)
     Cell5 v;
     v.m = d_add(mid, mt[0]);
     v.m = log_add(v.m, d_add(upSY, gy[0]), K); v.m = log_add(v.m, d_add(upLY, gy[2]), K);
@@ -330,6 +342,7 @@ PC_HD void bwd_diag(const Job &J, const uint8_t *sx, const uint8_t *sy, const Ct
     g.Lt = mt_.L; g.w1 = mt2.co - mt1.co; g.w2 = (t + 2 <= top) ? mt3.co - mt2.co : 0;
     g.s1 = (g.Lt - 1 - mt1.L) >> 1; g.s2 = (g.Lt - mt2.L) >> 1;
     g.i0 = ring_i0(g.Lt, t, J, cm.RW);
+    g.x0 = (t + g.Lt) >> 1; g.y0 = (t - g.Lt) >> 1;
     const int w = mt1.co - mt_.co, cbase = mt_.co, RW = cm.RW, Lt = g.Lt;
     const double total = fuse_emit ? *cm.total : 0.0;
     PC_THREADS(tid, cm.T) {
