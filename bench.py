@@ -635,14 +635,23 @@ def gpu_arm(args):
                 extra["shapes"] = shapes_leg(eng)
             except Exception as e:  # noqa: BLE001
                 extra["shapes"] = {"error": str(e)}
-            try:
-                fl, _ = flowers_leg(eng, 5000000, max(8, n_ends // 4), 16, my_cells / max(1, n_ends))
-                fl["single_batch_e2e_gcells_per_s"] = my_cells / e2e_ms / 1e6 if e2e_ms == e2e_ms else None
-                extra["e2e_flowers"] = fl
-            except Exception as e:  # noqa: BLE001
-                extra["e2e_flowers"] = {"error": str(e)}
     stage.close()
     eng.close()
+    if rank == 0 and not args.no_extras:
+        # the end queue driven by 16 host threads, in a fresh process like the cPecan section below (this one has just run the reference
+        # arm's allocator settings, OpenMP teams of two libraries and a dozen arena shapes; a clean process is what a Cactus run looks like)
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--flowers-only", str(max(8, n_ends // 4)), "--cells-per-end", repr(my_cells / max(1, n_ends))]
+            env = dict(os.environ)
+            env["LOCAL_RANK"] = str(local_rank)
+            for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+                env.pop(k, None)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+            fl = json.loads(out.stdout.strip().splitlines()[-1])
+            fl["single_batch_e2e_gcells_per_s"] = my_cells / e2e_ms / 1e6 if e2e_ms == e2e_ms else None
+            extra["e2e_flowers"] = fl
+        except Exception as e:  # noqa: BLE001
+            extra["e2e_flowers"] = {"error": str(e)}
     # ---- N > 1: the same host-buffer call IN ONE PROCESS over all N devices (one context, devices[] = 0..N-1; the ends are dealt by
     # estimated cost, results land in the caller's buffers, no gather); rank 0 drives, the other ranks idle at the barrier ----
     if world > 1 and not args.no_e2e and not args.no_extras:
@@ -771,11 +780,20 @@ def main():
                     "to a RUNNING kernel from the host, which deadlocks under ncu's kernel serialisation)")
     ap.add_argument("--workload", default=None, help="replay a record made by shim/cactus_bar_harvest.c (BARB200_HARVEST=<file> during a reference "
                     "bar() run) instead of the synthetic workload")
+    ap.add_argument("--flowers-only", type=int, default=0, help="internal: this process only runs the e2e_flowers leg over that many flowers and prints its numbers")
+    ap.add_argument("--cells-per-end", type=float, default=0.0, help="internal (with --flowers-only)")
     ap.add_argument("--pecan-only", action="store_true", help="internal: this process only measures the cPecan section and prints its raw numbers")
     ap.add_argument("--pecan-pairs-per-step", type=int, default=int(os.environ.get("BARB200_PECAN_PAIRS_PER_STEP", "4736")),
                     help="cPecan-mode pairs per GPU per step (default 32 x 148 SMs); 0 skips the cPecan section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    if args.flowers_only:
+        import cactus_b200 as cb
+        eng = cb.Engine(cb.PoaParams(device=int(os.environ.get("LOCAL_RANK", "0")), host_threads=usable_cores()))
+        fl, _ = flowers_leg(eng, 5000000, args.flowers_only, 16, args.cells_per_end)
+        eng.close()
+        print(json.dumps(fl))
+        return 0
     if args.pecan_only:
         world = int(os.environ.get("WORLD_SIZE", "1"))
         local_rank = int(os.environ.get("LOCAL_RANK", "0"))

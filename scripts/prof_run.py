@@ -15,7 +15,8 @@ L = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
 T = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 cps = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 eng = cb.Engine(cb.PoaParams(threads_per_block=T, ctas_per_sm=cps))
-st = eng.stage(packed=workload.synth_ends(0, n, K, L))
+kw = {k: float(os.environ["SYNTH_" + k.upper()]) for k in ("sub", "ins", "dele") if "SYNTH_" + k.upper() in os.environ}   # divergence of the synthetic reads
+st = eng.stage(packed=workload.synth_ends(0, n, K, L, **kw))
 for r in range(reps):
     ms = st.run()
     print("run", r, ms, "ms", flush=True)
