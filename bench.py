@@ -32,7 +32,27 @@ import sys
 import threading
 import time
 
-import numpy as np
+
+def _cpu_quota():
+    """CPUs this container may really use: affinity mask capped by the cgroup quota (the GPU boxes show 128 logical CPUs under a 16-CPU quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+# Thread pools sized for the 128 visible CPUs (numpy / torch / OpenMP defaults) spin on 128 threads under a 16-CPU quota and get the
+# whole container throttled by the CFS bandwidth controller for hundreds of milliseconds at a time (seen as 250 ms stalls inside timed
+# host-side calls; cpu.stat nr_throttled). Size them for the quota, and let idle OpenMP workers sleep. Set before numpy / torch load.
+for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ.setdefault(_k, str(_cpu_quota()))
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -113,16 +133,8 @@ class ClockSampler(threading.Thread):
 
 
 def usable_cores():
-    """host threads the box really gives us: affinity mask capped by the cgroup CPU quota (the GPU boxes show 128
-    logical CPUs but run the container under a 16-CPU quota; oversubscribing them makes the CPU arm slower, not faster)"""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if quota != "max":
-            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
-    except Exception:  # noqa: BLE001
-        pass
-    return n
+    """host threads the box really gives us (oversubscribing the quota makes the CPU arm slower, not faster)"""
+    return _cpu_quota()
 
 
 PECAN_BYTES_PER_CELL = 120.0   # SURVEY.md 8d: 5 fp64 states x (forward write + forward read at the traceback + backward write)
