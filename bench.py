@@ -598,8 +598,7 @@ def gpu_arm(args):
             tg = time.time()
             D.gather_msa_bytes(outs, ml, K_SEQS, dev)
             phases["gather_ms"] += (time.time() - tg) * 1e3
-        for i in range(n_ends):
-            eng.lib.barb200_free(outs[i])
+        eng.lib.barb200_free_many(outs, n_ends)
         return d2h
     d2h, e2e_ms = 0, float("nan")
     if not args.no_e2e:
@@ -685,8 +684,7 @@ def gpu_arm(args):
                     cc = np.zeros(nA, np.int64)
                     eng_all._check(eng_all.lib.barb200_poa_msa_batch(eng_all.ctx, nA, q_nseq.ctypes.data, q_lens.ctypes.data, q_flat.ctypes.data, None, outs,
                                                                      ml.ctypes.data, cc.ctypes.data))
-                    for i in range(nA):
-                        eng_all.lib.barb200_free(outs[i])
+                    eng_all.lib.barb200_free_many(outs, nA)
                     return float(cc.sum())
                 all_once()
                 t2 = time.time()

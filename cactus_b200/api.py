@@ -106,6 +106,10 @@ def load_library():
     lib.barb200_device_info.restype = ci
     lib.barb200_free.argtypes = [vp]
     lib.barb200_free.restype = None
+    lib.barb200_free_many.argtypes = [vp, C.c_int64]
+    lib.barb200_free_many.restype = None
+    lib.barb200_pack_rows.argtypes = [vp, vp, C.c_int64, vp]
+    lib.barb200_pack_rows.restype = None
     pp = C.POINTER(_CPecanParams)
     lib.barb200_pecan_params_default.argtypes = [pp]
     lib.barb200_pecan_params_default.restype = None

@@ -120,9 +120,12 @@ static int usable_host_threads() {
     }
     return n;
 }
+// a batch over several devices runs one host thread per device: each takes its share of the host threads for its parallel loops
+static thread_local int tl_thread_divisor = 1;
 int host_threads(barb200_ctx *ctx) {
     static const int dflt = usable_host_threads();
-    return ctx->p.host_threads > 0 ? ctx->p.host_threads : dflt;
+    const int n = ctx->p.host_threads > 0 ? ctx->p.host_threads : dflt;
+    return std::max(1, n / std::max(1, tl_thread_divisor));
 }
 int default_progressive(barb200_ctx *ctx) { return ctx->p.progressive_poa; }
 std::mutex &device_mutex(barb200_ctx *ctx) { return ctx->mu; }
@@ -329,6 +332,19 @@ extern "C" const char *barb200_last_error(barb200_ctx *ctx) {
     return out.c_str();
 }
 extern "C" void barb200_free(void *p) { free(p); }
+extern "C" void barb200_free_many(void *const *p, int64_t n) {
+    if (!p) return;
+    for (int64_t i = 0; i < n; ++i) free(p[i]);
+}
+// rows[i] (bytes[i] bytes each, e.g. the MSAs of a batch) -> dst back to back; parallel copy
+extern "C" void barb200_pack_rows(void *const *rows, const int64_t *bytes, int64_t n, uint8_t *dst) {
+    if (!rows || !bytes || !dst || n <= 0) return;
+    std::vector<int64_t> off((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) off[i + 1] = off[i] + bytes[i];
+    static const int nt = std::min(usable_host_threads(), 16);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t i = 0; i < n; ++i) if (rows[i] && bytes[i] > 0) memcpy(dst + off[i], rows[i], (size_t)bytes[i]);
+}
 
 extern "C" int barb200_device_count(barb200_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
@@ -948,7 +964,10 @@ extern "C" int barb200_poa_msa_batch(barb200_ctx *ctx, int64_t n_jobs, const int
     }
     std::vector<int> rcs(ndev, BARB200_OK);
     std::vector<std::string> errs(ndev);
+    int active_devs = 0;
+    for (int d = 0; d < ndev; ++d) active_devs += !share[d].empty();
     auto run_device = [&](int d) {
+        tl_thread_divisor = std::max(1, active_devs);
         const std::vector<int64_t> &mine = share[d];
         const int lane = d * ctx->lanes_per_device;
         std::lock_guard<std::mutex> lk(lane_of(ctx, lane).busy);

@@ -101,13 +101,9 @@ def gather_msa_bytes(outs, msa_len, K, device):
     """the MSA rows of this rank's ends (malloc'd K x msa_len blocks, `outs[i]`) -> one pinned host buffer -> rank 0 (gather_bytes)"""
     import ctypes as C
     import numpy as np
-    sizes = msa_len.astype(np.int64) * K
+    sizes = np.ascontiguousarray(msa_len.astype(np.int64) * K)
     total = int(sizes.sum())
     buf = _pinned(total, "msa")
-    base = buf.data_ptr()
-    o = 0
-    for i in range(len(sizes)):
-        nb = int(sizes[i])
-        C.memmove(base + o, outs[i], nb)
-        o += nb
+    from .api import load_library
+    load_library().barb200_pack_rows(outs, sizes.ctypes.data, len(sizes), buf.data_ptr())      # parallel copy into the pinned block
     return gather_bytes(buf, device)

@@ -215,6 +215,10 @@ int barb200_device_count(barb200_ctx *ctx);
 int barb200_device_info(barb200_ctx *ctx, int *sm_count, int64_t *mem_total, int64_t *mem_free, char *name, int name_len);
 
 void barb200_free(void *p);
+/* barb200_free on n pointers (the MSAs of a batch), and a parallel gather of n buffers into one (rows[i], bytes[i]) -> dst: what a
+ * caller in a scripting language would otherwise do one foreign call at a time. */
+void barb200_free_many(void *const *p, int64_t n);
+void barb200_pack_rows(void *const *rows, const int64_t *bytes, int64_t n, uint8_t *dst);
 
 #ifdef __cplusplus
 }
