@@ -47,10 +47,10 @@ def _cpu_quota():
 
 # Thread pools sized for the 128 visible CPUs (numpy / torch / OpenMP defaults) spin on 128 threads under a 16-CPU quota and get the
 # whole container throttled by the CFS bandwidth controller for hundreds of milliseconds at a time (seen as 250 ms stalls inside timed
-# host-side calls; cpu.stat nr_throttled). Size them for the quota, and let idle OpenMP workers sleep. Set before numpy / torch load.
+# host-side calls; cpu.stat nr_throttled). Size them for the quota. Set before numpy / torch load. (OMP_WAIT_POLICY=passive on top of
+# this cost the library's short parallel loops ~9 ms per step in wake-ups and is not needed once the pools fit the quota.)
 for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
     os.environ.setdefault(_k, str(_cpu_quota()))
-os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 import numpy as np  # noqa: E402
 
