@@ -443,7 +443,16 @@ static int plan_stage(barb200_stage *st) {
             // rows the graph can reach: worst case every base a new node; optimistic: the longest read plus a share of the rest
             int64_t rows = sum + 2;
             if (!st->worst_case) rows = std::min<int64_t>(rows, (int64_t)(st->grow * (double)(ml + (sum - ml) / 8 + 256)));
-            plane_need = std::max(plane_need, rows * (TB / CPT) * (align_up(ml + 1, CPT) + CPT));
+            // columns a row stores: the adaptive band is [min(maxL, d) - w, max(maxR, d) + w] (abpoa_align_simd.c:946-960), i.e. 2w plus
+            // however far the best columns of the predecessors have drifted from the row's diagonal d; a quarter of 2w is allowed for
+            // that before the geometric retries take over. Only windows longer than ~2.5 kbp are narrower than the whole row
+            // (w = 1000 + 0.1 L): a 10 kbp window plans 0.77 GB of planes instead of 1.53 GB, so every SM gets a resident CTA.
+            int64_t width = ml + 1;
+            if (!st->worst_case) {
+                const int64_t w = (int64_t)ctx->P.wb + (int64_t)(ctx->P.wf * (double)ml);
+                width = std::min<int64_t>(width, (int64_t)(st->grow * (2.5 * (double)w + 64.0)));
+            }
+            plane_need = std::max(plane_need, rows * (TB / CPT) * (align_up(width, CPT) + CPT));
         }
         SlotLayout &Y = B.lay;
         memset(&Y, 0, sizeof(Y));
