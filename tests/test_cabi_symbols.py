@@ -52,6 +52,28 @@ def test_synth_is_deterministic_and_sorted(lib):
     assert np.array_equal(c[1], a[1][8:16])        # end index, not call order, defines the data
 
 
+def test_bulk_release_and_row_gather(lib):
+    """barb200_pack_rows / barb200_free_many: host-only helpers (no device needed)"""
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(0, 5000, 300).astype(np.int64)
+    sizes[[3, 77]] = 0
+    rows = (C.c_void_p * len(sizes))()
+    want = []
+    for i, n in enumerate(sizes):
+        data = rng.integers(0, 256, int(n)).astype(np.uint8)
+        rows[i] = libc.malloc(max(1, int(n)))
+        C.memmove(rows[i], data.ctypes.data, int(n))
+        want.append(data)
+    dst = np.full(int(sizes.sum()) + 8, 0xEE, np.uint8)
+    lib.barb200_pack_rows(rows, sizes.ctypes.data, len(sizes), dst.ctypes.data)
+    assert np.array_equal(dst[:-8], np.concatenate(want)) and np.all(dst[-8:] == 0xEE)
+    lib.barb200_free_many(rows, len(sizes))
+    lib.barb200_free_many(None, 0)
+    lib.barb200_pack_rows(None, None, 0, None)
+
+
 def test_no_cpu_fallback():
     import torch
     import cactus_b200 as cb

@@ -257,6 +257,22 @@ def test_capacity_misses_grow_geometrically(oracle_built):
         assert msas[j].shape == o.shape and np.array_equal(msas[j], o), j
 
 
+def test_band_wider_than_planned_is_retried(oracle_built):
+    """long windows are planned at 2.5 w columns per row; reads whose best columns drift far from the diagonal (block indels of up to
+    1 kbp under a narrow band constant) outgrow that, are re-run with more room, and still equal the oracle"""
+    rng = np.random.default_rng(77)
+    p = R.cactus_params(wb=60, wf=0.01)
+    e = engine_for(R.params_dict(p))
+    jobs = [gapped_family(rng, int(rng.integers(3, 6)), 3000, [300, 600, 1000, 1000]) for _ in range(6)]
+    jobs += [gapped_family(rng, 4, 2600, [5, 10]) for _ in range(3)]
+    msas, cells = e.poa_msa_batch(jobs, return_cells=True)
+    e.close()
+    for j, job in enumerate(jobs):
+        tr = R.oracle_poa_msa_trace(job, p)
+        assert msas[j].shape == tr["msa"].shape and np.array_equal(msas[j], tr["msa"]), j
+        assert int(cells[j]) == tr["cells"], j
+
+
 def test_flower_submit_wait_equals_the_synchronous_call(engine, oracle_built):
     """barb200_flower_submit / barb200_flower_wait: 30 tickets submitted before the first wait share a few device batches and
     deliver what the synchronous call (and the oracle) delivers"""
