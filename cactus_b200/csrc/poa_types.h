@@ -112,8 +112,9 @@ struct alignas(16) RowInfo {
 //      below 65535 (barb200_create checks). 0xffff encodes "minus infinity" (row 0, where E does not derive from H);
 //      cells outside the band hold H = inf_min, D = 0.
 //   F1 / F2 are NOT stored: the traceback reads them only at the few cells where an insertion starts or continues, and they
-//      are a pure function of the row's H' = max(M + s, E1, E2), which the predecessor rows' H / D give back; the
-//      traceback recomputes the row prefix it needs (poa_graph.cuh: row_f_cache).
+//      are a pure function of the row's H' = max(M + s, E1, E2), which the predecessor rows' H / D give back. The warp traceback
+//      decides "H == F" and the insertion's length from the row's own H values (poa_cta.cuh: warp_backtrack_step); the serial form
+//      (host build, debug mode) recomputes the row prefix it needs (poa_graph.cuh: row_f_cache).
 constexpr int CPT = 16;
 constexpr int E_NEG16 = 0xffff;
 struct DpState {
