@@ -434,14 +434,81 @@ HD int backtrack_step(const Graph &g, const RowTables &rt, DpState &d, const Poa
     return -1;
 }
 
+// The rule the kernel's warp traceback applies (poa_cta.cuh: warp_backtrack_step), stated serially: M and E exactly as in
+// backtrack_step; an insertion is taken WHOLE and without F planes. With F[j] = max_t H[i][j-t] - oe - (t-1) e (:1060-1075) and
+// H[i][j] >= F[j]: H[i][j] == F1[j] iff some t >= 1 has H[i][j-t] == H[i][j] + oe1 + (t-1) e1, the smallest such t is the length of
+// the insertion the reference walks ("open" is tested before "extend" at every column, :401-415), and since H[i][j] >= F2[j] bounds
+// H[i][j-t] <= H[i][j] + oe2 + (t-1) e2 the F1 equation has no solution beyond (oe2 - oe1) / (e1 - e2) + 1 columns when e1 > e2.
+// Returns the op, `len` = its length (1 unless CINS), moves (i, j, cur_op) past the whole op. The host build runs it in lock step
+// with the reference's rule on every traceback (dp_backtrack below): the CPU suite checks the claim on all of its inputs.
+HD int backtrack_step_without_f(const RowTables &rt, const DpState &d, const PoaParams &P, const uint8_t *q, int &i, int &j, int &cur_op, int &len) {
+    const int inf = P.inf_min, e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    len = 1;
+    const int s = P.mat[5 * row_base(rt, i) + q[j - 1]];
+    const int p0 = rt.rec[i].pre_off, p1 = p0 + row_npre(rt, i);
+    const int hij = plane_cell(d, inf, i, 0, j);
+    if (cur_op & OP_M)
+        for (int k = p0; k < p1; ++k) {
+            const int pi = rt.pre_row[k];
+            if (j - 1 < d.info[pi].beg || j - 1 > d.info[pi].end) continue;
+            if (plane_cell(d, inf, pi, 0, j - 1) + s == hij) { i = pi; --j; cur_op = OP_ALL; return CMATCH; }
+        }
+    if (cur_op & OP_E)
+        for (int k = p0; k < p1; ++k) {
+            const int pi = rt.pre_row[k];
+            if (j < d.info[pi].beg || j > d.info[pi].end) continue;
+            const int ph = plane_cell(d, inf, pi, 0, j), pe1 = plane_cell(d, inf, pi, 1, j), pe2 = plane_cell(d, inf, pi, 2, j);
+            const bool ok1 = (cur_op & OP_E1) && ((cur_op & OP_M) ? hij == pe1 : plane_cell(d, inf, i, 1, j) == pe1 - e1);
+            const bool ok2 = (cur_op & OP_E2) && ((cur_op & OP_M) ? hij == pe2 : plane_cell(d, inf, i, 2, j) == pe2 - e2);
+            if (ok1) { cur_op = (ph - oe1 == pe1) ? (OP_M | OP_F) : OP_E1; i = pi; return CDEL; }
+            if (ok2) { cur_op = (ph - oe2 == pe2) ? (OP_M | OP_F) : OP_E2; i = pi; return CDEL; }
+        }
+    if (cur_op & OP_F) {
+        if (!(cur_op & OP_M)) return -1;                     // F states always carry M: insertions are never left half walked
+        const int avail = j - d.info[i].beg;
+        int t1_max;
+        if (e1 > e2) t1_max = oe2 >= oe1 ? (oe2 - oe1) / (e1 - e2) + 1 : 0;
+        else t1_max = (e1 < e2 || oe1 <= oe2) ? avail : 0;
+        if (t1_max > avail) t1_max = avail;
+        for (int which = 0; which < 2; ++which) {
+            if (!(cur_op & (which ? OP_F2 : OP_F1))) continue;
+            const int oe = which ? oe2 : oe1, e = which ? e2 : e1, tmax = which ? avail : t1_max;
+            for (int t = 1; t <= tmax; ++t)
+                if (plane_cell(d, inf, i, 0, j - t) == hij + oe + (t - 1) * e) { len = t; j -= t; cur_op = OP_M | OP_E; return CINS; }
+        }
+    }
+    return -1;
+}
+
 // simd_abpoa_cg_backtrack (abpoa_align_simd.c:309-458), serial form. Emits the graph cigar in forward order.
 HD void dp_backtrack(Graph &g, const RowTables &rt, DpState &d, const PoaParams &P, const uint8_t *q, int L) {
     d.n_cigar = 0; d.fc_row = -1; d.fc_hi = -1;
     int i = d.best_i, j = d.best_j, cur_op = OP_ALL;
     if (j < L) push_cigar(d, g, CINS, L - j, -1, L - 1);
+#if !defined(__CUDA_ARCH__)
+    int chk_op = -1, chk_left = 0, chk_i = 0, chk_j = 0, chk_cur = 0;     // the F-free rule's prediction (below)
+#endif
     while (i > 0 && j > 0 && !g.err) {
         const int id = g.index_to_node[i], jq = j - 1;
+#if !defined(__CUDA_ARCH__)
+        // host build: the F-free rule must walk the same ops (an insertion = its `len` single steps of the reference's rule)
+        if (!(cur_op == OP_F1 || cur_op == OP_F2)) {
+            int ci = i, cj = j, cop = cur_op, clen = 1;
+            chk_op = backtrack_step_without_f(rt, d, P, q, ci, cj, cop, clen);
+            chk_left = chk_op == CINS ? clen : 1; chk_i = ci; chk_j = cj; chk_cur = cop;
+        }
+#endif
         const int op = backtrack_step(g, rt, d, P, q, L, i, j, cur_op);
+#if !defined(__CUDA_ARCH__)
+        if (op >= 0) {
+            bool same = op == chk_op && chk_left >= 1;
+            if (same && --chk_left == 0) same = i == chk_i && j == chk_j && cur_op == chk_cur;
+            if (!same) {
+                fprintf(stderr, "barb200: the F-free traceback rule disagrees with the reference's at row %d col %d (op %d vs %d)\n", i, j, op, chk_op);
+                g.err = JOB_ERR_BACKTRACK; return;
+            }
+        }
+#endif
         if (op < 0) {
 #if defined(__CUDA_ARCH__)
             printf("barb200: backtrack stuck at row %d col %d cur_op %d (band %d..%d, H %d) best %d,%d n_cigar %d\n", i, j, cur_op,
