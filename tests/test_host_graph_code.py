@@ -6,7 +6,7 @@ import numpy as np
 
 import _golden as G
 import _reflib as R
-from _synth import family
+from _synth import family, gapped_family
 from test_oracle_vs_ref import assert_same_trace
 
 
@@ -33,6 +33,20 @@ def test_hosttest_random_vs_oracle(oracle_built):
         p = R.cactus_params() if rng.random() < 0.5 else R.cactus_params(
             wb=int(rng.choice([0, 5, 10, 30, 100])), wf=float(rng.choice([0.0, 0.01, 0.02, 0.1])), progressive=int(rng.integers(0, 2)))
         assert_same_trace(R.oracle_poa_msa_trace(seqs, p), R.hosttest_poa_msa_trace(seqs, p), (it, K, L, kw))
+
+
+def test_traceback_rule_without_f_planes_many_gap_models():
+    """the warp traceback's rule (insertions whole, from the row's H values; F1 only within the convex crossover distance), stated
+    serially, runs in lock step with the reference's rule inside the host build's traceback (poa_graph.cuh: dp_backtrack) and fails the
+    job on any disagreement: a few hundred alignments with block indels under random convex gap penalties of every ordering"""
+    rng = np.random.default_rng(2024)
+    fixed = [(400, 30, 1200, 1), (4, 2, 24, 1), (10, 3, 10, 3), (50, 1, 3, 9), (7, 5, 100, 5), (300, 2, 20, 40), (1, 1, 1, 1)]
+    for it in range(60):
+        o1, e1, o2, e2 = fixed[it] if it < len(fixed) else (int(rng.integers(1, 600)), int(rng.integers(1, 40)), int(rng.integers(1, 1500)), int(rng.integers(1, 40)))
+        p = R.cactus_params(o1=o1, e1=e1, o2=o2, e2=e2, wb=int(rng.choice([20, 100, 1000])), wf=0.05)
+        seqs = gapped_family(rng, int(rng.integers(2, 7)), int(rng.choice([40, 150, 400])), [1, 2, 3, 5, 9, 20, 27, 28, 33, 64, 90])
+        tr = R.hosttest_poa_msa_trace(seqs, p)           # asserts job status 0
+        assert tr["msa"].shape[0] == len(seqs)
 
 
 def test_hosttest_unrelated_ragged(oracle_built):
