@@ -35,6 +35,18 @@ def test_queue_merges_tickets_and_matches_the_oracle(oracle_built):
     _check(flowers, res, p)
 
 
+def test_a_burst_of_submissions_shares_one_batch(oracle_built):
+    """one thread submits 40 flowers back to back before its first wait (the shim's bar() does this with thousands): the lane worker
+    lingers while tickets keep arriving instead of launching a batch of the first few"""
+    rng = np.random.default_rng(15)
+    p = R.cactus_params(wb=10, wf=0.01)
+    flowers = _flowers(rng, 40, L=30, kmax=3)
+    res, rcs, batches = R.hosttest_flowers(flowers, p=p, n_lanes=2, n_threads=1)
+    assert not rcs.any()
+    assert batches <= 3, batches
+    _check(flowers, res, p)
+
+
 def test_small_batch_limit_and_many_windows(oracle_built):
     """a tiny job limit forces many batches; a tiny window forces several rounds per end (tickets re-enter the queue)"""
     rng = np.random.default_rng(12)
